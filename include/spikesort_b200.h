@@ -1,0 +1,186 @@
+/*
+ * spikesort_b200 - C ABI of the B200-native SpikeSort front end
+ * (filter -> threshold -> detect -> align/extract -> PCA).
+ *
+ * This is the drop-in boundary for the hot path of btel/SpikeSort
+ * (reference paths relative to src/spike_sort/core/).  The reference has no
+ * FFI of its own: its hot path is NumPy/SciPy calls inside
+ *   filters.py:99-143   Filter.__call__ / filter_proxy
+ *   extract.py:43-94    detect_spikes
+ *   extract.py:97-184   filter_spt / extract_spikes
+ *   extract.py:208-288  align_spikes / remove_doubles
+ *   features.py:200-232 PCA, features.py:310-346 fetPCA
+ * Each entry point below names the lines it replaces.  A ctypes binding (what a
+ * SpikeSort maintainer would add) is shown in INTEGRATION.md and implemented in
+ * spikesort_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only, no C++/torch types;
+ *   - every pointer named d_* is DEVICE memory owned by the caller, everything
+ *     else is host memory; the library never allocates device memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all
+ *     work is enqueued on it and NO call synchronises the host;
+ *   - return value: 0 on success, negative ss_status on failure, message via
+ *     ss_last_error() (thread-local);
+ *   - recordings are row-major (n_contacts, n_samples) with a row stride `ld`
+ *     in elements, dtype one of ss_dtype;
+ *   - several contacts ("rows") are processed by one call; per-row results are
+ *     concatenated and delimited by an offsets array of n_rows+1 int64.
+ */
+#ifndef SPIKESORT_B200_H
+#define SPIKESORT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_VERSION 100            /* 0.1.0 */
+
+typedef enum { SS_I16 = 0, SS_F32 = 1, SS_F64 = 2 } ss_dtype;
+
+typedef enum {
+    SS_OK = 0,
+    SS_ERR_ARG = -1,              /* bad argument                                        */
+    SS_ERR_CUDA = -2,             /* CUDA runtime error (message has the detail)         */
+    SS_ERR_PADLEN = -3,           /* a chunk is not longer than padlen (SciPy ValueError) */
+    SS_ERR_WORKSPACE = -4,        /* workspace too small                                 */
+    SS_ERR_UNSUPPORTED = -5       /* filter order / window size outside compiled range   */
+} ss_status;
+
+int         ss_version(void);
+const char *ss_last_error(void);
+/* limits compiled into the library */
+int         ss_max_filter_order(void);      /* total number of delay states     */
+int         ss_max_window(void);            /* largest n_win for align/extract/PCA */
+
+/* ------------------------------------------------------------------ filter
+ * Replaces Filter.__call__ -> scipy.signal.filtfilt (filters.py:99-101) looped
+ * over (contact, chunk) by filter_proxy (filters.py:135-141): zero-phase IIR,
+ * odd extension of `padlen` samples at both ends of EVERY chunk, steady-state
+ * initial conditions, float64 output.
+ *
+ * The filter is given as a cascade of `n_sections` second-order sections in
+ * SciPy's sos layout [b0 b1 b2 a0 a1 a2] (a0 must be 1; a first-order section
+ * has b2 = a2 = 0 and must come last).  The Python host derives the sections
+ * from the reference's (b, a) coefficients (spikesort_b200/_design.py).
+ * padlen is the reference's 3*max(len(a), len(b)).
+ */
+size_t ss_filtfilt_workspace_bytes(int64_t n_contacts, int64_t n_samples,
+                                   int64_t chunksize, int padlen, int n_sections);
+int ss_filtfilt_sos(const void *d_x, int dtype, int64_t n_contacts, int64_t n_samples,
+                    int64_t ld_in, const double *sos, int n_sections, int padlen,
+                    int64_t chunksize, double *d_out, int64_t ld_out,
+                    void *d_ws, size_t ws_bytes, void *stream);
+
+/* --------------------------------------------------------------- threshold
+ * Replaces extract.py:79: thr[r] = factor * sqrt(var(x[r, :n0])) (population
+ * variance, float64).  `factor` carries the sign (negative for falling edges,
+ * extract.py:80-81).  d_ws: at least ss_threshold_workspace_bytes(n_rows).
+ */
+size_t ss_threshold_workspace_bytes(int64_t n_rows);
+int ss_var_threshold(const void *d_x, int dtype, int64_t n_rows, int64_t ld, int64_t n0,
+                     double factor, double *d_thr, void *d_ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------ detect
+ * Replaces extract.py:86-93.  Row r has a crossing at i when
+ *   rising : x[r,i] < thr[r] && x[r,i+1] > thr[r]      (falling: swapped)
+ * and reports t = i*1000.0/FS (float64 ms), ascending per row.
+ * ss_detect_mark   : one pass over the data -> crossing bitmask + counts in the
+ *                    workspace, and d_offsets[n_rows+1] (exclusive prefix sum of
+ *                    the per-row counts; last entry = total).
+ * ss_detect_emit   : writes the total times into d_spt (capacity `cap`); reads
+ *                    only the workspace.  The caller reads d_offsets in between
+ *                    to size d_spt.
+ */
+size_t ss_detect_workspace_bytes(int64_t n_rows, int64_t n_samples);
+int ss_detect_mark(const void *d_x, int dtype, int64_t n_rows, int64_t n_samples, int64_t ld,
+                   const double *d_thr, int falling, void *d_ws, size_t ws_bytes,
+                   int64_t *d_offsets, void *stream);
+int ss_detect_emit(int64_t n_rows, int64_t n_samples, double FS, const void *d_ws,
+                   size_t ws_bytes, double *d_spt, int64_t cap, void *stream);
+
+/* ------------------------------------------------------------------- align
+ * Replaces the loop of align_spikes (extract.py:235-265), resample == 1.
+ * Spikes d_spt[d_offsets[r] .. d_offsets[r+1]) are aligned on row
+ * d_rows[r] of the recording (d_rows NULL: row r).  For each spike, while
+ * t_min <= t <= t_max: centre = (int32)(t/1000.0*FS); find the FIRST max (or
+ * min) of float32(x[centre+win0 .. centre+win1)); t += k*1000.0/FS + sp_win0;
+ * stop unless that shift is < lo or > hi.  All doubles are computed by the
+ * host exactly as NumPy does (extract.py:108-109,151-152,229,263-264).
+ */
+int ss_align(const void *d_x, int dtype, int64_t n_samples, int64_t ld, double FS,
+             const int32_t *d_rows, int64_t n_rows, const int64_t *d_offsets,
+             double sp_win0, int win0, int win1, double t_min, double t_max,
+             double lo, double hi, int use_min, double *d_spt, int64_t n_spk,
+             int max_iter, void *stream);
+
+/* Replaces remove_doubles (extract.py:277-288) per row: keeps the first time
+ * of each row and every time with (int64)((t[k]-t[k-1])/tol) > 1.
+ * mark: flags + d_offsets_out[n_rows+1]; emit: compacted times into d_out.
+ */
+size_t ss_remove_doubles_workspace_bytes(int64_t n_spk);
+int ss_remove_doubles_mark(const double *d_spt, int64_t n_spk, const int64_t *d_offsets,
+                           int64_t n_rows, double tol, void *d_ws, size_t ws_bytes,
+                           int64_t *d_offsets_out, void *stream);
+int ss_remove_doubles_emit(const double *d_spt, int64_t n_spk, const void *d_ws,
+                           size_t ws_bytes, double *d_out, int64_t cap, void *stream);
+
+/* ----------------------------------------------------------------- extract
+ * Replaces extract_spikes (extract.py:146-177), resample == 1.
+ * Output d_waves is float32 (n_win, n_spk, n_c) C-contiguous, n_win = win1-win0.
+ *   d_contacts != NULL : every spike is cut on the n_c listed contacts
+ *                        (the reference's `contacts` argument);
+ *   d_contacts == NULL : n_c must be 1 and spike s is cut on row
+ *                        d_rows[r] (NULL: r) for d_offsets[r] <= s < d_offsets[r+1]
+ *                        (the per-contact chain).
+ * Windows leaving [0, n_samples) are clipped and zero-filled.
+ * d_valid[s] = (t_min <= t <= t_max) (extract.py:147-148,174-177);
+ * *d_n_invalid counts the invalid ones (0 -> the reference omits 'is_valid').
+ */
+int ss_extract(const void *d_x, int dtype, int64_t n_samples, int64_t ld, double FS,
+               const int32_t *d_contacts, int n_c,
+               const int32_t *d_rows, int64_t n_rows, const int64_t *d_offsets,
+               int win0, int win1, double t_min, double t_max,
+               const double *d_spt, int64_t n_spk,
+               float *d_waves, uint8_t *d_valid, int32_t *d_n_invalid, void *stream);
+
+/* --------------------------------------------------------------------- PCA
+ * Replaces PCA / fetPCA (features.py:224-231, 326-344) on a float32 waveform
+ * block (n_win, n_spk, n_c).  A "group" is one PCA problem:
+ *   d_offsets == NULL : n_groups = n_c, group g = contact g over all spikes
+ *                       (fetPCA's loop, features.py:335-336);
+ *   d_offsets != NULL : n_c must be 1, group g = spikes [d_offsets[g], d_offsets[g+1]).
+ * ss_pca_gram    : d_gram[g] = sum_s (x_s - ref_g)(x_s - ref_g)^T (n_win x n_win,
+ *                  float64), d_sum[g] = sum_s (x_s - ref_g).  d_ref[g][n_win] is an
+ *                  INPUT: any waveform close to the mean (the host passes the first
+ *                  spike of the group); it only conditions the arithmetic, the
+ *                  covariance does not depend on it.  Partial Grams of time shards
+ *                  computed with the same ref add up: this is what the multi-GPU
+ *                  path all-reduces.
+ * ss_pca_eig     : covariance (ddof=1) from gram/sum/count, symmetric Jacobi
+ *                  eigensolve, eigenvalues |.| sorted descending, eigenvectors
+ *                  in columns (features.py:225-229).  d_counts[g] = spikes per group.
+ * ss_pca_project : d_scores[s, g*ncomps + j] = (v_j . x_s) / sqrt(eval_j) on the
+ *                  UN-centred data (features.py:230-231); (n_spk, n_groups*ncomps)
+ *                  float64 when d_offsets == NULL, else (n_spk, ncomps).
+ */
+size_t ss_pca_workspace_bytes(int n_win, int64_t n_groups);
+int ss_pca_gram(const float *d_waves, int n_win, int64_t n_spk, int n_c,
+                const int64_t *d_offsets, int64_t n_groups, const double *d_ref,
+                double *d_gram, double *d_sum,
+                void *d_ws, size_t ws_bytes, void *stream);
+int ss_pca_eig(const double *d_gram, const double *d_sum,
+               const int64_t *d_counts, int n_win, int64_t n_groups,
+               double *d_evals, double *d_evecs, void *stream);
+int ss_pca_project(const float *d_waves, int n_win, int64_t n_spk, int n_c,
+                   const int64_t *d_offsets, int64_t n_groups,
+                   const double *d_evals, const double *d_evecs, int ncomps,
+                   double *d_scores, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPIKESORT_B200_H */

@@ -1,0 +1,73 @@
+// Shared helpers for the spikesort_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include "spikesort_b200.h"
+
+void ss_set_error(const char *fmt, ...);
+
+#define SS_CUDA_CHECK(expr)                                                          \
+    do {                                                                             \
+        cudaError_t e__ = (expr);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            ss_set_error("%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                         __LINE__);                                                  \
+            return SS_ERR_CUDA;                                                      \
+        }                                                                            \
+    } while (0)
+
+#define SS_LAUNCH_CHECK(name)                                                        \
+    do {                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) {                                                    \
+            ss_set_error("launch of %s: %s", name, cudaGetErrorString(e__));         \
+            return SS_ERR_CUDA;                                                      \
+        }                                                                            \
+    } while (0)
+
+#define SS_REQUIRE(cond, code, ...)                                                  \
+    do {                                                                             \
+        if (!(cond)) {                                                               \
+            ss_set_error(__VA_ARGS__);                                               \
+            return code;                                                             \
+        }                                                                            \
+    } while (0)
+
+static inline size_t ss_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static inline int64_t ss_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__device__ __forceinline__ int64_t ss_cdiv_dev(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+constexpr unsigned SS_FULL = 0xffffffffu;
+constexpr int SS_NUM_SMS = 148;   // B200
+
+// One recording element as float64 (exact for all three dtypes).
+__device__ __forceinline__ double ss_load(const void *base, int dtype, int64_t i)
+{
+    if (dtype == SS_I16) return (double)__ldg(reinterpret_cast<const int16_t *>(base) + i);
+    if (dtype == SS_F32) return (double)__ldg(reinterpret_cast<const float *>(base) + i);
+    return __ldg(reinterpret_cast<const double *>(base) + i);
+}
+
+// The same element rounded to float32 (what extract_spikes stores, extract.py:157-163).
+__device__ __forceinline__ float ss_load_f32(const void *base, int dtype, int64_t i)
+{
+    if (dtype == SS_I16) return (float)__ldg(reinterpret_cast<const int16_t *>(base) + i);
+    if (dtype == SS_F32) return __ldg(reinterpret_cast<const float *>(base) + i);
+    return __double2float_rn(__ldg(reinterpret_cast<const double *>(base) + i));
+}
+
+__device__ __forceinline__ double ss_shfl_up(double v, int d)
+{
+    return __shfl_up_sync(SS_FULL, v, d);
+}
+__device__ __forceinline__ double ss_shfl_down(double v, int d)
+{
+    return __shfl_down_sync(SS_FULL, v, d);
+}
+__device__ __forceinline__ double ss_shfl(double v, int src)
+{
+    return __shfl_sync(SS_FULL, v, src);
+}
+
+static inline int ss_elem_size(int dtype) { return dtype == SS_I16 ? 2 : dtype == SS_F32 ? 4 : 8; }

@@ -1,0 +1,771 @@
+// K1 - zero-phase IIR filter (filtfilt) of every (contact, chunk) unit as a
+// tiled two-sweep linear-recurrence scan over second-order-section state.
+//
+// Replaces Filter.__call__ -> scipy.signal.filtfilt (reference
+// src/spike_sort/core/filters.py:99-101) and the (contact, chunk) double loop
+// of filter_proxy (filters.py:135-141).
+//
+// One unit = one contact x one chunk of `chunksize` samples, filtered on its
+// own exactly as the reference does: odd extension by `edge` samples at both
+// ends (in the input dtype, as NumPy computes it), forward pass from the
+// steady state zi*ext[0], backward pass over the forward output from
+// zi*y[-1], then the extension is dropped.
+//
+// Parallel formulation (DESIGN.md "K1"):
+//   - the extended unit is left-padded with copies of ext[0] up to a multiple
+//     of the tile length T = 32*S; because zi is the steady state for a
+//     constant input, starting from zi*ext[0] at the beginning of the padding
+//     reproduces zi*ext[0] at ext[0];
+//   - a warp owns one tile: lane l keeps samples [l*S, (l+1)*S) in registers,
+//     runs the section cascade locally from a zero state (the seeded lane
+//     from the true tile state), an inclusive warp scan with A^(S*2^k)
+//     propagates lane end states, and y[i] += (C A^i) . prefix corrects the
+//     local outputs;
+//   - sweep 1 (filt_summary_kernel) reads x once and emits per tile the
+//     zero-state forward end state F, the zero-state backward end state Bz of
+//     the zero-state forward output, and the last zero-state output;
+//   - filt_tilescan_kernel (one warp per unit) scans F over the tiles of a
+//     unit, forms y[-1], then scans Bz + M*Zf backwards (M = backward response
+//     to the forward homogeneous response of a tile);
+//   - sweep 2 (filt_apply_kernel) reads x again, redoes the forward pass from
+//     the true tile state Zf, the backward pass from Zb, and writes float64.
+// HBM traffic: 2 reads of x + 1 write of float64 (+ ~(4*NS+1)*8/T bytes of tile
+// summaries per sample).  All tables are computed on the host in binary128.
+#include "common.cuh"
+#include <vector>
+#include <cstring>
+#include <mutex>
+#include <map>
+
+namespace {
+
+constexpr int FS_S = 16;            // samples per lane
+constexpr int FS_T = 32 * FS_S;     // samples per tile (one warp)
+constexpr int FS_WPB = 4;           // warps per block
+constexpr int FS_PADT = FS_T + FS_T / FS_S;   // padded smem tile (bank-conflict free)
+constexpr int MAX_NB = 6;           // up to 6 biquads (+1 first-order) -> 13 states
+constexpr int MAX_NS = 2 * MAX_NB + 1;
+
+struct FiltGeom {
+    int64_t n_contacts, n_samples, ld_in, ld_out, chunksize;
+    int64_t n_full;              // number of chunks of full length
+    int64_t len_last;            // length of the trailing shorter chunk (0: none)
+    int64_t nt_full, nt_last;    // tiles per full / last unit
+    int64_t tiles_per_contact, total_tiles;
+    int64_t units_per_contact, n_units;
+    int edge, dtype;
+};
+
+struct TileInfo {
+    int64_t c, cs0, L, nt, t, pad, g0;   // contact, chunk start, chunk length, tiles in unit,
+                                         // tile in unit, left padding, first tile of unit
+};
+
+__device__ __forceinline__ TileInfo decode_unit(const FiltGeom &g, int64_t c, int64_t j)
+{
+    TileInfo ti;
+    ti.c = c;
+    ti.cs0 = j * g.chunksize;
+    const bool last = j >= g.n_full;
+    ti.L = last ? g.len_last : g.chunksize;
+    ti.nt = last ? g.nt_last : g.nt_full;
+    ti.t = 0;
+    ti.pad = ti.nt * FS_T - (ti.L + 2 * (int64_t)g.edge);
+    ti.g0 = c * g.tiles_per_contact + j * g.nt_full;
+    return ti;
+}
+
+__device__ __forceinline__ TileInfo decode_tile(const FiltGeom &g, int64_t tile)
+{
+    const int64_t c = tile / g.tiles_per_contact;
+    const int64_t r = tile - c * g.tiles_per_contact;
+    int64_t j = r / g.nt_full;
+    if (j > g.n_full) j = g.n_full;
+    TileInfo ti = decode_unit(g, c, j);
+    ti.t = r - j * g.nt_full;
+    return ti;
+}
+
+// 2*x[iend] - x[iin] in the INPUT dtype (scipy.signal._arraytools.odd_ext on a
+// NumPy array: int16 wraps around, float32 rounds to float32).
+__device__ __forceinline__ double odd_value(const void *x, int dtype, int64_t iend, int64_t iin)
+{
+    if (dtype == SS_I16) {
+        const int16_t *p = reinterpret_cast<const int16_t *>(x);
+        const int16_t two = (int16_t)(2 * (int)__ldg(p + iend));
+        return (double)(int16_t)((int)two - (int)__ldg(p + iin));
+    }
+    if (dtype == SS_F32) {
+        const float *p = reinterpret_cast<const float *>(x);
+        return (double)__fsub_rn(__fmul_rn(2.0f, __ldg(p + iend)), __ldg(p + iin));
+    }
+    const double *p = reinterpret_cast<const double *>(x);
+    return __dsub_rn(__dmul_rn(2.0, __ldg(p + iend)), __ldg(p + iin));
+}
+
+// value of the extended chunk at index e (e < 0: constant left padding = ext[0])
+__device__ __forceinline__ double ext_value(const void *x, int dtype, int64_t row0,
+                                            const TileInfo &ti, int edge, int64_t e)
+{
+    if (e < 0) e = 0;
+    const int64_t r = e - edge;
+    const int64_t base = row0 + ti.cs0;
+    if (r < 0) return odd_value(x, dtype, base, base - r);
+    if (r < ti.L) return ss_load(x, dtype, base + r);
+    const int64_t k = r - (ti.L - 1);
+    return odd_value(x, dtype, base + ti.L - 1, base + ti.L - 1 - k);
+}
+
+template <int NB, bool FO>
+struct FiltParams {
+    static constexpr int NS = 2 * NB + (FO ? 1 : 0);
+    static constexpr int NSEC = NB + (FO ? 1 : 0);
+    double sec[NSEC][5];          // b0 b1 b2 a1 a2 per section (first-order: b2 = a2 = 0)
+    double hrow[FS_S][NS];        // C A^i, i < S
+    double P[5][NS][NS];          // A^(S 2^k)
+};
+
+template <int NS>
+struct ScanParams {
+    double Q[5][NS][NS];          // (A^T)^(2^k)
+    double AT[NS][NS];            // A^T
+    double M[NS][NS];             // backward end state per unit of forward start state
+    double hlast[NS];             // C A^(T-1)
+    double zi[NS];                // steady state for a unit step
+};
+
+// one sample through the cascade; z updated; returns the cascade output
+template <int NB, bool FO>
+__device__ __forceinline__ double cascade_step(const FiltParams<NB, FO> &P,
+                                               double (&z)[FiltParams<NB, FO>::NS], double x)
+{
+#pragma unroll
+    for (int s = 0; s < NB; ++s) {
+        const double y = z[2 * s] + P.sec[s][0] * x;
+        z[2 * s] = z[2 * s + 1] + P.sec[s][1] * x - P.sec[s][3] * y;
+        z[2 * s + 1] = P.sec[s][2] * x - P.sec[s][4] * y;
+        x = y;
+    }
+    if (FO) {
+        const double y = z[2 * NB] + P.sec[NB][0] * x;
+        z[2 * NB] = P.sec[NB][1] * x - P.sec[NB][3] * y;
+        x = y;
+    }
+    return x;
+}
+
+template <int NB, bool FO, bool REV>
+__device__ __forceinline__ void local_pass(const FiltParams<NB, FO> &P, double (&v)[FS_S],
+                                           double (&z)[FiltParams<NB, FO>::NS])
+{
+#pragma unroll
+    for (int ii = 0; ii < FS_S; ++ii) {
+        const int i = REV ? FS_S - 1 - ii : ii;
+        v[i] = cascade_step<NB, FO>(P, z, v[i]);
+    }
+}
+
+// inclusive scan of lane end states in processing order (REV: lane 31 first)
+template <int NS, bool REV>
+__device__ __forceinline__ void warp_scan(double (&e)[NS], const double (&Pm)[5][NS][NS], int lane)
+{
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const int d = 1 << k;
+        double o[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) o[i] = REV ? ss_shfl_down(e[i], d) : ss_shfl_up(e[i], d);
+        const bool act = REV ? (lane + d < 32) : (lane >= d);
+        if (act) {
+#pragma unroll
+            for (int r = 0; r < NS; ++r) {
+                double acc = e[r];
+#pragma unroll
+                for (int c = 0; c < NS; ++c) acc += Pm[k][r][c] * o[c];
+                e[r] = acc;
+            }
+        }
+    }
+}
+
+// state at the start of each lane's segment (zero for the seeded lane: its
+// local pass already started from the true state)
+template <int NS, bool REV>
+__device__ __forceinline__ void exclusive_prefix(const double (&e)[NS], double (&pre)[NS], int lane)
+{
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const double t = REV ? ss_shfl_down(e[i], 1) : ss_shfl_up(e[i], 1);
+        pre[i] = (REV ? lane == 31 : lane == 0) ? 0.0 : t;
+    }
+}
+
+template <int NB, bool FO, bool REV>
+__device__ __forceinline__ void correct(const FiltParams<NB, FO> &P, double (&v)[FS_S],
+                                        const double (&pre)[FiltParams<NB, FO>::NS])
+{
+    constexpr int NS = FiltParams<NB, FO>::NS;
+#pragma unroll
+    for (int ii = 0; ii < FS_S; ++ii) {
+        const int i = REV ? FS_S - 1 - ii : ii;
+        double acc = v[i];
+#pragma unroll
+        for (int c = 0; c < NS; ++c) acc += P.hrow[ii][c] * pre[c];
+        v[i] = acc;
+    }
+}
+
+// coalesced read of one tile into padded shared memory, then per-lane segments
+__device__ __forceinline__ void load_tile(const void *x, const FiltGeom &g, const TileInfo &ti,
+                                          double *sm, int lane, double (&v)[FS_S])
+{
+    const int64_t row0 = ti.c * g.ld_in;
+    const int64_t e0 = ti.t * FS_T - ti.pad;            // ext index of the tile's first sample
+    const int64_t r0 = e0 - g.edge;                     // chunk-relative index
+    if (r0 >= 0 && r0 + FS_T <= ti.L) {
+        const int64_t base = row0 + ti.cs0 + r0;
+#pragma unroll
+        for (int k = 0; k < FS_S; ++k) {
+            const int j = 32 * k + lane;
+            sm[j + j / FS_S] = ss_load(x, g.dtype, base + j);
+        }
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < FS_S; ++k) {
+            const int j = 32 * k + lane;
+            sm[j + j / FS_S] = ext_value(x, g.dtype, row0, ti, g.edge, e0 + j);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < FS_S; ++i) v[i] = sm[lane * (FS_S + 1) + i];
+    __syncwarp();
+}
+
+template <int NB, bool FO>
+__global__ void __launch_bounds__(32 * FS_WPB)
+filt_summary_kernel(const void *__restrict__ x, const FiltGeom g,
+                    const __grid_constant__ FiltParams<NB, FO> P,
+                    double *__restrict__ F, double *__restrict__ Bz, double *__restrict__ ylast)
+{
+    constexpr int NS = FiltParams<NB, FO>::NS;
+    __shared__ double sm_all[FS_WPB][FS_PADT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * FS_WPB + warp;
+    if (tile >= g.total_tiles) return;
+    const TileInfo ti = decode_tile(g, tile);
+    double v[FS_S];
+    load_tile(x, g, ti, sm_all[warp], lane, v);
+
+    double e[NS], pre[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) e[i] = 0.0;
+    local_pass<NB, FO, false>(P, v, e);
+    warp_scan<NS, false>(e, P.P, lane);
+    exclusive_prefix<NS, false>(e, pre, lane);
+    correct<NB, FO, false>(P, v, pre);
+    if (lane == 31) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) F[tile * NS + i] = e[i];
+        ylast[tile] = v[FS_S - 1];
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) e[i] = 0.0;
+    local_pass<NB, FO, true>(P, v, e);
+    warp_scan<NS, true>(e, P.P, lane);
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) Bz[tile * NS + i] = e[i];
+    }
+}
+
+template <int NB, bool FO>
+__global__ void __launch_bounds__(32 * FS_WPB)
+filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
+                  const __grid_constant__ FiltParams<NB, FO> P,
+                  const double *__restrict__ Zf, const double *__restrict__ Zb,
+                  double *__restrict__ out)
+{
+    constexpr int NS = FiltParams<NB, FO>::NS;
+    __shared__ double sm_all[FS_WPB][FS_PADT];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * FS_WPB + warp;
+    if (tile >= g.total_tiles) return;
+    const TileInfo ti = decode_tile(g, tile);
+    double *sm = sm_all[warp];
+    double v[FS_S];
+    load_tile(x, g, ti, sm, lane, v);
+
+    double e[NS], pre[NS];
+    // forward from the true tile state
+#pragma unroll
+    for (int i = 0; i < NS; ++i) e[i] = (lane == 0) ? Zf[tile * NS + i] : 0.0;
+    local_pass<NB, FO, false>(P, v, e);
+    warp_scan<NS, false>(e, P.P, lane);
+    exclusive_prefix<NS, false>(e, pre, lane);
+    correct<NB, FO, false>(P, v, pre);
+    // backward over the forward output
+#pragma unroll
+    for (int i = 0; i < NS; ++i) e[i] = (lane == 31) ? Zb[tile * NS + i] : 0.0;
+    local_pass<NB, FO, true>(P, v, e);
+    warp_scan<NS, true>(e, P.P, lane);
+    exclusive_prefix<NS, true>(e, pre, lane);
+    correct<NB, FO, true>(P, v, pre);
+
+    // transpose through shared memory, coalesced float64 stores of the chunk part
+#pragma unroll
+    for (int i = 0; i < FS_S; ++i) sm[lane * (FS_S + 1) + i] = v[i];
+    __syncwarp();
+    const int64_t r0 = ti.t * FS_T - ti.pad - g.edge;
+    double *orow = out + ti.c * g.ld_out + ti.cs0;
+#pragma unroll
+    for (int k = 0; k < FS_S; ++k) {
+        const int j = 32 * k + lane;
+        const int64_t r = r0 + j;
+        if (r >= 0 && r < ti.L) __stcs(orow + r, sm[j + j / FS_S]);
+    }
+}
+
+// One warp per unit: forward scan of the tile summaries, y[-1], backward scan.
+template <int NS>
+__global__ void __launch_bounds__(32 * FS_WPB)
+filt_tilescan_kernel(const void *__restrict__ x, const FiltGeom g,
+                     const __grid_constant__ ScanParams<NS> P,
+                     const double *__restrict__ F, const double *__restrict__ Bz,
+                     const double *__restrict__ ylast, double *__restrict__ Zf,
+                     double *__restrict__ Zb)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t unit = (int64_t)blockIdx.x * FS_WPB + warp;
+    if (unit >= g.n_units) return;
+    const int64_t c = unit / g.units_per_contact;
+    const int64_t j = unit - c * g.units_per_contact;
+    const TileInfo ti = decode_unit(g, c, j);
+    const int64_t nt = ti.nt, g0 = ti.g0;
+    const int64_t nrows = (nt + 31) / 32;
+
+    const double x0 = ext_value(x, g.dtype, c * g.ld_in, ti, g.edge, 0);
+    double carry[NS], e[NS], pre[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) carry[i] = P.zi[i] * x0;
+
+    double y_last = 0.0;
+    for (int64_t row = 0; row < nrows; ++row) {
+        const int64_t t = row * 32 + lane;
+        const bool valid = t < nt;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) e[i] = valid ? F[(g0 + t) * NS + i] : 0.0;
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < NS; ++r) {
+                double acc = e[r];
+#pragma unroll
+                for (int q = 0; q < NS; ++q) acc += P.AT[r][q] * carry[q];
+                e[r] = acc;
+            }
+        }
+        warp_scan<NS, false>(e, P.Q, lane);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const double up = ss_shfl_up(e[i], 1);
+            pre[i] = lane == 0 ? carry[i] : up;
+        }
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) Zf[(g0 + t) * NS + i] = pre[i];
+        }
+        if (row == nrows - 1) {
+            double yl = 0.0;
+            if (t == nt - 1) {
+                yl = ylast[g0 + t];
+#pragma unroll
+                for (int i = 0; i < NS; ++i) yl += P.hlast[i] * pre[i];
+            }
+            y_last = ss_shfl(yl, (int)((nt - 1) & 31));
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) carry[i] = ss_shfl(e[i], 31);
+    }
+
+#pragma unroll
+    for (int i = 0; i < NS; ++i) carry[i] = P.zi[i] * y_last;
+    for (int64_t row = nrows - 1; row >= 0; --row) {
+        const int64_t t = row * 32 + lane;
+        const bool valid = t < nt;
+        const int64_t left = nt - row * 32;
+        const int seed = (int)(left < 32 ? left : 32) - 1;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) e[i] = 0.0;
+        if (valid) {
+            double zf[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) zf[i] = Zf[(g0 + t) * NS + i];
+#pragma unroll
+            for (int r = 0; r < NS; ++r) {
+                double acc = Bz[(g0 + t) * NS + r];
+#pragma unroll
+                for (int q = 0; q < NS; ++q) acc += P.M[r][q] * zf[q];
+                e[r] = acc;
+            }
+        }
+        if (lane == seed) {
+#pragma unroll
+            for (int r = 0; r < NS; ++r) {
+                double acc = e[r];
+#pragma unroll
+                for (int q = 0; q < NS; ++q) acc += P.AT[r][q] * carry[q];
+                pre[r] = acc;
+            }
+#pragma unroll
+            for (int r = 0; r < NS; ++r) e[r] = pre[r];
+        }
+        warp_scan<NS, true>(e, P.Q, lane);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const double dn = ss_shfl_down(e[i], 1);
+            pre[i] = lane == seed ? carry[i] : dn;
+        }
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) Zb[(g0 + t) * NS + i] = pre[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) carry[i] = ss_shfl(e[i], 0);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+typedef __float128 q_t;
+
+struct QMat {
+    int n;
+    q_t a[MAX_NS][MAX_NS];
+};
+
+static void qmul(const QMat &x, const QMat &y, QMat &r)
+{
+    QMat t;
+    t.n = x.n;
+    for (int i = 0; i < x.n; ++i)
+        for (int j = 0; j < x.n; ++j) {
+            q_t s = 0;
+            for (int k = 0; k < x.n; ++k) s += x.a[i][k] * y.a[k][j];
+            t.a[i][j] = s;
+        }
+    r = t;
+}
+
+struct QSections {
+    int nsec, ns;
+    bool first_order_last;
+    q_t c[MAX_NB + 1][5];
+};
+
+// cascade step in binary128 (same structure as cascade_step)
+static q_t qstep(const QSections &S, q_t *z, q_t x)
+{
+    int p = 0;
+    for (int s = 0; s < S.nsec; ++s) {
+        const bool fo = S.first_order_last && s == S.nsec - 1;
+        const q_t y = z[p] + S.c[s][0] * x;
+        if (fo) {
+            z[p] = S.c[s][1] * x - S.c[s][3] * y;
+            p += 1;
+        } else {
+            z[p] = z[p + 1] + S.c[s][1] * x - S.c[s][3] * y;
+            z[p + 1] = S.c[s][2] * x - S.c[s][4] * y;
+            p += 2;
+        }
+        x = y;
+    }
+    return x;
+}
+
+struct HostTables {
+    int ns;
+    double hrow[FS_S][MAX_NS];
+    double P[5][MAX_NS][MAX_NS];
+    double Q[5][MAX_NS][MAX_NS];
+    double AT[MAX_NS][MAX_NS];
+    double M[MAX_NS][MAX_NS];
+    double hlast[MAX_NS];
+    double zi[MAX_NS];
+};
+
+static int build_tables(const QSections &S, HostTables &T)
+{
+    const int n = S.ns;
+    T.ns = n;
+    QMat A;
+    A.n = n;
+    q_t Bv[MAX_NS], Cv[MAX_NS];
+    for (int k = 0; k < n; ++k) {
+        q_t z[MAX_NS];
+        for (int i = 0; i < n; ++i) z[i] = (i == k) ? 1 : 0;
+        Cv[k] = qstep(S, z, 0);
+        for (int i = 0; i < n; ++i) A.a[i][k] = z[i];
+    }
+    {
+        q_t z[MAX_NS];
+        for (int i = 0; i < n; ++i) z[i] = 0;
+        (void)qstep(S, z, 1);
+        for (int i = 0; i < n; ++i) Bv[i] = z[i];
+    }
+    // rows C A^i for i < T (needed for hrow, hlast and M)
+    std::vector<q_t> rows((size_t)FS_T * n);
+    {
+        q_t r[MAX_NS];
+        for (int i = 0; i < n; ++i) r[i] = Cv[i];
+        for (int t = 0; t < FS_T; ++t) {
+            for (int i = 0; i < n; ++i) rows[(size_t)t * n + i] = r[i];
+            q_t nr[MAX_NS];
+            for (int j = 0; j < n; ++j) {
+                q_t s = 0;
+                for (int i = 0; i < n; ++i) s += r[i] * A.a[i][j];
+                nr[j] = s;
+            }
+            for (int i = 0; i < n; ++i) r[i] = nr[i];
+        }
+    }
+    for (int t = 0; t < FS_S; ++t)
+        for (int i = 0; i < n; ++i) T.hrow[t][i] = (double)rows[(size_t)t * n + i];
+    for (int i = 0; i < n; ++i) T.hlast[i] = (double)rows[(size_t)(FS_T - 1) * n + i];
+    // A^S by repeated multiplication, then squarings
+    QMat pw = A;
+    for (int i = 1; i < FS_S; ++i) qmul(pw, A, pw);
+    for (int k = 0; k < 5; ++k) {
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) T.P[k][i][j] = (double)pw.a[i][j];
+        qmul(pw, pw, pw);
+    }
+    // pw is now A^(32 S) = A^T
+    for (int k = 0; k < 5; ++k) {
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n; ++j) {
+                T.Q[k][i][j] = (double)pw.a[i][j];
+                if (k == 0) T.AT[i][j] = (double)pw.a[i][j];
+            }
+        qmul(pw, pw, pw);
+    }
+    // M[:, k] = backward zero-state end state for the input C A^i e_k, i = T-1 .. 0
+    for (int k = 0; k < n; ++k) {
+        q_t z[MAX_NS];
+        for (int i = 0; i < n; ++i) z[i] = 0;
+        for (int t = FS_T - 1; t >= 0; --t) (void)qstep(S, z, rows[(size_t)t * n + k]);
+        for (int i = 0; i < n; ++i) T.M[i][k] = (double)z[i];
+    }
+    // zi: (I - A) z = Bv   (Gaussian elimination, partial pivoting, binary128)
+    q_t G[MAX_NS][MAX_NS + 1];
+    for (int i = 0; i < n; ++i) {
+        for (int j = 0; j < n; ++j) G[i][j] = (i == j ? (q_t)1 : (q_t)0) - A.a[i][j];
+        G[i][n] = Bv[i];
+    }
+    for (int k = 0; k < n; ++k) {
+        int p = k;
+        for (int i = k + 1; i < n; ++i) {
+            q_t ai = G[i][k] < 0 ? -G[i][k] : G[i][k];
+            q_t ap = G[p][k] < 0 ? -G[p][k] : G[p][k];
+            if (ai > ap) p = i;
+        }
+        if (G[p][k] == 0) return SS_ERR_ARG;      // pole at z = 1
+        if (p != k)
+            for (int j = 0; j <= n; ++j) { q_t t = G[k][j]; G[k][j] = G[p][j]; G[p][j] = t; }
+        for (int i = k + 1; i < n; ++i) {
+            const q_t f = G[i][k] / G[k][k];
+            for (int j = k; j <= n; ++j) G[i][j] -= f * G[k][j];
+        }
+    }
+    q_t zi[MAX_NS];
+    for (int i = n - 1; i >= 0; --i) {
+        q_t s = G[i][n];
+        for (int j = i + 1; j < n; ++j) s -= G[i][j] * zi[j];
+        zi[i] = s / G[i][i];
+    }
+    for (int i = 0; i < n; ++i) T.zi[i] = (double)zi[i];
+    return SS_OK;
+}
+
+struct TableKey {
+    std::vector<double> v;
+    bool operator<(const TableKey &o) const { return v < o.v; }
+};
+static std::mutex g_table_mutex;
+static std::map<TableKey, HostTables> g_table_cache;
+
+static int get_tables(const double *sos, int n_sections, bool fo, const QSections &S, HostTables &T)
+{
+    TableKey key;
+    key.v.assign(sos, sos + (size_t)n_sections * 6);
+    key.v.push_back(fo ? 1.0 : 0.0);
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    auto it = g_table_cache.find(key);
+    if (it != g_table_cache.end()) {
+        T = it->second;
+        return SS_OK;
+    }
+    const int rc = build_tables(S, T);
+    if (rc == SS_OK) {
+        if (g_table_cache.size() > 64) g_table_cache.clear();
+        g_table_cache[key] = T;
+    }
+    return rc;
+}
+
+static int make_geom(FiltGeom &g, int dtype, int64_t n_contacts, int64_t n_samples, int64_t ld_in,
+                     int64_t ld_out, int64_t chunksize, int padlen)
+{
+    SS_REQUIRE(dtype >= SS_I16 && dtype <= SS_F64, SS_ERR_ARG, "filtfilt: bad dtype %d", dtype);
+    SS_REQUIRE(n_contacts > 0 && n_samples > 0 && chunksize > 0 && padlen >= 0, SS_ERR_ARG,
+               "filtfilt: bad shape (%lld x %lld, chunk %lld, padlen %d)", (long long)n_contacts,
+               (long long)n_samples, (long long)chunksize, padlen);
+    g.n_contacts = n_contacts;
+    g.n_samples = n_samples;
+    g.ld_in = ld_in;
+    g.ld_out = ld_out;
+    g.chunksize = chunksize;
+    g.n_full = n_samples / chunksize;
+    g.len_last = n_samples - g.n_full * chunksize;
+    g.edge = padlen;
+    g.dtype = dtype;
+    // scipy: "The length of the input vector x must be greater than padlen"
+    const int64_t shortest = g.len_last > 0 ? g.len_last : chunksize;
+    if (shortest <= padlen || (g.n_full > 0 && chunksize <= padlen)) {
+        ss_set_error("The length of the input vector x must be greater than padlen, which is %d.",
+                     padlen);
+        return SS_ERR_PADLEN;
+    }
+    g.nt_full = ss_cdiv(chunksize + 2 * (int64_t)padlen, FS_T);
+    g.nt_last = g.len_last > 0 ? ss_cdiv(g.len_last + 2 * (int64_t)padlen, FS_T) : 0;
+    g.tiles_per_contact = g.n_full * g.nt_full + g.nt_last;
+    g.total_tiles = g.tiles_per_contact * n_contacts;
+    g.units_per_contact = g.n_full + (g.len_last > 0 ? 1 : 0);
+    g.n_units = g.units_per_contact * n_contacts;
+    return SS_OK;
+}
+
+template <int NB, bool FO>
+static int launch_filter(const void *d_x, const FiltGeom &g, const HostTables &T,
+                         const double *sos, double *d_out, void *d_ws, cudaStream_t st)
+{
+    constexpr int NS = FiltParams<NB, FO>::NS;
+    constexpr int NSEC = FiltParams<NB, FO>::NSEC;
+    FiltParams<NB, FO> P;
+    for (int s = 0; s < NSEC; ++s) {
+        P.sec[s][0] = sos[s * 6 + 0];
+        P.sec[s][1] = sos[s * 6 + 1];
+        P.sec[s][2] = sos[s * 6 + 2];
+        P.sec[s][3] = sos[s * 6 + 4];
+        P.sec[s][4] = sos[s * 6 + 5];
+    }
+    for (int t = 0; t < FS_S; ++t)
+        for (int i = 0; i < NS; ++i) P.hrow[t][i] = T.hrow[t][i];
+    ScanParams<NS> SP;
+    for (int k = 0; k < 5; ++k)
+        for (int i = 0; i < NS; ++i)
+            for (int j = 0; j < NS; ++j) {
+                P.P[k][i][j] = T.P[k][i][j];
+                SP.Q[k][i][j] = T.Q[k][i][j];
+            }
+    for (int i = 0; i < NS; ++i) {
+        for (int j = 0; j < NS; ++j) {
+            SP.AT[i][j] = T.AT[i][j];
+            SP.M[i][j] = T.M[i][j];
+        }
+        SP.hlast[i] = T.hlast[i];
+        SP.zi[i] = T.zi[i];
+    }
+    double *F = reinterpret_cast<double *>(d_ws);
+    double *Bz = F + g.total_tiles * NS;
+    double *Zf = Bz + g.total_tiles * NS;
+    double *Zb = Zf + g.total_tiles * NS;
+    double *yl = Zb + g.total_tiles * NS;
+    const unsigned tile_blocks = (unsigned)ss_cdiv(g.total_tiles, FS_WPB);
+    const unsigned unit_blocks = (unsigned)ss_cdiv(g.n_units, FS_WPB);
+    filt_summary_kernel<NB, FO><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, F, Bz, yl);
+    SS_LAUNCH_CHECK("filt_summary_kernel");
+    filt_tilescan_kernel<NS><<<unit_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, SP, F, Bz, yl, Zf, Zb);
+    SS_LAUNCH_CHECK("filt_tilescan_kernel");
+    filt_apply_kernel<NB, FO><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out);
+    SS_LAUNCH_CHECK("filt_apply_kernel");
+    return SS_OK;
+}
+
+}  // namespace
+
+extern "C" int ss_max_filter_order(void) { return MAX_NS; }
+
+extern "C" size_t ss_filtfilt_workspace_bytes(int64_t n_contacts, int64_t n_samples,
+                                              int64_t chunksize, int padlen, int n_sections)
+{
+    if (n_contacts <= 0 || n_samples <= 0 || chunksize <= 0 || padlen < 0 || n_sections <= 0)
+        return 0;
+    const int64_t n_full = n_samples / chunksize, len_last = n_samples - n_full * chunksize;
+    const int64_t nt_full = ss_cdiv(chunksize + 2 * (int64_t)padlen, FS_T);
+    const int64_t nt_last = len_last > 0 ? ss_cdiv(len_last + 2 * (int64_t)padlen, FS_T) : 0;
+    const int64_t tiles = (n_full * nt_full + nt_last) * n_contacts;
+    const int64_t ns = 2 * (int64_t)n_sections;   // upper bound on the state count
+    return (size_t)tiles * (size_t)(4 * ns + 1) * sizeof(double);
+}
+
+extern "C" int ss_filtfilt_sos(const void *d_x, int dtype, int64_t n_contacts, int64_t n_samples,
+                               int64_t ld_in, const double *sos, int n_sections, int padlen,
+                               int64_t chunksize, double *d_out, int64_t ld_out, void *d_ws,
+                               size_t ws_bytes, void *stream)
+{
+    SS_REQUIRE(d_x && d_out && sos && d_ws, SS_ERR_ARG, "filtfilt: null pointer");
+    SS_REQUIRE(n_sections >= 1 && n_sections <= MAX_NB + 1, SS_ERR_UNSUPPORTED,
+               "filtfilt: %d sections not supported (max %d)", n_sections, MAX_NB + 1);
+    QSections S;
+    S.nsec = n_sections;
+    bool fo = false;
+    for (int s = 0; s < n_sections; ++s) {
+        const double *c = sos + s * 6;
+        SS_REQUIRE(c[3] == 1.0, SS_ERR_ARG, "filtfilt: section %d has a0 != 1", s);
+        const bool first_order = (c[2] == 0.0 && c[5] == 0.0);
+        if (first_order && s == n_sections - 1) fo = true;
+        S.c[s][0] = c[0];
+        S.c[s][1] = c[1];
+        S.c[s][2] = c[2];
+        S.c[s][3] = c[4];
+        S.c[s][4] = c[5];
+    }
+    S.first_order_last = fo;
+    const int nb = n_sections - (fo ? 1 : 0);
+    S.ns = 2 * nb + (fo ? 1 : 0);
+    SS_REQUIRE(nb <= MAX_NB, SS_ERR_UNSUPPORTED, "filtfilt: %d biquads not supported (max %d)",
+               nb, MAX_NB);
+
+    FiltGeom g;
+    int rc = make_geom(g, dtype, n_contacts, n_samples, ld_in, ld_out, chunksize, padlen);
+    if (rc) return rc;
+    const size_t need = (size_t)g.total_tiles * (size_t)(4 * S.ns + 1) * sizeof(double);
+    SS_REQUIRE(ws_bytes >= need, SS_ERR_WORKSPACE, "filtfilt: workspace %zu < %zu bytes", ws_bytes,
+               need);
+    SS_REQUIRE(ss_cdiv(g.total_tiles, FS_WPB) < 0x7fffffffLL, SS_ERR_ARG,
+               "filtfilt: too many tiles");
+
+    HostTables T;
+    rc = get_tables(sos, n_sections, fo, S, T);
+    SS_REQUIRE(rc == SS_OK, rc, "filtfilt: filter has a pole at z = 1 (no steady state)");
+
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define SS_FILT_CASE(NB_, FO_)                                                        \
+    if (nb == NB_ && fo == FO_)                                                       \
+        return launch_filter<NB_, FO_>(d_x, g, T, sos, d_out, d_ws, st);
+    SS_FILT_CASE(0, true)
+    SS_FILT_CASE(1, false)
+    SS_FILT_CASE(1, true)
+    SS_FILT_CASE(2, false)
+    SS_FILT_CASE(2, true)
+    SS_FILT_CASE(3, false)
+    SS_FILT_CASE(3, true)
+    SS_FILT_CASE(4, false)
+    SS_FILT_CASE(4, true)
+    SS_FILT_CASE(5, false)
+    SS_FILT_CASE(5, true)
+    SS_FILT_CASE(6, false)
+    SS_FILT_CASE(6, true)
+#undef SS_FILT_CASE
+    ss_set_error("filtfilt: unsupported section layout (%d biquads, first-order %d)", nb, (int)fo);
+    return SS_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,356 @@
+// K6-K8 - per-contact PCA of spike waveforms.
+//
+// Replaces PCA / fetPCA, reference src/spike_sort/core/features.py:224-231 and
+// 326-344:  K = np.cov(data) (ddof = 1); eig; sort descending; |evals|;
+// score = evecs[:, :ncomps].T @ data / sqrt(evals[:ncomps])  (UN-centred data).
+//
+//   pca_gram_kernel    : float64 Gram matrix and column sums of the waveforms
+//                        shifted by a reference waveform (kills the cancellation
+//                        in sum(x x^T) - n mu mu^T for peak-aligned spikes);
+//                        4x4 register tiles over the upper triangle, spikes staged
+//                        in shared memory; per-(group, part) partials reduced in a
+//                        fixed order (deterministic, and additive across time
+//                        shards -> the quantity the multi-GPU path all-reduces);
+//   pca_eig_kernel     : covariance from Gram/sums/count, parallel-ordering
+//                        (round-robin) cyclic Jacobi in float64, one CTA per group;
+//   pca_project_kernel : scores, one thread per (spike, group).
+#include "common.cuh"
+
+namespace {
+
+constexpr int PC_THREADS = 256;
+constexpr int PC_SC = 64;               // spikes per staged chunk
+constexpr int PC_MAX_WIN = 96;
+constexpr int PC_MAX_TILES = 2;         // 4x4 tiles per thread (24*25/2 = 300 <= 512)
+constexpr int PC_MAX_COMPS = 8;
+
+__host__ __device__ inline int pc_pad4(int n) { return (n + 3) & ~3; }
+
+static int pc_parts(int64_t n_groups)
+{
+    int64_t p = 592 / n_groups;
+    if (p < 1) p = 1;
+    if (p > 148) p = 148;
+    return (int)p;
+}
+
+// grid (parts, n_groups)
+__global__ void __launch_bounds__(PC_THREADS)
+pca_gram_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, int n_c,
+                const int64_t *__restrict__ offsets, const double *__restrict__ ref,
+                double *__restrict__ ws_gram, double *__restrict__ ws_sum)
+{
+    extern __shared__ __align__(16) double sh[];         // [PC_SC][RS]
+    __shared__ double s_ref[PC_MAX_WIN + 4];
+    __shared__ unsigned char s_ti[PC_THREADS * PC_MAX_TILES], s_tj[PC_THREADS * PC_MAX_TILES];
+    const int nwp = pc_pad4(n_win), RS = nwp + 2, ntile = nwp / 4;
+    const int n_tiles = ntile * (ntile + 1) / 2;
+    const int tid = threadIdx.x;
+    const int64_t g = blockIdx.y;
+    const int parts = gridDim.x, part = blockIdx.x;
+
+    for (int i = tid; i < nwp; i += PC_THREADS) s_ref[i] = i < n_win ? ref[g * n_win + i] : 0.0;
+    if (tid == 0) {                                       // enumerate upper-triangle tiles row-major
+        int k = 0;
+        for (int a = 0; a < ntile; ++a)
+            for (int b = a; b < ntile; ++b) { s_ti[k] = (unsigned char)a; s_tj[k] = (unsigned char)b; ++k; }
+    }
+    int64_t lo_all, hi_all, c;
+    if (offsets) { lo_all = offsets[g]; hi_all = offsets[g + 1]; c = 0; }
+    else { lo_all = 0; hi_all = n_spk; c = g; }
+    const int64_t cnt = hi_all - lo_all;
+    const int64_t per = (cnt + parts - 1) / parts;
+    const int64_t lo = min(lo_all + (int64_t)part * per, hi_all), hi = min(lo + per, hi_all);
+    __syncthreads();
+
+    double acc[PC_MAX_TILES][4][4];
+#pragma unroll
+    for (int t = 0; t < PC_MAX_TILES; ++t)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.0;
+    double sacc = 0.0;
+    int my_ti[PC_MAX_TILES], my_tj[PC_MAX_TILES];
+    bool my_ok[PC_MAX_TILES];
+#pragma unroll
+    for (int t = 0; t < PC_MAX_TILES; ++t) {
+        const int k = tid + t * PC_THREADS;
+        my_ok[t] = k < n_tiles;
+        my_ti[t] = my_ok[t] ? s_ti[k] : 0;
+        my_tj[t] = my_ok[t] ? s_tj[k] : 0;
+    }
+
+    for (int64_t base = lo; base < hi; base += PC_SC) {
+        const int ns = (int)min((int64_t)PC_SC, hi - base);
+        // stage: threads along spikes (global stride n_c floats), shifted to float64
+        for (int idx = tid; idx < PC_SC * nwp; idx += PC_THREADS) {
+            const int w = idx / PC_SC, sl = idx - w * PC_SC;
+            double v = 0.0;
+            if (sl < ns && w < n_win)
+                v = (double)__ldg(waves + ((int64_t)w * n_spk + base + sl) * n_c + c) - s_ref[w];
+            sh[sl * RS + w] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < PC_MAX_TILES; ++t) {
+            if (my_ok[t]) {
+                const double *pa = sh + 4 * my_ti[t], *pb = sh + 4 * my_tj[t];
+#pragma unroll 4
+                for (int s = 0; s < ns; ++s) {
+                    const double2 a01 = *reinterpret_cast<const double2 *>(pa + s * RS);
+                    const double2 a23 = *reinterpret_cast<const double2 *>(pa + s * RS + 2);
+                    const double2 b01 = *reinterpret_cast<const double2 *>(pb + s * RS);
+                    const double2 b23 = *reinterpret_cast<const double2 *>(pb + s * RS + 2);
+                    const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+                    const double b[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[t][i][j] += a[i] * b[j];
+                }
+            }
+        }
+        if (tid < nwp)
+            for (int s = 0; s < ns; ++s) sacc += sh[s * RS + tid];
+        __syncthreads();
+    }
+
+    double *og = ws_gram + ((int64_t)g * parts + part) * nwp * nwp;
+#pragma unroll
+    for (int t = 0; t < PC_MAX_TILES; ++t)
+        if (my_ok[t])
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    og[(4 * my_ti[t] + i) * nwp + 4 * my_tj[t] + j] = acc[t][i][j];
+    if (tid < nwp) ws_sum[((int64_t)g * parts + part) * nwp + tid] = sacc;
+}
+
+// grid (n_groups): sums the partials in part order, mirrors the upper triangle
+__global__ void __launch_bounds__(PC_THREADS)
+pca_gram_reduce_kernel(const double *__restrict__ ws_gram, const double *__restrict__ ws_sum,
+                       int n_win, int parts, double *__restrict__ gram, double *__restrict__ sum)
+{
+    const int nwp = pc_pad4(n_win);
+    const int64_t g = blockIdx.x;
+    for (int idx = threadIdx.x; idx < n_win * n_win; idx += PC_THREADS) {
+        const int i = idx / n_win, j = idx - i * n_win;
+        const int a = i <= j ? i : j, b = i <= j ? j : i;
+        double s = 0.0;
+        for (int p = 0; p < parts; ++p) s += ws_gram[((int64_t)g * parts + p) * nwp * nwp + a * nwp + b];
+        gram[(int64_t)g * n_win * n_win + idx] = s;
+    }
+    for (int i = threadIdx.x; i < n_win; i += PC_THREADS) {
+        double s = 0.0;
+        for (int p = 0; p < parts; ++p) s += ws_sum[((int64_t)g * parts + p) * nwp + i];
+        sum[(int64_t)g * n_win + i] = s;
+    }
+}
+
+// One CTA per group.  smem: A[ne*ne], V[ne*ne], cs[ne] (c, s per pair), red[...]
+__global__ void __launch_bounds__(PC_THREADS)
+pca_eig_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
+               const int64_t *__restrict__ counts, int n, double *__restrict__ evals,
+               double *__restrict__ evecs)
+{
+    extern __shared__ double sm[];
+    const int ne = (n + 1) & ~1;
+    double *A = sm, *V = A + ne * ne, *rc = V + ne * ne, *rs = rc + ne / 2, *red = rs + ne / 2;
+    __shared__ int s_p[PC_MAX_WIN / 2 + 1], s_q[PC_MAX_WIN / 2 + 1];
+    __shared__ int s_done;
+    const int tid = threadIdx.x;
+    const int64_t g = blockIdx.x;
+    const double cnt = (double)counts[g];
+    for (int idx = tid; idx < ne * ne; idx += PC_THREADS) {
+        const int i = idx / ne, j = idx - i * ne;
+        double a = 0.0;
+        if (i < n && j < n)
+            a = (gram[(g * n + i) * n + j] - sum[g * n + i] * sum[g * n + j] / cnt) / (cnt - 1.0);
+        A[idx] = a;
+        V[idx] = i == j ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const int half = ne / 2;
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        // convergence: off-diagonal energy against diagonal energy
+        double off = 0.0, dg = 0.0;
+        for (int idx = tid; idx < n * n; idx += PC_THREADS) {
+            const int i = idx / n, j = idx - i * n;
+            const double a = A[i * ne + j];
+            if (i == j) dg += a * a; else off += a * a;
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            off += __shfl_xor_sync(SS_FULL, off, d);
+            dg += __shfl_xor_sync(SS_FULL, dg, d);
+        }
+        if ((tid & 31) == 0) { red[2 * (tid >> 5)] = off; red[2 * (tid >> 5) + 1] = dg; }
+        __syncthreads();
+        if (tid == 0) {
+            double o = 0.0, d2 = 0.0;
+            for (int w = 0; w < PC_THREADS / 32; ++w) { o += red[2 * w]; d2 += red[2 * w + 1]; }
+            s_done = !(o > 1e-30 * d2);          // also stops on NaN
+        }
+        __syncthreads();
+        if (s_done) break;
+        for (int rd = 0; rd < ne - 1; ++rd) {
+            if (tid < half) {
+                int p, q;
+                if (tid == 0) { p = ne - 1; q = rd; }
+                else { p = (rd + tid) % (ne - 1); q = (rd - tid + (ne - 1)) % (ne - 1); }
+                if (p > q) { const int t = p; p = q; q = t; }
+                double c = 1.0, s = 0.0;
+                if (q < n) {
+                    const double apq = A[p * ne + q];
+                    if (apq != 0.0) {
+                        const double theta = (A[q * ne + q] - A[p * ne + p]) / (2.0 * apq);
+                        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                        c = 1.0 / sqrt(t * t + 1.0);
+                        s = t * c;
+                    }
+                }
+                s_p[tid] = p; s_q[tid] = q; rc[tid] = c; rs[tid] = s;
+            }
+            __syncthreads();
+            // columns of A and V
+            for (int idx = tid; idx < half * ne; idx += PC_THREADS) {
+                const int k = idx / ne, i = idx - k * ne;
+                const int p = s_p[k], q = s_q[k];
+                const double c = rc[k], s = rs[k];
+                const double aip = A[i * ne + p], aiq = A[i * ne + q];
+                A[i * ne + p] = c * aip - s * aiq;
+                A[i * ne + q] = s * aip + c * aiq;
+                const double vip = V[i * ne + p], viq = V[i * ne + q];
+                V[i * ne + p] = c * vip - s * viq;
+                V[i * ne + q] = s * vip + c * viq;
+            }
+            __syncthreads();
+            // rows of A
+            for (int idx = tid; idx < half * ne; idx += PC_THREADS) {
+                const int k = idx / ne, j = idx - k * ne;
+                const int p = s_p[k], q = s_q[k];
+                const double c = rc[k], s = rs[k];
+                const double apj = A[p * ne + j], aqj = A[q * ne + j];
+                A[p * ne + j] = c * apj - s * aqj;
+                A[q * ne + j] = s * apj + c * aqj;
+            }
+            __syncthreads();
+        }
+    }
+    // rank by signed eigenvalue, descending (np.argsort(evals)[::-1]), then |.|
+    for (int k = tid; k < n; k += PC_THREADS) {
+        const double lk = A[k * ne + k];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const double lj = A[j * ne + j];
+            if (lj > lk || (lj == lk && j > k)) ++rank;
+        }
+        evals[g * n + rank] = fabs(lk);
+        for (int i = 0; i < n; ++i) evecs[(g * n + i) * n + rank] = V[i * ne + k];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+pca_project_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, int n_c,
+                   const int64_t *__restrict__ offsets, int64_t n_groups,
+                   const double *__restrict__ evals, const double *__restrict__ evecs, int ncomps,
+                   double *__restrict__ scores)
+{
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // (s, c) flattened
+    if (idx >= n_spk * n_c) return;
+    const int64_t s = idx / n_c;
+    const int c = (int)(idx - s * n_c);
+    int64_t g = c;
+    if (offsets) {
+        int64_t lo = 0, hi = n_groups;
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (__ldg(offsets + mid) <= s) lo = mid; else hi = mid;
+        }
+        g = lo;
+    }
+    double acc[PC_MAX_COMPS];
+#pragma unroll
+    for (int j = 0; j < PC_MAX_COMPS; ++j) acc[j] = 0.0;
+    const double *V = evecs + g * n_win * n_win;
+    const int64_t step = n_spk * (int64_t)n_c;
+    for (int w = 0; w < n_win; ++w) {
+        const double xv = (double)__ldg(waves + (int64_t)w * step + idx);
+#pragma unroll
+        for (int j = 0; j < PC_MAX_COMPS; ++j)
+            if (j < ncomps) acc[j] += __ldg(V + w * n_win + j) * xv;
+    }
+    double *o = scores + idx * ncomps;
+#pragma unroll
+    for (int j = 0; j < PC_MAX_COMPS; ++j)
+        if (j < ncomps) o[j] = acc[j] / sqrt(__ldg(evals + g * n_win + j));
+}
+
+}  // namespace
+
+extern "C" size_t ss_pca_workspace_bytes(int n_win, int64_t n_groups)
+{
+    if (n_win <= 0 || n_win > PC_MAX_WIN || n_groups <= 0) return 0;
+    const int nwp = pc_pad4(n_win);
+    return (size_t)n_groups * pc_parts(n_groups) * ((size_t)nwp * nwp + nwp) * sizeof(double);
+}
+
+extern "C" int ss_pca_gram(const float *d_waves, int n_win, int64_t n_spk, int n_c,
+                           const int64_t *d_offsets, int64_t n_groups, const double *d_ref,
+                           double *d_gram, double *d_sum, void *d_ws, size_t ws_bytes, void *stream)
+{
+    SS_REQUIRE(d_waves && d_ref && d_gram && d_sum && d_ws, SS_ERR_ARG, "pca_gram: null pointer");
+    SS_REQUIRE(n_win >= 1 && n_win <= PC_MAX_WIN, SS_ERR_UNSUPPORTED, "pca_gram: n_win %d outside [1, %d]", n_win, PC_MAX_WIN);
+    SS_REQUIRE(n_spk >= 0 && n_c >= 1 && n_groups >= 1 && n_groups <= 65535, SS_ERR_ARG, "pca_gram: bad shape");
+    SS_REQUIRE(d_offsets ? n_c == 1 : n_groups == n_c, SS_ERR_ARG, "pca_gram: group layout mismatch");
+    SS_REQUIRE(ws_bytes >= ss_pca_workspace_bytes(n_win, n_groups), SS_ERR_WORKSPACE, "pca_gram: workspace too small");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int parts = pc_parts(n_groups), nwp = pc_pad4(n_win);
+    double *ws_gram = reinterpret_cast<double *>(d_ws);
+    double *ws_sum = ws_gram + (size_t)n_groups * parts * nwp * nwp;
+    const size_t smem = (size_t)PC_SC * (nwp + 2) * sizeof(double);
+    SS_CUDA_CHECK(cudaFuncSetAttribute(pca_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)((size_t)PC_SC * (PC_MAX_WIN + 2) * sizeof(double))));
+    // unused upper-triangle tiles of partials are never read; no memset needed
+    pca_gram_kernel<<<dim3(parts, (unsigned)n_groups), PC_THREADS, smem, st>>>(
+        d_waves, n_win, n_spk, n_c, d_offsets, d_ref, ws_gram, ws_sum);
+    SS_LAUNCH_CHECK("pca_gram_kernel");
+    pca_gram_reduce_kernel<<<(unsigned)n_groups, PC_THREADS, 0, st>>>(ws_gram, ws_sum, n_win, parts, d_gram, d_sum);
+    SS_LAUNCH_CHECK("pca_gram_reduce_kernel");
+    return SS_OK;
+}
+
+extern "C" int ss_pca_eig(const double *d_gram, const double *d_sum, const int64_t *d_counts,
+                          int n_win, int64_t n_groups, double *d_evals, double *d_evecs, void *stream)
+{
+    SS_REQUIRE(d_gram && d_sum && d_counts && d_evals && d_evecs, SS_ERR_ARG, "pca_eig: null pointer");
+    SS_REQUIRE(n_win >= 1 && n_win <= PC_MAX_WIN, SS_ERR_UNSUPPORTED, "pca_eig: n_win %d outside [1, %d]", n_win, PC_MAX_WIN);
+    SS_REQUIRE(n_groups >= 1, SS_ERR_ARG, "pca_eig: bad shape");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int ne = (n_win + 1) & ~1;
+    const size_t smem = ((size_t)2 * ne * ne + ne + 2 * (PC_THREADS / 32) + 8) * sizeof(double);
+    const int ne_max = (PC_MAX_WIN + 1) & ~1;
+    SS_CUDA_CHECK(cudaFuncSetAttribute(pca_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(((size_t)2 * ne_max * ne_max + ne_max + 2 * (PC_THREADS / 32) + 8) * sizeof(double))));
+    pca_eig_kernel<<<(unsigned)n_groups, PC_THREADS, smem, st>>>(d_gram, d_sum, d_counts, n_win, d_evals, d_evecs);
+    SS_LAUNCH_CHECK("pca_eig_kernel");
+    return SS_OK;
+}
+
+extern "C" int ss_pca_project(const float *d_waves, int n_win, int64_t n_spk, int n_c,
+                              const int64_t *d_offsets, int64_t n_groups, const double *d_evals,
+                              const double *d_evecs, int ncomps, double *d_scores, void *stream)
+{
+    if (n_spk == 0) return SS_OK;
+    SS_REQUIRE(d_waves && d_evals && d_evecs && d_scores, SS_ERR_ARG, "pca_project: null pointer");
+    SS_REQUIRE(n_win >= 1 && n_win <= PC_MAX_WIN, SS_ERR_UNSUPPORTED, "pca_project: n_win %d outside [1, %d]", n_win, PC_MAX_WIN);
+    SS_REQUIRE(ncomps >= 1 && ncomps <= PC_MAX_COMPS && ncomps <= n_win, SS_ERR_UNSUPPORTED, "pca_project: ncomps %d outside [1, %d]", ncomps, PC_MAX_COMPS);
+    SS_REQUIRE(d_offsets ? n_c == 1 : n_groups == n_c, SS_ERR_ARG, "pca_project: group layout mismatch");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int64_t total = n_spk * n_c;
+    pca_project_kernel<<<(unsigned)ss_cdiv(total, 256), 256, 0, st>>>(d_waves, n_win, n_spk, n_c, d_offsets, n_groups, d_evals, d_evecs, ncomps, d_scores);
+    SS_LAUNCH_CHECK("pca_project_kernel");
+    return SS_OK;
+}
