@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py - channel-samples/s of the SpikeSort front end on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): channel-samples/sec of filter -> detect -> extract -> PCA.
+Workload at one GPU: configs[1], a 32-channel 30 kHz 10-minute synthetic int16
+recording (32 x 18 000 000).  A step = one pass of the whole chain
+(fltLinearIIR(800, 100) -> 'auto' threshold -> detect -> align -> remove doubles ->
+extract -> per-contact PCA, all 32 contacts) over the recording.
+
+  value      : chain throughput with the recording resident in HBM (CUDA events)
+  e2e        : the same chain through the spike_sort.core-compatible public API with
+               HOST buffers (pinned raw recording in, NumPy results out)
+  roofline   : the filter stage (the three launches of ss_filtfilt_sos, ~all of the
+               step) against the measured HBM peak
+  cpu_baseline: the oracle port (CPU restatement of the reference, oracle/) timed on a
+               bounded sample of the same workload, on rank 0
+
+With N > 1 every rank owns one recording-sized time shard (weak scaling): thresholds
+come from the rank owning the first 10 s (broadcast), per-contact Gram matrices and
+spike counts are all-reduced / all-gathered over NCCL (spikesort_b200/dist.py).
+
+--impl reference times the CPU oracle port itself (all host cores, process pool over
+contacts) on bounded samples of the same workload: the reference is pure Python and
+cannot travel, the port restates it (oracle/port.py).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np                                             # noqa: E402
+
+METRIC = "channel-samples/sec filter->detect->extract->PCA"
+UNIT = "channel-samples/s"
+FS = 30000
+N_CONTACTS = 32
+N_SAMPLES = 18000000
+SP_WIN = [-0.2, 0.8]
+CHUNK = 1000000
+SEED = 2
+RATE_HZ = 10.0
+CONFIG = {
+    "workload": "configs[1]: 32-channel 30 kHz 10-minute synthetic int16 recording "
+                "(32 x 18,000,000), fltLinearIIR(800,100) -> auto threshold -> detect(falling) "
+                "-> align(min) -> extract -> fetPCA(ncomps=2), every contact",
+    "n_contacts": N_CONTACTS, "n_samples": N_SAMPLES, "FS": FS, "sp_win": SP_WIN,
+    "chunksize": CHUNK, "spike_rate_hz": RATE_HZ, "seed": SEED,
+    "l2": "inputs larger than L2 (1.15 GB in, 4.6 GB filtered per step)",
+}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ----------------------------------------------------------------- CPU arms
+def _cpu_chain_one(args):
+    """One contact of the oracle chain (runs in a worker process)."""
+    import warnings
+    from oracle import port
+    x, c = args
+    raw = {'data': x, 'FS': FS, 'n_contacts': 1}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, res = port.chain_per_contact(raw, port.Filter(800., 100.), SP_WIN, edge='falling',
+                                        align_type='min', ncomps=2, chunksize=CHUNK)
+    return c, len(res[0][1]['data'])
+
+
+def cpu_chain(x, pool=None):
+    """Oracle chain over all contacts of host array x; returns (seconds, n_spikes)."""
+    t0 = time.perf_counter()
+    jobs = [(x[c:c + 1], c) for c in range(x.shape[0])]
+    if pool is None:
+        out = [_cpu_chain_one(j) for j in jobs]
+    else:
+        out = list(pool.map(_cpu_chain_one, jobs))
+    return time.perf_counter() - t0, sum(n for _, n in out)
+
+
+def run_reference(args):
+    """--impl reference: the CPU oracle port, all host cores, bounded sample per step."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import port
+    from spikesort_b200 import synth
+    port.build()
+    cores = os.cpu_count() or 1
+    n_sample = 3000000                                   # 32 contacts x 100 s per step
+    x = synth.make_recording(N_CONTACTS, n_sample, FS, seed=SEED, rate_hz=RATE_HZ,
+                             noise=10.0).numpy()
+    ctx = mp.get_context("fork")
+    with ctx.Pool(min(cores, N_CONTACTS)) as pool:
+        for _ in range(max(args.warmup, 1)):
+            cpu_chain(x[:, :300000], pool)
+        times = []
+        for _ in range(args.steps):
+            dt, _ = cpu_chain(x, pool)
+            times.append(dt)
+    total = sum(times)
+    value = N_CONTACTS * n_sample * args.steps / total
+    sample = ("%d contacts x %d samples (100 s of the 600 s recording) per step, process pool "
+              "over contacts" % (N_CONTACTS, n_sample))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": CONFIG,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(cores, N_CONTACTS),
+                         "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ GPU arm
+class ClockSampler(object):
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        self.path = "/tmp/ss_clocks_%d_%d.csv" % (os.getpid(), index)
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                f = [v.strip() for v in ln.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[0]))
+                    mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for name, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["sm_max_mhz"] = max(mx)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from spikesort_b200 import _lib, _ops, filters, pipeline, synth, extract, features
+    from spikesort_b200 import dist as ssdist
+
+    rank, world = env_int("RANK", 0), env_int("WORLD_SIZE", 1)
+    local = env_int("LOCAL_RANK", 0)
+    _lib.load()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    flt = filters.Filter(800., 100.)
+    # shard r of a 10*world-minute recording: same statistics, seed + rank
+    x = synth.make_recording(N_CONTACTS, N_SAMPLES, FS, seed=SEED + rank, device=dev,
+                             rate_hz=RATE_HZ, noise=10.0)
+    torch.cuda.synchronize()
+
+    def step():
+        if world > 1:
+            return ssdist.run_chain_sharded(x, FS, flt, SP_WIN, edge='falling', align_type='min',
+                                            ncomps=2, chunksize=CHUNK)
+        return pipeline.run_chain(x, FS, filt=flt, sp_win=SP_WIN, edge='falling',
+                                  align_type='min', ncomps=2, chunksize=CHUNK)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    res = None
+    for _ in range(args.warmup):
+        res = step()
+    barrier()
+
+    # filter-stage events (the dominant kernels) + whole-step events, all on the
+    # current stream the library launches on
+    sos, padlen = flt.sections(FS)
+    f_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            for _ in range(args.steps)]
+    orig_filtfilt = _ops.filtfilt_sos
+    idx = {"i": 0}
+
+    def timed_filtfilt(*a, **k):
+        i = idx["i"]
+        if i < len(f_ev):
+            f_ev[i][0].record()
+        out = orig_filtfilt(*a, **k)
+        if i < len(f_ev):
+            f_ev[i][1].record()
+            idx["i"] += 1
+        return out
+
+    _ops.filtfilt_sos = timed_filtfilt
+    sampler = ClockSampler(local)
+    _ops.LAUNCHES["count"] = 0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        res = step()
+    ev1.record()
+    barrier()
+    launches = _ops.LAUNCHES["count"]
+    clocks = sampler.stop()
+    _ops.filtfilt_sos = orig_filtfilt
+    ms_total = ev0.elapsed_time(ev1)
+    ms_filter = [a.elapsed_time(b) for a, b in f_ev[:idx["i"]]]
+    n_spk = int(res.spt.numel())
+    n_det = int(res.spt_detected.numel())
+
+    tt = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    ms_step = ms_total / args.steps
+    value = world * N_CONTACTS * N_SAMPLES / (ms_step / 1000.0)
+
+    # ---- e2e: public API, host buffers in, NumPy out (rank-local, then max over ranks)
+    e2e_steps = max(1, min(args.steps, 3))
+    host = torch.empty((N_CONTACTS, N_SAMPLES), dtype=torch.int16).pin_memory()
+    host.copy_(x)
+    torch.cuda.synchronize()
+    raw = {'data': host, 'FS': FS, 'n_contacts': N_CONTACTS}
+    import warnings
+
+    def e2e_step():
+        d2h = 0
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            f = filters.fltLinearIIR(raw, 800., 100.)          # H2D of the raw recording inside
+            for c in range(N_CONTACTS):
+                spt = extract.detect_spikes(f, thresh='auto', edge='falling', contact=c)
+                spa = extract.align_spikes(f, spt, SP_WIN, type='min', contact=c)
+                wv = extract.extract_spikes(f, spa, SP_WIN, contacts=c)
+                ft = features.fetPCA(wv, ncomps=2)
+                d2h += spt['data'].nbytes + spa['data'].nbytes + wv['data'].nbytes + \
+                    ft['data'].nbytes + 8
+        return d2h
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(e2e_steps):
+        d2h = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_value = world * N_CONTACTS * N_SAMPLES / e2e_s
+
+    # ---- roofline of the filter stage
+    peak, peak_src = measured_peak()
+    filt_ms = statistics.mean(ms_filter) if ms_filter else float("nan")
+    alg_bytes = N_CONTACTS * N_SAMPLES * (2 + 8)               # C*N*(s_in + 8)
+    achieved = alg_bytes / (filt_ms / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "kernel": "ss_filtfilt_sos = filt_summary_kernel + filt_tilescan_kernel + "
+                          "filt_apply_kernel (one filter pass over the recording)",
+                "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": filt_ms,
+                "share_of_step": filt_ms / ms_step, "peak_source": peak_src}
+    # whole-chain roofline: 18 B + spikes
+    n_win = int(res.waves.shape[0])
+    chain_bytes = N_CONTACTS * N_SAMPLES * 18 + n_det * 8 + n_det * (n_win * 8 + 16) + \
+        n_spk * (n_win * 12 + 8) + n_spk * (n_win * 8 + 16)
+    chain = {"algorithmic_bytes_per_step": chain_bytes,
+             "achieved_GBs": chain_bytes / (ms_step / 1000.0) / 1e9,
+             "frac": chain_bytes / (ms_step / 1000.0) / 1e9 / peak}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- CPU baseline on a bounded sample (oracle port, 1 core as the reference runs)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import port
+        port.build()
+        n_sample = 1500000
+        xs = x[:, :n_sample].cpu().numpy()
+        dt, _ = cpu_chain(xs, None)
+        cpu = {"value": N_CONTACTS * n_sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "first %d samples (50 s) of all %d contacts of the same recording, "
+                         "oracle/port.py chain (C filtfilt + NumPy), 1 core, %.1f s"
+                         % (n_sample, N_CONTACTS, dt)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dict(CONFIG, parallelism="time-sharded x%d" % world if world > 1 else "1 GPU",
+                       spikes_detected_rank0=n_det, spikes_kept_rank0=n_spk),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT,
+                "h2d_bytes_per_step": int(host.numel() * 2), "d2h_bytes_per_step": int(d2h),
+                "steps": e2e_steps, "ms_per_step": e2e_s * 1000.0,
+                "api": "filters.fltLinearIIR + per-contact extract.detect_spikes/align_spikes/"
+                       "extract_spikes + features.fetPCA, pinned host recording in, NumPy out"},
+        "gpu_launches": launches,
+        "roofline": roofline, "chain_roofline": chain, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

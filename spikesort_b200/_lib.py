@@ -1,0 +1,172 @@
+"""ctypes binding of ``libspikesort_b200.so`` (``include/spikesort_b200.h``).
+
+This is the binding a SpikeSort maintainer would add.  There
+is NO CPU fallback: if the library is missing or no CUDA device is present the
+calls raise.  PyTorch is used only to own device buffers and streams.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libspikesort_b200.so")
+
+SS_I16, SS_F32, SS_F64 = 0, 1, 2
+SS_ERR_PADLEN = -3
+SS_ERR_UNSUPPORTED = -5
+
+_c = ctypes
+_i64, _int, _dbl, _vp, _sz = _c.c_int64, _c.c_int, _c.c_double, _c.c_void_p, _c.c_size_t
+_dp = _c.POINTER(_c.c_double)
+
+# name -> (restype, argtypes); must list EVERY symbol declared in the header
+SIGNATURES = {
+    "ss_version": (_int, []),
+    "ss_last_error": (_c.c_char_p, []),
+    "ss_max_filter_order": (_int, []),
+    "ss_max_window": (_int, []),
+    "ss_filtfilt_workspace_bytes": (_sz, [_i64, _i64, _i64, _int, _int]),
+    "ss_filtfilt_sos": (_int, [_vp, _int, _i64, _i64, _i64, _dp, _int, _int, _i64, _vp, _i64,
+                               _vp, _sz, _vp]),
+    "ss_threshold_workspace_bytes": (_sz, [_i64]),
+    "ss_var_threshold": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _vp, _vp, _sz, _vp]),
+    "ss_detect_workspace_bytes": (_sz, [_i64, _i64]),
+    "ss_detect_mark": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _vp, _sz, _vp, _vp]),
+    "ss_detect_emit": (_int, [_i64, _i64, _dbl, _vp, _sz, _vp, _i64, _vp]),
+    "ss_align": (_int, [_vp, _int, _i64, _i64, _dbl, _vp, _i64, _vp, _dbl, _int, _int, _dbl,
+                        _dbl, _dbl, _dbl, _int, _vp, _i64, _int, _vp]),
+    "ss_remove_doubles_workspace_bytes": (_sz, [_i64]),
+    "ss_remove_doubles_mark": (_int, [_vp, _i64, _vp, _i64, _dbl, _vp, _sz, _vp, _vp]),
+    "ss_remove_doubles_emit": (_int, [_vp, _i64, _vp, _sz, _vp, _i64, _vp]),
+    "ss_extract": (_int, [_vp, _int, _i64, _i64, _dbl, _vp, _int, _vp, _i64, _vp, _int, _int,
+                          _dbl, _dbl, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "ss_pca_workspace_bytes": (_sz, [_int, _i64]),
+    "ss_pca_gram": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ss_pca_eig": (_int, [_vp, _vp, _vp, _int, _i64, _vp, _vp, _vp]),
+    "ss_pca_project": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp, _int, _vp, _vp]),
+}
+
+_lib = None
+
+
+class SpikeSortB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise SpikeSortB200Error(
+            "%s not found: build it with `python -m spikesort_b200._build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.ss_version() != 100:
+        raise SpikeSortB200Error("libspikesort_b200.so version mismatch")
+    _lib = lib
+    return lib
+
+
+def last_error():
+    return load().ss_last_error().decode("utf-8", "replace")
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    msg = last_error()
+    if rc == SS_ERR_PADLEN:
+        raise ValueError(msg)                 # what scipy.signal.filtfilt raises
+    if rc == SS_ERR_UNSUPPORTED:
+        raise NotImplementedError("%s: %s" % (what, msg))
+    raise SpikeSortB200Error("%s failed (%d): %s" % (what, rc, msg))
+
+
+# --------------------------------------------------------------------------
+# torch glue: device buffers and streams only
+# --------------------------------------------------------------------------
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+def require_cuda():
+    t = torch()
+    if not t.cuda.is_available():
+        raise SpikeSortB200Error("spikesort_b200 needs a CUDA device (B200); there is no "
+                                 "CPU fallback")
+    return t
+
+
+def device():
+    t = require_cuda()
+    return t.device("cuda", t.cuda.current_device())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch().cuda.current_stream().cuda_stream)
+
+
+def ptr(tensor):
+    return ctypes.c_void_p(tensor.data_ptr()) if tensor is not None else ctypes.c_void_p(0)
+
+
+_NP2SS = {np.dtype(np.int16): SS_I16, np.dtype(np.float32): SS_F32, np.dtype(np.float64): SS_F64}
+
+
+def ss_dtype_of(tensor):
+    t = torch()
+    return {t.int16: SS_I16, t.float32: SS_F32, t.float64: SS_F64}[tensor.dtype]
+
+
+def np_dtype_of(tensor):
+    t = torch()
+    return {t.int16: np.int16, t.float32: np.float32, t.float64: np.float64}[tensor.dtype]
+
+
+def to_device_2d(data):
+    """Recording (n_contacts, n_samples) -> CUDA tensor of a supported dtype with
+    unit stride along time.  Accepts DeviceSignal, torch tensors and anything
+    NumPy can view (ndarray, memmap, PyTables-like with __getitem__)."""
+    t = require_cuda()
+    if hasattr(data, "device_tensor"):
+        return data.device_tensor()
+    if isinstance(data, t.Tensor):
+        x = data
+    else:
+        arr = np.asarray(data[:] if not isinstance(data, np.ndarray) else data)
+        if arr.dtype not in _NP2SS:
+            # NumPy promotes every other real dtype to float64 before filtering/comparing
+            arr = arr.astype(np.float64)
+        x = t.from_numpy(np.ascontiguousarray(arr))
+    if x.dtype not in (t.int16, t.float32, t.float64):
+        x = x.to(t.float64)
+    if x.dim() == 1:
+        x = x.unsqueeze(0)
+    x = x.to(device(), non_blocking=True)
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    return x
+
+
+def empty(shape, dtype):
+    return torch().empty(shape, dtype=dtype, device=device())
+
+
+def workspace(nbytes):
+    t = torch()
+    return t.empty(max(int(nbytes), 8), dtype=t.uint8, device=device())

@@ -1,0 +1,232 @@
+"""Device-level wrappers of the C ABI: CUDA tensors in, CUDA tensors out.
+
+Everything here only allocates buffers (torch) and calls ``libspikesort_b200.so``;
+host<->device synchronisation happens only where a size must be known to allocate
+the result (number of detected / kept spikes), exactly as documented in the header.
+The exact float64 host expressions the reference evaluates with NumPy/Python
+(window, time axis, bounds) are computed here the same way.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+MAX_ALIGN_ITER = 100000      # the reference loops until no spike moves; a spike
+                             # advances by >= 1 sample per pass, so this is a safety net
+
+
+# kernels of libspikesort_b200.so launched through this module (bench.py reports it)
+LAUNCHES = {"count": 0}
+
+
+def _launched(n):
+    LAUNCHES["count"] += n
+
+
+# ------------------------------------------------------------------ host math
+def window_params(sp_win, FS):
+    """win (int32, truncating), n_win and the float64 time axis, exactly as
+    extract.py:151-152."""
+    win = (np.asarray(sp_win) / 1000.0 * FS).astype(np.int32)
+    time = np.arange(win[1] - win[0]) * 1000.0 / FS + sp_win[0]
+    return int(win[0]), int(win[1]), time
+
+
+def time_bounds(n_pts, FS, sp_win):
+    """Inclusive [t_min, t_max] of filter_spt, extract.py:106-109."""
+    max_time = n_pts * 1000.0 / FS
+    t_min = np.max((-sp_win[0], 0))
+    t_max = np.min((max_time, max_time - sp_win[1]))
+    return float(t_min), float(t_max)
+
+
+# --------------------------------------------------------------------- filter
+def filtfilt_sos(x, sos, padlen, chunksize, out=None):
+    """x: CUDA (n_contacts, n_samples) int16/float32/float64, unit time stride."""
+    lib = _lib.load()
+    t = _lib.torch()
+    n_c, n = x.shape
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    n_sec = sos.shape[0]
+    if out is None:
+        out = t.empty((n_c, n), dtype=t.float64, device=x.device)
+    nbytes = lib.ss_filtfilt_workspace_bytes(n_c, n, int(chunksize), int(padlen), n_sec)
+    ws = _lib.workspace(nbytes)
+    rc = lib.ss_filtfilt_sos(_lib.ptr(x), _lib.ss_dtype_of(x), n_c, n, x.stride(0),
+                             sos.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_sec,
+                             int(padlen), int(chunksize), _lib.ptr(out), out.stride(0),
+                             _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "ss_filtfilt_sos")
+    _launched(3)          # summary, tilescan, apply
+    return out
+
+
+# ------------------------------------------------------------------ threshold
+def var_threshold(x, n0, factor):
+    """factor * sqrt(var(x[r, :n0])) for every row of the CUDA tensor x -> CUDA float64."""
+    lib = _lib.load()
+    t = _lib.torch()
+    n_rows = x.shape[0]
+    n0 = min(int(n0), x.shape[1])
+    thr = t.empty(n_rows, dtype=t.float64, device=x.device)
+    ws = _lib.workspace(lib.ss_threshold_workspace_bytes(n_rows))
+    rc = lib.ss_var_threshold(_lib.ptr(x), _lib.ss_dtype_of(x), n_rows, x.stride(0), n0,
+                              float(factor), _lib.ptr(thr), _lib.ptr(ws), ws.numel(),
+                              _lib.stream_ptr())
+    _lib.check(rc, "ss_var_threshold")
+    _launched(2)
+    return thr
+
+
+# --------------------------------------------------------------------- detect
+def detect(x, thr, falling, FS):
+    """Threshold crossings of every row.  Returns (spt, offsets): CUDA float64 times
+    (ms) concatenated row by row and CUDA int64 offsets[n_rows+1]."""
+    lib = _lib.load()
+    t = _lib.torch()
+    n_rows, n = x.shape
+    ws = _lib.workspace(lib.ss_detect_workspace_bytes(n_rows, n))
+    offsets = t.empty(n_rows + 1, dtype=t.int64, device=x.device)
+    rc = lib.ss_detect_mark(_lib.ptr(x), _lib.ss_dtype_of(x), n_rows, n, x.stride(0),
+                            _lib.ptr(thr), int(bool(falling)), _lib.ptr(ws), ws.numel(),
+                            _lib.ptr(offsets), _lib.stream_ptr())
+    _lib.check(rc, "ss_detect_mark")
+    _launched(2)          # mark, scan
+    total = int(offsets[-1].item())                 # the one sync: size of the result
+    spt = t.empty(total, dtype=t.float64, device=x.device)
+    rc = lib.ss_detect_emit(n_rows, n, float(FS), _lib.ptr(ws), ws.numel(), _lib.ptr(spt),
+                            total, _lib.stream_ptr())
+    _lib.check(rc, "ss_detect_emit")
+    _launched(1 if total > 0 else 0)
+    return spt, offsets
+
+
+# ---------------------------------------------------------------------- align
+def align(x, spt, offsets, rows, FS, sp_win, use_min):
+    """In-place alignment of CUDA float64 times `spt`.  offsets: CUDA int64
+    [n_rows+1] or None (single row); rows: CUDA int32 row ids or None."""
+    lib = _lib.load()
+    n = x.shape[1]
+    win0, win1, _ = window_params(sp_win, FS)
+    t_min, t_max = time_bounds(n, FS, sp_win)
+    tol = 0.1                                       # extract.py:229
+    lo, hi = sp_win[0] + tol, sp_win[1] - tol       # extract.py:263-264
+    n_rows = 1 if offsets is None else offsets.numel() - 1
+    rc = lib.ss_align(_lib.ptr(x), _lib.ss_dtype_of(x), n, x.stride(0), float(FS),
+                      _lib.ptr(rows), n_rows, _lib.ptr(offsets), float(sp_win[0]), win0, win1,
+                      t_min, t_max, float(lo), float(hi), int(bool(use_min)), _lib.ptr(spt),
+                      spt.numel(), MAX_ALIGN_ITER, _lib.stream_ptr())
+    _lib.check(rc, "ss_align")
+    _launched(1 if spt.numel() > 0 else 0)
+    return spt
+
+
+def remove_doubles(spt, offsets, tol):
+    """Returns (kept times, new offsets); offsets None = one row."""
+    lib = _lib.load()
+    t = _lib.torch()
+    n_spk = spt.numel()
+    single = offsets is None
+    if single:
+        offsets = t.tensor([0, n_spk], dtype=t.int64, device=spt.device)
+    n_rows = offsets.numel() - 1
+    ws = _lib.workspace(lib.ss_remove_doubles_workspace_bytes(n_spk))
+    new_off = t.empty(n_rows + 1, dtype=t.int64, device=spt.device)
+    rc = lib.ss_remove_doubles_mark(_lib.ptr(spt), n_spk, _lib.ptr(offsets), n_rows, float(tol),
+                                    _lib.ptr(ws), ws.numel(), _lib.ptr(new_off),
+                                    _lib.stream_ptr())
+    _lib.check(rc, "ss_remove_doubles_mark")
+    _launched(3)          # mark, scan, row offsets
+    total = int(new_off[-1].item())
+    out = t.empty(total, dtype=t.float64, device=spt.device)
+    rc = lib.ss_remove_doubles_emit(_lib.ptr(spt), n_spk, _lib.ptr(ws), ws.numel(), _lib.ptr(out),
+                                    total, _lib.stream_ptr())
+    _lib.check(rc, "ss_remove_doubles_emit")
+    _launched(1 if (n_spk > 0 and total > 0) else 0)
+    return out, (None if single else new_off)
+
+
+# -------------------------------------------------------------------- extract
+def extract(x, spt, FS, sp_win, contacts=None, offsets=None, rows=None):
+    """Returns (waves float32 (n_win, n_spk, n_c), valid uint8[n_spk], n_invalid int32[1])
+    as CUDA tensors.  contacts: CUDA int32 list (reference mode) or None (row mode)."""
+    lib = _lib.load()
+    t = _lib.torch()
+    n = x.shape[1]
+    win0, win1, _ = window_params(sp_win, FS)
+    t_min, t_max = time_bounds(n, FS, sp_win)
+    n_spk = spt.numel()
+    n_c = 1 if contacts is None else contacts.numel()
+    waves = t.empty((win1 - win0, n_spk, n_c), dtype=t.float32, device=x.device)
+    valid = t.empty(n_spk, dtype=t.uint8, device=x.device)
+    n_invalid = t.empty(1, dtype=t.int32, device=x.device)
+    n_rows = 1 if offsets is None else offsets.numel() - 1
+    rc = lib.ss_extract(_lib.ptr(x), _lib.ss_dtype_of(x), n, x.stride(0), float(FS),
+                        _lib.ptr(contacts), n_c, _lib.ptr(rows), n_rows, _lib.ptr(offsets),
+                        win0, win1, t_min, t_max, _lib.ptr(spt), n_spk, _lib.ptr(waves),
+                        _lib.ptr(valid), _lib.ptr(n_invalid), _lib.stream_ptr())
+    _lib.check(rc, "ss_extract")
+    _launched(1 if n_spk > 0 else 0)
+    return waves, valid, n_invalid
+
+
+# ------------------------------------------------------------------------ PCA
+def pca_gram(waves, offsets=None, ref=None):
+    """Gram / sums of CUDA float32 waves (n_win, n_spk, n_c) per group.
+    Returns (gram (G, n_win, n_win), sum (G, n_win), ref (G, n_win), counts (G,))."""
+    lib = _lib.load()
+    t = _lib.torch()
+    n_win, n_spk, n_c = waves.shape
+    if offsets is None:
+        n_groups = n_c
+        counts = t.full((n_groups,), n_spk, dtype=t.int64, device=waves.device)
+        if ref is None:
+            ref = (waves[:, 0, :].t().to(t.float64).contiguous() if n_spk > 0
+                   else t.zeros((n_groups, n_win), dtype=t.float64, device=waves.device))
+    else:
+        n_groups = offsets.numel() - 1
+        counts = (offsets[1:] - offsets[:-1]).contiguous()
+        if ref is None:
+            if n_spk > 0:
+                first = offsets[:-1].clamp(max=n_spk - 1)
+                ref = waves[:, first, 0].t().to(t.float64).contiguous()
+            else:
+                ref = t.zeros((n_groups, n_win), dtype=t.float64, device=waves.device)
+    gram = t.empty((n_groups, n_win, n_win), dtype=t.float64, device=waves.device)
+    ssum = t.empty((n_groups, n_win), dtype=t.float64, device=waves.device)
+    ws = _lib.workspace(lib.ss_pca_workspace_bytes(n_win, n_groups))
+    rc = lib.ss_pca_gram(_lib.ptr(waves), n_win, n_spk, n_c, _lib.ptr(offsets), n_groups,
+                         _lib.ptr(ref), _lib.ptr(gram), _lib.ptr(ssum), _lib.ptr(ws), ws.numel(),
+                         _lib.stream_ptr())
+    _lib.check(rc, "ss_pca_gram")
+    _launched(2)          # partial Grams, ordered reduction
+    return gram, ssum, ref, counts
+
+
+def pca_eig(gram, ssum, counts):
+    lib = _lib.load()
+    t = _lib.torch()
+    n_groups, n_win, _ = gram.shape
+    evals = t.empty((n_groups, n_win), dtype=t.float64, device=gram.device)
+    evecs = t.empty((n_groups, n_win, n_win), dtype=t.float64, device=gram.device)
+    rc = lib.ss_pca_eig(_lib.ptr(gram), _lib.ptr(ssum), _lib.ptr(counts), n_win, n_groups,
+                        _lib.ptr(evals), _lib.ptr(evecs), _lib.stream_ptr())
+    _lib.check(rc, "ss_pca_eig")
+    _launched(1)
+    return evals, evecs
+
+
+def pca_project(waves, evals, evecs, ncomps, offsets=None):
+    lib = _lib.load()
+    t = _lib.torch()
+    n_win, n_spk, n_c = waves.shape
+    n_groups = evals.shape[0]
+    width = ncomps * (n_c if offsets is None else 1)
+    scores = t.empty((n_spk, width), dtype=t.float64, device=waves.device)
+    rc = lib.ss_pca_project(_lib.ptr(waves), n_win, n_spk, n_c, _lib.ptr(offsets), n_groups,
+                            _lib.ptr(evals), _lib.ptr(evecs), int(ncomps), _lib.ptr(scores),
+                            _lib.stream_ptr())
+    _lib.check(rc, "ss_pca_project")
+    _launched(1 if n_spk > 0 else 0)
+    return scores

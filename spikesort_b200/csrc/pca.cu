@@ -301,7 +301,7 @@ extern "C" int ss_pca_gram(const float *d_waves, int n_win, int64_t n_spk, int n
                            const int64_t *d_offsets, int64_t n_groups, const double *d_ref,
                            double *d_gram, double *d_sum, void *d_ws, size_t ws_bytes, void *stream)
 {
-    SS_REQUIRE(d_waves && d_ref && d_gram && d_sum && d_ws, SS_ERR_ARG, "pca_gram: null pointer");
+    SS_REQUIRE((d_waves || n_spk == 0) && d_ref && d_gram && d_sum && d_ws, SS_ERR_ARG, "pca_gram: null pointer");
     SS_REQUIRE(n_win >= 1 && n_win <= PC_MAX_WIN, SS_ERR_UNSUPPORTED, "pca_gram: n_win %d outside [1, %d]", n_win, PC_MAX_WIN);
     SS_REQUIRE(n_spk >= 0 && n_c >= 1 && n_groups >= 1 && n_groups <= 65535, SS_ERR_ARG, "pca_gram: bad shape");
     SS_REQUIRE(d_offsets ? n_c == 1 : n_groups == n_c, SS_ERR_ARG, "pca_gram: group layout mismatch");

@@ -1,0 +1,100 @@
+"""The multi-contact front-end chain, device-resident and batched over contacts.
+
+The reference processes one contact per call (``detect_spikes(contact=c)``,
+``extract.py:43-44``); a 32..384-channel recording is therefore a Python loop over
+contacts (SURVEY.md section 8d "multi-contact semantics"):
+
+    for c in contacts:
+        spt   = detect_spikes(filtered, contact=c, thresh='auto', edge=edge)
+        spt   = align_spikes(filtered, spt, sp_win, type=align_type, contact=c)
+        waves = extract_spikes(filtered, spt, sp_win, contacts=c)
+        feats = fetPCA(waves, ncomps)
+
+``run_chain`` computes exactly that for all contacts at once: every stage is one
+batched launch sequence over (contact, ...) with per-contact results concatenated
+and delimited by an offsets array, and nothing leaves HBM between the stages.
+"""
+import numpy as np
+
+from . import _lib, _ops
+
+_FALLING = ('falling', 'min')
+
+
+class ChainResult(object):
+    """Device-resident result of run_chain (CUDA tensors)."""
+
+    def __init__(self):
+        self.filtered = None        # float64 (n_contacts, n_samples) or the input if unfiltered
+        self.thresh = None          # float64 (n_contacts,)
+        self.spt_detected = None    # float64, concatenated per contact
+        self.offsets_detected = None
+        self.spt = None             # aligned, doubles removed
+        self.offsets = None         # int64 (n_contacts+1,)
+        self.waves = None           # float32 (n_win, n_spk, 1)
+        self.valid = None           # uint8 (n_spk,)
+        self.n_invalid = None
+        self.evals = None           # float64 (n_contacts, n_win)
+        self.evecs = None           # float64 (n_contacts, n_win, n_win)
+        self.scores = None          # float64 (n_spk, ncomps)
+        self.time = None            # host float64 (n_win,)
+
+    def per_contact(self, c):
+        """Host copies shaped like the reference's per-contact results."""
+        off = self.offsets.cpu().numpy()
+        offd = self.offsets_detected.cpu().numpy()
+        lo, hi = int(off[c]), int(off[c + 1])
+        out = {
+            'spt_detected': self.spt_detected[int(offd[c]):int(offd[c + 1])].cpu().numpy(),
+            'thresh': float(self.thresh[c].item()),
+            'spt': self.spt[lo:hi].cpu().numpy(),
+            'waves': np.ascontiguousarray(self.waves[:, lo:hi, :].cpu().numpy()),
+            'is_valid': self.valid[lo:hi].cpu().numpy().astype(bool),
+        }
+        if self.scores is not None:
+            out['scores'] = self.scores[lo:hi].cpu().numpy()
+            out['evals'] = self.evals[c].cpu().numpy()
+            out['evecs'] = self.evecs[c].cpu().numpy()
+        return out
+
+
+def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
+              thresh='auto', ncomps=2, chunksize=1E6, pca=True, thr_override=None):
+    """x: CUDA tensor (n_contacts, n_samples), int16/float32/float64.
+    filt: a spikesort_b200.filters filter object or None.
+    thresh: 'auto' / numeric string (multiple of the std of the first 10 s) or a number.
+    thr_override: optional CUDA float64 (n_contacts,) thresholds (e.g. broadcast from the
+    rank owning the first 10 s when the recording is time-sharded)."""
+    t = _lib.require_cuda()
+    res = ChainResult()
+    sp_win = list(sp_win)
+    if filt is not None:
+        sos, padlen = filt.sections(FS)
+        sig = _ops.filtfilt_sos(x, sos, padlen, int(chunksize))
+    else:
+        sig = x
+    res.filtered = sig
+    falling = edge in _FALLING
+    n_rows = sig.shape[0]
+    if thr_override is not None:
+        thr = thr_override
+    elif isinstance(thresh, str):
+        frac = 8.0 if thresh == 'auto' else float(thresh)
+        thr = _ops.var_threshold(sig, int(10 * FS), -frac if falling else frac)
+    else:
+        thr = t.full((n_rows,), float(thresh), dtype=t.float64, device=sig.device)
+    res.thresh = thr
+    spt, offsets = _ops.detect(sig, thr, falling, FS)
+    res.spt_detected, res.offsets_detected = spt, offsets
+    spt = spt.clone()
+    _ops.align(sig, spt, offsets, None, FS, sp_win, align_type == 'min')
+    spt, offsets = _ops.remove_doubles(spt, offsets, 1000.0 / FS)
+    res.spt, res.offsets = spt, offsets
+    waves, valid, n_invalid = _ops.extract(sig, spt, FS, sp_win, contacts=None, offsets=offsets)
+    res.waves, res.valid, res.n_invalid = waves, valid, n_invalid
+    res.time = _ops.window_params(sp_win, FS)[2]
+    if pca and spt.numel() > 0:
+        gram, ssum, _, counts = _ops.pca_gram(waves, offsets=offsets)
+        res.evals, res.evecs = _ops.pca_eig(gram, ssum, counts)
+        res.scores = _ops.pca_project(waves, res.evals, res.evecs, ncomps, offsets=offsets)
+    return res

@@ -1,0 +1,70 @@
+"""CPU tier: host logic above the C ABI - filter factorisation and the exact float64
+expressions the host evaluates for the kernels."""
+import numpy as np
+import pytest
+from scipy import signal
+
+from spikesort_b200 import _ops
+from spikesort_b200._design import tf2sos_exact
+
+
+DESIGNS = {
+    'hp1': lambda: signal.iirdesign(800 * 2 / 25000, 100 * 2 / 25000, 1, 10, ftype='butter'),
+    'bp8': lambda: signal.iirdesign(np.array([300, 6000]) * 2 / 30000,
+                                    np.array([100, 8000]) * 2 / 30000, 1, 10, ftype='butter'),
+    'ellip10': lambda: signal.iirdesign(np.array([300, 6000]) * 2 / 30000,
+                                        np.array([150, 7000]) * 2 / 30000, 1, 40, ftype='ellip'),
+    'butter12': lambda: signal.butter(6, [300 / 15000, 6000 / 15000], 'bandpass'),
+    'lp3': lambda: signal.butter(3, 0.2),
+    'ellip_hp3': lambda: signal.iirdesign(0.02, 0.016, 1, 10, ftype='ellip'),
+    'cheby2_lp': lambda: signal.iirdesign(0.2, 0.3, 1, 40, ftype='cheby2'),
+}
+
+
+@pytest.mark.parametrize("name", sorted(DESIGNS))
+def test_sections_are_the_same_filter(name):
+    b, a = DESIGNS[name]()
+    sos, padlen = tf2sos_exact(b, a)
+    assert padlen == 3 * max(len(a), len(b))
+    assert np.all(sos[:, 3] == 1.0)
+    order = max(len(a), len(b)) - 1
+    n_states = sum(1 if (s[2] == 0 and s[5] == 0) else 2 for s in sos)
+    assert n_states in (order, order + 1)     # odd orders may carry one idle delay
+    first_order = [i for i, s in enumerate(sos) if s[2] == 0 and s[5] == 0]
+    assert first_order in ([], [len(sos) - 1])
+    # same frequency response as (b, a)
+    w, h0 = signal.freqz(b, a, worN=2048)
+    _, h1 = signal.sosfreqz(sos, worN=2048)
+    # (freqz of a 12th-order (b, a) polynomial pair is itself only good to ~1e-7)
+    assert np.abs(h0 - h1).max() <= 1e-6 * max(1.0, np.abs(h0).max())
+    # and the same zero-phase output (the reference's (b, a) arithmetic is the noisier one)
+    x = np.random.default_rng(0).standard_normal(4000)
+    y0 = signal.filtfilt(b, a, x)
+    y1 = signal.sosfiltfilt(sos, x, padlen=padlen)
+    assert np.abs(y0 - y1).max() <= 1e-6 * np.abs(y0).max()
+
+
+def test_unstable_and_fir_rejected():
+    with pytest.raises(ValueError):
+        tf2sos_exact([1.0, 0.5], [1.0, -1.5])
+    with pytest.raises(NotImplementedError):
+        tf2sos_exact([0.25, 0.5, 0.25], [1.0])
+
+
+@pytest.mark.parametrize("FS", [25000, 25E3, 30000, 10000, 44100.0])
+@pytest.mark.parametrize("sp_win", [[-0.2, 0.8], [-0.6, 0.8], [0, 0.4], [-1.0, 2.0]])
+def test_window_and_bounds_match_reference_expressions(FS, sp_win):
+    win0, win1, time = _ops.window_params(sp_win, FS)
+    win = (np.asarray(sp_win) / 1000.0 * FS).astype(np.int32)           # extract.py:151
+    assert (win0, win1) == (int(win[0]), int(win[1]))
+    assert np.array_equal(time, np.arange(win[1] - win[0]) * 1000.0 / FS + sp_win[0])
+    n = 123457
+    t_min, t_max = _ops.time_bounds(n, FS, sp_win)
+    max_time = n * 1000.0 / FS                                          # extract.py:106-109
+    assert t_min == np.max((-sp_win[0], 0)) and t_max == np.min((max_time, max_time - sp_win[1]))
+
+
+def test_known_truncation_quirks():
+    # sp_win=[-0.6, 0.8] at 25 kHz gives win=[-14, 20], not [-15, 20]
+    assert _ops.window_params([-0.6, 0.8], 25000)[:2] == (-14, 20)
+    assert _ops.window_params([-0.2, 0.8], 25000)[:2] == (-5, 20)

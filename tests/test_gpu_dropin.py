@@ -1,0 +1,192 @@
+"""GPU tier: the CUDA drop-in (spikesort_b200.{filters,extract,features}) against
+
+* the reference's own unit tests restated in tests/ref_cases.py,
+* the golden vectors produced by the unmodified reference (tests/golden/),
+through the public spike_sort.core-compatible API, i.e. through the C ABI.
+
+Bars: bit-exact for spike times, indices and waveforms; rel 1e-5 (north_star) for the
+filtered signal and PCA scores - the asserts below use the much tighter bounds the
+kernels actually meet, and say so.
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+import ref_cases
+from util import sine_fixture, sign_normalise, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ss(cuda):
+    import spikesort_b200
+    from spikesort_b200 import _lib
+    _lib.load()                       # must be the native library, no fallback
+    return spikesort_b200
+
+
+def test_native_library_is_loaded(ss):
+    from spikesort_b200 import _lib
+    assert _lib._lib is not None
+    maps = open("/proc/self/maps").read()
+    assert "libspikesort_b200.so" in maps
+
+
+@pytest.mark.parametrize("case", ref_cases.EXTRACT_CASES, ids=lambda f: f.__name__)
+def test_reference_extract_cases(ss, case):
+    case(ss.extract)
+
+
+@pytest.mark.parametrize("case", ref_cases.FEATURE_CASES, ids=lambda f: f.__name__)
+def test_reference_feature_cases(ss, case):
+    case(ss.features)
+
+
+def test_reference_filter_cases(ss):
+    ref_cases.check_filter_proxy_shape(ss.filters)
+    ref_cases.check_linear_iir_detect(ss.filters, ss.extract)
+
+
+def test_doc_known_answers(ss, golden):
+    raw = {'data': np.array([[0, 1, 0, 0, 0, 1]]), 'FS': 10000, 'n_contacts': 1}
+    spt = ss.extract.detect_spikes(raw, thresh=0.8)
+    assert np.array_equal(spt['data'], [0.0, 0.4]) and spt['data'].dtype == np.float64
+    assert set(spt.keys()) == {'thresh', 'contact', 'data'}
+    raw = {'data': golden['doc_extract_in'], 'FS': 10000, 'n_contacts': 1}
+    w = ss.extract.extract_spikes(raw, {'data': np.array([0.15, 0.65, 1])}, [0, 0.4])
+    assert sorted(w.keys()) == ['FS', 'data', 'is_valid', 'time']
+    assert w['data'].dtype == np.float32 and w['data'].shape == (4, 3, 1)
+    assert np.array_equal(w['data'], golden['doc_extract_waves'])
+    assert np.array_equal(w['time'], golden['doc_extract_time'])
+    assert np.array_equal(w['is_valid'], [True, True, False])
+
+
+def test_sine_golden_bit_exact(ss, golden):
+    ex = ss.extract
+    sp, period, time = sine_fixture()
+    d = ex.detect_spikes(sp, thresh=0.5)
+    assert np.array_equal(d['data'], golden['sine_detect'])
+    df = ex.detect_spikes(sp, thresh=-0.5, edge='falling')
+    assert np.array_equal(df['data'], golden['sine_detect_falling'])
+    sp_win = list(golden['sine_sp_win'])
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        a = ex.align_spikes(sp, d, sp_win, type='max')
+        assert np.array_equal(a['data'], golden['sine_align_max'])
+        a2 = ex.align_spikes(sp, d, [-period / 24, period / 24], type='max')
+        assert np.array_equal(a2['data'], golden['sine_align_short'])
+        a3 = ex.align_spikes(sp, {'data': golden['sine_align_doubles_in']}, sp_win, type='max')
+        assert np.array_equal(a3['data'], golden['sine_align_doubles'])
+        a4 = ex.align_spikes(sp, d, sp_win, type='min')
+        assert np.array_equal(a4['data'], golden['sine_align_min'])
+    w = ex.extract_spikes(sp, a, sp_win)
+    assert np.array_equal(w['data'], golden['sine_extract'])
+    assert np.array_equal(w['time'], golden['sine_extract_time'])
+    we = ex.extract_spikes(sp, {'data': golden['sine_edge_spt']}, [-0.5, 1.0])
+    assert np.array_equal(we['data'], golden['sine_edge_waves'])
+    assert np.array_equal(we['is_valid'], golden['sine_edge_valid'])
+    out = ex.remove_doubles({'data': golden['rd_in']}, 1000.0 / 25000.0)
+    assert np.array_equal(out['data'], golden['rd_out'])
+
+
+def test_chain_golden(ss, golden):
+    FS = 25000
+    raw = {'data': golden['chain_raw'], 'FS': FS, 'n_contacts': 2}
+    f = ss.filters.filter_proxy(raw, ss.filters.Filter(800., 100.), chunksize=25000)
+    assert f['data'].shape == (2, 60000) and f['data'].dtype == np.float64
+    got = np.asarray(f['data'])
+    assert rel_err(got, golden['chain_filtered']) < 1e-11          # bar: 1e-5
+    # spike indices / waveforms: bit-exact GIVEN the reference's filtered signal
+    fd = {'data': golden['chain_filtered'], 'FS': FS, 'n_contacts': 2}
+    det = ss.extract.detect_spikes(fd, contact=1, thresh='auto')
+    assert abs(det['thresh'] - golden['chain_thresh'][0]) <= 1e-12 * golden['chain_thresh'][0]
+    det = ss.extract.detect_spikes(fd, contact=1, thresh=float(golden['chain_thresh'][0]))
+    assert np.array_equal(det['data'], golden['chain_detect'])
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        al = ss.extract.align_spikes(fd, det, [-0.2, 0.8], type='max', contact=1)
+    assert np.array_equal(al['data'], golden['chain_align'])
+    wv = ss.extract.extract_spikes(fd, al, [-0.2, 0.8])
+    assert np.array_equal(wv['data'], golden['chain_waves'])
+    pc = ss.features.fetPCA(wv, ncomps=2)
+    assert pc['names'] == ['Ch0:PC0', 'Ch0:PC1', 'Ch1:PC0', 'Ch1:PC1']
+    assert rel_err(sign_normalise(pc['data'], golden['chain_pca']), golden['chain_pca']) < 1e-9
+    ev, evec, sc = ss.features.PCA(wv['data'][:, :, 0], 3)
+    assert np.allclose(ev[:10], golden['chain_pca0_evals'][:10], rtol=1e-9)
+    assert rel_err(sign_normalise(sc.T, golden['chain_pca0_score'].T), golden['chain_pca0_score'].T) < 1e-9
+    # end to end on the GPU-filtered signal: count spike-time mismatches (north_star)
+    det_g = ss.extract.detect_spikes(f, contact=1, thresh='auto')
+    mism = len(np.setxor1d(det_g['data'], golden['chain_detect']))
+    print("end-to-end spike-time mismatches: %d of %d" % (mism, len(golden['chain_detect'])))
+    assert mism == 0
+
+
+def test_bandpass_float32_golden(ss, golden):
+    raw = {'data': golden['bp_raw'], 'FS': 30000, 'n_contacts': 1}
+    f = ss.filters.filter_proxy(raw, ss.filters.Filter(np.array([300., 6000.]),
+                                                        np.array([100., 8000.])))
+    assert rel_err(np.asarray(f['data']), golden['bp_filtered']) < 1e-8   # bar: 1e-5
+
+
+def test_sine_highpass_golden(ss, golden):
+    sp, period, _ = sine_fixture()
+    sp['data'] = sp['data'] + 2
+    f = ss.filters.fltLinearIIR(sp, 1000.0 / period * 0.5, 1000.0 / period * 0.4, 1, 10, 'ellip')
+    assert rel_err(np.asarray(f['data']), golden['sine_hp_filtered']) < 1e-9
+    spt = ss.extract.detect_spikes(f, thresh=0.5)
+    assert np.array_equal(spt['data'], golden['sine_hp_detect'])
+
+
+def test_errors_and_warnings(ss):
+    sp, period, _ = sine_fixture()
+    with pytest.raises(TypeError):
+        ss.extract.detect_spikes(sp, thresh=0.5, edge='sideways')
+    with pytest.raises(TypeError):
+        ss.filters.filter_proxy(sp, lambda x, fs: x)          # no CPU fallback
+    assert ss.filters.filter_proxy(sp, None) is sp
+    with pytest.raises(ValueError):                           # chunk not longer than padlen
+        ss.filters.filter_proxy({'data': np.zeros((1, 5)), 'FS': 25000, 'n_contacts': 1},
+                                ss.filters.Filter(800., 100.))
+    with pytest.warns(UserWarning):
+        ss.extract.align_spikes(sp, {'data': np.array([10.0])}, [-0.05, 0.05])
+    with pytest.raises(IndexError):
+        ss.features.fetPCA({'data': np.zeros((5, 10, 2), np.float32)}, contacts=[4])
+    out = ss.extract.detect_spikes(sp, thresh=5.0)            # nothing crosses
+    assert out['data'].shape == (0,) and out['data'].dtype == np.float64
+    al = ss.extract.align_spikes(sp, out, [-0.5, 0.5])
+    assert al['data'].shape == (0,)
+    w = ss.extract.extract_spikes(sp, al, [-0.5, 0.5])
+    assert w['data'].shape[1:] == (0, 1)
+
+
+def test_filter_object_call_and_device_signal(ss):
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal(3000)
+    from scipy import signal
+    flt = ss.filters.Filter(800., 100.)
+    y = flt(x, 25000)
+    b, a = flt._design_filter(25000)
+    assert rel_err(y, signal.filtfilt(b, a, x)) < 1e-11
+    zp = ss.filters.ZeroPhaseFilter('ellip', [300., 3000.])
+    b, a = zp._design_filter(25000)
+    assert rel_err(zp(x, 25000), signal.filtfilt(b, a, x)) < 1e-7
+    raw = {'data': rng.standard_normal((3, 5000)), 'FS': 25000, 'n_contacts': 3}
+    f = ss.filters.filter_proxy(raw, flt)
+    d = f['data']
+    assert d.shape == (3, 5000) and d[1, :].shape == (5000,) and d[[0, 2], 10:20].shape == (2, 10)
+    assert np.array_equal(d[:], np.asarray(d))
+    assert f['FS'] == 25000 and raw['data'] is not f['data']
+
+
+def test_install_rebinds_reference_namespace(ss):
+    import types
+    fake = types.SimpleNamespace(filters=types.SimpleNamespace(fltLinearIIR=1),
+                                 extract=types.SimpleNamespace(detect_spikes=2),
+                                 features=types.SimpleNamespace())
+    orig = ss.install(fake)
+    assert fake.extract.detect_spikes is ss.extract.detect_spikes
+    assert fake.filters.fltLinearIIR is ss.filters.fltLinearIIR
+    assert fake.features.fetPCA is ss.features.fetPCA
+    assert orig[("extract", "detect_spikes")] == 2

@@ -1,0 +1,326 @@
+"""GPU tier: CUDA kernels (through the C ABI) against the CPU oracle on the same seeded
+inputs, at sizes the oracle finishes in seconds; edge cases; and size-independent
+properties at the BASELINE.json configuration size.
+
+Bars (north_star): spike times / indices / waveforms bit-exact given the same input
+signal; filtered signal and PCA scores within rel 1e-5 (sign-normalised components).
+"""
+import warnings
+
+import numpy as np
+import pytest
+from scipy import signal
+
+from util import sign_normalise, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env(cuda):
+    import torch
+    import spikesort_b200
+    from spikesort_b200 import _ops, _lib, pipeline, synth
+    _lib.load()
+    return dict(torch=torch, ss=spikesort_b200, ops=_ops, pipeline=pipeline, synth=synth,
+                dev=cuda)
+
+
+def _dev(env, arr):
+    return env['torch'].from_numpy(np.ascontiguousarray(arr)).to(env['dev'])
+
+
+DESIGNS = {
+    'hp1_butter': lambda: signal.iirdesign(800 * 2 / 25000, 100 * 2 / 25000, 1, 10, ftype='butter'),
+    'bp2': lambda: signal.butter(1, [0.02, 0.4], 'bandpass'),
+    'lp3': lambda: signal.butter(3, 0.2),
+    'ellip_hp3': lambda: signal.iirdesign(0.02, 0.016, 1, 10, ftype='ellip'),
+    'bp4': lambda: signal.butter(2, [300 / 15000, 6000 / 15000], 'bandpass'),
+    'bp8': lambda: signal.iirdesign(np.array([300, 6000]) * 2 / 30000,
+                                    np.array([100, 8000]) * 2 / 30000, 1, 10, ftype='butter'),
+    'ellip10': lambda: signal.iirdesign(np.array([300, 6000]) * 2 / 30000,
+                                        np.array([150, 7000]) * 2 / 30000, 1, 40, ftype='ellip'),
+    'butter12': lambda: signal.butter(6, [300 / 15000, 6000 / 15000], 'bandpass'),
+}
+# measured agreement is far inside the 1e-5 bar; these bounds catch regressions.  The
+# high orders are limited by the REFERENCE's (b, a)-form round-off, not by the scan.
+TIGHT = {'hp1_butter': 1e-12, 'bp2': 1e-12, 'lp3': 1e-12, 'ellip_hp3': 1e-11, 'bp4': 1e-10,
+         'bp8': 1e-8, 'ellip10': 1e-6, 'butter12': 1e-6}
+
+
+@pytest.mark.parametrize("name", sorted(DESIGNS))
+@pytest.mark.parametrize("dtype", ["int16", "float32", "float64"])
+def test_filtfilt_vs_oracle(env, oracle, name, dtype):
+    from spikesort_b200._design import tf2sos_exact
+    b, a = DESIGNS[name]()
+    sos, padlen = tf2sos_exact(b, a)
+    rng = np.random.default_rng(11)
+    # 3 contacts, chunks of 7000 (several tiles + ragged), last chunk short (1234)
+    n, cs = 3 * 7000 + 1234, 7000
+    x = rng.standard_normal((3, n)) * 500 + 300
+    x = np.round(x).astype(np.int16) if dtype == "int16" else x.astype(dtype)
+    ref = np.empty((3, n))
+    for c in range(3):
+        for lo in range(0, n, cs):
+            ref[c, lo:lo + cs] = oracle.filtfilt(b, a, x[c, lo:lo + cs])
+    got = env['ops'].filtfilt_sos(_dev(env, x), sos, padlen, cs).cpu().numpy()
+    err = rel_err(got, ref)
+    print("%s %s rel err %.3g" % (name, dtype, err))
+    assert err < 1e-5                      # the north_star bar
+    assert err < TIGHT[name]
+
+
+def test_filtfilt_chunk_shapes_and_int16_wrap(env, oracle):
+    from spikesort_b200._design import tf2sos_exact
+    b, a = DESIGNS['hp1_butter']()
+    sos, padlen = tf2sos_exact(b, a)
+    rng = np.random.default_rng(5)
+    for n, cs in [(7, 7), (500, 500), (512, 512), (1000, 100), (1024 - 12, 1024 - 12),
+                  (4096, 1000), (30000, 1000000), (2999, 1000)]:
+        x = np.round(rng.standard_normal((2, n)) * 9000).astype(np.int16)
+        x[:, 0] = 30000                      # 2*x[0] - x[k] wraps around in int16
+        x[:, -1] = -30000
+        ref = np.empty((2, n))
+        for c in range(2):
+            for lo in range(0, n, cs):
+                ref[c, lo:lo + cs] = oracle.filtfilt(b, a, x[c, lo:lo + cs])
+        got = env['ops'].filtfilt_sos(_dev(env, x), sos, padlen, cs).cpu().numpy()
+        assert rel_err(got, ref) < 1e-12, (n, cs)
+    with pytest.raises(ValueError):
+        env['ops'].filtfilt_sos(_dev(env, np.zeros((1, 1006), np.int16)), sos, padlen, 1000)
+    # strided rows (ld > n_samples)
+    big = np.round(rng.standard_normal((4, 6000)) * 100).astype(np.int16)
+    view = _dev(env, big)[:, 500:5500]
+    got = env['ops'].filtfilt_sos(view, sos, padlen, 2000).cpu().numpy()
+    ref = np.stack([np.concatenate([oracle.filtfilt(b, a, big[c, 500 + lo:500 + lo + 2000])
+                                    for lo in range(0, 5000, 2000)]) for c in range(4)])
+    assert rel_err(got, ref) < 1e-12
+
+
+def test_auto_threshold(env, oracle):
+    rng = np.random.default_rng(8)
+    for dtype in (np.int16, np.float32, np.float64):
+        x = (rng.standard_normal((5, 40000)) * 37 + 11).astype(dtype)
+        for n0 in (40000, 25000, 10 * 30000):
+            ref = np.array([8.0 * np.sqrt(x[r, :n0].var(dtype=np.float64)) for r in range(5)])
+            got = env['ops'].var_threshold(_dev(env, x), n0, -8.0).cpu().numpy()
+            assert np.all(np.abs(got + ref) <= 1e-12 * ref)
+
+
+@pytest.mark.parametrize("dtype", ["int16", "float32", "float64"])
+def test_detect_bit_exact(env, oracle, dtype):
+    rng = np.random.default_rng(21)
+    n = 3 * 8192 + 77
+    x = rng.standard_normal((4, n)) * 50
+    x = np.round(x).astype(np.int16) if dtype == "int16" else x.astype(dtype)
+    x[2, :] = 0                                         # a silent contact: no spikes
+    for FS in (25000, 30000.0):
+        for edge, thr in (("rising", 60.0), ("falling", -60.0), ("max", 0.0), ("min", 49.5)):
+            thr_dev = _dev(env, np.full(4, thr))
+            spt, off = env['ops'].detect(_dev(env, x), thr_dev, edge in ("falling", "min"), FS)
+            spt, off = spt.cpu().numpy(), off.cpu().numpy()
+            assert off[0] == 0 and off[-1] == len(spt)
+            for c in range(4):
+                ref = oracle.detect_spikes({'data': x, 'FS': FS, 'n_contacts': 4},
+                                           thresh=np.float64(thr), edge=edge, contact=c)['data']
+                assert np.array_equal(spt[off[c]:off[c + 1]], ref), (FS, edge, c)
+
+
+def test_detect_python_float_threshold_on_float32(env, oracle):
+    # NumPy compares a float32 array with a PYTHON float in float32 (weak promotion)
+    x = np.array([[0.0, 0.1, 0.30000001192092896, 0.5, 0.2, 0.30000001192092896, 0.31]],
+                 dtype=np.float32)
+    sp = {'data': x, 'FS': 1000, 'n_contacts': 1}
+    for thr in (0.3, np.float64(0.3), np.float32(0.3)):
+        ref = oracle.detect_spikes(sp, thresh=thr)['data']
+        got = env['ss'].extract.detect_spikes(sp, thresh=thr)['data']
+        assert np.array_equal(got, ref), thr
+
+
+def _burst_recording(env, n_c=3, n=120000, FS=30000, seed=4):
+    x = env['synth'].make_recording(n_c, n, FS, seed=seed, rate_hz=200.0, noise=6.0,
+                                    amp=(60.0, 150.0), burst=True, negative=True).numpy()
+    return x, FS
+
+
+@pytest.mark.parametrize("align_type", ["min", "max"])
+def test_align_extract_bit_exact_burst(env, oracle, align_type):
+    x, FS = _burst_recording(env)
+    raw = {'data': x.astype(np.float64) * 0.37, 'FS': FS, 'n_contacts': x.shape[0]}
+    sp_win = [-0.6, 0.8]                                  # 42 samples: more than one warp pass
+    for c in range(x.shape[0]):
+        edge = 'falling' if align_type == 'min' else 'rising'
+        thr = -30.0 if align_type == 'min' else 12.0
+        det = oracle.detect_spikes(raw, thresh=thr, edge=edge, contact=c)
+        assert len(det['data']) > 200
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ref = oracle.align_spikes(raw, det, sp_win, type=align_type, contact=c)
+            got = env['ss'].extract.align_spikes(raw, det, sp_win, type=align_type, contact=c)
+            ref_keep = oracle.align_spikes(raw, det, sp_win, type=align_type, contact=c, remove=False)
+            got_keep = env['ss'].extract.align_spikes(raw, det, sp_win, type=align_type, contact=c,
+                                                      remove=False)
+        assert np.array_equal(got_keep['data'], ref_keep['data'])
+        assert np.array_equal(got['data'], ref['data'])
+        assert len(ref['data']) < len(det['data'])        # doubles were actually removed
+        wr = oracle.extract_spikes(raw, ref, sp_win)
+        wg = env['ss'].extract.extract_spikes(raw, ref, sp_win)
+        assert np.array_equal(wg['data'], wr['data']) and np.array_equal(wg['time'], wr['time'])
+        assert ('is_valid' in wg) == ('is_valid' in wr)
+        for contacts in (1, [2, 0], np.array([1])):
+            wr = oracle.extract_spikes(raw, ref, sp_win, contacts=contacts)
+            wg = env['ss'].extract.extract_spikes(raw, ref, sp_win, contacts=contacts)
+            assert np.array_equal(wg['data'], wr['data'])
+
+
+def test_align_ties_and_plateaus(env, oracle):
+    # flat tops: argmax must return the FIRST maximum, also after float32 rounding
+    FS = 10000
+    x = np.zeros((1, 4000))
+    for k in range(20, 3900, 200):
+        x[0, k:k + 7] = [1, 3, 5, 5, 5.0000000001, 3, 1]   # equal in float32
+    x[0, 3000:3030] = 7.0                                   # long plateau: walks left edge by edge
+    raw = {'data': x, 'FS': FS, 'n_contacts': 1}
+    det = oracle.detect_spikes(raw, thresh=2.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for sp_win in ([-0.5, 0.5], [-0.3, 1.0], [-0.2, 0.2]):
+            ref = oracle.align_spikes(raw, det, sp_win, type='max', remove=False)
+            got = env['ss'].extract.align_spikes(raw, det, sp_win, type='max', remove=False)
+            assert np.array_equal(got['data'], ref['data']), sp_win
+
+
+def test_extract_truncated_and_outside(env, oracle):
+    rng = np.random.default_rng(3)
+    FS = 25000
+    x = np.round(rng.standard_normal((4, 5000)) * 100).astype(np.int16)
+    raw = {'data': x, 'FS': FS, 'n_contacts': 4}
+    tmax = 5000 * 1000.0 / FS
+    spt = {'data': np.array([-3.0, -0.1, 0.0, 0.04, 0.19, 0.2, 0.21, 100.0, tmax - 0.81, tmax - 0.8,
+                             tmax - 0.79, tmax - 0.01, tmax, tmax + 0.1, tmax + 50.0])}
+    for sp_win in ([-0.2, 0.8], [-0.6, 0.8], [0, 0.4]):
+        wr = oracle.extract_spikes(raw, spt, sp_win)
+        wg = env['ss'].extract.extract_spikes(raw, spt, sp_win)
+        assert np.array_equal(wg['data'], wr['data']), sp_win
+        assert np.array_equal(wg['is_valid'], wr['is_valid'])
+
+
+@pytest.mark.parametrize("n_spk,n_c,n_win", [(500, 4, 25), (3000, 1, 30), (77, 2, 42), (5000, 3, 96)])
+def test_pca_vs_oracle(env, oracle, n_spk, n_c, n_win):
+    w = env['synth'].make_waveforms(n_win, n_spk, n_c, seed=5).numpy()
+    w += 3.0                                              # large mean: cancellation stress
+    sp = {'data': w, 'time': np.arange(n_win, dtype=float), 'FS': 25000}
+    ref = oracle.fetPCA(sp, ncomps=3)
+    got = env['ss'].features.fetPCA(sp, ncomps=3)
+    assert got['names'] == ref['names'] and got['data'].shape == ref['data'].shape
+    err = rel_err(sign_normalise(got['data'], ref['data']), ref['data'])
+    print("pca rel err %.3g" % err)
+    assert err < 1e-5 and err < 1e-9
+    ev_r, evec_r, sc_r = oracle.PCA(w[:, :, 0], 2)
+    ev_g, evec_g, sc_g = env['ss'].features.PCA(w[:, :, 0], 2)
+    k = min(n_win, 8)
+    assert np.allclose(ev_g[:k], ev_r[:k], rtol=1e-9)
+    assert rel_err(sign_normalise(evec_g[:, :3], evec_r[:, :3]), evec_r[:, :3]) < 1e-7
+    assert np.all(np.diff(ev_g) <= 1e-12 * ev_g[0])       # sorted descending
+
+
+def test_chain_vs_oracle_per_contact(env, oracle):
+    """The batched device-resident chain equals the reference-style per-contact loop."""
+    FS = 30000
+    x = env['synth'].make_recording(6, 150000, FS, seed=2, rate_hz=40.0, noise=8.0,
+                                    amp=(70.0, 180.0), negative=True).numpy()
+    raw = {'data': x, 'FS': FS, 'n_contacts': 6}
+    sp_win = [-0.2, 0.8]
+    flt_g = env['ss'].filters.Filter(800., 100.)
+    res = env['pipeline'].run_chain(_dev(env, x), FS, filt=flt_g, sp_win=sp_win, edge='falling',
+                                    align_type='min', ncomps=2, chunksize=50000)
+    filtered, ref = oracle.chain_per_contact(raw, oracle.Filter(800., 100.), sp_win,
+                                             edge='falling', align_type='min', ncomps=2,
+                                             chunksize=50000)
+    assert rel_err(res.filtered.cpu().numpy(), filtered['data']) < 1e-11
+    total = mism = 0
+    for c in range(6):
+        spt_d, spt_a, waves, feats = ref[c]
+        got = res.per_contact(c)
+        assert abs(got['thresh'] - spt_d['thresh']) <= 1e-12 * abs(spt_d['thresh'])
+        total += len(spt_a['data'])
+        mism += len(np.setxor1d(got['spt'], spt_a['data']))
+    print("end-to-end spike-time mismatches (GPU filter + auto threshold): %d of %d" % (mism, total))
+    assert total > 100
+    assert mism <= max(1, total // 1000)        # a sample within 1 ulp of the threshold may flip
+    # bit-exact GIVEN the reference's filtered signal and thresholds
+    thr = _dev(env, np.array([ref[c][0]['thresh'] for c in range(6)]))
+    res2 = env['pipeline'].run_chain(_dev(env, filtered['data']), FS, filt=None, sp_win=sp_win,
+                                     edge='falling', align_type='min', ncomps=2, thr_override=thr)
+    for c in range(6):
+        spt_d, spt_a, waves, feats = ref[c]
+        got = res2.per_contact(c)
+        assert np.array_equal(got['spt_detected'], spt_d['data'])
+        assert np.array_equal(got['spt'], spt_a['data'])
+        assert np.array_equal(got['waves'], waves['data'])
+        assert np.array_equal(got['is_valid'].all(), 'is_valid' not in waves)
+        err = rel_err(sign_normalise(got['scores'], feats['data']), feats['data'])
+        assert err < 1e-9, (c, err)
+
+
+def test_full_size_properties(env):
+    """BASELINE.json configs[1] (32 contacts x 18 000 000 samples @ 30 kHz, int16):
+    size-independent properties of the chain."""
+    torch, ops = env['torch'], env['ops']
+    FS, n_c, n = 30000, 32, 18000000
+    x = env['synth'].make_recording(n_c, n, FS, seed=2, device=env['dev'], rate_hz=10.0,
+                                    noise=10.0)
+    flt = env['ss'].filters.Filter(800., 100.)
+    sos, padlen = flt.sections(FS)
+    y = ops.filtfilt_sos(x, sos, padlen, 1000000)
+    assert bool(torch.isfinite(y).all())
+    # (1) chunk independence: filtering one (contact, chunk) alone gives the same values
+    for c, j in ((0, 0), (17, 9), (31, 17)):
+        alone = ops.filtfilt_sos(x[c:c + 1, j * 1000000:(j + 1) * 1000000], sos, padlen, 1000000)
+        assert torch.equal(alone[0], y[c, j * 1000000:(j + 1) * 1000000])
+    # (2) linearity: filter(2x) == 2 filter(x) exactly (power-of-two scaling is exact;
+    #     int16 inputs here stay far from the wrap-around range)
+    y2 = ops.filtfilt_sos((x[:2] * 2).contiguous(), sos, padlen, 1000000)
+    assert torch.equal(y2, 2 * y[:2])
+    # (3) a high-pass removes the mean: per-contact mean of the output ~ 0
+    assert float(y.mean(dim=1).abs().max()) < 0.05
+    # (4) detection: sorted per contact, all within the recording, crossings verified
+    thr = ops.var_threshold(y, 10 * FS, -8.0)
+    spt, off = ops.detect(y, thr, True, FS)
+    offh = off.cpu().numpy()
+    assert offh[-1] == spt.numel() and offh[-1] > 1000
+    d = spt[1:] - spt[:-1]
+    starts = torch.zeros(spt.numel() - 1, dtype=torch.bool, device=spt.device)
+    starts[torch.from_numpy(offh[1:-1][(offh[1:-1] > 0) & (offh[1:-1] < spt.numel())] - 1).to(spt.device)] = True
+    assert bool((d[~starts] > 0).all())
+    idx = torch.round(spt / 1000.0 * FS).long()
+    rows = torch.repeat_interleave(torch.arange(n_c, device=spt.device), (off[1:] - off[:-1]))
+    a, b = y[rows, idx], y[rows, idx + 1]
+    assert bool(((a > thr[rows]) & (b < thr[rows])).all())
+    # checksum of checksums: the number of crossings equals a torch recount
+    recount = ((y[:, :-1] > thr[:, None]) & (y[:, 1:] < thr[:, None])).sum()
+    assert int(recount) == spt.numel()
+    # (5) alignment never moves to a shallower sample and lands on the window minimum
+    sp_win = [-0.2, 0.8]
+    al = spt.clone()
+    ops.align(y, al, off, None, FS, sp_win, True)
+    i_det = torch.round(spt / 1000.0 * FS).long()
+    i_al = (al / 1000.0 * FS).long().clamp(0, n - 1)
+    assert bool((y[rows, i_al] <= y[rows, i_det]).all())    # moved to a deeper sample or stayed
+    kept, off2 = ops.remove_doubles(al, off, 1000.0 / FS)
+    assert kept.numel() <= al.numel() and int(off2[-1]) == kept.numel()
+    waves, valid, n_inv = ops.extract(y, kept, FS, sp_win, contacts=None, offsets=off2)
+    win0, win1, _ = ops.window_params(sp_win, FS)
+    inner = valid.bool()
+    amin = waves[:, inner, 0].argmin(dim=0)
+    assert bool((amin == -win0).float().mean() > 0.95)      # minimum at t = 0 of the window
+    # (6) PCA: whitened scores have unit variance per contact
+    gram, ssum, _, counts = ops.pca_gram(waves, offsets=off2)
+    evals, evecs = ops.pca_eig(gram, ssum, counts)
+    scores = ops.pca_project(waves, evals, evecs, 2, offsets=off2)
+    o2 = off2.cpu().numpy()
+    for c in (0, 13, 31):
+        s = scores[o2[c]:o2[c + 1]]
+        assert abs(float(s[:, 0].var()) - 1.0) < 1e-6
+        vt = evecs[c].t() @ evecs[c]
+        assert float((vt - torch.eye(vt.shape[0], device=vt.device, dtype=vt.dtype)).abs().max()) < 1e-12
