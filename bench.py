@@ -30,7 +30,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import time
 
@@ -130,55 +129,51 @@ def run_reference(args):
 
 # ------------------------------------------------------------------ GPU arm
 class ClockSampler(object):
-    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock and clock-event reasons of one GPU DURING the timed region
+    (NVML from a background thread, ~2 ms period)."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+               "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
-        self.proc = None
-        self.path = "/tmp/ss_clocks_%d_%d.csv" % (os.getpid(), index)
+        import threading
+        self.samples, self.bits, self.max_mhz = [], 0, None
+        self._stop = threading.Event()
+        self._thread = None
         try:
-            self.fh = open(self.path, "w")
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
-                stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            return
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": []}
+        if self._thread is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        self.fh.close()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for ln in open(self.path):
-                f = [v.strip() for v in ln.split(",")]
-                if len(f) < 8:
-                    continue
-                try:
-                    sm.append(float(f[0]))
-                    mx.append(float(f[1]))
-                except ValueError:
-                    continue
-                for name, v in zip(names, f[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.remove(self.path)
-        except OSError:
-            pass
-        if sm:
-            out["sm_mhz"] = statistics.median(sm)
-            out["sm_max_mhz"] = max(mx)
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+        self._stop.set()
+        self._thread.join(timeout=2)
+        if self.samples:
+            out["sm_mhz"] = statistics.median(self.samples)
+            out["samples"] = len(self.samples)
+        out["reasons"] = sorted(k for k, b in self.REASONS.items() if self.bits & b)
         return out
 
 
@@ -272,6 +267,12 @@ def run_gpu(args):
     value = world * N_CONTACTS * N_SAMPLES / (ms_step / 1000.0)
 
     # ---- e2e: public API, host buffers in, NumPy out (rank-local, then max over ranks)
+    if args.no_e2e:
+        print(json.dumps({"profiling_run": True, "ms_per_step": ms_step,
+                          "ms_filter": ms_filter, "gpu_launches": launches}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     e2e_steps = max(1, min(args.steps, 3))
     host = torch.empty((N_CONTACTS, N_SAMPLES), dtype=torch.int16).pin_memory()
     host.copy_(x)
@@ -371,6 +372,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

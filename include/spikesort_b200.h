@@ -54,7 +54,8 @@ int         ss_version(void);
 const char *ss_last_error(void);
 /* limits compiled into the library */
 int         ss_max_filter_order(void);      /* total number of delay states     */
-int         ss_max_window(void);            /* largest n_win for align/extract/PCA */
+int         ss_max_window(void);            /* largest n_win for align/extract  */
+int         ss_max_pca_window(void);        /* largest n_win for the PCA kernels */
 
 /* ------------------------------------------------------------------ filter
  * Replaces Filter.__call__ -> scipy.signal.filtfilt (filters.py:99-101) looped

@@ -26,6 +26,7 @@ SIGNATURES = {
     "ss_last_error": (_c.c_char_p, []),
     "ss_max_filter_order": (_int, []),
     "ss_max_window": (_int, []),
+    "ss_max_pca_window": (_int, []),
     "ss_filtfilt_workspace_bytes": (_sz, [_i64, _i64, _i64, _int, _int]),
     "ss_filtfilt_sos": (_int, [_vp, _int, _i64, _i64, _i64, _dp, _int, _int, _i64, _vp, _i64,
                                _vp, _sz, _vp]),

@@ -18,7 +18,7 @@
 namespace {
 
 constexpr int EX_PAIRS = 256;           // (spike, contact) windows per CTA = threads per CTA
-constexpr int EX_MAX_WIN = 96;
+constexpr int EX_MAX_WIN = 192;          // 192 * 257 * 4 B = 197 KB of shared memory
 
 __device__ __forceinline__ int64_t ex_find_row(const int64_t *__restrict__ offsets, int64_t n_rows,
                                                int64_t s)

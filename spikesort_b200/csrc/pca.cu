@@ -20,8 +20,8 @@ namespace {
 
 constexpr int PC_THREADS = 256;
 constexpr int PC_SC = 64;               // spikes per staged chunk
-constexpr int PC_MAX_WIN = 96;
-constexpr int PC_MAX_TILES = 2;         // 4x4 tiles per thread (24*25/2 = 300 <= 512)
+constexpr int PC_MAX_WIN = 112;             // eig: 2 * 112^2 * 8 B = 200 KB of shared memory
+constexpr int PC_MAX_TILES = 2;         // 4x4 tiles per thread (28*29/2 = 406 <= 512)
 constexpr int PC_MAX_COMPS = 8;
 
 __host__ __device__ inline int pc_pad4(int n) { return (n + 3) & ~3; }
@@ -289,6 +289,8 @@ pca_project_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
 }
 
 }  // namespace
+
+extern "C" int ss_max_pca_window(void) { return PC_MAX_WIN; }
 
 extern "C" size_t ss_pca_workspace_bytes(int n_win, int64_t n_groups)
 {

@@ -92,7 +92,7 @@ def test_filtfilt_chunk_shapes_and_int16_wrap(env, oracle):
     big = np.round(rng.standard_normal((4, 6000)) * 100).astype(np.int16)
     view = _dev(env, big)[:, 500:5500]
     got = env['ops'].filtfilt_sos(view, sos, padlen, 2000).cpu().numpy()
-    ref = np.stack([np.concatenate([oracle.filtfilt(b, a, big[c, 500 + lo:500 + lo + 2000])
+    ref = np.stack([np.concatenate([oracle.filtfilt(b, a, big[c, 500:5500][lo:lo + 2000])
                                     for lo in range(0, 5000, 2000)]) for c in range(4)])
     assert rel_err(got, ref) < 1e-12
 
@@ -205,7 +205,7 @@ def test_extract_truncated_and_outside(env, oracle):
         assert np.array_equal(wg['is_valid'], wr['is_valid'])
 
 
-@pytest.mark.parametrize("n_spk,n_c,n_win", [(500, 4, 25), (3000, 1, 30), (77, 2, 42), (5000, 3, 96)])
+@pytest.mark.parametrize("n_spk,n_c,n_win", [(500, 4, 25), (3000, 1, 30), (77, 2, 42), (5000, 3, 112)])
 def test_pca_vs_oracle(env, oracle, n_spk, n_c, n_win):
     w = env['synth'].make_waveforms(n_win, n_spk, n_c, seed=5).numpy()
     w += 3.0                                              # large mean: cancellation stress
@@ -305,15 +305,19 @@ def test_full_size_properties(env):
     al = spt.clone()
     ops.align(y, al, off, None, FS, sp_win, True)
     i_det = torch.round(spt / 1000.0 * FS).long()
-    i_al = (al / 1000.0 * FS).long().clamp(0, n - 1)
-    assert bool((y[rows, i_al] <= y[rows, i_det]).all())    # moved to a deeper sample or stayed
+    # (the reference's truncating ms->index round trip reports ~12 % of the times one
+    #  sample late, SURVEY.md 0.4, so the extremum is at the reported sample or the one before;
+    #  the arg-min runs on float32-rounded values)
+    i_al = torch.round(al / 1000.0 * FS).long().clamp(1, n - 1)
+    deepest = torch.minimum(y[rows, i_al], y[rows, i_al - 1])
+    assert bool((deepest <= y[rows, i_det] + 1e-6 * y[rows, i_det].abs()).all())
     kept, off2 = ops.remove_doubles(al, off, 1000.0 / FS)
     assert kept.numel() <= al.numel() and int(off2[-1]) == kept.numel()
     waves, valid, n_inv = ops.extract(y, kept, FS, sp_win, contacts=None, offsets=off2)
     win0, win1, _ = ops.window_params(sp_win, FS)
     inner = valid.bool()
     amin = waves[:, inner, 0].argmin(dim=0)
-    assert bool((amin == -win0).float().mean() > 0.95)      # minimum at t = 0 of the window
+    assert bool(((amin + win0).abs() <= 1).float().mean() > 0.95)   # minimum at t = 0 (+-1 sample)
     # (6) PCA: whitened scores have unit variance per contact
     gram, ssum, _, counts = ops.pca_gram(waves, offsets=off2)
     evals, evecs = ops.pca_eig(gram, ssum, counts)
