@@ -43,14 +43,13 @@ DetLayout det_layout(int64_t n_rows, int64_t n_samples)
     return L;
 }
 
-template <typename T>
-__device__ __forceinline__ bool crossing(const T *row, int64_t i, int64_t n, double thr, int falling)
+constexpr int DT_BATCH = 8;     // words (of 32 samples) whose loads are in flight together
+
+// comparisons in float64: exact for int16/float32/float64 inputs (NumPy promotes the
+// array to the float64 threshold; the float32-array-vs-Python-float case is handled
+// by the host, which rounds the threshold to float32)
+__device__ __forceinline__ bool crossing(double a, double b, double thr, int falling)
 {
-    if (i + 1 >= n) return false;
-    // comparisons in float64: exact for int16/float32/float64 inputs (NumPy
-    // promotes the array to the float64 threshold; the float32-array-vs-Python-
-    // float case is handled by the host, which rounds the threshold to float32)
-    const double a = (double)__ldg(row + i), b = (double)__ldg(row + i + 1);
     return falling ? (a > thr && b < thr) : (a < thr && b > thr);
 }
 
@@ -69,12 +68,32 @@ detect_mark_kernel(const T *__restrict__ x, int64_t n_samples, int64_t ld,
     const int64_t word0 = b * DT_BLOCK_WORDS + warp * DT_WORDS_PER_WARP;
     uint32_t mine = 0;
     int cnt = 0;
-#pragma unroll 4
-    for (int w = 0; w < DT_WORDS_PER_WARP; ++w) {
-        const int64_t i = (word0 + w) * 32 + lane;
-        const uint32_t m = __ballot_sync(SS_FULL, crossing(row, i, n_samples, th, falling));
-        if (lane == w) mine = m;
-        cnt += __popc(m);
+    // every sample is loaded ONCE: x[i+1] comes from the neighbouring lane / next word
+#pragma unroll 1
+    for (int w0 = 0; w0 < DT_WORDS_PER_WARP; w0 += DT_BATCH) {
+        const int64_t i0 = (word0 + w0) * 32;
+        double v[DT_BATCH + 1];
+        if (i0 + 32 * DT_BATCH + 1 <= n_samples) {
+#pragma unroll
+            for (int k = 0; k < DT_BATCH; ++k) v[k] = (double)__ldg(row + i0 + 32 * k + lane);
+            v[DT_BATCH] = (double)__ldg(row + i0 + 32 * DT_BATCH);        // broadcast load
+        } else {
+#pragma unroll
+            for (int k = 0; k <= DT_BATCH; ++k) {
+                const int64_t i = i0 + 32 * k + (k < DT_BATCH ? lane : 0);
+                // past the end: NaN compares false on both sides -> no crossing
+                v[k] = i < n_samples ? (double)__ldg(row + i) : __longlong_as_double(0x7ff8000000000000LL);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < DT_BATCH; ++k) {
+            const double dn = ss_shfl_down(v[k], 1);
+            const double first_next = ss_shfl(v[k + 1], 0);
+            const double nxt = lane == 31 ? (k + 1 < DT_BATCH ? first_next : v[DT_BATCH]) : dn;
+            const uint32_t m = __ballot_sync(SS_FULL, crossing(v[k], nxt, th, falling));
+            if (lane == w0 + k) mine = m;
+            cnt += __popc(m);
+        }
     }
     mask[r * blocks_per_row * DT_BLOCK_WORDS + word0 + lane] = mine;   // coalesced
     if (lane == 0) warp_cnt[warp] = cnt;

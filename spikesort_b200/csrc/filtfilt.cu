@@ -215,6 +215,19 @@ __device__ __forceinline__ void correct(const FiltParams<NB, FO> &P, double (&v)
     }
 }
 
+// interior tile: all FS_S loads of a lane are issued before the first use (the
+// element type is a template parameter so the unrolled loop has no control flow)
+template <typename T>
+__device__ __forceinline__ void load_tile_fast(const T *__restrict__ p, double *sm, int lane)
+{
+    T raw[FS_S];
+#pragma unroll
+    for (int k = 0; k < FS_S; ++k) raw[k] = __ldg(p + 32 * k + lane);
+    const int base = lane + (lane >> 4);               // (32k + lane) + (32k + lane)/16
+#pragma unroll
+    for (int k = 0; k < FS_S; ++k) sm[34 * k + base] = (double)raw[k];
+}
+
 // coalesced read of one tile into padded shared memory, then per-lane segments
 __device__ __forceinline__ void load_tile(const void *x, const FiltGeom &g, const TileInfo &ti,
                                           double *sm, int lane, double (&v)[FS_S])
@@ -224,11 +237,12 @@ __device__ __forceinline__ void load_tile(const void *x, const FiltGeom &g, cons
     const int64_t r0 = e0 - g.edge;                     // chunk-relative index
     if (r0 >= 0 && r0 + FS_T <= ti.L) {
         const int64_t base = row0 + ti.cs0 + r0;
-#pragma unroll
-        for (int k = 0; k < FS_S; ++k) {
-            const int j = 32 * k + lane;
-            sm[j + j / FS_S] = ss_load(x, g.dtype, base + j);
-        }
+        if (g.dtype == SS_I16)
+            load_tile_fast(reinterpret_cast<const int16_t *>(x) + base, sm, lane);
+        else if (g.dtype == SS_F32)
+            load_tile_fast(reinterpret_cast<const float *>(x) + base, sm, lane);
+        else
+            load_tile_fast(reinterpret_cast<const double *>(x) + base, sm, lane);
     } else {
 #pragma unroll 1
         for (int k = 0; k < FS_S; ++k) {
