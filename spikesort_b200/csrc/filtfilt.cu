@@ -75,15 +75,16 @@ __device__ __forceinline__ TileInfo decode_unit(const FiltGeom &g, int64_t c, in
     return ti;
 }
 
-__device__ __forceinline__ TileInfo decode_tile(const FiltGeom &g, int64_t tile)
+// Tiles are addressed by a 3-D grid: x = tile within the unit (FS_WPB per block),
+// y = chunk, z = contact - no integer division on the device.  Returns false for
+// the padding blocks of the (shorter) last unit.
+__device__ __forceinline__ bool decode_tile(const FiltGeom &g, int warp, TileInfo &ti,
+                                            int64_t &tile)
 {
-    const int64_t c = tile / g.tiles_per_contact;
-    const int64_t r = tile - c * g.tiles_per_contact;
-    int64_t j = r / g.nt_full;
-    if (j > g.n_full) j = g.n_full;
-    TileInfo ti = decode_unit(g, c, j);
-    ti.t = r - j * g.nt_full;
-    return ti;
+    ti = decode_unit(g, blockIdx.z, blockIdx.y);
+    ti.t = (int64_t)blockIdx.x * FS_WPB + warp;
+    tile = ti.g0 + ti.t;
+    return ti.t < ti.nt;
 }
 
 // 2*x[iend] - x[iin] in the INPUT dtype (scipy.signal._arraytools.odd_ext on a
@@ -265,9 +266,9 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g,
     constexpr int NS = FiltParams<NB, FO>::NS;
     __shared__ double sm_all[FS_WPB][FS_PADT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tile = (int64_t)blockIdx.x * FS_WPB + warp;
-    if (tile >= g.total_tiles) return;
-    const TileInfo ti = decode_tile(g, tile);
+    TileInfo ti;
+    int64_t tile;
+    if (!decode_tile(g, warp, ti, tile)) return;
     double v[FS_S];
     load_tile(x, g, ti, sm_all[warp], lane, v);
 
@@ -303,9 +304,9 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
     constexpr int NS = FiltParams<NB, FO>::NS;
     __shared__ double sm_all[FS_WPB][FS_PADT];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t tile = (int64_t)blockIdx.x * FS_WPB + warp;
-    if (tile >= g.total_tiles) return;
-    const TileInfo ti = decode_tile(g, tile);
+    TileInfo ti;
+    int64_t tile;
+    if (!decode_tile(g, warp, ti, tile)) return;
     double *sm = sm_all[warp];
     double v[FS_S];
     load_tile(x, g, ti, sm, lane, v);
@@ -332,11 +333,17 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
     __syncwarp();
     const int64_t r0 = ti.t * FS_T - ti.pad - g.edge;
     double *orow = out + ti.c * g.ld_out + ti.cs0;
+    const int base = lane + (lane >> 4);
+    if (r0 >= 0 && r0 + FS_T <= ti.L) {
+        double *o = orow + r0 + lane;
 #pragma unroll
-    for (int k = 0; k < FS_S; ++k) {
-        const int j = 32 * k + lane;
-        const int64_t r = r0 + j;
-        if (r >= 0 && r < ti.L) __stcs(orow + r, sm[j + j / FS_S]);
+        for (int k = 0; k < FS_S; ++k) __stcs(o + 32 * k, sm[34 * k + base]);
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < FS_S; ++k) {
+            const int64_t r = r0 + 32 * k + lane;
+            if (r >= 0 && r < ti.L) __stcs(orow + r, sm[34 * k + base]);
+        }
     }
 }
 
@@ -693,7 +700,10 @@ static int launch_filter(const void *d_x, const FiltGeom &g, const HostTables &T
     double *Zf = Bz + g.total_tiles * NS;
     double *Zb = Zf + g.total_tiles * NS;
     double *yl = Zb + g.total_tiles * NS;
-    const unsigned tile_blocks = (unsigned)ss_cdiv(g.total_tiles, FS_WPB);
+    const int64_t nt_first = g.n_full > 0 ? g.nt_full : 0;
+    const int64_t nt_max = nt_first > g.nt_last ? nt_first : g.nt_last;
+    const dim3 tile_blocks((unsigned)ss_cdiv(nt_max, FS_WPB), (unsigned)g.units_per_contact,
+                           (unsigned)g.n_contacts);
     const unsigned unit_blocks = (unsigned)ss_cdiv(g.n_units, FS_WPB);
     filt_summary_kernel<NB, FO><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, F, Bz, yl);
     SS_LAUNCH_CHECK("filt_summary_kernel");
@@ -755,8 +765,9 @@ extern "C" int ss_filtfilt_sos(const void *d_x, int dtype, int64_t n_contacts, i
     const size_t need = (size_t)g.total_tiles * (size_t)(4 * S.ns + 1) * sizeof(double);
     SS_REQUIRE(ws_bytes >= need, SS_ERR_WORKSPACE, "filtfilt: workspace %zu < %zu bytes", ws_bytes,
                need);
-    SS_REQUIRE(ss_cdiv(g.total_tiles, FS_WPB) < 0x7fffffffLL, SS_ERR_ARG,
-               "filtfilt: too many tiles");
+    SS_REQUIRE(g.units_per_contact <= 65535 && g.n_contacts <= 65535, SS_ERR_ARG,
+               "filtfilt: more than 65535 chunks per contact or contacts (%lld, %lld)",
+               (long long)g.units_per_contact, (long long)g.n_contacts);
 
     HostTables T;
     rc = get_tables(sos, n_sections, fo, S, T);
