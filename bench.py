@@ -228,7 +228,7 @@ def run_gpu(args):
     sos, padlen = flt.sections(FS)
     f_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             for _ in range(args.steps)]
-    orig_filtfilt = _ops.filtfilt_sos
+    orig_filtfilt = _ops.filtfilt_detect
     idx = {"i": 0}
 
     def timed_filtfilt(*a, **k):
@@ -241,7 +241,7 @@ def run_gpu(args):
             idx["i"] += 1
         return out
 
-    _ops.filtfilt_sos = timed_filtfilt
+    _ops.filtfilt_detect = timed_filtfilt
     sampler = ClockSampler(local)
     _ops.LAUNCHES["count"] = 0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -253,7 +253,7 @@ def run_gpu(args):
     barrier()
     launches = _ops.LAUNCHES["count"]
     clocks = sampler.stop()
-    _ops.filtfilt_sos = orig_filtfilt
+    _ops.filtfilt_detect = orig_filtfilt
     ms_total = ev0.elapsed_time(ev1)
     ms_filter = [a.elapsed_time(b) for a, b in f_ev[:idx["i"]]]
     n_spk = int(res.spt.numel())
@@ -311,12 +311,16 @@ def run_gpu(args):
     # ---- roofline of the filter stage
     peak, peak_src = measured_peak()
     filt_ms = statistics.mean(ms_filter) if ms_filter else float("nan")
-    alg_bytes = N_CONTACTS * N_SAMPLES * (2 + 8)               # C*N*(s_in + 8)
+    # filter C*N*(s_in+8) + auto-threshold min(N,10*FS)*8 per contact +
+    # detect N*8 + n_spk*8 per contact (the fused call covers all three stages)
+    alg_bytes = N_CONTACTS * N_SAMPLES * (2 + 8) + N_CONTACTS * min(N_SAMPLES, 10 * FS) * 8 + \
+        N_CONTACTS * N_SAMPLES * 8 + n_det * 8
     achieved = alg_bytes / (filt_ms / 1000.0) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None,
-                "kernel": "ss_filtfilt_sos = filt_summary_kernel + filt_tilescan_kernel + "
-                          "filt_apply_kernel (one filter pass over the recording)",
+                "kernel": "ss_filtfilt_detect_sos + ss_detect_emit = filter (summary, tilescan, "
+                          "apply with fused crossing marks) + auto threshold + count/scan/emit: "
+                          "the filter, threshold and detect stages of the chain",
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": filt_ms,
                 "share_of_step": filt_ms / ms_step, "peak_source": peak_src}
     # whole-chain roofline: 18 B + spikes

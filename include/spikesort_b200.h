@@ -76,6 +76,23 @@ int ss_filtfilt_sos(const void *d_x, int dtype, int64_t n_contacts, int64_t n_sa
                     int64_t chunksize, double *d_out, int64_t ld_out,
                     void *d_ws, size_t ws_bytes, void *stream);
 
+/* Fused K1 + K2 + K3(pass 1): the same filter, with the threshold crossings of the
+ * float64 output marked in the epilogue of the filter's second sweep (no second pass
+ * over the filtered signal).  Equivalent to ss_filtfilt_sos, [ss_var_threshold],
+ * ss_detect_mark on the output - same d_out, same d_thr, same workspace contents and
+ * d_offsets - so ss_detect_emit follows unchanged.
+ *   auto_thr != 0 : d_thr[c] = factor*sqrt(var(out[c, :n0])) is computed (extract.py:79):
+ *                   the chunks holding the first n0 samples are filtered first;
+ *   auto_thr == 0 : d_thr is an input.
+ * d_det_ws: ss_detect_workspace_bytes(n_contacts, n_samples).
+ */
+int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_contacts, int64_t n_samples,
+                           int64_t ld_in, const double *sos, int n_sections, int padlen,
+                           int64_t chunksize, double *d_out, int64_t ld_out,
+                           void *d_ws, size_t ws_bytes,
+                           int auto_thr, int64_t n0, double factor, double *d_thr, int falling,
+                           void *d_det_ws, size_t det_ws_bytes, int64_t *d_offsets, void *stream);
+
 /* --------------------------------------------------------------- threshold
  * Replaces extract.py:79: thr[r] = factor * sqrt(var(x[r, :n0])) (population
  * variance, float64).  `factor` carries the sign (negative for falling edges,

@@ -30,6 +30,8 @@ SIGNATURES = {
     "ss_filtfilt_workspace_bytes": (_sz, [_i64, _i64, _i64, _int, _int]),
     "ss_filtfilt_sos": (_int, [_vp, _int, _i64, _i64, _i64, _dp, _int, _int, _i64, _vp, _i64,
                                _vp, _sz, _vp]),
+    "ss_filtfilt_detect_sos": (_int, [_vp, _int, _i64, _i64, _i64, _dp, _int, _int, _i64, _vp, _i64,
+                                      _vp, _sz, _int, _i64, _dbl, _vp, _int, _vp, _sz, _vp, _vp]),
     "ss_threshold_workspace_bytes": (_sz, [_i64]),
     "ss_var_threshold": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _vp, _vp, _sz, _vp]),
     "ss_detect_workspace_bytes": (_sz, [_i64, _i64]),

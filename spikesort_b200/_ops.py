@@ -62,6 +62,40 @@ def filtfilt_sos(x, sos, padlen, chunksize, out=None):
     return out
 
 
+def filtfilt_detect(x, sos, padlen, chunksize, FS, falling, thr=None, n0=None, factor=None):
+    """Fused filter + (auto threshold) + crossing marking + emit.
+    thr: CUDA float64 (n_contacts,) thresholds, or None to derive them from the first
+    n0 filtered samples (factor carries the sign).  Returns (out, thr, spt, offsets)."""
+    lib = _lib.load()
+    t = _lib.torch()
+    n_c, n = x.shape
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    n_sec = sos.shape[0]
+    out = t.empty((n_c, n), dtype=t.float64, device=x.device)
+    ws = _lib.workspace(lib.ss_filtfilt_workspace_bytes(n_c, n, int(chunksize), int(padlen), n_sec))
+    dws = _lib.workspace(lib.ss_detect_workspace_bytes(n_c, n))
+    offsets = t.empty(n_c + 1, dtype=t.int64, device=x.device)
+    auto = thr is None
+    if auto:
+        thr = t.empty(n_c, dtype=t.float64, device=x.device)
+    rc = lib.ss_filtfilt_detect_sos(_lib.ptr(x), _lib.ss_dtype_of(x), n_c, n, x.stride(0),
+                                    sos.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_sec,
+                                    int(padlen), int(chunksize), _lib.ptr(out), out.stride(0),
+                                    _lib.ptr(ws), ws.numel(), int(auto),
+                                    int(n0) if auto else 0, float(factor) if auto else 0.0,
+                                    _lib.ptr(thr), int(bool(falling)), _lib.ptr(dws), dws.numel(),
+                                    _lib.ptr(offsets), _lib.stream_ptr())
+    _lib.check(rc, "ss_filtfilt_detect_sos")
+    _launched(12 if auto else 7)      # head: 3 filter + 2 threshold + 1 mark; rest: 4; edge, count, scan
+    total = int(offsets[-1].item())
+    spt = t.empty(total, dtype=t.float64, device=x.device)
+    rc = lib.ss_detect_emit(n_c, n, float(FS), _lib.ptr(dws), dws.numel(), _lib.ptr(spt), total,
+                            _lib.stream_ptr())
+    _lib.check(rc, "ss_detect_emit")
+    _launched(1 if total > 0 else 0)
+    return out, thr, spt, offsets
+
+
 # ------------------------------------------------------------------ threshold
 def var_threshold(x, n0, factor):
     """factor * sqrt(var(x[r, :n0])) for every row of the CUDA tensor x -> CUDA float64."""

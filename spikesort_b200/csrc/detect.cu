@@ -15,44 +15,18 @@
 //                        double mul then div, as NumPy evaluates it).
 #include "common.cuh"
 #include "scan.cuh"
+#include "internal.cuh"
 
 namespace {
 
-constexpr int DT_WARPS = 8;
-constexpr int DT_WORDS_PER_WARP = 32;                       // 32 words x 32 samples
-constexpr int DT_BLOCK_WORDS = DT_WARPS * DT_WORDS_PER_WARP; // 256 words
-constexpr int DT_BLOCK_SAMPLES = DT_BLOCK_WORDS * 32;        // 8192 samples
-constexpr int TH_PARTS = 64;
+using namespace ssi;
 constexpr int TH_THREADS = 256;
-
-struct DetLayout {
-    int64_t words_per_row, blocks_per_row, n_blocks;
-    size_t off_mask, off_counts, off_offsets, total;
-};
-
-DetLayout det_layout(int64_t n_rows, int64_t n_samples)
-{
-    DetLayout L;
-    L.blocks_per_row = ss_cdiv(n_samples, DT_BLOCK_SAMPLES);
-    L.words_per_row = L.blocks_per_row * DT_BLOCK_WORDS;
-    L.n_blocks = L.blocks_per_row * n_rows;
-    L.off_mask = 0;
-    L.off_counts = ss_align_up((size_t)L.words_per_row * n_rows * 4, 256);
-    L.off_offsets = ss_align_up(L.off_counts + (size_t)L.n_blocks * 4, 256);
-    L.total = ss_align_up(L.off_offsets + (size_t)(L.n_blocks + 1) * 8, 256);
-    return L;
-}
 
 constexpr int DT_BATCH = 8;     // words (of 32 samples) whose loads are in flight together
 
 // comparisons in float64: exact for int16/float32/float64 inputs (NumPy promotes the
 // array to the float64 threshold; the float32-array-vs-Python-float case is handled
 // by the host, which rounds the threshold to float32)
-__device__ __forceinline__ bool crossing(double a, double b, double thr, int falling)
-{
-    return falling ? (a > thr && b < thr) : (a < thr && b > thr);
-}
-
 template <typename T>
 __global__ void __launch_bounds__(32 * DT_WARPS)
 detect_mark_kernel(const T *__restrict__ x, int64_t n_samples, int64_t ld,
@@ -61,8 +35,8 @@ detect_mark_kernel(const T *__restrict__ x, int64_t n_samples, int64_t ld,
 {
     __shared__ int warp_cnt[DT_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t blk = blockIdx.x;
-    const int64_t r = blk / blocks_per_row, b = blk - r * blocks_per_row;
+    const int64_t r = blockIdx.y, b = blockIdx.x;
+    const int64_t blk = r * blocks_per_row + b;
     const T *row = x + r * ld;
     const double th = __ldg(thr + r);
     const int64_t word0 = b * DT_BLOCK_WORDS + warp * DT_WORDS_PER_WARP;
@@ -135,6 +109,26 @@ detect_emit_kernel(const uint32_t *__restrict__ mask, const int64_t *__restrict_
         m &= m - 1;
         if (pos < cap) spt[pos] = __ddiv_rn(__dmul_rn((double)(i0 + bit), 1000.0), FS);
         ++pos;
+    }
+}
+
+// counts[blk] = number of set bits in the block's 256 mask words (fused path: the mask
+// is filled by atomicOr from the filter kernel, counts are derived afterwards)
+__global__ void __launch_bounds__(32 * DT_WARPS)
+detect_count_kernel(const uint32_t *__restrict__ mask, int32_t *__restrict__ counts)
+{
+    __shared__ int warp_cnt[DT_WARPS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int c = __popc(mask[(int64_t)blockIdx.x * DT_BLOCK_WORDS + threadIdx.x]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(SS_FULL, c, d);
+    if (lane == 0) warp_cnt[warp] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+#pragma unroll
+        for (int w = 0; w < DT_WARPS; ++w) s += warp_cnt[w];
+        counts[blockIdx.x] = s;
     }
 }
 
@@ -225,29 +219,67 @@ extern "C" size_t ss_detect_workspace_bytes(int64_t n_rows, int64_t n_samples)
     return det_layout(n_rows, n_samples).total;
 }
 
+namespace {
+int launch_mark(const void *d_x, int dtype, int64_t n_rows, int64_t n_valid, int64_t ld,
+                const double *d_thr, int falling, const DetLayout &L, char *ws, cudaStream_t st)
+{
+    uint32_t *mask = reinterpret_cast<uint32_t *>(ws + L.off_mask);
+    int32_t *counts = reinterpret_cast<int32_t *>(ws + L.off_counts);
+    // only the blocks that hold valid samples; rows keep the full-recording layout
+    const int64_t blocks_valid = ss_cdiv(n_valid, DT_BLOCK_SAMPLES);
+    const dim3 grid((unsigned)blocks_valid, (unsigned)n_rows);
+    switch (dtype) {
+    case SS_I16: detect_mark_kernel<int16_t><<<grid, 32 * DT_WARPS, 0, st>>>((const int16_t *)d_x, n_valid, ld, d_thr, falling, L.blocks_per_row, mask, counts); break;
+    case SS_F32: detect_mark_kernel<float><<<grid, 32 * DT_WARPS, 0, st>>>((const float *)d_x, n_valid, ld, d_thr, falling, L.blocks_per_row, mask, counts); break;
+    case SS_F64: detect_mark_kernel<double><<<grid, 32 * DT_WARPS, 0, st>>>((const double *)d_x, n_valid, ld, d_thr, falling, L.blocks_per_row, mask, counts); break;
+    default: ss_set_error("detect_mark: bad dtype %d", dtype); return SS_ERR_ARG;
+    }
+    SS_LAUNCH_CHECK("detect_mark_kernel");
+    return SS_OK;
+}
+}  // namespace
+
+int ssi::mark_head(const void *d_x, int dtype, int64_t n_rows, int64_t n_valid, int64_t n_samples,
+                   int64_t ld, const double *d_thr, int falling, void *d_ws, cudaStream_t st)
+{
+    if (n_valid <= 0) return SS_OK;
+    const DetLayout L = det_layout(n_rows, n_samples);
+    return launch_mark(d_x, dtype, n_rows, n_valid, ld, d_thr, falling, L,
+                       reinterpret_cast<char *>(d_ws), st);
+}
+
+int ssi::count_and_scan(int64_t n_rows, int64_t n_samples, void *d_ws, int64_t *d_offsets,
+                        cudaStream_t st)
+{
+    const DetLayout L = det_layout(n_rows, n_samples);
+    char *ws = reinterpret_cast<char *>(d_ws);
+    int32_t *counts = reinterpret_cast<int32_t *>(ws + L.off_counts);
+    detect_count_kernel<<<(unsigned)L.n_blocks, 32 * DT_WARPS, 0, st>>>(
+        reinterpret_cast<const uint32_t *>(ws + L.off_mask), counts);
+    SS_LAUNCH_CHECK("detect_count_kernel");
+    ssb::scan_counts_kernel<<<1, ssb::SCAN_THREADS, 0, st>>>(
+        counts, L.n_blocks, reinterpret_cast<int64_t *>(ws + L.off_offsets), L.blocks_per_row,
+        n_rows, d_offsets);
+    SS_LAUNCH_CHECK("scan_counts_kernel");
+    return SS_OK;
+}
+
 extern "C" int ss_detect_mark(const void *d_x, int dtype, int64_t n_rows, int64_t n_samples,
                               int64_t ld, const double *d_thr, int falling, void *d_ws,
                               size_t ws_bytes, int64_t *d_offsets, void *stream)
 {
     SS_REQUIRE(d_x && d_thr && d_ws && d_offsets, SS_ERR_ARG, "detect_mark: null pointer");
-    SS_REQUIRE(n_rows > 0 && n_samples > 0, SS_ERR_ARG, "detect_mark: bad shape");
+    SS_REQUIRE(n_rows > 0 && n_rows <= 65535 && n_samples > 0, SS_ERR_ARG, "detect_mark: bad shape");
     const DetLayout L = det_layout(n_rows, n_samples);
     SS_REQUIRE(ws_bytes >= L.total, SS_ERR_WORKSPACE, "detect_mark: workspace %zu < %zu", ws_bytes, L.total);
-    SS_REQUIRE(L.n_blocks < 0x7fffffffLL, SS_ERR_ARG, "detect_mark: too many blocks");
+    SS_REQUIRE(L.blocks_per_row < 0x7fffffffLL, SS_ERR_ARG, "detect_mark: too many blocks");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     char *ws = reinterpret_cast<char *>(d_ws);
-    uint32_t *mask = reinterpret_cast<uint32_t *>(ws + L.off_mask);
-    int32_t *counts = reinterpret_cast<int32_t *>(ws + L.off_counts);
-    int64_t *offs = reinterpret_cast<int64_t *>(ws + L.off_offsets);
-    const unsigned grid = (unsigned)L.n_blocks;
-    switch (dtype) {
-    case SS_I16: detect_mark_kernel<int16_t><<<grid, 32 * DT_WARPS, 0, st>>>((const int16_t *)d_x, n_samples, ld, d_thr, falling, L.blocks_per_row, mask, counts); break;
-    case SS_F32: detect_mark_kernel<float><<<grid, 32 * DT_WARPS, 0, st>>>((const float *)d_x, n_samples, ld, d_thr, falling, L.blocks_per_row, mask, counts); break;
-    case SS_F64: detect_mark_kernel<double><<<grid, 32 * DT_WARPS, 0, st>>>((const double *)d_x, n_samples, ld, d_thr, falling, L.blocks_per_row, mask, counts); break;
-    default: ss_set_error("detect_mark: bad dtype %d", dtype); return SS_ERR_ARG;
-    }
-    SS_LAUNCH_CHECK("detect_mark_kernel");
-    ssb::scan_counts_kernel<<<1, ssb::SCAN_THREADS, 0, st>>>(counts, L.n_blocks, offs, L.blocks_per_row, n_rows, d_offsets);
+    const int rc = launch_mark(d_x, dtype, n_rows, n_samples, ld, d_thr, falling, L, ws, st);
+    if (rc) return rc;
+    ssb::scan_counts_kernel<<<1, ssb::SCAN_THREADS, 0, st>>>(
+        reinterpret_cast<int32_t *>(ws + L.off_counts), L.n_blocks,
+        reinterpret_cast<int64_t *>(ws + L.off_offsets), L.blocks_per_row, n_rows, d_offsets);
     SS_LAUNCH_CHECK("scan_counts_kernel");
     return SS_OK;
 }

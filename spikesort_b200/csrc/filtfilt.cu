@@ -32,6 +32,7 @@
 // HBM traffic: 2 reads of x + 1 write of float64 (+ ~(4*NS+1)*8/T bytes of tile
 // summaries per sample).  All tables are computed on the host in binary128.
 #include "common.cuh"
+#include "internal.cuh"
 #include <vector>
 #include <cstring>
 #include <mutex>
@@ -53,7 +54,17 @@ struct FiltGeom {
     int64_t nt_full, nt_last;    // tiles per full / last unit
     int64_t tiles_per_contact, total_tiles;
     int64_t units_per_contact, n_units;
+    int64_t j_begin, j_count;    // chunk range processed by this launch
     int edge, dtype;
+};
+
+// fused threshold-crossing marking in the apply kernel (K3 pass 1 in K1's epilogue)
+struct MarkParams {
+    const double *thr;           // per contact
+    uint32_t *mask;              // detection workspace bitmask
+    int64_t words_per_row;
+    int64_t n_samples;
+    int falling;
 };
 
 struct TileInfo {
@@ -81,7 +92,7 @@ __device__ __forceinline__ TileInfo decode_unit(const FiltGeom &g, int64_t c, in
 __device__ __forceinline__ bool decode_tile(const FiltGeom &g, int warp, TileInfo &ti,
                                             int64_t &tile)
 {
-    ti = decode_unit(g, blockIdx.z, blockIdx.y);
+    ti = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
     ti.t = (int64_t)blockIdx.x * FS_WPB + warp;
     tile = ti.g0 + ti.t;
     return ti.t < ti.nt;
@@ -294,12 +305,12 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g,
     }
 }
 
-template <int NB, bool FO>
+template <int NB, bool FO, bool MARK>
 __global__ void __launch_bounds__(32 * FS_WPB)
 filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
                   const __grid_constant__ FiltParams<NB, FO> P,
                   const double *__restrict__ Zf, const double *__restrict__ Zb,
-                  double *__restrict__ out)
+                  double *__restrict__ out, const MarkParams mk)
 {
     constexpr int NS = FiltParams<NB, FO>::NS;
     __shared__ double sm_all[FS_WPB][FS_PADT];
@@ -327,11 +338,40 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
     exclusive_prefix<NS, true>(e, pre, lane);
     correct<NB, FO, true>(P, v, pre);
 
+    const int64_t r0 = ti.t * FS_T - ti.pad - g.edge;
+    if (MARK) {
+        // crossings (i, i+1) with both samples in this tile and this chunk; the pair that
+        // ends a tile or a chunk is marked by filt_boundary_mark_kernel afterwards
+        const double th = __ldg(mk.thr + ti.c);
+        const double nx = ss_shfl_down(v[0], 1);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int i = 0; i < FS_S - 1; ++i)
+            bits |= (uint32_t)ssi::crossing(v[i], v[i + 1], th, mk.falling) << i;
+        if (lane < 31) bits |= (uint32_t)ssi::crossing(v[FS_S - 1], nx, th, mk.falling) << (FS_S - 1);
+        const int64_t rl = r0 + FS_S * lane;                  // chunk-relative index of bit 0
+        if (!(r0 >= 0 && r0 + FS_T <= ti.L)) {
+            // keep bits i with 0 <= rl + i and rl + i + 1 < L
+            const int64_t lo = rl < 0 ? -rl : 0, hi = ti.L - 1 - rl;
+            uint32_t keep = 0;
+            if (lo < FS_S && hi > 0) {
+                const int h = hi < FS_S ? (int)hi : FS_S;
+                keep = ((h >= 32 ? 0xffffffffu : ((1u << h) - 1u))) & ~((1u << (int)lo) - 1u);
+            }
+            bits &= keep;
+        }
+        if (bits) {
+            const int64_t s = ti.cs0 + rl;                    // sample index of bit 0 in the row
+            uint32_t *mrow = mk.mask + ti.c * mk.words_per_row;
+            const uint64_t w = (uint64_t)bits << (int)(s & 31);
+            atomicOr(mrow + (s >> 5), (uint32_t)w);
+            if (w >> 32) atomicOr(mrow + (s >> 5) + 1, (uint32_t)(w >> 32));
+        }
+    }
     // transpose through shared memory, coalesced float64 stores of the chunk part
 #pragma unroll
     for (int i = 0; i < FS_S; ++i) sm[lane * (FS_S + 1) + i] = v[i];
     __syncwarp();
-    const int64_t r0 = ti.t * FS_T - ti.pad - g.edge;
     double *orow = out + ti.c * g.ld_out + ti.cs0;
     const int base = lane + (lane >> 4);
     if (r0 >= 0 && r0 + FS_T <= ti.L) {
@@ -347,6 +387,27 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
     }
 }
 
+// One thread per tile: the crossing whose first sample is the last chunk sample of the
+// tile (its partner lives in the next tile or the next chunk).  Runs after the apply
+// kernel, reads the stored float64 output.
+__global__ void __launch_bounds__(256)
+filt_boundary_mark_kernel(const double *__restrict__ y, const FiltGeom g, const MarkParams mk)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const TileInfo ti = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
+    if (t >= ti.nt) return;
+    const int64_t r0 = t * FS_T - ti.pad - g.edge;
+    if (r0 > ti.L - 1) return;                              // tile entirely in the right extension
+    int64_t r = r0 + FS_T - 1;
+    if (r > ti.L - 1) r = ti.L - 1;
+    if (r < 0) return;
+    const int64_t s = ti.cs0 + r;
+    if (s + 1 >= mk.n_samples) return;
+    const double *row = y + ti.c * g.ld_out;
+    if (ssi::crossing(row[s], row[s + 1], __ldg(mk.thr + ti.c), mk.falling))
+        atomicOr(mk.mask + ti.c * mk.words_per_row + (s >> 5), 1u << (int)(s & 31));
+}
+
 // One warp per unit: forward scan of the tile summaries, y[-1], backward scan.
 template <int NS>
 __global__ void __launch_bounds__(32 * FS_WPB)
@@ -358,9 +419,9 @@ filt_tilescan_kernel(const void *__restrict__ x, const FiltGeom g,
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t unit = (int64_t)blockIdx.x * FS_WPB + warp;
-    if (unit >= g.n_units) return;
-    const int64_t c = unit / g.units_per_contact;
-    const int64_t j = unit - c * g.units_per_contact;
+    if (unit >= g.n_contacts * g.j_count) return;
+    const int64_t c = unit / g.j_count;
+    const int64_t j = g.j_begin + (unit - c * g.j_count);
     const TileInfo ti = decode_unit(g, c, j);
     const int64_t nt = ti.nt, g0 = ti.g0;
     const int64_t nrows = (nt + 31) / 32;
@@ -661,15 +722,23 @@ static int make_geom(FiltGeom &g, int dtype, int64_t n_contacts, int64_t n_sampl
     g.total_tiles = g.tiles_per_contact * n_contacts;
     g.units_per_contact = g.n_full + (g.len_last > 0 ? 1 : 0);
     g.n_units = g.units_per_contact * n_contacts;
+    g.j_begin = 0;
+    g.j_count = g.units_per_contact;
     return SS_OK;
 }
 
+// one filter pass over the chunk range [j_begin, j_begin + j_count) of every contact;
+// mk != nullptr fuses crossing marking into the apply kernel
 template <int NB, bool FO>
-static int launch_filter(const void *d_x, const FiltGeom &g, const HostTables &T,
-                         const double *sos, double *d_out, void *d_ws, cudaStream_t st)
+static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j_count,
+                         const HostTables &T, const double *sos, double *d_out, void *d_ws,
+                         const MarkParams *mk, cudaStream_t st)
 {
     constexpr int NS = FiltParams<NB, FO>::NS;
     constexpr int NSEC = FiltParams<NB, FO>::NSEC;
+    if (j_count <= 0) return SS_OK;
+    g.j_begin = j_begin;
+    g.j_count = j_count;
     FiltParams<NB, FO> P;
     for (int s = 0; s < NSEC; ++s) {
         P.sec[s][0] = sos[s * 6 + 0];
@@ -700,18 +769,104 @@ static int launch_filter(const void *d_x, const FiltGeom &g, const HostTables &T
     double *Zf = Bz + g.total_tiles * NS;
     double *Zb = Zf + g.total_tiles * NS;
     double *yl = Zb + g.total_tiles * NS;
-    const int64_t nt_first = g.n_full > 0 ? g.nt_full : 0;
-    const int64_t nt_max = nt_first > g.nt_last ? nt_first : g.nt_last;
-    const dim3 tile_blocks((unsigned)ss_cdiv(nt_max, FS_WPB), (unsigned)g.units_per_contact,
+    // tiles per unit in this range: full chunks and/or the trailing short one
+    const bool has_full = j_begin < g.n_full;
+    const bool has_last = g.len_last > 0 && j_begin + j_count > g.n_full;
+    const int64_t nt_max = (has_full && (!has_last || g.nt_full >= g.nt_last)) ? g.nt_full : g.nt_last;
+    const dim3 tile_blocks((unsigned)ss_cdiv(nt_max, FS_WPB), (unsigned)j_count,
                            (unsigned)g.n_contacts);
-    const unsigned unit_blocks = (unsigned)ss_cdiv(g.n_units, FS_WPB);
+    const unsigned unit_blocks = (unsigned)ss_cdiv(g.n_contacts * j_count, FS_WPB);
     filt_summary_kernel<NB, FO><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, F, Bz, yl);
     SS_LAUNCH_CHECK("filt_summary_kernel");
     filt_tilescan_kernel<NS><<<unit_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, SP, F, Bz, yl, Zf, Zb);
     SS_LAUNCH_CHECK("filt_tilescan_kernel");
-    filt_apply_kernel<NB, FO><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out);
-    SS_LAUNCH_CHECK("filt_apply_kernel");
+    if (mk) {
+        filt_apply_kernel<NB, FO, true><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, *mk);
+        SS_LAUNCH_CHECK("filt_apply_kernel<mark>");
+        const dim3 bgrid((unsigned)ss_cdiv(nt_max, 256), (unsigned)j_count, (unsigned)g.n_contacts);
+        filt_boundary_mark_kernel<<<bgrid, 256, 0, st>>>(d_out, g, *mk);
+        SS_LAUNCH_CHECK("filt_boundary_mark_kernel");
+    } else {
+        MarkParams none = {nullptr, nullptr, 0, 0, 0};
+        filt_apply_kernel<NB, FO, false><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, none);
+        SS_LAUNCH_CHECK("filt_apply_kernel");
+    }
     return SS_OK;
+}
+
+struct FiltPlan {
+    FiltGeom g;
+    HostTables T;
+    int nb;
+    bool fo;
+    int ns;
+};
+
+static int make_plan(FiltPlan &pl, int dtype, int64_t n_contacts, int64_t n_samples, int64_t ld_in,
+                     const double *sos, int n_sections, int padlen, int64_t chunksize,
+                     int64_t ld_out, size_t ws_bytes)
+{
+    SS_REQUIRE(n_sections >= 1 && n_sections <= MAX_NB + 1, SS_ERR_UNSUPPORTED,
+               "filtfilt: %d sections not supported (max %d)", n_sections, MAX_NB + 1);
+    QSections S;
+    S.nsec = n_sections;
+    bool fo = false;
+    for (int s = 0; s < n_sections; ++s) {
+        const double *c = sos + s * 6;
+        SS_REQUIRE(c[3] == 1.0, SS_ERR_ARG, "filtfilt: section %d has a0 != 1", s);
+        const bool first_order = (c[2] == 0.0 && c[5] == 0.0);
+        if (first_order && s == n_sections - 1) fo = true;
+        S.c[s][0] = c[0];
+        S.c[s][1] = c[1];
+        S.c[s][2] = c[2];
+        S.c[s][3] = c[4];
+        S.c[s][4] = c[5];
+    }
+    S.first_order_last = fo;
+    const int nb = n_sections - (fo ? 1 : 0);
+    S.ns = 2 * nb + (fo ? 1 : 0);
+    SS_REQUIRE(nb <= MAX_NB, SS_ERR_UNSUPPORTED, "filtfilt: %d biquads not supported (max %d)",
+               nb, MAX_NB);
+    int rc = make_geom(pl.g, dtype, n_contacts, n_samples, ld_in, ld_out, chunksize, padlen);
+    if (rc) return rc;
+    const size_t need = (size_t)pl.g.total_tiles * (size_t)(4 * S.ns + 1) * sizeof(double);
+    SS_REQUIRE(ws_bytes >= need, SS_ERR_WORKSPACE, "filtfilt: workspace %zu < %zu bytes", ws_bytes,
+               need);
+    SS_REQUIRE(pl.g.units_per_contact <= 65535 && pl.g.n_contacts <= 65535, SS_ERR_ARG,
+               "filtfilt: more than 65535 chunks per contact or contacts (%lld, %lld)",
+               (long long)pl.g.units_per_contact, (long long)pl.g.n_contacts);
+    rc = get_tables(sos, n_sections, fo, S, pl.T);
+    SS_REQUIRE(rc == SS_OK, rc, "filtfilt: filter has a pole at z = 1 (no steady state)");
+    pl.nb = nb;
+    pl.fo = fo;
+    pl.ns = S.ns;
+    return SS_OK;
+}
+
+static int run_plan(const FiltPlan &pl, const void *d_x, int64_t j_begin, int64_t j_count,
+                    const double *sos, double *d_out, void *d_ws, const MarkParams *mk,
+                    cudaStream_t st)
+{
+#define SS_FILT_CASE(NB_, FO_)                                                        \
+    if (pl.nb == NB_ && pl.fo == FO_)                                                 \
+        return launch_filter<NB_, FO_>(d_x, pl.g, j_begin, j_count, pl.T, sos, d_out, d_ws, mk, st);
+    SS_FILT_CASE(0, true)
+    SS_FILT_CASE(1, false)
+    SS_FILT_CASE(1, true)
+    SS_FILT_CASE(2, false)
+    SS_FILT_CASE(2, true)
+    SS_FILT_CASE(3, false)
+    SS_FILT_CASE(3, true)
+    SS_FILT_CASE(4, false)
+    SS_FILT_CASE(4, true)
+    SS_FILT_CASE(5, false)
+    SS_FILT_CASE(5, true)
+    SS_FILT_CASE(6, false)
+    SS_FILT_CASE(6, true)
+#undef SS_FILT_CASE
+    ss_set_error("filtfilt: unsupported section layout (%d biquads, first-order %d)", pl.nb,
+                 (int)pl.fo);
+    return SS_ERR_UNSUPPORTED;
 }
 
 }  // namespace
@@ -737,60 +892,72 @@ extern "C" int ss_filtfilt_sos(const void *d_x, int dtype, int64_t n_contacts, i
                                size_t ws_bytes, void *stream)
 {
     SS_REQUIRE(d_x && d_out && sos && d_ws, SS_ERR_ARG, "filtfilt: null pointer");
-    SS_REQUIRE(n_sections >= 1 && n_sections <= MAX_NB + 1, SS_ERR_UNSUPPORTED,
-               "filtfilt: %d sections not supported (max %d)", n_sections, MAX_NB + 1);
-    QSections S;
-    S.nsec = n_sections;
-    bool fo = false;
-    for (int s = 0; s < n_sections; ++s) {
-        const double *c = sos + s * 6;
-        SS_REQUIRE(c[3] == 1.0, SS_ERR_ARG, "filtfilt: section %d has a0 != 1", s);
-        const bool first_order = (c[2] == 0.0 && c[5] == 0.0);
-        if (first_order && s == n_sections - 1) fo = true;
-        S.c[s][0] = c[0];
-        S.c[s][1] = c[1];
-        S.c[s][2] = c[2];
-        S.c[s][3] = c[4];
-        S.c[s][4] = c[5];
-    }
-    S.first_order_last = fo;
-    const int nb = n_sections - (fo ? 1 : 0);
-    S.ns = 2 * nb + (fo ? 1 : 0);
-    SS_REQUIRE(nb <= MAX_NB, SS_ERR_UNSUPPORTED, "filtfilt: %d biquads not supported (max %d)",
-               nb, MAX_NB);
-
-    FiltGeom g;
-    int rc = make_geom(g, dtype, n_contacts, n_samples, ld_in, ld_out, chunksize, padlen);
+    FiltPlan pl;
+    const int rc = make_plan(pl, dtype, n_contacts, n_samples, ld_in, sos, n_sections, padlen,
+                             chunksize, ld_out, ws_bytes);
     if (rc) return rc;
-    const size_t need = (size_t)g.total_tiles * (size_t)(4 * S.ns + 1) * sizeof(double);
-    SS_REQUIRE(ws_bytes >= need, SS_ERR_WORKSPACE, "filtfilt: workspace %zu < %zu bytes", ws_bytes,
-               need);
-    SS_REQUIRE(g.units_per_contact <= 65535 && g.n_contacts <= 65535, SS_ERR_ARG,
-               "filtfilt: more than 65535 chunks per contact or contacts (%lld, %lld)",
-               (long long)g.units_per_contact, (long long)g.n_contacts);
+    return run_plan(pl, d_x, 0, pl.g.units_per_contact, sos, d_out, d_ws, nullptr,
+                    reinterpret_cast<cudaStream_t>(stream));
+}
 
-    HostTables T;
-    rc = get_tables(sos, n_sections, fo, S, T);
-    SS_REQUIRE(rc == SS_OK, rc, "filtfilt: filter has a pole at z = 1 (no steady state)");
-
+extern "C" int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_contacts,
+                                      int64_t n_samples, int64_t ld_in, const double *sos,
+                                      int n_sections, int padlen, int64_t chunksize, double *d_out,
+                                      int64_t ld_out, void *d_ws, size_t ws_bytes, int auto_thr,
+                                      int64_t n0, double factor, double *d_thr, int falling,
+                                      void *d_det_ws, size_t det_ws_bytes, int64_t *d_offsets,
+                                      void *stream)
+{
+    SS_REQUIRE(d_x && d_out && sos && d_ws && d_thr && d_det_ws && d_offsets, SS_ERR_ARG,
+               "filtfilt_detect: null pointer");
+    FiltPlan pl;
+    int rc = make_plan(pl, dtype, n_contacts, n_samples, ld_in, sos, n_sections, padlen, chunksize,
+                       ld_out, ws_bytes);
+    if (rc) return rc;
+    const ssi::DetLayout L = ssi::det_layout(n_contacts, n_samples);
+    SS_REQUIRE(det_ws_bytes >= L.total, SS_ERR_WORKSPACE, "filtfilt_detect: detect workspace %zu < %zu",
+               det_ws_bytes, L.total);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define SS_FILT_CASE(NB_, FO_)                                                        \
-    if (nb == NB_ && fo == FO_)                                                       \
-        return launch_filter<NB_, FO_>(d_x, g, T, sos, d_out, d_ws, st);
-    SS_FILT_CASE(0, true)
-    SS_FILT_CASE(1, false)
-    SS_FILT_CASE(1, true)
-    SS_FILT_CASE(2, false)
-    SS_FILT_CASE(2, true)
-    SS_FILT_CASE(3, false)
-    SS_FILT_CASE(3, true)
-    SS_FILT_CASE(4, false)
-    SS_FILT_CASE(4, true)
-    SS_FILT_CASE(5, false)
-    SS_FILT_CASE(5, true)
-    SS_FILT_CASE(6, false)
-    SS_FILT_CASE(6, true)
-#undef SS_FILT_CASE
-    ss_set_error("filtfilt: unsupported section layout (%d biquads, first-order %d)", nb, (int)fo);
-    return SS_ERR_UNSUPPORTED;
+    char *dws = reinterpret_cast<char *>(d_det_ws);
+    MarkParams mk;
+    mk.thr = d_thr;
+    mk.mask = reinterpret_cast<uint32_t *>(dws + L.off_mask);
+    mk.words_per_row = L.words_per_row;
+    mk.n_samples = n_samples;
+    mk.falling = falling;
+    SS_CUDA_CHECK(cudaMemsetAsync(mk.mask, 0, (size_t)L.words_per_row * n_contacts * 4, st));
+    int64_t j0 = 0;
+    if (auto_thr) {
+        // the threshold needs the filtered first n0 samples: filter the chunks that hold
+        // them first (plain), derive the thresholds, mark those chunks with the streaming
+        // kernel, then filter the rest with the marking fused into the apply kernel
+        SS_REQUIRE(n0 > 0, SS_ERR_ARG, "filtfilt_detect: n0 must be positive");
+        if (n0 > n_samples) n0 = n_samples;
+        j0 = ss_cdiv(n0, chunksize);
+        if (j0 > pl.g.units_per_contact) j0 = pl.g.units_per_contact;
+        rc = run_plan(pl, d_x, 0, j0, sos, d_out, d_ws, nullptr, st);
+        if (rc) return rc;
+        rc = ss_var_threshold(d_out, SS_F64, n_contacts, ld_out, n0, factor, d_thr,
+                              dws + L.off_scratch, L.total - L.off_scratch, st);
+        if (rc) return rc;
+        int64_t head_end = j0 * chunksize;
+        if (head_end > n_samples) head_end = n_samples;
+        rc = ssi::mark_head(d_out, SS_F64, n_contacts, head_end, n_samples, ld_out, d_thr, falling,
+                            d_det_ws, st);
+        if (rc) return rc;
+        // the pair (head_end-1, head_end) straddles the two passes: mark it once the
+        // second pass has written head_end (boundary kernel of the head range, below)
+    }
+    rc = run_plan(pl, d_x, j0, pl.g.units_per_contact - j0, sos, d_out, d_ws, &mk, st);
+    if (rc) return rc;
+    if (j0 > 0 && j0 < pl.g.units_per_contact) {
+        // chunk-end pair of the last head chunk of every contact
+        FiltGeom g = pl.g;
+        g.j_begin = j0 - 1;
+        g.j_count = 1;
+        const int64_t nt = g.nt_full;
+        filt_boundary_mark_kernel<<<dim3((unsigned)ss_cdiv(nt, 256), 1, (unsigned)n_contacts), 256, 0, st>>>(d_out, g, mk);
+        SS_LAUNCH_CHECK("filt_boundary_mark_kernel");
+    }
+    return ssi::count_and_scan(n_contacts, n_samples, d_det_ws, d_offsets, st);
 }

@@ -150,6 +150,8 @@ pca_gram_reduce_kernel(const double *__restrict__ ws_gram, const double *__restr
 }
 
 // One CTA per group.  smem: A[ne*ne], V[ne*ne], cs[ne] (c, s per pair), red[...]
+// (measured on B200, 30x30: 256 threads 288 us, one warp 868 us - the element updates,
+// not the barriers, dominate a round.)
 __global__ void __launch_bounds__(PC_THREADS)
 pca_eig_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
                const int64_t *__restrict__ counts, int n, double *__restrict__ evals,
@@ -160,10 +162,10 @@ pca_eig_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
     double *A = sm, *V = A + ne * ne, *rc = V + ne * ne, *rs = rc + ne / 2, *red = rs + ne / 2;
     __shared__ int s_p[PC_MAX_WIN / 2 + 1], s_q[PC_MAX_WIN / 2 + 1];
     __shared__ int s_done;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
     const int64_t g = blockIdx.x;
     const double cnt = (double)counts[g];
-    for (int idx = tid; idx < ne * ne; idx += PC_THREADS) {
+    for (int idx = tid; idx < ne * ne; idx += nthr) {
         const int i = idx / ne, j = idx - i * ne;
         double a = 0.0;
         if (i < n && j < n)
@@ -176,7 +178,7 @@ pca_eig_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
     for (int sweep = 0; sweep < 60; ++sweep) {
         // convergence: off-diagonal energy against diagonal energy
         double off = 0.0, dg = 0.0;
-        for (int idx = tid; idx < n * n; idx += PC_THREADS) {
+        for (int idx = tid; idx < n * n; idx += nthr) {
             const int i = idx / n, j = idx - i * n;
             const double a = A[i * ne + j];
             if (i == j) dg += a * a; else off += a * a;
@@ -190,32 +192,39 @@ pca_eig_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
         __syncthreads();
         if (tid == 0) {
             double o = 0.0, d2 = 0.0;
-            for (int w = 0; w < PC_THREADS / 32; ++w) { o += red[2 * w]; d2 += red[2 * w + 1]; }
+            for (int w = 0; w < nthr / 32; ++w) { o += red[2 * w]; d2 += red[2 * w + 1]; }
             s_done = !(o > 1e-30 * d2);          // also stops on NaN
         }
         __syncthreads();
         if (s_done) break;
         for (int rd = 0; rd < ne - 1; ++rd) {
-            if (tid < half) {
+            for (int k = tid; k < half; k += nthr) {
                 int p, q;
-                if (tid == 0) { p = ne - 1; q = rd; }
-                else { p = (rd + tid) % (ne - 1); q = (rd - tid + (ne - 1)) % (ne - 1); }
+                if (k == 0) { p = ne - 1; q = rd; }
+                else { p = (rd + k) % (ne - 1); q = (rd - k + (ne - 1)) % (ne - 1); }
                 if (p > q) { const int t = p; p = q; q = t; }
                 double c = 1.0, s = 0.0;
                 if (q < n) {
+                    // rotation that zeroes A[p][q] (the smaller angle), without divisions:
+                    // cos 2t = |alpha|/hyp, c = sqrt((1 + cos 2t)/2), s = sgn(alpha) beta/(2 c hyp)
                     const double apq = A[p * ne + q];
                     if (apq != 0.0) {
-                        const double theta = (A[q * ne + q] - A[p * ne + p]) / (2.0 * apq);
-                        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                        c = 1.0 / sqrt(t * t + 1.0);
-                        s = t * c;
+                        const double alpha = A[q * ne + q] - A[p * ne + p], beta = 2.0 * apq;
+                        const double h2 = alpha * alpha + beta * beta;
+                        if (h2 > 0.0 && h2 < 1e300) {
+                            const double ih = rsqrt(h2);
+                            const double c2 = 0.5 + 0.5 * fabs(alpha) * ih;
+                            const double ic = rsqrt(c2);
+                            c = c2 * ic;
+                            s = (alpha >= 0.0 ? 0.5 : -0.5) * beta * ih * ic;
+                        }
                     }
                 }
-                s_p[tid] = p; s_q[tid] = q; rc[tid] = c; rs[tid] = s;
+                s_p[k] = p; s_q[k] = q; rc[k] = c; rs[k] = s;
             }
             __syncthreads();
             // columns of A and V
-            for (int idx = tid; idx < half * ne; idx += PC_THREADS) {
+            for (int idx = tid; idx < half * ne; idx += nthr) {
                 const int k = idx / ne, i = idx - k * ne;
                 const int p = s_p[k], q = s_q[k];
                 const double c = rc[k], s = rs[k];
@@ -228,7 +237,7 @@ pca_eig_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
             }
             __syncthreads();
             // rows of A
-            for (int idx = tid; idx < half * ne; idx += PC_THREADS) {
+            for (int idx = tid; idx < half * ne; idx += nthr) {
                 const int k = idx / ne, j = idx - k * ne;
                 const int p = s_p[k], q = s_q[k];
                 const double c = rc[k], s = rs[k];
@@ -240,7 +249,7 @@ pca_eig_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
         }
     }
     // rank by signed eigenvalue, descending (np.argsort(evals)[::-1]), then |.|
-    for (int k = tid; k < n; k += PC_THREADS) {
+    for (int k = tid; k < n; k += nthr) {
         const double lk = A[k * ne + k];
         int rank = 0;
         for (int j = 0; j < n; ++j) {
@@ -336,7 +345,8 @@ extern "C" int ss_pca_eig(const double *d_gram, const double *d_sum, const int64
     const int ne_max = (PC_MAX_WIN + 1) & ~1;
     SS_CUDA_CHECK(cudaFuncSetAttribute(pca_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(((size_t)2 * ne_max * ne_max + ne_max + 2 * (PC_THREADS / 32) + 8) * sizeof(double))));
-    pca_eig_kernel<<<(unsigned)n_groups, PC_THREADS, smem, st>>>(d_gram, d_sum, d_counts, n_win, d_evals, d_evecs);
+    const int eig_threads = PC_THREADS;
+    pca_eig_kernel<<<(unsigned)n_groups, eig_threads, smem, st>>>(d_gram, d_sum, d_counts, n_win, d_evals, d_evecs);
     SS_LAUNCH_CHECK("pca_eig_kernel");
     return SS_OK;
 }

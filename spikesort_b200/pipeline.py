@@ -59,32 +59,49 @@ class ChainResult(object):
 
 
 def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
-              thresh='auto', ncomps=2, chunksize=1E6, pca=True, thr_override=None):
+              thresh='auto', ncomps=2, chunksize=1E6, pca=True, thr_override=None, fused=True):
     """x: CUDA tensor (n_contacts, n_samples), int16/float32/float64.
     filt: a spikesort_b200.filters filter object or None.
     thresh: 'auto' / numeric string (multiple of the std of the first 10 s) or a number.
     thr_override: optional CUDA float64 (n_contacts,) thresholds (e.g. broadcast from the
-    rank owning the first 10 s when the recording is time-sharded)."""
+    rank owning the first 10 s when the recording is time-sharded).
+    fused: mark the crossings in the filter's second sweep (default) instead of a
+    separate pass over the filtered signal; the results are identical."""
     t = _lib.require_cuda()
     res = ChainResult()
     sp_win = list(sp_win)
-    if filt is not None:
-        sos, padlen = filt.sections(FS)
-        sig = _ops.filtfilt_sos(x, sos, padlen, int(chunksize))
-    else:
-        sig = x
-    res.filtered = sig
     falling = edge in _FALLING
-    n_rows = sig.shape[0]
-    if thr_override is not None:
-        thr = thr_override
-    elif isinstance(thresh, str):
-        frac = 8.0 if thresh == 'auto' else float(thresh)
-        thr = _ops.var_threshold(sig, int(10 * FS), -frac if falling else frac)
+    auto = thr_override is None and isinstance(thresh, str)
+    frac = (8.0 if thresh == 'auto' else float(thresh)) if auto else None
+    if filt is not None and fused:
+        # filter with the threshold and the crossing marks produced in the same sweep
+        sos, padlen = filt.sections(FS)
+        if auto:
+            thr = None
+        elif thr_override is not None:
+            thr = thr_override
+        else:
+            thr = t.full((x.shape[0],), float(thresh), dtype=t.float64, device=x.device)
+        sig, thr, spt, offsets = _ops.filtfilt_detect(
+            x, sos, padlen, int(chunksize), FS, falling, thr=thr, n0=int(10 * FS),
+            factor=(-frac if falling else frac) if auto else None)
+        res.filtered, res.thresh = sig, thr
     else:
-        thr = t.full((n_rows,), float(thresh), dtype=t.float64, device=sig.device)
-    res.thresh = thr
-    spt, offsets = _ops.detect(sig, thr, falling, FS)
+        if filt is not None:
+            sos, padlen = filt.sections(FS)
+            sig = _ops.filtfilt_sos(x, sos, padlen, int(chunksize))
+        else:
+            sig = x
+        res.filtered = sig
+        n_rows = sig.shape[0]
+        if thr_override is not None:
+            thr = thr_override
+        elif auto:
+            thr = _ops.var_threshold(sig, int(10 * FS), -frac if falling else frac)
+        else:
+            thr = t.full((n_rows,), float(thresh), dtype=t.float64, device=sig.device)
+        res.thresh = thr
+        spt, offsets = _ops.detect(sig, thr, falling, FS)
     res.spt_detected, res.offsets_detected = spt, offsets
     spt = spt.clone()
     _ops.align(sig, spt, offsets, None, FS, sp_win, align_type == 'min')

@@ -263,6 +263,42 @@ def test_chain_vs_oracle_per_contact(env, oracle):
         assert err < 1e-9, (c, err)
 
 
+@pytest.mark.parametrize("FS,n,cs", [(1000, 50000, 3000), (1000, 50000, 50000), (30000, 200000, 60000),
+                                     (500, 9000, 2000), (1000, 8192 * 3, 8192), (1000, 20001, 512)])
+def test_fused_filter_detect_equals_separate_passes(env, FS, n, cs):
+    """ss_filtfilt_detect_sos == ss_filtfilt_sos + ss_var_threshold + ss_detect_mark/emit,
+    bit for bit (output, thresholds, spike times), for auto and given thresholds."""
+    ops, torch = env['ops'], env['torch']
+    x = env['synth'].make_recording(5, n, FS, seed=9, rate_hz=max(40.0, FS / 100.0), noise=7.0,
+                                    amp=(60.0, 160.0)).to(env['dev'])
+    x[3] = 0                                                # silent contact
+    flt = env['ss'].filters.Filter(FS * 0.03, FS * 0.004)
+    sos, padlen = flt.sections(FS)
+    for falling in (True, False):
+        y = ops.filtfilt_sos(x, sos, padlen, cs)
+        thr = ops.var_threshold(y, int(10 * FS), -1.5 if falling else 1.5)
+        spt, off = ops.detect(y, thr, falling, FS)
+        assert spt.numel() > 3
+        y2, thr2, spt2, off2 = ops.filtfilt_detect(x, sos, padlen, cs, FS, falling, thr=None,
+                                                   n0=int(10 * FS), factor=-1.5 if falling else 1.5)
+        assert torch.equal(y, y2) and torch.equal(thr, thr2)
+        assert torch.equal(off, off2) and torch.equal(spt, spt2)
+        y3, thr3, spt3, off3 = ops.filtfilt_detect(x, sos, padlen, cs, FS, falling, thr=thr)
+        assert torch.equal(y, y3) and torch.equal(off, off3) and torch.equal(spt, spt3)
+        # a threshold inside the noise: crossings everywhere, incl. tile and chunk edges
+        low = torch.full((5,), -2.0 if falling else 2.0, dtype=torch.float64, device=env['dev'])
+        spt4, off4 = ops.detect(y, low, falling, FS)
+        assert spt4.numel() > n // 10
+        y5, thr5, spt5, off5 = ops.filtfilt_detect(x, sos, padlen, cs, FS, falling, thr=low)
+        assert torch.equal(off4, off5) and torch.equal(spt4, spt5)
+    # the chain gives the same result either way
+    win = (-5000.0 / FS, 10000.0 / FS)
+    a = env['pipeline'].run_chain(x, FS, filt=flt, sp_win=win, chunksize=cs, thresh='1.5', fused=True)
+    b = env['pipeline'].run_chain(x, FS, filt=flt, sp_win=win, chunksize=cs, thresh='1.5', fused=False)
+    assert torch.equal(a.spt, b.spt) and torch.equal(a.waves, b.waves)
+    assert torch.equal(a.offsets, b.offsets) and torch.equal(a.thresh, b.thresh)
+
+
 def test_full_size_properties(env):
     """BASELINE.json configs[1] (32 contacts x 18 000 000 samples @ 30 kHz, int16):
     size-independent properties of the chain."""
