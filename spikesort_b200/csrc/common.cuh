@@ -70,4 +70,15 @@ __device__ __forceinline__ double ss_shfl(double v, int src)
     return __shfl_sync(SS_FULL, v, src);
 }
 
+// Exact element -> float64 conversions for the streaming kernels.  int16 goes through the
+// 2^52 trick (one integer op + one full-rate DADD) because I2F.F64 runs at a quarter of
+// the FP64 rate: bits(2^52 + 2^31 + v) = 0x43300000'80000000 ^ (uint32)v  for |v| < 2^31.
+__device__ __forceinline__ double ss_to_f64(int16_t v)
+{
+    const double m = __hiloint2double(0x43300000, (int)(0x80000000u ^ (unsigned)(int)v));
+    return m - 4503601774854144.0;                       // 2^52 + 2^31
+}
+__device__ __forceinline__ double ss_to_f64(float v) { return (double)v; }
+__device__ __forceinline__ double ss_to_f64(double v) { return v; }
+
 static inline int ss_elem_size(int dtype) { return dtype == SS_I16 ? 2 : dtype == SS_F32 ? 4 : 8; }

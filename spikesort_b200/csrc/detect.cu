@@ -80,35 +80,38 @@ detect_mark_kernel(const T *__restrict__ x, int64_t n_samples, int64_t ld,
     }
 }
 
+// one WARP per 8192-sample block (most blocks hold no crossing and leave at once)
 __global__ void __launch_bounds__(32 * DT_WARPS)
 detect_emit_kernel(const uint32_t *__restrict__ mask, const int64_t *__restrict__ offsets,
-                   int64_t blocks_per_row, double FS, double *__restrict__ spt, int64_t cap)
+                   int64_t n_blocks, int64_t blocks_per_row, double FS, double *__restrict__ spt,
+                   int64_t cap)
 {
-    __shared__ int warp_cnt[DT_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t blk = blockIdx.x;
-    if (offsets[blk + 1] == offsets[blk]) return;             // nothing in this block
+    const int64_t blk = (int64_t)blockIdx.x * DT_WARPS + warp;
+    if (blk >= n_blocks) return;
+    const int64_t first = offsets[blk];
+    if (offsets[blk + 1] == first) return;
     const int64_t b = blk % blocks_per_row;
-    uint32_t m = mask[blk * DT_BLOCK_WORDS + threadIdx.x];
-    const int c = __popc(m);
-    int inc = c;
+    int64_t pos = first;
+#pragma unroll 1
+    for (int j = 0; j < DT_BLOCK_WORDS / 32; ++j) {
+        uint32_t m = mask[blk * DT_BLOCK_WORDS + 32 * j + lane];
+        const int c = __popc(m);
+        int inc = c;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(SS_FULL, inc, d);
-        if (lane >= d) inc += o;
-    }
-    if (lane == 31) warp_cnt[warp] = inc;
-    __syncthreads();
-    int base = 0;
-#pragma unroll
-    for (int w = 0; w < DT_WARPS; ++w) base += (w < warp) ? warp_cnt[w] : 0;
-    int64_t pos = offsets[blk] + base + inc - c;
-    const int64_t i0 = (b * DT_BLOCK_WORDS + threadIdx.x) * 32;
-    while (m) {
-        const int bit = __ffs(m) - 1;
-        m &= m - 1;
-        if (pos < cap) spt[pos] = __ddiv_rn(__dmul_rn((double)(i0 + bit), 1000.0), FS);
-        ++pos;
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(SS_FULL, inc, d);
+            if (lane >= d) inc += o;
+        }
+        int64_t p = pos + inc - c;
+        const int64_t i0 = (b * DT_BLOCK_WORDS + 32 * j + lane) * 32;
+        while (m) {
+            const int bit = __ffs(m) - 1;
+            m &= m - 1;
+            if (p < cap) spt[p] = __ddiv_rn(__dmul_rn((double)(i0 + bit), 1000.0), FS);
+            ++p;
+        }
+        pos += __shfl_sync(SS_FULL, inc, 31);
     }
 }
 
@@ -295,9 +298,10 @@ extern "C" int ss_detect_emit(int64_t n_rows, int64_t n_samples, double FS, cons
     SS_REQUIRE(d_spt, SS_ERR_ARG, "detect_emit: null output");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const char *ws = reinterpret_cast<const char *>(d_ws);
-    detect_emit_kernel<<<(unsigned)L.n_blocks, 32 * DT_WARPS, 0, st>>>(
+    detect_emit_kernel<<<(unsigned)ss_cdiv(L.n_blocks, DT_WARPS), 32 * DT_WARPS, 0, st>>>(
         reinterpret_cast<const uint32_t *>(ws + L.off_mask),
-        reinterpret_cast<const int64_t *>(ws + L.off_offsets), L.blocks_per_row, FS, d_spt, cap);
+        reinterpret_cast<const int64_t *>(ws + L.off_offsets), L.n_blocks, L.blocks_per_row, FS,
+        d_spt, cap);
     SS_LAUNCH_CHECK("detect_emit_kernel");
     return SS_OK;
 }

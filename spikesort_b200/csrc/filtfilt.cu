@@ -237,7 +237,7 @@ __device__ __forceinline__ void load_tile_fast(const T *__restrict__ p, double *
     for (int k = 0; k < FS_S; ++k) raw[k] = __ldg(p + 32 * k + lane);
     const int base = lane + (lane >> 4);               // (32k + lane) + (32k + lane)/16
 #pragma unroll
-    for (int k = 0; k < FS_S; ++k) sm[34 * k + base] = (double)raw[k];
+    for (int k = 0; k < FS_S; ++k) sm[34 * k + base] = ss_to_f64(raw[k]);
 }
 
 // coalesced read of one tile into padded shared memory, then per-lane segments
@@ -268,40 +268,109 @@ __device__ __forceinline__ void load_tile(const void *x, const FiltGeom &g, cons
     __syncwarp();
 }
 
-template <int NB, bool FO>
-__global__ void __launch_bounds__(32 * FS_WPB)
-filt_summary_kernel(const void *__restrict__ x, const FiltGeom g,
-                    const __grid_constant__ FiltParams<NB, FO> P,
+// Sweep 1.  The three tile summaries are LINEAR functionals of the tile input, so they
+// are evaluated as 2*NS+1 dot products with host-computed weights (no recurrence, no
+// scan, no transposition): lane l takes samples 32k+l, coalesced, and the partial sums
+// are folded with shuffles.  Each warp walks SM_TPW consecutive tiles so that the
+// weight table (in shared memory) is loaded once per SM_WPB*SM_TPW tiles.
+constexpr int SM_WPB = 8;            // warps per block
+// tiles processed together (each weight read from shared memory feeds R FMAs); bounded
+// by the accumulator registers R*(2*NS+1)
+__host__ __device__ constexpr int sm_r(int ns) { return ns <= 2 ? 4 : (ns <= 6 ? 2 : 1); }
+constexpr int SM_TPW = 8;            // tiles per warp (multiple of every sm_r)
+
+// R interior tiles at once: all R*FS_S loads of a lane are in flight together and
+// every weight fetched from shared memory is used R times
+template <typename T, int NS>
+__device__ __forceinline__ void summary_group_fast(const T *__restrict__ p, int lane,
+                                                   const double *tab_s, double (&acc)[sm_r(NS)][2 * NS + 1])
+{
+    constexpr int NQ = 2 * NS + 1;
+    constexpr int SM_R = sm_r(NS);
+    T raw[SM_R][FS_S];
+#pragma unroll
+    for (int r = 0; r < SM_R; ++r)
+#pragma unroll
+        for (int k = 0; k < FS_S; ++k) raw[r][k] = __ldg(p + r * FS_T + 32 * k + lane);
+#pragma unroll
+    for (int k = 0; k < FS_S; ++k) {
+        double w[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) w[q] = tab_s[q * FS_T + 32 * k + lane];
+#pragma unroll
+        for (int r = 0; r < SM_R; ++r) {
+            const double xv = ss_to_f64(raw[r][k]);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) acc[r][q] += w[q] * xv;
+        }
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32 * SM_WPB)
+filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *__restrict__ tab,
                     double *__restrict__ F, double *__restrict__ Bz, double *__restrict__ ylast)
 {
-    constexpr int NS = FiltParams<NB, FO>::NS;
-    __shared__ double sm_all[FS_WPB][FS_PADT];
+    constexpr int NQ = 2 * NS + 1;
+    constexpr int SM_R = sm_r(NS);
+    extern __shared__ double tab_s[];                       // [NQ][FS_T]
+    for (int i = threadIdx.x; i < NQ * FS_T; i += 32 * SM_WPB) tab_s[i] = tab[i];
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    TileInfo ti;
-    int64_t tile;
-    if (!decode_tile(g, warp, ti, tile)) return;
-    double v[FS_S];
-    load_tile(x, g, ti, sm_all[warp], lane, v);
-
-    double e[NS], pre[NS];
+    TileInfo ti = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
+    const int64_t t_first = ((int64_t)blockIdx.x * SM_WPB + warp) * SM_TPW;
+    const int64_t row0 = ti.c * g.ld_in;
+#pragma unroll 1
+    for (int it = 0; it < SM_TPW; it += SM_R) {
+        const int64_t t0 = t_first + it;
+        if (t0 >= ti.nt) break;
+        const int nr = (int)(ti.nt - t0 < SM_R ? ti.nt - t0 : SM_R);
+        double acc[SM_R][NQ];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) e[i] = 0.0;
-    local_pass<NB, FO, false>(P, v, e);
-    warp_scan<NS, false>(e, P.P, lane);
-    exclusive_prefix<NS, false>(e, pre, lane);
-    correct<NB, FO, false>(P, v, pre);
-    if (lane == 31) {
+        for (int r = 0; r < SM_R; ++r)
 #pragma unroll
-        for (int i = 0; i < NS; ++i) F[tile * NS + i] = e[i];
-        ylast[tile] = v[FS_S - 1];
-    }
+            for (int q = 0; q < NQ; ++q) acc[r][q] = 0.0;
+        const int64_t r0 = t0 * FS_T - ti.pad - g.edge;     // chunk-relative start of the group
+        if (nr == SM_R && r0 >= 0 && r0 + SM_R * FS_T <= ti.L) {
+            const int64_t base = row0 + ti.cs0 + r0;
+            if (g.dtype == SS_I16)
+                summary_group_fast<int16_t, NS>(reinterpret_cast<const int16_t *>(x) + base, lane, tab_s, acc);
+            else if (g.dtype == SS_F32)
+                summary_group_fast<float, NS>(reinterpret_cast<const float *>(x) + base, lane, tab_s, acc);
+            else
+                summary_group_fast<double, NS>(reinterpret_cast<const double *>(x) + base, lane, tab_s, acc);
+        } else {
+            // group touching the padding / odd extension / end of the unit: one tile at a time
 #pragma unroll
-    for (int i = 0; i < NS; ++i) e[i] = 0.0;
-    local_pass<NB, FO, true>(P, v, e);
-    warp_scan<NS, true>(e, P.P, lane);
-    if (lane == 0) {
+            for (int r = 0; r < SM_R; ++r) {
+                if (r < nr) {
+                    ti.t = t0 + r;
+                    const int64_t e0 = ti.t * FS_T - ti.pad;
+#pragma unroll 1
+                    for (int k = 0; k < FS_S; ++k) {
+                        const double xv = ext_value(x, g.dtype, row0, ti, g.edge, e0 + 32 * k + lane);
 #pragma unroll
-        for (int i = 0; i < NS; ++i) Bz[tile * NS + i] = e[i];
+                        for (int q = 0; q < NQ; ++q) acc[r][q] += tab_s[q * FS_T + 32 * k + lane] * xv;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < SM_R; ++r) {
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) acc[r][q] += __shfl_xor_sync(SS_FULL, acc[r][q], d);
+            if (lane == 0 && r < nr) {
+                const int64_t tile = ti.g0 + t0 + r;
+#pragma unroll
+                for (int i = 0; i < NS; ++i) {
+                    F[tile * NS + i] = acc[r][i];
+                    Bz[tile * NS + i] = acc[r][NS + i];
+                }
+                ylast[tile] = acc[r][2 * NS];
+            }
+        }
     }
 }
 
@@ -432,11 +501,19 @@ filt_tilescan_kernel(const void *__restrict__ x, const FiltGeom g,
     for (int i = 0; i < NS; ++i) carry[i] = P.zi[i] * x0;
 
     double y_last = 0.0;
+    // the loads of row+1 are issued before the (latency-bound) scan of row
+    double nxt[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) nxt[i] = lane < nt ? F[(g0 + lane) * NS + i] : 0.0;
     for (int64_t row = 0; row < nrows; ++row) {
         const int64_t t = row * 32 + lane;
         const bool valid = t < nt;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) e[i] = valid ? F[(g0 + t) * NS + i] : 0.0;
+        for (int i = 0; i < NS; ++i) e[i] = nxt[i];
+        if (row + 1 < nrows) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) nxt[i] = t + 32 < nt ? F[(g0 + t + 32) * NS + i] : 0.0;
+        }
         if (lane == 0) {
 #pragma unroll
             for (int r = 0; r < NS; ++r) {
@@ -471,23 +548,33 @@ filt_tilescan_kernel(const void *__restrict__ x, const FiltGeom g,
 
 #pragma unroll
     for (int i = 0; i < NS; ++i) carry[i] = P.zi[i] * y_last;
+    double nzf[NS], nbz[NS];
+    {
+        const int64_t t = (nrows - 1) * 32 + lane;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            nzf[i] = t < nt ? Zf[(g0 + t) * NS + i] : 0.0;
+            nbz[i] = t < nt ? Bz[(g0 + t) * NS + i] : 0.0;
+        }
+    }
     for (int64_t row = nrows - 1; row >= 0; --row) {
         const int64_t t = row * 32 + lane;
         const bool valid = t < nt;
         const int64_t left = nt - row * 32;
         const int seed = (int)(left < 32 ? left : 32) - 1;
+        // e = Bz + M Zf of this row (invalid lanes hold zeros), then prefetch row-1
 #pragma unroll
-        for (int i = 0; i < NS; ++i) e[i] = 0.0;
-        if (valid) {
-            double zf[NS];
+        for (int r = 0; r < NS; ++r) {
+            double acc = nbz[r];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) zf[i] = Zf[(g0 + t) * NS + i];
+            for (int q = 0; q < NS; ++q) acc += P.M[r][q] * nzf[q];
+            e[r] = acc;
+        }
+        if (row > 0) {
 #pragma unroll
-            for (int r = 0; r < NS; ++r) {
-                double acc = Bz[(g0 + t) * NS + r];
-#pragma unroll
-                for (int q = 0; q < NS; ++q) acc += P.M[r][q] * zf[q];
-                e[r] = acc;
+            for (int i = 0; i < NS; ++i) {
+                nzf[i] = Zf[(g0 + t - 32) * NS + i];
+                nbz[i] = Bz[(g0 + t - 32) * NS + i];
             }
         }
         if (lane == seed) {
@@ -572,6 +659,9 @@ struct HostTables {
     double M[MAX_NS][MAX_NS];
     double hlast[MAX_NS];
     double zi[MAX_NS];
+    // tile summaries as linear functionals of the tile input, SoA [q][i], q = F[0..ns),
+    // Bz[0..ns), ylast; pinned host memory owned by the table cache (never freed)
+    double *dot;
 };
 
 static int build_tables(const QSections &S, HostTables &T)
@@ -636,6 +726,54 @@ static int build_tables(const QSections &S, HostTables &T)
         for (int t = FS_T - 1; t >= 0; --t) (void)qstep(S, z, rows[(size_t)t * n + k]);
         for (int i = 0; i < n; ++i) T.M[i][k] = (double)z[i];
     }
+    // dot-product weights of the summary sweep:
+    //   u_m = A^m Bv;  h(0) = D, h(d) = C u_{d-1}
+    //   F  = sum_i u_{T-1-i} x_i          (zero-state forward end state)
+    //   y_zs[T-1] = sum_i h(T-1-i) x_i
+    //   Bz = sum_m u_m y_zs[m] = sum_i x_i G_i,  G_i = sum_{d=0}^{T-1-i} u_{i+d} h(d)
+    {
+        q_t Dq;
+        {
+            q_t z[MAX_NS];
+            for (int i = 0; i < n; ++i) z[i] = 0;
+            Dq = qstep(S, z, 1);
+        }
+        std::vector<q_t> u((size_t)FS_T * n), h(FS_T);
+        {
+            q_t cur[MAX_NS];
+            for (int i = 0; i < n; ++i) cur[i] = Bv[i];
+            for (int m = 0; m < FS_T; ++m) {
+                for (int i = 0; i < n; ++i) u[(size_t)m * n + i] = cur[i];
+                q_t nx[MAX_NS];
+                for (int i = 0; i < n; ++i) {
+                    q_t sacc = 0;
+                    for (int j = 0; j < n; ++j) sacc += A.a[i][j] * cur[j];
+                    nx[i] = sacc;
+                }
+                for (int i = 0; i < n; ++i) cur[i] = nx[i];
+            }
+        }
+        h[0] = Dq;
+        for (int d = 1; d < FS_T; ++d) {
+            q_t sacc = 0;
+            for (int i = 0; i < n; ++i) sacc += Cv[i] * u[(size_t)(d - 1) * n + i];
+            h[d] = sacc;
+        }
+        const size_t bytes = (size_t)(2 * n + 1) * FS_T * sizeof(double);
+        if (cudaHostAlloc(reinterpret_cast<void **>(&T.dot), bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return SS_ERR_CUDA;
+        }
+        for (int i = 0; i < FS_T; ++i) {
+            for (int k = 0; k < n; ++k) {
+                T.dot[(size_t)k * FS_T + i] = (double)u[(size_t)(FS_T - 1 - i) * n + k];
+                q_t gacc = 0;
+                for (int d = 0; d <= FS_T - 1 - i; ++d) gacc += u[(size_t)(i + d) * n + k] * h[d];
+                T.dot[(size_t)(n + k) * FS_T + i] = (double)gacc;
+            }
+            T.dot[(size_t)(2 * n) * FS_T + i] = (double)h[FS_T - 1 - i];
+        }
+    }
     // zi: (I - A) z = Bv   (Gaussian elimination, partial pivoting, binary128)
     q_t G[MAX_NS][MAX_NS + 1];
     for (int i = 0; i < n; ++i) {
@@ -685,11 +823,10 @@ static int get_tables(const double *sos, int n_sections, bool fo, const QSection
         T = it->second;
         return SS_OK;
     }
+    SS_REQUIRE(g_table_cache.size() < 256, SS_ERR_UNSUPPORTED,
+               "filtfilt: more than 256 distinct filters in one process");
     const int rc = build_tables(S, T);
-    if (rc == SS_OK) {
-        if (g_table_cache.size() > 64) g_table_cache.clear();
-        g_table_cache[key] = T;
-    }
+    if (rc == SS_OK) g_table_cache[key] = T;      // entries (and their pinned tables) live forever
     return rc;
 }
 
@@ -727,12 +864,14 @@ static int make_geom(FiltGeom &g, int dtype, int64_t n_contacts, int64_t n_sampl
     return SS_OK;
 }
 
+enum { PH_SUMMARY = 1, PH_APPLY = 2, PH_ALL = 3 };
+
 // one filter pass over the chunk range [j_begin, j_begin + j_count) of every contact;
 // mk != nullptr fuses crossing marking into the apply kernel
 template <int NB, bool FO>
 static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j_count,
                          const HostTables &T, const double *sos, double *d_out, void *d_ws,
-                         const MarkParams *mk, cudaStream_t st)
+                         const MarkParams *mk, int phases, cudaStream_t st)
 {
     constexpr int NS = FiltParams<NB, FO>::NS;
     constexpr int NSEC = FiltParams<NB, FO>::NSEC;
@@ -769,6 +908,8 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
     double *Zf = Bz + g.total_tiles * NS;
     double *Zb = Zf + g.total_tiles * NS;
     double *yl = Zb + g.total_tiles * NS;
+    double *d_tab = yl + g.total_tiles;                     // (2*NS+1) * FS_T weights
+    const size_t tab_bytes = (size_t)(2 * NS + 1) * FS_T * sizeof(double);
     // tiles per unit in this range: full chunks and/or the trailing short one
     const bool has_full = j_begin < g.n_full;
     const bool has_last = g.len_last > 0 && j_begin + j_count > g.n_full;
@@ -776,10 +917,19 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
     const dim3 tile_blocks((unsigned)ss_cdiv(nt_max, FS_WPB), (unsigned)j_count,
                            (unsigned)g.n_contacts);
     const unsigned unit_blocks = (unsigned)ss_cdiv(g.n_contacts * j_count, FS_WPB);
-    filt_summary_kernel<NB, FO><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, F, Bz, yl);
-    SS_LAUNCH_CHECK("filt_summary_kernel");
-    filt_tilescan_kernel<NS><<<unit_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, SP, F, Bz, yl, Zf, Zb);
-    SS_LAUNCH_CHECK("filt_tilescan_kernel");
+    if (phases & PH_SUMMARY) {
+        const dim3 sum_blocks((unsigned)ss_cdiv(nt_max, SM_WPB * SM_TPW), (unsigned)j_count,
+                              (unsigned)g.n_contacts);
+        SS_CUDA_CHECK(cudaMemcpyAsync(d_tab, T.dot, tab_bytes, cudaMemcpyHostToDevice, st));
+        SS_CUDA_CHECK(cudaFuncSetAttribute(filt_summary_kernel<NS>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)tab_bytes));
+        filt_summary_kernel<NS><<<sum_blocks, 32 * SM_WPB, tab_bytes, st>>>(d_x, g, d_tab, F, Bz, yl);
+        SS_LAUNCH_CHECK("filt_summary_kernel");
+        filt_tilescan_kernel<NS><<<unit_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, SP, F, Bz, yl, Zf, Zb);
+        SS_LAUNCH_CHECK("filt_tilescan_kernel");
+    }
+    if (!(phases & PH_APPLY)) return SS_OK;
     if (mk) {
         filt_apply_kernel<NB, FO, true><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, *mk);
         SS_LAUNCH_CHECK("filt_apply_kernel<mark>");
@@ -829,7 +979,8 @@ static int make_plan(FiltPlan &pl, int dtype, int64_t n_contacts, int64_t n_samp
                nb, MAX_NB);
     int rc = make_geom(pl.g, dtype, n_contacts, n_samples, ld_in, ld_out, chunksize, padlen);
     if (rc) return rc;
-    const size_t need = (size_t)pl.g.total_tiles * (size_t)(4 * S.ns + 1) * sizeof(double);
+    const size_t need = (size_t)pl.g.total_tiles * (size_t)(4 * S.ns + 1) * sizeof(double) +
+                        (size_t)(2 * S.ns + 1) * FS_T * sizeof(double);
     SS_REQUIRE(ws_bytes >= need, SS_ERR_WORKSPACE, "filtfilt: workspace %zu < %zu bytes", ws_bytes,
                need);
     SS_REQUIRE(pl.g.units_per_contact <= 65535 && pl.g.n_contacts <= 65535, SS_ERR_ARG,
@@ -845,11 +996,11 @@ static int make_plan(FiltPlan &pl, int dtype, int64_t n_contacts, int64_t n_samp
 
 static int run_plan(const FiltPlan &pl, const void *d_x, int64_t j_begin, int64_t j_count,
                     const double *sos, double *d_out, void *d_ws, const MarkParams *mk,
-                    cudaStream_t st)
+                    int phases, cudaStream_t st)
 {
 #define SS_FILT_CASE(NB_, FO_)                                                        \
     if (pl.nb == NB_ && pl.fo == FO_)                                                 \
-        return launch_filter<NB_, FO_>(d_x, pl.g, j_begin, j_count, pl.T, sos, d_out, d_ws, mk, st);
+        return launch_filter<NB_, FO_>(d_x, pl.g, j_begin, j_count, pl.T, sos, d_out, d_ws, mk, phases, st);
     SS_FILT_CASE(0, true)
     SS_FILT_CASE(1, false)
     SS_FILT_CASE(1, true)
@@ -883,7 +1034,8 @@ extern "C" size_t ss_filtfilt_workspace_bytes(int64_t n_contacts, int64_t n_samp
     const int64_t nt_last = len_last > 0 ? ss_cdiv(len_last + 2 * (int64_t)padlen, FS_T) : 0;
     const int64_t tiles = (n_full * nt_full + nt_last) * n_contacts;
     const int64_t ns = 2 * (int64_t)n_sections;   // upper bound on the state count
-    return (size_t)tiles * (size_t)(4 * ns + 1) * sizeof(double);
+    return (size_t)tiles * (size_t)(4 * ns + 1) * sizeof(double) +
+           (size_t)(2 * ns + 1) * FS_T * sizeof(double);
 }
 
 extern "C" int ss_filtfilt_sos(const void *d_x, int dtype, int64_t n_contacts, int64_t n_samples,
@@ -896,7 +1048,7 @@ extern "C" int ss_filtfilt_sos(const void *d_x, int dtype, int64_t n_contacts, i
     const int rc = make_plan(pl, dtype, n_contacts, n_samples, ld_in, sos, n_sections, padlen,
                              chunksize, ld_out, ws_bytes);
     if (rc) return rc;
-    return run_plan(pl, d_x, 0, pl.g.units_per_contact, sos, d_out, d_ws, nullptr,
+    return run_plan(pl, d_x, 0, pl.g.units_per_contact, sos, d_out, d_ws, nullptr, PH_ALL,
                     reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -935,7 +1087,10 @@ extern "C" int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_cont
         if (n0 > n_samples) n0 = n_samples;
         j0 = ss_cdiv(n0, chunksize);
         if (j0 > pl.g.units_per_contact) j0 = pl.g.units_per_contact;
-        rc = run_plan(pl, d_x, 0, j0, sos, d_out, d_ws, nullptr, st);
+        // sweep 1 and the tile scan do not depend on the thresholds: all chunks at once
+        rc = run_plan(pl, d_x, 0, pl.g.units_per_contact, sos, d_out, d_ws, nullptr, PH_SUMMARY, st);
+        if (rc) return rc;
+        rc = run_plan(pl, d_x, 0, j0, sos, d_out, d_ws, nullptr, PH_APPLY, st);
         if (rc) return rc;
         rc = ss_var_threshold(d_out, SS_F64, n_contacts, ld_out, n0, factor, d_thr,
                               dws + L.off_scratch, L.total - L.off_scratch, st);
@@ -948,7 +1103,8 @@ extern "C" int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_cont
         // the pair (head_end-1, head_end) straddles the two passes: mark it once the
         // second pass has written head_end (boundary kernel of the head range, below)
     }
-    rc = run_plan(pl, d_x, j0, pl.g.units_per_contact - j0, sos, d_out, d_ws, &mk, st);
+    rc = run_plan(pl, d_x, j0, pl.g.units_per_contact - j0, sos, d_out, d_ws, &mk,
+                  auto_thr ? PH_APPLY : PH_ALL, st);
     if (rc) return rc;
     if (j0 > 0 && j0 < pl.g.units_per_contact) {
         // chunk-end pair of the last head chunk of every contact

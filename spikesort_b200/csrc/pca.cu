@@ -20,7 +20,7 @@ namespace {
 
 constexpr int PC_THREADS = 256;
 constexpr int PC_SC = 64;               // spikes per staged chunk
-constexpr int PC_MAX_WIN = 112;             // eig: 2 * 112^2 * 8 B = 200 KB of shared memory
+constexpr int PC_MAX_WIN = 112;             // eig: 2 * 112 * 113 * 8 B = 202 KB of shared memory
 constexpr int PC_MAX_TILES = 2;         // 4x4 tiles per thread (28*29/2 = 406 <= 512)
 constexpr int PC_MAX_COMPS = 8;
 
@@ -149,67 +149,70 @@ pca_gram_reduce_kernel(const double *__restrict__ ws_gram, const double *__restr
     }
 }
 
-// One CTA per group.  smem: A[ne*ne], V[ne*ne], cs[ne] (c, s per pair), red[...]
-// (measured on B200, 30x30: 256 threads 288 us, one warp 868 us - the element updates,
-// not the barriers, dominate a round.)
+// One CTA per group.  smem: A[ne*ld], V[ne*ld] (row stride ld odd: column sweeps are
+// bank-conflict free), rotation (c, s) per pair, reduction scratch.  Warps take pairs,
+// lanes take the row/column index: no integer division in the sweeps.
 __global__ void __launch_bounds__(PC_THREADS)
 pca_eig_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
                const int64_t *__restrict__ counts, int n, double *__restrict__ evals,
                double *__restrict__ evecs)
 {
     extern __shared__ double sm[];
-    const int ne = (n + 1) & ~1;
-    double *A = sm, *V = A + ne * ne, *rc = V + ne * ne, *rs = rc + ne / 2, *red = rs + ne / 2;
+    const int ne = (n + 1) & ~1, ld = ne | 1;
+    double *A = sm, *V = A + ne * ld, *rc = V + ne * ld, *rs = rc + ne / 2, *red = rs + ne / 2;
     __shared__ int s_p[PC_MAX_WIN / 2 + 1], s_q[PC_MAX_WIN / 2 + 1];
     __shared__ int s_done;
-    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
     const int64_t g = blockIdx.x;
     const double cnt = (double)counts[g];
-    for (int idx = tid; idx < ne * ne; idx += nthr) {
-        const int i = idx / ne, j = idx - i * ne;
-        double a = 0.0;
-        if (i < n && j < n)
-            a = (gram[(g * n + i) * n + j] - sum[g * n + i] * sum[g * n + j] / cnt) / (cnt - 1.0);
-        A[idx] = a;
-        V[idx] = i == j ? 1.0 : 0.0;
-    }
+    for (int i = warp; i < ne; i += nwarps)
+        for (int j = lane; j < ne; j += 32) {
+            double a = 0.0;
+            if (i < n && j < n)
+                a = (gram[(g * n + i) * n + j] - sum[g * n + i] * sum[g * n + j] / cnt) / (cnt - 1.0);
+            A[i * ld + j] = a;
+            V[i * ld + j] = i == j ? 1.0 : 0.0;
+        }
     __syncthreads();
     const int half = ne / 2;
     for (int sweep = 0; sweep < 60; ++sweep) {
         // convergence: off-diagonal energy against diagonal energy
         double off = 0.0, dg = 0.0;
-        for (int idx = tid; idx < n * n; idx += nthr) {
-            const int i = idx / n, j = idx - i * n;
-            const double a = A[i * ne + j];
-            if (i == j) dg += a * a; else off += a * a;
-        }
+        for (int i = warp; i < n; i += nwarps)
+            for (int j = lane; j < n; j += 32) {
+                const double a = A[i * ld + j];
+                if (i == j) dg += a * a; else off += a * a;
+            }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             off += __shfl_xor_sync(SS_FULL, off, d);
             dg += __shfl_xor_sync(SS_FULL, dg, d);
         }
-        if ((tid & 31) == 0) { red[2 * (tid >> 5)] = off; red[2 * (tid >> 5) + 1] = dg; }
+        if (lane == 0) { red[2 * warp] = off; red[2 * warp + 1] = dg; }
         __syncthreads();
         if (tid == 0) {
             double o = 0.0, d2 = 0.0;
-            for (int w = 0; w < nthr / 32; ++w) { o += red[2 * w]; d2 += red[2 * w + 1]; }
+            for (int w = 0; w < nwarps; ++w) { o += red[2 * w]; d2 += red[2 * w + 1]; }
             s_done = !(o > 1e-30 * d2);          // also stops on NaN
         }
         __syncthreads();
         if (s_done) break;
         for (int rd = 0; rd < ne - 1; ++rd) {
-            for (int k = tid; k < half; k += nthr) {
+            for (int k = tid; k < half; k += blockDim.x) {
                 int p, q;
                 if (k == 0) { p = ne - 1; q = rd; }
-                else { p = (rd + k) % (ne - 1); q = (rd - k + (ne - 1)) % (ne - 1); }
+                else {
+                    p = rd + k; if (p >= ne - 1) p -= ne - 1;
+                    q = rd - k; if (q < 0) q += ne - 1;
+                }
                 if (p > q) { const int t = p; p = q; q = t; }
                 double c = 1.0, s = 0.0;
                 if (q < n) {
                     // rotation that zeroes A[p][q] (the smaller angle), without divisions:
                     // cos 2t = |alpha|/hyp, c = sqrt((1 + cos 2t)/2), s = sgn(alpha) beta/(2 c hyp)
-                    const double apq = A[p * ne + q];
+                    const double apq = A[p * ld + q];
                     if (apq != 0.0) {
-                        const double alpha = A[q * ne + q] - A[p * ne + p], beta = 2.0 * apq;
+                        const double alpha = A[q * ld + q] - A[p * ld + p], beta = 2.0 * apq;
                         const double h2 = alpha * alpha + beta * beta;
                         if (h2 > 0.0 && h2 < 1e300) {
                             const double ih = rsqrt(h2);
@@ -224,40 +227,44 @@ pca_eig_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
             }
             __syncthreads();
             // columns of A and V
-            for (int idx = tid; idx < half * ne; idx += nthr) {
-                const int k = idx / ne, i = idx - k * ne;
+            for (int k = warp; k < half; k += nwarps) {
                 const int p = s_p[k], q = s_q[k];
                 const double c = rc[k], s = rs[k];
-                const double aip = A[i * ne + p], aiq = A[i * ne + q];
-                A[i * ne + p] = c * aip - s * aiq;
-                A[i * ne + q] = s * aip + c * aiq;
-                const double vip = V[i * ne + p], viq = V[i * ne + q];
-                V[i * ne + p] = c * vip - s * viq;
-                V[i * ne + q] = s * vip + c * viq;
+                if (s != 0.0)
+                    for (int i = lane; i < ne; i += 32) {
+                        const double aip = A[i * ld + p], aiq = A[i * ld + q];
+                        A[i * ld + p] = c * aip - s * aiq;
+                        A[i * ld + q] = s * aip + c * aiq;
+                        const double vip = V[i * ld + p], viq = V[i * ld + q];
+                        V[i * ld + p] = c * vip - s * viq;
+                        V[i * ld + q] = s * vip + c * viq;
+                    }
             }
             __syncthreads();
             // rows of A
-            for (int idx = tid; idx < half * ne; idx += nthr) {
-                const int k = idx / ne, j = idx - k * ne;
+            for (int k = warp; k < half; k += nwarps) {
                 const int p = s_p[k], q = s_q[k];
                 const double c = rc[k], s = rs[k];
-                const double apj = A[p * ne + j], aqj = A[q * ne + j];
-                A[p * ne + j] = c * apj - s * aqj;
-                A[q * ne + j] = s * apj + c * aqj;
+                if (s != 0.0)
+                    for (int j = lane; j < ne; j += 32) {
+                        const double apj = A[p * ld + j], aqj = A[q * ld + j];
+                        A[p * ld + j] = c * apj - s * aqj;
+                        A[q * ld + j] = s * apj + c * aqj;
+                    }
             }
             __syncthreads();
         }
     }
     // rank by signed eigenvalue, descending (np.argsort(evals)[::-1]), then |.|
-    for (int k = tid; k < n; k += nthr) {
-        const double lk = A[k * ne + k];
+    for (int k = tid; k < n; k += blockDim.x) {
+        const double lk = A[k * ld + k];
         int rank = 0;
         for (int j = 0; j < n; ++j) {
-            const double lj = A[j * ne + j];
+            const double lj = A[j * ld + j];
             if (lj > lk || (lj == lk && j > k)) ++rank;
         }
         evals[g * n + rank] = fabs(lk);
-        for (int i = 0; i < n; ++i) evecs[(g * n + i) * n + rank] = V[i * ne + k];
+        for (int i = 0; i < n; ++i) evecs[(g * n + i) * n + rank] = V[i * ld + k];
     }
 }
 
@@ -341,10 +348,10 @@ extern "C" int ss_pca_eig(const double *d_gram, const double *d_sum, const int64
     SS_REQUIRE(n_groups >= 1, SS_ERR_ARG, "pca_eig: bad shape");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int ne = (n_win + 1) & ~1;
-    const size_t smem = ((size_t)2 * ne * ne + ne + 2 * (PC_THREADS / 32) + 8) * sizeof(double);
+    const size_t smem = ((size_t)2 * ne * (ne | 1) + ne + 2 * (PC_THREADS / 32) + 8) * sizeof(double);
     const int ne_max = (PC_MAX_WIN + 1) & ~1;
     SS_CUDA_CHECK(cudaFuncSetAttribute(pca_eig_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(((size_t)2 * ne_max * ne_max + ne_max + 2 * (PC_THREADS / 32) + 8) * sizeof(double))));
+                                       (int)(((size_t)2 * ne_max * (ne_max | 1) + ne_max + 2 * (PC_THREADS / 32) + 8) * sizeof(double))));
     const int eig_threads = PC_THREADS;
     pca_eig_kernel<<<(unsigned)n_groups, eig_threads, smem, st>>>(d_gram, d_sum, d_counts, n_win, d_evals, d_evecs);
     SS_LAUNCH_CHECK("pca_eig_kernel");
