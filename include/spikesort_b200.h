@@ -91,7 +91,25 @@ int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_contacts, int64
                            int64_t chunksize, double *d_out, int64_t ld_out,
                            void *d_ws, size_t ws_bytes,
                            int auto_thr, int64_t n0, double factor, double *d_thr, int falling,
-                           void *d_det_ws, size_t det_ws_bytes, int64_t *d_offsets, void *stream);
+                           void *d_det_ws, size_t det_ws_bytes, int64_t *d_offsets,
+                           int prepared, void *stream);
+
+/* Split form of the above for time shards (the thresholds come from another rank):
+ *   ss_filtfilt_prepare_sos        : sweep 1 + tile scan of every chunk into d_ws (needs
+ *                                    no threshold);
+ *   ss_filtfilt_head_threshold_sos : with d_ws prepared, filters the chunks holding the
+ *                                    first n0 samples into d_out and computes d_thr;
+ *   ss_filtfilt_detect_sos with prepared != 0 skips sweep 1.
+ */
+int ss_filtfilt_prepare_sos(const void *d_x, int dtype, int64_t n_contacts, int64_t n_samples,
+                            int64_t ld_in, const double *sos, int n_sections, int padlen,
+                            int64_t chunksize, void *d_ws, size_t ws_bytes, void *stream);
+int ss_filtfilt_head_threshold_sos(const void *d_x, int dtype, int64_t n_contacts,
+                                   int64_t n_samples, int64_t ld_in, const double *sos,
+                                   int n_sections, int padlen, int64_t chunksize, double *d_out,
+                                   int64_t ld_out, void *d_ws, size_t ws_bytes, int64_t n0,
+                                   double factor, double *d_thr, void *d_thr_ws, size_t thr_ws_bytes,
+                                   void *stream);
 
 /* --------------------------------------------------------------- threshold
  * Replaces extract.py:79: thr[r] = factor * sqrt(var(x[r, :n0])) (population
@@ -111,14 +129,26 @@ int ss_var_threshold(const void *d_x, int dtype, int64_t n_rows, int64_t ld, int
  *                    the per-row counts; last entry = total).
  * ss_detect_emit   : writes the total times into d_spt (capacity `cap`); reads
  *                    only the workspace.  The caller reads d_offsets in between
- *                    to size d_spt.
+ *                    to size d_spt.  index_offset = index of x[.,0] in the whole
+ *                    recording (0 unless x is a time shard, see "time shards").
  */
 size_t ss_detect_workspace_bytes(int64_t n_rows, int64_t n_samples);
 int ss_detect_mark(const void *d_x, int dtype, int64_t n_rows, int64_t n_samples, int64_t ld,
                    const double *d_thr, int falling, void *d_ws, size_t ws_bytes,
                    int64_t *d_offsets, void *stream);
-int ss_detect_emit(int64_t n_rows, int64_t n_samples, double FS, const void *d_ws,
-                   size_t ws_bytes, double *d_spt, int64_t cap, void *stream);
+int ss_detect_emit(int64_t n_rows, int64_t n_samples, double FS, int64_t index_offset,
+                   const void *d_ws, size_t ws_bytes, double *d_spt, int64_t cap, void *stream);
+
+/* -------------------------------------------------------------- time shards
+ * A recording sharded by time across GPUs keeps GLOBAL spike times: the kernels that
+ * turn indices into times or back take
+ *   index_offset : index in the whole recording of the shard's sample x[., 0];
+ *   halo_before / halo_after : number of valid samples stored immediately before
+ *                  x[., 0] / after x[., n_samples-1] in the same rows (neighbour
+ *                  shards' filtered samples), readable by windows that cross the edge.
+ * t_min / t_max passed to align / extract are then those of the WHOLE recording.
+ * All three are 0 for an unsharded recording.
+ */
 
 /* ------------------------------------------------------------------- align
  * Replaces the loop of align_spikes (extract.py:235-265), resample == 1.
@@ -133,15 +163,20 @@ int ss_align(const void *d_x, int dtype, int64_t n_samples, int64_t ld, double F
              const int32_t *d_rows, int64_t n_rows, const int64_t *d_offsets,
              double sp_win0, int win0, int win1, double t_min, double t_max,
              double lo, double hi, int use_min, double *d_spt, int64_t n_spk,
-             int max_iter, void *stream);
+             int max_iter, int64_t index_offset, int64_t halo_before, int64_t halo_after,
+             void *stream);
 
 /* Replaces remove_doubles (extract.py:277-288) per row: keeps the first time
  * of each row and every time with (int64)((t[k]-t[k-1])/tol) > 1.
  * mark: flags + d_offsets_out[n_rows+1]; emit: compacted times into d_out.
+ * d_prev_last (may be NULL): per row, the last ALIGNED time of the previous time
+ * shard (NaN: none) - the first time of a row is then compared with it, as np.diff
+ * does on the unsharded list.
  */
 size_t ss_remove_doubles_workspace_bytes(int64_t n_spk);
 int ss_remove_doubles_mark(const double *d_spt, int64_t n_spk, const int64_t *d_offsets,
-                           int64_t n_rows, double tol, void *d_ws, size_t ws_bytes,
+                           int64_t n_rows, double tol, const double *d_prev_last,
+                           void *d_ws, size_t ws_bytes,
                            int64_t *d_offsets_out, void *stream);
 int ss_remove_doubles_emit(const double *d_spt, int64_t n_spk, const void *d_ws,
                            size_t ws_bytes, double *d_out, int64_t cap, void *stream);
@@ -163,7 +198,8 @@ int ss_extract(const void *d_x, int dtype, int64_t n_samples, int64_t ld, double
                const int32_t *d_rows, int64_t n_rows, const int64_t *d_offsets,
                int win0, int win1, double t_min, double t_max,
                const double *d_spt, int64_t n_spk,
-               float *d_waves, uint8_t *d_valid, int32_t *d_n_invalid, void *stream);
+               float *d_waves, uint8_t *d_valid, int32_t *d_n_invalid,
+               int64_t index_offset, int64_t halo_before, int64_t halo_after, void *stream);
 
 /* --------------------------------------------------------------------- PCA
  * Replaces PCA / fetPCA (features.py:224-231, 326-344) on a float32 waveform

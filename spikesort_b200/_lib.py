@@ -31,19 +31,24 @@ SIGNATURES = {
     "ss_filtfilt_sos": (_int, [_vp, _int, _i64, _i64, _i64, _dp, _int, _int, _i64, _vp, _i64,
                                _vp, _sz, _vp]),
     "ss_filtfilt_detect_sos": (_int, [_vp, _int, _i64, _i64, _i64, _dp, _int, _int, _i64, _vp, _i64,
-                                      _vp, _sz, _int, _i64, _dbl, _vp, _int, _vp, _sz, _vp, _vp]),
+                                      _vp, _sz, _int, _i64, _dbl, _vp, _int, _vp, _sz, _vp, _int,
+                                      _vp]),
+    "ss_filtfilt_prepare_sos": (_int, [_vp, _int, _i64, _i64, _i64, _dp, _int, _int, _i64, _vp, _sz,
+                                       _vp]),
+    "ss_filtfilt_head_threshold_sos": (_int, [_vp, _int, _i64, _i64, _i64, _dp, _int, _int, _i64,
+                                              _vp, _i64, _vp, _sz, _i64, _dbl, _vp, _vp, _sz, _vp]),
     "ss_threshold_workspace_bytes": (_sz, [_i64]),
     "ss_var_threshold": (_int, [_vp, _int, _i64, _i64, _i64, _dbl, _vp, _vp, _sz, _vp]),
     "ss_detect_workspace_bytes": (_sz, [_i64, _i64]),
     "ss_detect_mark": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _vp, _sz, _vp, _vp]),
-    "ss_detect_emit": (_int, [_i64, _i64, _dbl, _vp, _sz, _vp, _i64, _vp]),
+    "ss_detect_emit": (_int, [_i64, _i64, _dbl, _i64, _vp, _sz, _vp, _i64, _vp]),
     "ss_align": (_int, [_vp, _int, _i64, _i64, _dbl, _vp, _i64, _vp, _dbl, _int, _int, _dbl,
-                        _dbl, _dbl, _dbl, _int, _vp, _i64, _int, _vp]),
+                        _dbl, _dbl, _dbl, _int, _vp, _i64, _int, _i64, _i64, _i64, _vp]),
     "ss_remove_doubles_workspace_bytes": (_sz, [_i64]),
-    "ss_remove_doubles_mark": (_int, [_vp, _i64, _vp, _i64, _dbl, _vp, _sz, _vp, _vp]),
+    "ss_remove_doubles_mark": (_int, [_vp, _i64, _vp, _i64, _dbl, _vp, _vp, _sz, _vp, _vp]),
     "ss_remove_doubles_emit": (_int, [_vp, _i64, _vp, _sz, _vp, _i64, _vp]),
     "ss_extract": (_int, [_vp, _int, _i64, _i64, _dbl, _vp, _int, _vp, _i64, _vp, _int, _int,
-                          _dbl, _dbl, _vp, _i64, _vp, _vp, _vp, _vp]),
+                          _dbl, _dbl, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "ss_pca_workspace_bytes": (_sz, [_int, _i64]),
     "ss_pca_gram": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ss_pca_eig": (_int, [_vp, _vp, _vp, _int, _i64, _vp, _vp, _vp]),

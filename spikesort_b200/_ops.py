@@ -24,6 +24,21 @@ def _launched(n):
     LAUNCHES["count"] += n
 
 
+class Shard(object):
+    """Position of a time shard in the whole recording (include/spikesort_b200.h,
+    "time shards"): global index of its first sample, total length of the recording and
+    the number of neighbour samples stored before / after it in the same buffer."""
+
+    def __init__(self, index_offset=0, n_total=None, halo_before=0, halo_after=0):
+        self.index_offset = int(index_offset)
+        self.n_total = n_total
+        self.halo_before = int(halo_before)
+        self.halo_after = int(halo_after)
+
+
+_WHOLE = Shard()
+
+
 # ------------------------------------------------------------------ host math
 def window_params(sp_win, FS):
     """win (int32, truncating), n_win and the float64 time axis, exactly as
@@ -62,7 +77,8 @@ def filtfilt_sos(x, sos, padlen, chunksize, out=None):
     return out
 
 
-def filtfilt_detect(x, sos, padlen, chunksize, FS, falling, thr=None, n0=None, factor=None):
+def filtfilt_detect(x, sos, padlen, chunksize, FS, falling, thr=None, n0=None, factor=None,
+                    out=None, ws=None, shard=_WHOLE):
     """Fused filter + (auto threshold) + crossing marking + emit.
     thr: CUDA float64 (n_contacts,) thresholds, or None to derive them from the first
     n0 filtered samples (factor carries the sign).  Returns (out, thr, spt, offsets)."""
@@ -71,8 +87,12 @@ def filtfilt_detect(x, sos, padlen, chunksize, FS, falling, thr=None, n0=None, f
     n_c, n = x.shape
     sos = np.ascontiguousarray(sos, dtype=np.float64)
     n_sec = sos.shape[0]
-    out = t.empty((n_c, n), dtype=t.float64, device=x.device)
-    ws = _lib.workspace(lib.ss_filtfilt_workspace_bytes(n_c, n, int(chunksize), int(padlen), n_sec))
+    if out is None:
+        out = t.empty((n_c, n), dtype=t.float64, device=x.device)
+    prepared = ws is not None                       # sweep 1 already done by filtfilt_prepare
+    if ws is None:
+        ws = _lib.workspace(lib.ss_filtfilt_workspace_bytes(n_c, n, int(chunksize), int(padlen),
+                                                            n_sec))
     dws = _lib.workspace(lib.ss_detect_workspace_bytes(n_c, n))
     offsets = t.empty(n_c + 1, dtype=t.int64, device=x.device)
     auto = thr is None
@@ -84,16 +104,53 @@ def filtfilt_detect(x, sos, padlen, chunksize, FS, falling, thr=None, n0=None, f
                                     _lib.ptr(ws), ws.numel(), int(auto),
                                     int(n0) if auto else 0, float(factor) if auto else 0.0,
                                     _lib.ptr(thr), int(bool(falling)), _lib.ptr(dws), dws.numel(),
-                                    _lib.ptr(offsets), _lib.stream_ptr())
+                                    _lib.ptr(offsets), int(prepared), _lib.stream_ptr())
     _lib.check(rc, "ss_filtfilt_detect_sos")
-    _launched(12 if auto else 7)      # head: 3 filter + 2 threshold + 1 mark; rest: 4; edge, count, scan
+    # summary, tilescan | apply(head), 2 threshold, mark(head), edge | apply+marks, edge | count, scan
+    _launched((0 if prepared else 2) + (5 if auto else 0) + 4)
     total = int(offsets[-1].item())
     spt = t.empty(total, dtype=t.float64, device=x.device)
-    rc = lib.ss_detect_emit(n_c, n, float(FS), _lib.ptr(dws), dws.numel(), _lib.ptr(spt), total,
-                            _lib.stream_ptr())
+    rc = lib.ss_detect_emit(n_c, n, float(FS), shard.index_offset, _lib.ptr(dws), dws.numel(),
+                            _lib.ptr(spt), total, _lib.stream_ptr())
     _lib.check(rc, "ss_detect_emit")
     _launched(1 if total > 0 else 0)
     return out, thr, spt, offsets
+
+
+def filtfilt_prepare(x, sos, padlen, chunksize):
+    """Sweep 1 + tile scan of every chunk (no threshold needed).  Returns the workspace
+    to hand to filtfilt_head_threshold / filtfilt_detect."""
+    lib = _lib.load()
+    n_c, n = x.shape
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    n_sec = sos.shape[0]
+    ws = _lib.workspace(lib.ss_filtfilt_workspace_bytes(n_c, n, int(chunksize), int(padlen), n_sec))
+    rc = lib.ss_filtfilt_prepare_sos(_lib.ptr(x), _lib.ss_dtype_of(x), n_c, n, x.stride(0),
+                                     sos.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_sec,
+                                     int(padlen), int(chunksize), _lib.ptr(ws), ws.numel(),
+                                     _lib.stream_ptr())
+    _lib.check(rc, "ss_filtfilt_prepare_sos")
+    _launched(2)
+    return ws
+
+
+def filtfilt_head_threshold(x, sos, padlen, chunksize, out, ws, n0, factor):
+    """With `ws` prepared: filter the chunks holding the first n0 samples into `out`
+    and return factor*sqrt(var(out[:, :n0])) per contact."""
+    lib = _lib.load()
+    t = _lib.torch()
+    n_c, n = x.shape
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    thr = t.empty(n_c, dtype=t.float64, device=x.device)
+    tws = _lib.workspace(lib.ss_threshold_workspace_bytes(n_c))
+    rc = lib.ss_filtfilt_head_threshold_sos(
+        _lib.ptr(x), _lib.ss_dtype_of(x), n_c, n, x.stride(0),
+        sos.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), sos.shape[0], int(padlen),
+        int(chunksize), _lib.ptr(out), out.stride(0), _lib.ptr(ws), ws.numel(), int(n0),
+        float(factor), _lib.ptr(thr), _lib.ptr(tws), tws.numel(), _lib.stream_ptr())
+    _lib.check(rc, "ss_filtfilt_head_threshold_sos")
+    _launched(3)
+    return thr
 
 
 # ------------------------------------------------------------------ threshold
@@ -114,7 +171,7 @@ def var_threshold(x, n0, factor):
 
 
 # --------------------------------------------------------------------- detect
-def detect(x, thr, falling, FS):
+def detect(x, thr, falling, FS, shard=_WHOLE):
     """Threshold crossings of every row.  Returns (spt, offsets): CUDA float64 times
     (ms) concatenated row by row and CUDA int64 offsets[n_rows+1]."""
     lib = _lib.load()
@@ -129,34 +186,35 @@ def detect(x, thr, falling, FS):
     _launched(2)          # mark, scan
     total = int(offsets[-1].item())                 # the one sync: size of the result
     spt = t.empty(total, dtype=t.float64, device=x.device)
-    rc = lib.ss_detect_emit(n_rows, n, float(FS), _lib.ptr(ws), ws.numel(), _lib.ptr(spt),
-                            total, _lib.stream_ptr())
+    rc = lib.ss_detect_emit(n_rows, n, float(FS), shard.index_offset, _lib.ptr(ws), ws.numel(),
+                            _lib.ptr(spt), total, _lib.stream_ptr())
     _lib.check(rc, "ss_detect_emit")
     _launched(1 if total > 0 else 0)
     return spt, offsets
 
 
 # ---------------------------------------------------------------------- align
-def align(x, spt, offsets, rows, FS, sp_win, use_min):
+def align(x, spt, offsets, rows, FS, sp_win, use_min, shard=_WHOLE):
     """In-place alignment of CUDA float64 times `spt`.  offsets: CUDA int64
     [n_rows+1] or None (single row); rows: CUDA int32 row ids or None."""
     lib = _lib.load()
     n = x.shape[1]
     win0, win1, _ = window_params(sp_win, FS)
-    t_min, t_max = time_bounds(n, FS, sp_win)
+    t_min, t_max = time_bounds(n if shard.n_total is None else shard.n_total, FS, sp_win)
     tol = 0.1                                       # extract.py:229
     lo, hi = sp_win[0] + tol, sp_win[1] - tol       # extract.py:263-264
     n_rows = 1 if offsets is None else offsets.numel() - 1
     rc = lib.ss_align(_lib.ptr(x), _lib.ss_dtype_of(x), n, x.stride(0), float(FS),
                       _lib.ptr(rows), n_rows, _lib.ptr(offsets), float(sp_win[0]), win0, win1,
                       t_min, t_max, float(lo), float(hi), int(bool(use_min)), _lib.ptr(spt),
-                      spt.numel(), MAX_ALIGN_ITER, _lib.stream_ptr())
+                      spt.numel(), MAX_ALIGN_ITER, shard.index_offset, shard.halo_before,
+                      shard.halo_after, _lib.stream_ptr())
     _lib.check(rc, "ss_align")
     _launched(1 if spt.numel() > 0 else 0)
     return spt
 
 
-def remove_doubles(spt, offsets, tol):
+def remove_doubles(spt, offsets, tol, prev_last=None):
     """Returns (kept times, new offsets); offsets None = one row."""
     lib = _lib.load()
     t = _lib.torch()
@@ -168,7 +226,7 @@ def remove_doubles(spt, offsets, tol):
     ws = _lib.workspace(lib.ss_remove_doubles_workspace_bytes(n_spk))
     new_off = t.empty(n_rows + 1, dtype=t.int64, device=spt.device)
     rc = lib.ss_remove_doubles_mark(_lib.ptr(spt), n_spk, _lib.ptr(offsets), n_rows, float(tol),
-                                    _lib.ptr(ws), ws.numel(), _lib.ptr(new_off),
+                                    _lib.ptr(prev_last), _lib.ptr(ws), ws.numel(), _lib.ptr(new_off),
                                     _lib.stream_ptr())
     _lib.check(rc, "ss_remove_doubles_mark")
     _launched(3)          # mark, scan, row offsets
@@ -182,14 +240,14 @@ def remove_doubles(spt, offsets, tol):
 
 
 # -------------------------------------------------------------------- extract
-def extract(x, spt, FS, sp_win, contacts=None, offsets=None, rows=None):
+def extract(x, spt, FS, sp_win, contacts=None, offsets=None, rows=None, shard=_WHOLE):
     """Returns (waves float32 (n_win, n_spk, n_c), valid uint8[n_spk], n_invalid int32[1])
     as CUDA tensors.  contacts: CUDA int32 list (reference mode) or None (row mode)."""
     lib = _lib.load()
     t = _lib.torch()
     n = x.shape[1]
     win0, win1, _ = window_params(sp_win, FS)
-    t_min, t_max = time_bounds(n, FS, sp_win)
+    t_min, t_max = time_bounds(n if shard.n_total is None else shard.n_total, FS, sp_win)
     n_spk = spt.numel()
     n_c = 1 if contacts is None else contacts.numel()
     waves = t.empty((win1 - win0, n_spk, n_c), dtype=t.float32, device=x.device)
@@ -199,7 +257,8 @@ def extract(x, spt, FS, sp_win, contacts=None, offsets=None, rows=None):
     rc = lib.ss_extract(_lib.ptr(x), _lib.ss_dtype_of(x), n, x.stride(0), float(FS),
                         _lib.ptr(contacts), n_c, _lib.ptr(rows), n_rows, _lib.ptr(offsets),
                         win0, win1, t_min, t_max, _lib.ptr(spt), n_spk, _lib.ptr(waves),
-                        _lib.ptr(valid), _lib.ptr(n_invalid), _lib.stream_ptr())
+                        _lib.ptr(valid), _lib.ptr(n_invalid), shard.index_offset,
+                        shard.halo_before, shard.halo_after, _lib.stream_ptr())
     _lib.check(rc, "ss_extract")
     _launched(1 if n_spk > 0 else 0)
     return waves, valid, n_invalid

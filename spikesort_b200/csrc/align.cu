@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(32 * AL_WARPS)
 align_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t ld, double FS,
              const int32_t *__restrict__ rows, int64_t n_rows, const int64_t *__restrict__ offsets,
              double sp_win0, int win0, int win1, double t_min, double t_max, double lo, double hi,
-             int use_min, double *__restrict__ spt, int64_t n_spk, int max_iter)
+             int use_min, double *__restrict__ spt, int64_t n_spk, int max_iter,
+             int64_t index_offset, int64_t halo_before, int64_t halo_after)
 {
     const int lane = threadIdx.x & 31;
     const int64_t s = (int64_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
@@ -50,13 +51,13 @@ align_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t l
     for (int it = 0; it < max_iter; ++it) {
         if (!(t >= t_min && t <= t_max)) break;                 // filter_spt, extract.py:108-110
         const int centre = __double2int_rz(__dmul_rn(__ddiv_rn(t, 1000.0), FS));   // :150
-        const int64_t first = (int64_t)centre + win0;
+        const int64_t first = (int64_t)centre + win0 - index_offset;   // local index
         float best = 0.f;
         int best_k = AL_NONE;
         for (int k = lane; k < n_win; k += 32) {
             const int64_t i = first + k;
             float v = 0.f;
-            if (i >= 0 && i < n_samples) v = ss_load_f32(x, dtype, row0 + i);
+            if (i >= -halo_before && i < n_samples + halo_after) v = ss_load_f32(x, dtype, row0 + i);
             if (use_min) v = -v;                                // argmin(v) == argmax(-v), ties alike
             if (best_k == AL_NONE || v > best) { best = v; best_k = k; }
         }
@@ -82,15 +83,23 @@ align_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t l
 // keep[k] = first of its row, or (int64)((t[k]-t[k-1])/tol) > 1
 __global__ void __launch_bounds__(RD_BLOCK)
 rd_mark_kernel(const double *__restrict__ spt, int64_t n_spk, const int64_t *__restrict__ offsets,
-               int64_t n_rows, double tol, uint8_t *__restrict__ keep, int32_t *__restrict__ counts)
+               int64_t n_rows, double tol, const double *__restrict__ prev_last,
+               uint8_t *__restrict__ keep, int32_t *__restrict__ counts)
 {
     __shared__ int warp_cnt[RD_BLOCK / 32];
     const int64_t k = (int64_t)blockIdx.x * RD_BLOCK + threadIdx.x;
     bool kp = false;
     if (k < n_spk) {
         const int64_t r = n_rows > 1 ? find_row(offsets, n_rows, k) : 0;
-        if (k == __ldg(offsets + r)) kp = true;
-        else {
+        if (k == __ldg(offsets + r)) {
+            // first of its row: kept, unless the previous time shard ended within tol
+            // (prev_last[r] = last aligned time of the row there, NaN if none)
+            kp = true;
+            if (prev_last) {
+                const double pl = prev_last[r];
+                if (pl == pl) kp = __double2ll_rz(__ddiv_rn(__dsub_rn(spt[k], pl), tol)) > 1;
+            }
+        } else {
             const double isi = __dsub_rn(spt[k], spt[k - 1]);
             kp = __double2ll_rz(__ddiv_rn(isi, tol)) > 1;
         }
@@ -172,6 +181,7 @@ extern "C" int ss_align(const void *d_x, int dtype, int64_t n_samples, int64_t l
                         const int32_t *d_rows, int64_t n_rows, const int64_t *d_offsets,
                         double sp_win0, int win0, int win1, double t_min, double t_max, double lo,
                         double hi, int use_min, double *d_spt, int64_t n_spk, int max_iter,
+                        int64_t index_offset, int64_t halo_before, int64_t halo_after,
                         void *stream)
 {
     if (n_spk == 0) return SS_OK;
@@ -183,10 +193,11 @@ extern "C" int ss_align(const void *d_x, int dtype, int64_t n_samples, int64_t l
     SS_REQUIRE(win1 - win0 <= ss_max_window(), SS_ERR_UNSUPPORTED,
                "align: window of %d samples > %d", win1 - win0, ss_max_window());
     SS_REQUIRE(n_spk > 0 && max_iter > 0, SS_ERR_ARG, "align: bad n_spk/max_iter");
+    SS_REQUIRE(halo_before >= 0 && halo_after >= 0, SS_ERR_ARG, "align: negative halo");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     align_kernel<<<(unsigned)ss_cdiv(n_spk, AL_WARPS), 32 * AL_WARPS, 0, st>>>(
         d_x, dtype, n_samples, ld, FS, d_rows, n_rows, d_offsets, sp_win0, win0, win1, t_min,
-        t_max, lo, hi, use_min, d_spt, n_spk, max_iter);
+        t_max, lo, hi, use_min, d_spt, n_spk, max_iter, index_offset, halo_before, halo_after);
     SS_LAUNCH_CHECK("align_kernel");
     return SS_OK;
 }
@@ -197,8 +208,9 @@ extern "C" size_t ss_remove_doubles_workspace_bytes(int64_t n_spk)
 }
 
 extern "C" int ss_remove_doubles_mark(const double *d_spt, int64_t n_spk, const int64_t *d_offsets,
-                                      int64_t n_rows, double tol, void *d_ws, size_t ws_bytes,
-                                      int64_t *d_offsets_out, void *stream)
+                                      int64_t n_rows, double tol, const double *d_prev_last,
+                                      void *d_ws, size_t ws_bytes, int64_t *d_offsets_out,
+                                      void *stream)
 {
     SS_REQUIRE(d_offsets && d_offsets_out && d_ws, SS_ERR_ARG, "remove_doubles: null pointer");
     SS_REQUIRE(n_spk >= 0 && n_rows >= 1, SS_ERR_ARG, "remove_doubles: bad shape");
@@ -210,7 +222,7 @@ extern "C" int ss_remove_doubles_mark(const double *d_spt, int64_t n_spk, const 
     int32_t *counts = reinterpret_cast<int32_t *>(ws + L.off_counts);
     int64_t *boff = reinterpret_cast<int64_t *>(ws + L.off_offsets);
     rd_mark_kernel<<<(unsigned)L.n_blocks, RD_BLOCK, 0, st>>>(d_spt, n_spk, d_offsets, n_rows, tol,
-                                                             keep, counts);
+                                                             d_prev_last, keep, counts);
     SS_LAUNCH_CHECK("rd_mark_kernel");
     ssb::scan_counts_kernel<<<1, ssb::SCAN_THREADS, 0, st>>>(counts, L.n_blocks, boff, 0, 0,
                                                              nullptr);

@@ -83,8 +83,8 @@ detect_mark_kernel(const T *__restrict__ x, int64_t n_samples, int64_t ld,
 // one WARP per 8192-sample block (most blocks hold no crossing and leave at once)
 __global__ void __launch_bounds__(32 * DT_WARPS)
 detect_emit_kernel(const uint32_t *__restrict__ mask, const int64_t *__restrict__ offsets,
-                   int64_t n_blocks, int64_t blocks_per_row, double FS, double *__restrict__ spt,
-                   int64_t cap)
+                   int64_t n_blocks, int64_t blocks_per_row, double FS, int64_t index_offset,
+                   double *__restrict__ spt, int64_t cap)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t blk = (int64_t)blockIdx.x * DT_WARPS + warp;
@@ -104,7 +104,7 @@ detect_emit_kernel(const uint32_t *__restrict__ mask, const int64_t *__restrict_
             if (lane >= d) inc += o;
         }
         int64_t p = pos + inc - c;
-        const int64_t i0 = (b * DT_BLOCK_WORDS + 32 * j + lane) * 32;
+        const int64_t i0 = (b * DT_BLOCK_WORDS + 32 * j + lane) * 32 + index_offset;
         while (m) {
             const int bit = __ffs(m) - 1;
             m &= m - 1;
@@ -287,8 +287,9 @@ extern "C" int ss_detect_mark(const void *d_x, int dtype, int64_t n_rows, int64_
     return SS_OK;
 }
 
-extern "C" int ss_detect_emit(int64_t n_rows, int64_t n_samples, double FS, const void *d_ws,
-                              size_t ws_bytes, double *d_spt, int64_t cap, void *stream)
+extern "C" int ss_detect_emit(int64_t n_rows, int64_t n_samples, double FS, int64_t index_offset,
+                              const void *d_ws, size_t ws_bytes, double *d_spt, int64_t cap,
+                              void *stream)
 {
     SS_REQUIRE(d_ws, SS_ERR_ARG, "detect_emit: null pointer");
     SS_REQUIRE(n_rows > 0 && n_samples > 0, SS_ERR_ARG, "detect_emit: bad shape");
@@ -301,7 +302,7 @@ extern "C" int ss_detect_emit(int64_t n_rows, int64_t n_samples, double FS, cons
     detect_emit_kernel<<<(unsigned)ss_cdiv(L.n_blocks, DT_WARPS), 32 * DT_WARPS, 0, st>>>(
         reinterpret_cast<const uint32_t *>(ws + L.off_mask),
         reinterpret_cast<const int64_t *>(ws + L.off_offsets), L.n_blocks, L.blocks_per_row, FS,
-        d_spt, cap);
+        index_offset, d_spt, cap);
     SS_LAUNCH_CHECK("detect_emit_kernel");
     return SS_OK;
 }

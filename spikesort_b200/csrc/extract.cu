@@ -38,7 +38,8 @@ extract_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t
                const int32_t *__restrict__ rows, int64_t n_rows, const int64_t *__restrict__ offsets,
                int win0, int n_win, double t_min, double t_max,
                const double *__restrict__ spt, int64_t n_spk,
-               float *__restrict__ waves, uint8_t *__restrict__ valid, int32_t *__restrict__ n_invalid)
+               float *__restrict__ waves, uint8_t *__restrict__ valid, int32_t *__restrict__ n_invalid,
+               int64_t index_offset, int64_t halo_before, int64_t halo_after)
 {
     extern __shared__ float tile[];                 // [n_win][EX_PAIRS + 1]
     __shared__ int64_t s_first[EX_PAIRS];           // first sample of the window, per local spike
@@ -54,7 +55,7 @@ extract_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t
         if (s < n_spk) {
             const double t = spt[s];
             const int centre = __double2int_rz(__dmul_rn(__ddiv_rn(t, 1000.0), FS));
-            first = (int64_t)centre + win0;
+            first = (int64_t)centre + win0 - index_offset;          // local index
             if (!contacts) {
                 int64_t r = n_rows > 1 ? ex_find_row(offsets, n_rows, s) : 0;
                 if (rows) r = rows[r];
@@ -83,7 +84,8 @@ extract_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t
         for (int w = lane; w < n_win; w += 32) {
             const int64_t i = first + w;
             float v = 0.f;
-            if (live && i >= 0 && i < n_samples) v = ss_load_f32(x, dtype, base + i);
+            if (live && i >= -halo_before && i < n_samples + halo_after)
+                v = ss_load_f32(x, dtype, base + i);
             tile[w * (EX_PAIRS + 1) + p] = v;
         }
     }
@@ -108,7 +110,8 @@ extern "C" int ss_extract(const void *d_x, int dtype, int64_t n_samples, int64_t
                           const int32_t *d_contacts, int n_c, const int32_t *d_rows, int64_t n_rows,
                           const int64_t *d_offsets, int win0, int win1, double t_min, double t_max,
                           const double *d_spt, int64_t n_spk, float *d_waves, uint8_t *d_valid,
-                          int32_t *d_n_invalid, void *stream)
+                          int32_t *d_n_invalid, int64_t index_offset, int64_t halo_before,
+                          int64_t halo_after, void *stream)
 {
     SS_REQUIRE(d_n_invalid, SS_ERR_ARG, "extract: null d_n_invalid");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -135,7 +138,8 @@ extern "C" int ss_extract(const void *d_x, int dtype, int64_t n_samples, int64_t
     const dim3 grid((unsigned)ss_cdiv(n_spk, SB), (unsigned)ss_cdiv(n_c, CB));
     extract_kernel<<<grid, EX_PAIRS, smem, st>>>(d_x, dtype, n_samples, ld, FS, d_contacts, n_c, CB,
                                                 d_rows, n_rows, d_offsets, win0, n_win, t_min, t_max,
-                                                d_spt, n_spk, d_waves, d_valid, d_n_invalid);
+                                                d_spt, n_spk, d_waves, d_valid, d_n_invalid,
+                                                index_offset, halo_before, halo_after);
     SS_LAUNCH_CHECK("extract_kernel");
     return SS_OK;
 }

@@ -247,7 +247,10 @@ __device__ __forceinline__ void load_tile(const void *x, const FiltGeom &g, cons
     const int64_t row0 = ti.c * g.ld_in;
     const int64_t e0 = ti.t * FS_T - ti.pad;            // ext index of the tile's first sample
     const int64_t r0 = e0 - g.edge;                     // chunk-relative index
-    if (r0 >= 0 && r0 + FS_T <= ti.L) {
+    const bool interior = r0 >= 0 && r0 + FS_T <= ti.L;
+    if (interior) {
+        // (staging int16 tiles as int16 + 128-bit reads was measured SLOWER on B200: the
+        //  unpacking instructions cost more issue slots than the shared-memory bytes saved)
         const int64_t base = row0 + ti.cs0 + r0;
         if (g.dtype == SS_I16)
             load_tile_fast(reinterpret_cast<const int16_t *>(x) + base, sm, lane);
@@ -307,7 +310,7 @@ __device__ __forceinline__ void summary_group_fast(const T *__restrict__ p, int 
 }
 
 template <int NS>
-__global__ void __launch_bounds__(32 * SM_WPB)
+__global__ void __launch_bounds__(32 * SM_WPB, NS <= 2 ? 4 : 1)
 filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *__restrict__ tab,
                     double *__restrict__ F, double *__restrict__ Bz, double *__restrict__ ylast)
 {
@@ -1058,7 +1061,7 @@ extern "C" int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_cont
                                       int64_t ld_out, void *d_ws, size_t ws_bytes, int auto_thr,
                                       int64_t n0, double factor, double *d_thr, int falling,
                                       void *d_det_ws, size_t det_ws_bytes, int64_t *d_offsets,
-                                      void *stream)
+                                      int prepared, void *stream)
 {
     SS_REQUIRE(d_x && d_out && sos && d_ws && d_thr && d_det_ws && d_offsets, SS_ERR_ARG,
                "filtfilt_detect: null pointer");
@@ -1088,8 +1091,10 @@ extern "C" int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_cont
         j0 = ss_cdiv(n0, chunksize);
         if (j0 > pl.g.units_per_contact) j0 = pl.g.units_per_contact;
         // sweep 1 and the tile scan do not depend on the thresholds: all chunks at once
-        rc = run_plan(pl, d_x, 0, pl.g.units_per_contact, sos, d_out, d_ws, nullptr, PH_SUMMARY, st);
-        if (rc) return rc;
+        if (!prepared) {
+            rc = run_plan(pl, d_x, 0, pl.g.units_per_contact, sos, d_out, d_ws, nullptr, PH_SUMMARY, st);
+            if (rc) return rc;
+        }
         rc = run_plan(pl, d_x, 0, j0, sos, d_out, d_ws, nullptr, PH_APPLY, st);
         if (rc) return rc;
         rc = ss_var_threshold(d_out, SS_F64, n_contacts, ld_out, n0, factor, d_thr,
@@ -1104,7 +1109,7 @@ extern "C" int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_cont
         // second pass has written head_end (boundary kernel of the head range, below)
     }
     rc = run_plan(pl, d_x, j0, pl.g.units_per_contact - j0, sos, d_out, d_ws, &mk,
-                  auto_thr ? PH_APPLY : PH_ALL, st);
+                  (auto_thr || prepared) ? PH_APPLY : PH_ALL, st);
     if (rc) return rc;
     if (j0 > 0 && j0 < pl.g.units_per_contact) {
         // chunk-end pair of the last head chunk of every contact
@@ -1116,4 +1121,43 @@ extern "C" int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_cont
         SS_LAUNCH_CHECK("filt_boundary_mark_kernel");
     }
     return ssi::count_and_scan(n_contacts, n_samples, d_det_ws, d_offsets, st);
+}
+
+extern "C" int ss_filtfilt_prepare_sos(const void *d_x, int dtype, int64_t n_contacts,
+                                       int64_t n_samples, int64_t ld_in, const double *sos,
+                                       int n_sections, int padlen, int64_t chunksize, void *d_ws,
+                                       size_t ws_bytes, void *stream)
+{
+    SS_REQUIRE(d_x && sos && d_ws, SS_ERR_ARG, "filtfilt_prepare: null pointer");
+    FiltPlan pl;
+    const int rc = make_plan(pl, dtype, n_contacts, n_samples, ld_in, sos, n_sections, padlen,
+                             chunksize, n_samples, ws_bytes);
+    if (rc) return rc;
+    return run_plan(pl, d_x, 0, pl.g.units_per_contact, sos, nullptr, d_ws, nullptr, PH_SUMMARY,
+                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ss_filtfilt_head_threshold_sos(const void *d_x, int dtype, int64_t n_contacts,
+                                              int64_t n_samples, int64_t ld_in, const double *sos,
+                                              int n_sections, int padlen, int64_t chunksize,
+                                              double *d_out, int64_t ld_out, void *d_ws,
+                                              size_t ws_bytes, int64_t n0, double factor,
+                                              double *d_thr, void *d_thr_ws, size_t thr_ws_bytes,
+                                              void *stream)
+{
+    SS_REQUIRE(d_x && d_out && sos && d_ws && d_thr && d_thr_ws, SS_ERR_ARG,
+               "filtfilt_head_threshold: null pointer");
+    SS_REQUIRE(n0 > 0, SS_ERR_ARG, "filtfilt_head_threshold: n0 must be positive");
+    FiltPlan pl;
+    int rc = make_plan(pl, dtype, n_contacts, n_samples, ld_in, sos, n_sections, padlen, chunksize,
+                       ld_out, ws_bytes);
+    if (rc) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (n0 > n_samples) n0 = n_samples;
+    int64_t j0 = ss_cdiv(n0, chunksize);
+    if (j0 > pl.g.units_per_contact) j0 = pl.g.units_per_contact;
+    rc = run_plan(pl, d_x, 0, j0, sos, d_out, d_ws, nullptr, PH_APPLY, st);
+    if (rc) return rc;
+    return ss_var_threshold(d_out, SS_F64, n_contacts, ld_out, n0, factor, d_thr, d_thr_ws,
+                            thr_ws_bytes, stream);
 }

@@ -4,25 +4,38 @@ NVLink on the B200 box, gloo in the CPU tests) for the few real exchange steps.
 The reference filters every (contact, chunk) unit independently
 (``src/spike_sort/core/filters.py:137-141``), so a recording sharded by TIME in
 multiples of ``chunksize`` needs no filter halo and no communication for the filter
-(SURVEY.md section 8e).  What does cross shard boundaries:
+(SURVEY.md section 8e).  What does cross shard boundaries, and how it is exchanged:
 
-* the ``'auto'`` threshold uses only the first ``int(10*FS)`` samples
-  (``extract.py:79``): the rank owning them computes it, everyone gets it by
-  **broadcast**;
-* a crossing between the last sample of shard r and the first of shard r+1
-  (``extract.py:91``): one float64 per contact from the right neighbour
-  (**send/recv**), merged into the spike list of shard r;
-* PCA is over ALL spikes of a contact (``features.py:224-231``): per-contact Gram
-  matrices, sums and counts are **all-reduced** (float64, a few MB), the reference
-  waveform that conditions the Gram is **broadcast** from rank 0, the tiny eigensolve
-  is replicated, projection stays local;
-* per-shard spike counts are **all-gathered** so every rank knows the global layout
-  of the (time-ordered) concatenated spike list.
+====================================  ===========================================
+``'auto'`` threshold: first            computed by rank 0 (which owns them) from its
+``int(10*FS)`` samples                 head chunks, **broadcast** (n_contacts float64)
+(``extract.py:79``)
+crossing between the last sample of    first filtered sample of every contact from
+shard r and the first of r+1           the right neighbour (**send/recv**)
+(``extract.py:91``)
+windows of spikes near a shard edge    ``H`` filtered samples per contact from both
+(``extract.py:160-163,245``)           neighbours (**send/recv**) into the margins of
+                                       the shard's own buffer (kernels take
+                                       ``halo_before/halo_after``)
+``np.diff`` across the boundary in     last ALIGNED time of every contact from the
+``remove_doubles`` (``:281``)          left neighbour (**send/recv**)
+PCA over ALL spikes of a contact       shared reference waveform (**all-gather**),
+(``features.py:224-231``)              Gram + sums + counts (**all-reduce**, float64,
+                                       2.9 MB at 384 contacts); eigensolve replicated
+global layout of the spike list        per-shard counts (**all-gather**)
+====================================  ===========================================
 
-The collective helpers below work on whatever device the tensors live on, so the
-world_size-2 gloo tests exercise exactly this code on CPU tensors.
+Spike times are GLOBAL (``index_offset``): the concatenation of the per-rank lists in
+rank order is, per contact, exactly the list the single-GPU chain produces
+(``tests/test_gpu_sharded.py`` checks this bit for bit by running the phases of
+several shards on one GPU).
+
+``ShardedChain`` splits the chain into phases separated by exactly those exchanges, so
+the same code runs under NCCL (``run_chain_sharded``), under gloo on CPU tensors (the
+helpers, ``tests/test_dist_gloo.py``) and in the single-GPU emulation.
 """
 from . import _lib, _ops
+from .pipeline import ChainResult
 
 _FALLING = ('falling', 'min')
 
@@ -39,6 +52,7 @@ def world():
     return 0, 1
 
 
+# ------------------------------------------------------------------ collectives
 def share_thresholds(thr, src=0):
     """Broadcast the per-contact thresholds from the rank owning the first 10 s."""
     rank, n = world()
@@ -47,24 +61,36 @@ def share_thresholds(thr, src=0):
     return thr
 
 
+def exchange_with_neighbours(to_left, to_right):
+    """Send `to_left` to rank-1 and `to_right` to rank+1; returns (from_left, from_right)
+    (None where there is no neighbour).  Tensors are contiguous and of equal shape on
+    every rank."""
+    t = _lib.torch()
+    rank, n = world()
+    if n == 1:
+        return None, None
+    d = _dist()
+    from_left = t.empty_like(to_right) if rank > 0 else None
+    from_right = t.empty_like(to_left) if rank < n - 1 else None
+    ops = []
+    if rank > 0:
+        ops.append(d.P2POp(d.isend, to_left.contiguous(), rank - 1))
+        ops.append(d.P2POp(d.irecv, from_left, rank - 1))
+    if rank < n - 1:
+        ops.append(d.P2POp(d.isend, to_right.contiguous(), rank + 1))
+        ops.append(d.P2POp(d.irecv, from_right, rank + 1))
+    for req in d.batch_isend_irecv(ops):
+        req.wait()
+    return from_left, from_right
+
+
 def exchange_first_samples(first):
     """`first`: (n_contacts,) float64, the first filtered sample of every contact of
     this shard.  Returns the right neighbour's `first` (NaN on the last rank: no
     crossing can be formed with NaN)."""
     t = _lib.torch()
-    rank, n = world()
-    nxt = t.full_like(first, float('nan'))
-    if n == 1:
-        return nxt
-    d = _dist()
-    ops = []
-    if rank > 0:
-        ops.append(d.P2POp(d.isend, first.contiguous(), rank - 1))
-    if rank < n - 1:
-        ops.append(d.P2POp(d.irecv, nxt, rank + 1))
-    for req in d.batch_isend_irecv(ops):
-        req.wait()
-    return nxt
+    _, from_right = exchange_with_neighbours(first, first.new_zeros(first.shape))
+    return from_right if from_right is not None else t.full_like(first, float('nan'))
 
 
 def boundary_crossings(last, nxt, thr, falling):
@@ -80,17 +106,19 @@ def append_boundary_spikes(spt, offsets, mask, t_last):
     (it is the largest index of the shard, so order is kept).  Returns (spt, offsets)."""
     t = _lib.torch()
     add = mask.to(t.int64)
-    if int(add.sum()) == 0:
+    n_add = int(add.sum())                                  # the one host sync of this step
+    if n_add == 0:
         return spt, offsets
     counts = offsets[1:] - offsets[:-1]
-    new_counts = counts + add
     new_off = t.zeros_like(offsets)
-    new_off[1:] = t.cumsum(new_counts, 0)
-    out = t.empty(int(new_off[-1]), dtype=spt.dtype, device=spt.device)
-    rows = t.repeat_interleave(t.arange(counts.numel(), device=spt.device), counts)
-    pos = t.arange(spt.numel(), device=spt.device) - offsets[:-1][rows] + new_off[:-1][rows]
-    out[pos] = spt
-    out[(new_off[1:] - 1)[mask]] = t_last
+    new_off[1:] = t.cumsum(counts + add, 0)
+    n_old = spt.numel()
+    out = t.full((n_old + n_add,), float(t_last), dtype=spt.dtype, device=spt.device)
+    # old element k of row r moves right by the number of boundary spikes of rows < r
+    shift = t.cumsum(add, 0) - add                          # exclusive
+    rows = t.repeat_interleave(t.arange(counts.numel(), device=spt.device), counts,
+                               output_size=n_old)
+    out[t.arange(n_old, device=spt.device) + shift[rows]] = spt
     return out, new_off
 
 
@@ -109,10 +137,18 @@ def merge_gram(gram, ssum, counts):
     return gram, ssum, counts
 
 
+def pick_reference(stack_flags, stack_refs):
+    """Per contact, the reference waveform of the lowest shard that has a spike there.
+    stack_flags: (world, n_contacts) bool, stack_refs: (world, n_contacts, n_win)."""
+    t = _lib.torch()
+    first = t.argmax(stack_flags.to(t.int64), dim=0)        # 0 if none
+    idx = first[None, :, None].expand(1, stack_refs.shape[1], stack_refs.shape[2])
+    return t.gather(stack_refs, 0, idx)[0].contiguous()
+
+
 def share_reference(ref, has_spikes):
     """Every rank must shift its waveforms by the SAME reference before the Gram
-    (ss_pca_gram): take, per contact, the reference of the lowest rank that has a
-    spike there.  Implemented as an all-gather of (flag, ref) and a local pick."""
+    (ss_pca_gram): all-gather of (flag, ref) and a local pick."""
     rank, n = world()
     if n == 1:
         return ref
@@ -122,10 +158,7 @@ def share_reference(ref, has_spikes):
     allp = [t.empty_like(packed) for _ in range(n)]
     d.all_gather(allp, packed)
     stack = t.stack(allp)                                   # (world, n_contacts, 1 + n_win)
-    flags = stack[:, :, 0] > 0.5
-    first = t.argmax(flags.to(t.int64), dim=0)              # lowest rank with a spike (0 if none)
-    idx = first[None, :, None].expand(1, stack.shape[1], stack.shape[2] - 1)
-    return t.gather(stack[:, :, 1:], 0, idx)[0].contiguous()
+    return pick_reference(stack[:, :, 0] > 0.5, stack[:, :, 1:])
 
 
 def gather_counts(offsets):
@@ -140,59 +173,143 @@ def gather_counts(offsets):
     return t.stack(allc)
 
 
+# ---------------------------------------------------------------- phased chain
+class ShardedChain(object):
+    """One time shard of the chain, as phases separated by the exchange steps."""
+
+    def __init__(self, x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
+                 thresh='auto', ncomps=2, chunksize=1E6, rank=0, n_ranks=1, index_offset=0,
+                 n_total=None, halo=None):
+        t = _lib.require_cuda()
+        self.t = t
+        self.x, self.FS, self.filt = x, FS, filt
+        self.sp_win = list(sp_win)
+        self.falling = edge in _FALLING
+        self.use_min = align_type == 'min'
+        self.thresh, self.ncomps, self.chunksize = thresh, ncomps, int(chunksize)
+        self.rank, self.n_ranks = rank, n_ranks
+        self.n_c, self.n = x.shape
+        win0, win1, self.time = _ops.window_params(self.sp_win, FS)
+        self.n_win = win1 - win0
+        self.H = min(4 * self.n_win if halo is None else int(halo), self.n)
+        self.shard = _ops.Shard(index_offset, self.n if n_total is None else n_total,
+                                self.H if rank > 0 else 0, self.H if rank < n_ranks - 1 else 0)
+        self.sos, self.padlen = filt.sections(FS)
+        self.res = ChainResult()
+        # filtered signal with room for the neighbours' samples on both sides
+        self.buf = t.empty((self.n_c, self.n + 2 * self.H), dtype=t.float64, device=x.device)
+        self.sig = self.buf[:, self.H:self.H + self.n]
+
+    # 1. sweep 1 of the filter (needs nothing from other ranks)
+    def prepare(self):
+        self.ws = _ops.filtfilt_prepare(self.x, self.sos, self.padlen, self.chunksize)
+
+    # 2. rank 0: thresholds from its head chunks (then broadcast)
+    def head_threshold(self):
+        if not isinstance(self.thresh, str):
+            return self.t.full((self.n_c,), float(self.thresh), dtype=self.t.float64,
+                               device=self.x.device)
+        frac = 8.0 if self.thresh == 'auto' else float(self.thresh)
+        return _ops.filtfilt_head_threshold(self.x, self.sos, self.padlen, self.chunksize,
+                                            self.sig, self.ws, int(10 * self.FS),
+                                            -frac if self.falling else frac)
+
+    # 3. sweep 2 with fused crossing marks; returns what the neighbours need
+    def filter_detect(self, thr):
+        r = self.res
+        r.thresh = thr
+        _, _, spt, offsets = _ops.filtfilt_detect(
+            self.x, self.sos, self.padlen, self.chunksize, self.FS, self.falling, thr=thr,
+            out=self.sig, ws=self.ws, shard=self.shard)
+        r.filtered = self.sig
+        self._spt, self._offsets = spt, offsets
+        H = self.H
+        left_slab = self.sig[:, :H].contiguous()            # becomes rank-1's right halo
+        right_slab = self.sig[:, self.n - H:].contiguous()  # becomes rank+1's left halo
+        return left_slab, right_slab
+
+    # 4. halos in place, boundary crossing, alignment; returns the last aligned times
+    def align(self, halo_left, halo_right):
+        t, r = self.t, self.res
+        H = self.H
+        if halo_left is not None:
+            self.buf[:, :H] = halo_left
+        if halo_right is not None:
+            self.buf[:, H + self.n:] = halo_right
+            nxt = halo_right[:, 0].contiguous()
+            mask = boundary_crossings(self.sig[:, self.n - 1], nxt, r.thresh, self.falling)
+            t_last = (self.shard.index_offset + self.n - 1) * 1000.0 / self.FS
+            self._spt, self._offsets = append_boundary_spikes(self._spt, self._offsets, mask,
+                                                              t_last)
+        r.spt_detected, r.offsets_detected = self._spt, self._offsets
+        spt = self._spt.clone()
+        _ops.align(self.sig, spt, self._offsets, None, self.FS, self.sp_win, self.use_min,
+                   shard=self.shard)
+        self._aligned = spt
+        off = self._offsets
+        last = t.full((self.n_c,), float('nan'), dtype=t.float64, device=spt.device)
+        if spt.numel() > 0:
+            has = off[1:] > off[:-1]
+            last = t.where(has, spt[(off[1:] - 1).clamp(min=0)], last)    # no host sync
+        return last
+
+    # 5. duplicate removal (knowing the left neighbour's last times), extraction
+    def extract(self, prev_last):
+        t, r = self.t, self.res
+        spt, offsets = _ops.remove_doubles(self._aligned, self._offsets, 1000.0 / self.FS,
+                                           prev_last=prev_last)
+        r.spt, r.offsets = spt, offsets
+        waves, valid, n_invalid = _ops.extract(self.sig, spt, self.FS, self.sp_win, contacts=None,
+                                               offsets=offsets, shard=self.shard)
+        r.waves, r.valid, r.n_invalid, r.time = waves, valid, n_invalid, self.time
+        counts = (offsets[1:] - offsets[:-1]).contiguous()
+        if spt.numel() > 0:
+            first = offsets[:-1].clamp(max=spt.numel() - 1)
+            ref = waves[:, first, 0].t().to(t.float64).contiguous()
+        else:
+            ref = t.zeros((self.n_c, self.n_win), dtype=t.float64, device=spt.device)
+        return ref, counts > 0
+
+    # 6. partial Gram with the shared reference
+    def gram(self, ref):
+        gram, ssum, _, counts = _ops.pca_gram(self.res.waves, offsets=self.res.offsets, ref=ref)
+        return gram, ssum, counts
+
+    # 7. replicated eigensolve + local projection
+    def project(self, gram, ssum, counts):
+        r = self.res
+        r.evals, r.evecs = _ops.pca_eig(gram.contiguous(), ssum.contiguous(), counts.contiguous())
+        r.scores = _ops.pca_project(r.waves, r.evals, r.evecs, self.ncomps, offsets=r.offsets)
+        return r
+
+
 def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
-                      thresh='auto', ncomps=2, chunksize=1E6):
-    """The chain of pipeline.run_chain on this rank's time shard `x` (CUDA tensor,
-    n_samples a multiple of chunksize), with the exchange steps listed in the module
-    docstring.  Spike times are relative to the start of the shard; `all_counts`
-    gives the global layout."""
-    from .pipeline import ChainResult
+                      thresh='auto', ncomps=2, chunksize=1E6, index_offset=None, n_total=None):
+    """The chain on this rank's time shard `x` (CUDA tensor, every rank the same number
+    of samples unless index_offset/n_total say otherwise), with the exchange steps of
+    the module docstring.  Spike times are global; `all_counts` gives the layout of the
+    concatenated list."""
     t = _lib.require_cuda()
     rank, n_ranks = world()
-    sp_win = list(sp_win)
-    res = ChainResult()
-    falling = edge in _FALLING
-    if filt is not None:
-        sos, padlen = filt.sections(FS)
-        sig = _ops.filtfilt_sos(x, sos, padlen, int(chunksize))
-    else:
-        sig = x
-    res.filtered = sig
-    n_rows, n = sig.shape
-    if isinstance(thresh, str):
-        frac = 8.0 if thresh == 'auto' else float(thresh)
-        if rank == 0:
-            thr = _ops.var_threshold(sig, int(10 * FS), -frac if falling else frac)
-        else:
-            thr = t.empty(n_rows, dtype=t.float64, device=sig.device)
-        thr = share_thresholds(thr, 0)
-    else:
-        thr = t.full((n_rows,), float(thresh), dtype=t.float64, device=sig.device)
-    res.thresh = thr
-    spt, offsets = _ops.detect(sig, thr, falling, FS)
-    nxt = exchange_first_samples(sig[:, 0].to(t.float64).contiguous())
-    mask = boundary_crossings(sig[:, n - 1].to(t.float64), nxt, thr, falling)
-    spt, offsets = append_boundary_spikes(spt, offsets, mask, (n - 1) * 1000.0 / FS)
-    res.spt_detected, res.offsets_detected = spt, offsets
-    spt = spt.clone()
-    _ops.align(sig, spt, offsets, None, FS, sp_win, align_type == 'min')
-    spt, offsets = _ops.remove_doubles(spt, offsets, 1000.0 / FS)
-    res.spt, res.offsets = spt, offsets
-    res.all_counts = gather_counts(offsets)
-    waves, valid, n_invalid = _ops.extract(sig, spt, FS, sp_win, contacts=None, offsets=offsets)
-    res.waves, res.valid, res.n_invalid = waves, valid, n_invalid
-    res.time = _ops.window_params(sp_win, FS)[2]
-    # PCA over all shards: shared reference, all-reduced Gram, replicated eigensolve
-    n_win = waves.shape[0]
-    counts = (offsets[1:] - offsets[:-1]).contiguous()
-    if spt.numel() > 0:
-        first = offsets[:-1].clamp(max=spt.numel() - 1)
-        ref = waves[:, first, 0].t().to(t.float64).contiguous()
-    else:
-        ref = t.zeros((n_rows, n_win), dtype=t.float64, device=sig.device)
-    ref = share_reference(ref, counts > 0)
-    gram, ssum, _, _ = _ops.pca_gram(waves, offsets=offsets, ref=ref)
+    n = x.shape[1]
+    if index_offset is None:
+        index_offset = rank * n
+    if n_total is None:
+        n_total = n_ranks * n
+    ch = ShardedChain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize, rank,
+                      n_ranks, index_offset, n_total)
+    ch.prepare()
+    thr = ch.head_threshold() if rank == 0 else t.empty(x.shape[0], dtype=t.float64,
+                                                        device=x.device)
+    thr = share_thresholds(thr, 0)
+    left_slab, right_slab = ch.filter_detect(thr)
+    halo_left, halo_right = exchange_with_neighbours(left_slab, right_slab)
+    last = ch.align(halo_left, halo_right)
+    prev_last, _ = exchange_with_neighbours(t.zeros_like(last), last)
+    ref, has = ch.extract(prev_last)
+    ref = share_reference(ref, has)
+    gram, ssum, counts = ch.gram(ref)
     gram, ssum, counts = merge_gram(gram, ssum, counts)
-    res.evals, res.evecs = _ops.pca_eig(gram.contiguous(), ssum.contiguous(), counts.contiguous())
-    res.scores = _ops.pca_project(waves, res.evals, res.evecs, ncomps, offsets=offsets)
+    res = ch.project(gram, ssum, counts)
+    res.all_counts = gather_counts(res.offsets)
     return res
