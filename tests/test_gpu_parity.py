@@ -364,3 +364,65 @@ def test_full_size_properties(env):
         assert abs(float(s[:, 0].var()) - 1.0) < 1e-6
         vt = evecs[c].t() @ evecs[c]
         assert float((vt - torch.eye(vt.shape[0], device=vt.device, dtype=vt.dtype)).abs().max()) < 1e-12
+
+
+def test_burst_stress_384_channels(env, oracle):
+    """BASELINE.json configs[3]: >= 200 Hz/channel bursts on 384 channels - compaction,
+    alignment re-queue, duplicate removal and the Gram at high spike density.  The whole
+    recording runs through the batched chain; a sample of contacts is checked against the
+    oracle (bit-exact given the same filtered signal), the rest through invariants."""
+    torch, ops = env['torch'], env['ops']
+    FS, n_c, n = 30000, 384, 300000                       # 10 s
+    x = env['synth'].make_recording(n_c, n, FS, seed=4, device=env['dev'], rate_hz=220.0,
+                                    noise=6.0, amp=(60.0, 150.0), burst=True, negative=True)
+    flt = env['ss'].filters.Filter(800., 100.)
+    sp_win = [-0.2, 0.8]
+    res = env['pipeline'].run_chain(x, FS, filt=flt, sp_win=sp_win, edge='falling',
+                                    align_type='min', thresh='4', ncomps=2, chunksize=100000)
+    off = res.offsets.cpu().numpy()
+    offd = res.offsets_detected.cpu().numpy()
+    counts = np.diff(off)
+    assert counts.min() > 1000 and off[-1] == res.spt.numel() == res.waves.shape[1]
+    assert (np.diff(offd) >= counts).all() and (np.diff(offd) > counts).any()   # doubles removed
+    assert res.scores.shape == (off[-1], 2) and bool(torch.isfinite(res.scores).all())
+    filtered = res.filtered
+    for c in (0, 191, 383):
+        raw = {'data': filtered[c:c + 1].cpu().numpy(), 'FS': FS, 'n_contacts': 1}
+        thr = float(res.thresh[c])
+        det = oracle.detect_spikes(raw, thresh=np.float64(thr), edge='falling', contact=0)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            al = oracle.align_spikes(raw, det, sp_win, type='min', contact=0)
+        wv = oracle.extract_spikes(raw, al, sp_win, contacts=0)
+        got = res.per_contact(c)
+        assert np.array_equal(got['spt_detected'], det['data'])
+        assert np.array_equal(got['spt'], al['data'])
+        assert np.array_equal(got['waves'], wv['data'])
+        ft = oracle.fetPCA(wv, ncomps=2)
+        assert rel_err(sign_normalise(got['scores'], ft['data']), ft['data']) < 1e-9
+
+
+def test_fetpca_ten_million_waveforms_properties(env):
+    """BASELINE.json configs[4]: fetPCA only on 10 M pre-extracted 4-contact waveforms
+    (25 x 10 000 000 x 4 float32 = 4 GB).  Size-independent properties: whitened scores
+    have unit variance and are uncorrelated; eigenvectors orthonormal; the Gram of a
+    subsample agrees with torch's float64 covariance."""
+    torch, ops = env['torch'], env['ops']
+    n_win, n_spk, n_c = 25, 10000000, 4
+    w = env['synth'].make_waveforms(n_win, n_spk, n_c, seed=5, device=env['dev'])
+    gram, ssum, ref, counts = ops.pca_gram(w)
+    evals, evecs = ops.pca_eig(gram, ssum, counts)
+    scores = ops.pca_project(w, evals, evecs, 2)
+    assert scores.shape == (n_spk, 8)
+    cov = torch.cov(scores[:2000000].t())
+    for c in range(n_c):                                   # PCs of ONE contact are uncorrelated
+        blk = cov[2 * c:2 * c + 2, 2 * c:2 * c + 2]
+        assert float((blk - torch.eye(2, device=cov.device, dtype=cov.dtype)).abs().max()) < 0.01
+    v = scores.var(dim=0)
+    assert float((v - 1).abs().max()) < 1e-6
+    for c in range(n_c):
+        vt = evecs[c].t() @ evecs[c]
+        assert float((vt - torch.eye(n_win, device=vt.device, dtype=vt.dtype)).abs().max()) < 1e-12
+        full = torch.cov(w[:, :, c].to(torch.float64))
+        mine = (gram[c] - torch.outer(ssum[c], ssum[c]) / n_spk) / (n_spk - 1)
+        assert float((mine - full).abs().max()) < 1e-9 * float(full.abs().max())
