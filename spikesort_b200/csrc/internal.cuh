@@ -45,4 +45,11 @@ int mark_head(const void *d_x, int dtype, int64_t n_rows, int64_t n_valid, int64
 int count_and_scan(int64_t n_rows, int64_t n_samples, void *d_ws, int64_t *d_offsets,
                    cudaStream_t st);
 
+// pca_tc.cu: Gram matrices on the tensor cores (tcgen05, 3xTF32); partials in the same
+// workspace layout as the float64 kernel of pca.cu
+bool pca_gram_tc_eligible(int n_win, int64_t n_spk, int n_c, bool offsets_mode);
+int pca_gram_tc(const float *d_waves, int n_win, int64_t n_spk, int n_c, const int64_t *d_offsets,
+                int64_t n_groups, const double *d_ref, double *ws_gram, double *ws_sum, int parts,
+                int nwp, cudaStream_t st);
+
 }  // namespace ssi

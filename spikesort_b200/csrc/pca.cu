@@ -15,6 +15,8 @@
 //                        (round-robin) cyclic Jacobi in float64, one CTA per group;
 //   pca_project_kernel : scores, one thread per (spike, group).
 #include "common.cuh"
+#include "internal.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -331,10 +333,27 @@ extern "C" int ss_pca_gram(const float *d_waves, int n_win, int64_t n_spk, int n
     const size_t smem = (size_t)PC_SC * (nwp + 2) * sizeof(double);
     SS_CUDA_CHECK(cudaFuncSetAttribute(pca_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)((size_t)PC_SC * (PC_MAX_WIN + 2) * sizeof(double))));
-    // unused upper-triangle tiles of partials are never read; no memset needed
-    pca_gram_kernel<<<dim3(parts, (unsigned)n_groups), PC_THREADS, smem, st>>>(
-        d_waves, n_win, n_spk, n_c, d_offsets, d_ref, ws_gram, ws_sum);
-    SS_LAUNCH_CHECK("pca_gram_kernel");
+    // Large problems go to the tensor cores (3xTF32, ~1e-7 relative on the covariance);
+    // small ones stay on the float64 CUDA-core kernel (exact products, ~1e-15).
+    // SS_PCA_TC=0 / 1 forces the choice.
+    const char *force = getenv("SS_PCA_TC");
+    const int64_t per_group = d_offsets ? n_spk / (n_groups > 0 ? n_groups : 1) : n_spk;
+    bool use_tc = ssi::pca_gram_tc_eligible(n_win, n_spk, n_c, d_offsets != nullptr) &&
+                  (reinterpret_cast<uintptr_t>(d_waves) % 16 == 0) && per_group >= 65536;
+    if (force && force[0] == '0') use_tc = false;
+    if (force && force[0] == '1')
+        use_tc = ssi::pca_gram_tc_eligible(n_win, n_spk, n_c, d_offsets != nullptr) &&
+                 (reinterpret_cast<uintptr_t>(d_waves) % 16 == 0);
+    if (use_tc) {
+        const int rc = ssi::pca_gram_tc(d_waves, n_win, n_spk, n_c, d_offsets, n_groups, d_ref,
+                                        ws_gram, ws_sum, parts, nwp, st);
+        if (rc) return rc;
+    } else {
+        // unused upper-triangle tiles of partials are never read; no memset needed
+        pca_gram_kernel<<<dim3(parts, (unsigned)n_groups), PC_THREADS, smem, st>>>(
+            d_waves, n_win, n_spk, n_c, d_offsets, d_ref, ws_gram, ws_sum);
+        SS_LAUNCH_CHECK("pca_gram_kernel");
+    }
     pca_gram_reduce_kernel<<<(unsigned)n_groups, PC_THREADS, 0, st>>>(ws_gram, ws_sum, n_win, parts, d_gram, d_sum);
     SS_LAUNCH_CHECK("pca_gram_reduce_kernel");
     return SS_OK;
