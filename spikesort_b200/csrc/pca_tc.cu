@@ -14,7 +14,7 @@
 //    cross-contact products nobody reads);
 //  * raw float32 rows (one (time step, K-block) = 32 spikes x n_c contacts, contiguous in
 //    the reference's (n_win, n_spk, n_c) layout) arrive in shared memory by 1-D bulk
-//    async copies (cp.async.bulk + mbarrier complete_tx), 4 stages deep;
+//    async copies (cp.async.bulk + mbarrier complete_tx), 128 spikes per copy, 2 stages;
 //  * all threads convert a raw stage into the canonical K-major SWIZZLE_128B UMMA layout:
 //    d = x - ref, hi = tf32(d), lo = d - hi;
 //  * one thread issues, per 8 spikes, hi.hi^T + hi.lo^T + lo.hi^T as three
@@ -31,7 +31,10 @@ namespace {
 
 constexpr int TC_KB = 32;                  // spikes per K-block
 constexpr int TC_RW = 32;                  // rows per contact in the tile (n_win + 1 <= 32)
-constexpr int TC_R = 4;                    // raw stages
+constexpr int TC_R = 2;                    // raw stages
+constexpr int TC_RB = 4;                   // K-blocks per raw stage: one bulk copy moves a row of
+                                           // 128 spikes (2 KB at 4 contacts); 512-byte copies cost
+                                           // ~10 % more (copy-engine overhead per request)
 constexpr int TC_C = 2;                    // canonical (hi/lo) stages
 constexpr int TC_CHUNK = 8;                // K-blocks per float32 accumulation chunk (256 spikes:
                                            // the TMEM accumulation truncates, so chunks stay short)
@@ -116,7 +119,7 @@ pca_gram_tc_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
     const int parts = gridDim.x, part = blockIdx.x;
     const int P = offsets ? 1 : n_c;                       // contacts in the tile
     const int64_t g0 = offsets ? blockIdx.y : 0;           // first group of this CTA
-    const int raw_row = TC_KB * n_c * 4 + 16;              // bytes, 16 B pad: conflict-free reads
+    const int raw_row = TC_RB * TC_KB * n_c * 4 + 16;      // bytes, 16 B pad: conflict-free reads
 
     unsigned char *canon_hi = smem;                                    // [C][16 KB]
     unsigned char *canon_lo = canon_hi + TC_C * TC_CANON_BYTES;        // [C][16 KB]
@@ -170,10 +173,10 @@ pca_gram_tc_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
 
     // warp 7 issues the bulk copies of a block: lane 0 arms the barrier with the byte count,
     // lane w copies row w (one elected thread issuing all rows serialises ~25 copies per block)
-    auto issue_load = [&](int b) {
-        const int st = b % TC_R;
-        const int64_t s0 = b0 + (int64_t)b * TC_KB;
-        const int64_t nsp = min((int64_t)TC_KB, n_spk - s0);
+    auto issue_load = [&](int sb) {                        // super-block = TC_RB K-blocks
+        const int st = sb % TC_R;
+        const int64_t s0 = b0 + (int64_t)sb * (TC_RB * TC_KB);
+        const int64_t nsp = min((int64_t)(TC_RB * TC_KB), n_spk - s0);
         const uint32_t bytes = (uint32_t)(nsp * n_c * 4);
         const uint32_t bar = smem_u32(raw_full + st);
         if (lane == 0)
@@ -191,8 +194,9 @@ pca_gram_tc_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
         }
     };
 
+    const int nsb = (nblk + TC_RB - 1) / TC_RB;
     if (warp == TC_THREADS / 32 - 1)
-        for (int b = 0; b < TC_R - 1 && b < nblk; ++b) issue_load(b);
+        for (int sb = 0; sb < TC_R - 1 && sb < nsb; ++sb) issue_load(sb);
 
     // every thread converts the same <= 4 (row, 4-spike group) items of every block: decode once
     const int WG = (n_win + 1 + 7) / 8;                    // 8-row groups per contact (incl. ones row)
@@ -222,14 +226,15 @@ pca_gram_tc_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
         }
     }
     const int cstride = n_c * 4;                           // bytes between consecutive spikes of a row
-    int chunk = 0;
     for (int b = 0; b < nblk; ++b) {
-        if (warp == TC_THREADS / 32 - 1 && b + TC_R - 1 < nblk) issue_load(b + TC_R - 1);
-        mbar_wait(raw_full + b % TC_R, (uint32_t)((b / TC_R) & 1));
+        const int sb = b / TC_RB;
+        if (warp == TC_THREADS / 32 - 1 && b % TC_RB == 0 && sb + TC_R - 1 < nsb)
+            issue_load(sb + TC_R - 1);
+        mbar_wait(raw_full + sb % TC_R, (uint32_t)((sb / TC_R) & 1));
         if (b >= TC_C) mbar_wait(canon_empty + b % TC_C, (uint32_t)(((b / TC_C) - 1) & 1));
 
         // ---- raw float32 -> canonical hi / lo tf32 tiles
-        const unsigned char *rs = raw + (b % TC_R) * raw_stage;
+        const unsigned char *rs = raw + (sb % TC_R) * raw_stage + (b % TC_RB) * (TC_KB * n_c * 4);
         unsigned char *ch = canon_hi + (b % TC_C) * TC_CANON_BYTES;
         unsigned char *cl = canon_lo + (b % TC_C) * TC_CANON_BYTES;
         const int64_t s0 = b0 + (int64_t)b * TC_KB;
@@ -387,7 +392,7 @@ int ssi::pca_gram_tc(const float *d_waves, int n_win, int64_t n_spk, int n_c,
                      const int64_t *d_offsets, int64_t n_groups, const double *d_ref,
                      double *ws_gram, double *ws_sum, int parts, int nwp, cudaStream_t st)
 {
-    const int raw_row = TC_KB * n_c * 4 + 16;
+    const int raw_row = TC_RB * TC_KB * n_c * 4 + 16;
     const int raw_stage = ((n_win * raw_row) + 127) & ~127;
     const size_t smem = (size_t)2 * TC_C * TC_CANON_BYTES + (size_t)TC_R * raw_stage +
                         (TC_R + TC_C + 2) * 8 + 16 + (size_t)4 * TC_RW * 4 + 64 + 1024;
