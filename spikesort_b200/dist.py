@@ -19,10 +19,10 @@ windows of spikes near a shard edge    ``H`` filtered samples per contact from b
                                        ``halo_before/halo_after``)
 ``np.diff`` across the boundary in     last ALIGNED time of every contact from the
 ``remove_doubles`` (``:281``)          left neighbour (**send/recv**)
-PCA over ALL spikes of a contact       shared reference waveform (**all-gather**),
-(``features.py:224-231``)              Gram + sums + counts (**all-reduce**, float64,
-                                       2.9 MB at 384 contacts); eigensolve replicated
-global layout of the spike list        per-shard counts (**all-gather**)
+PCA over ALL spikes of a contact       Gram + sums + counts re-expressed for the zero
+(``features.py:224-231``)              reference (**all-reduce**, float64, 2.9 MB at 384
+                                       contacts); eigensolve replicated
+global layout of the spike list        per-shard counts ride in the same all-reduce
 ====================================  ===========================================
 
 Spike times are GLOBAL (``index_offset``): the concatenation of the per-rank lists in
@@ -122,19 +122,29 @@ def append_boundary_spikes(spt, offsets, mask, t_last):
     return out, new_off
 
 
-def merge_gram(gram, ssum, counts):
-    """All-reduce (sum) of per-contact Gram matrices, sums and spike counts."""
+def merge_gram(gram, ssum, counts, with_layout=False):
+    """All-reduce (sum) of per-contact Gram matrices, sums and spike counts (all expressed
+    for the same reference).  with_layout: the same collective also carries every rank's
+    per-contact counts (each rank fills its own slot of a zero vector), returned as a
+    (world, n_contacts) tensor - the layout of the concatenated spike list."""
     rank, n = world()
-    if n > 1:
-        d = _dist()
-        t = _lib.torch()
-        flat = t.cat([gram.reshape(-1), ssum.reshape(-1), counts.to(gram.dtype).reshape(-1)])
-        d.all_reduce(flat, op=d.ReduceOp.SUM)
-        g, s = gram.numel(), ssum.numel()
-        gram = flat[:g].reshape(gram.shape)
-        ssum = flat[g:g + s].reshape(ssum.shape)
-        counts = flat[g + s:].round().to(counts.dtype)
-    return gram, ssum, counts
+    t = _lib.torch()
+    if n == 1:
+        return (gram, ssum, counts, counts[None, :]) if with_layout else (gram, ssum, counts)
+    d = _dist()
+    parts = [gram.reshape(-1), ssum.reshape(-1), counts.to(gram.dtype).reshape(-1)]
+    if with_layout:
+        slots = t.zeros((n, counts.numel()), dtype=gram.dtype, device=gram.device)
+        slots[rank] = counts.to(gram.dtype)
+        parts.append(slots.reshape(-1))
+    flat = t.cat(parts)
+    d.all_reduce(flat, op=d.ReduceOp.SUM)
+    g, s_, c = gram.numel(), ssum.numel(), counts.numel()
+    out = (flat[:g].reshape(gram.shape), flat[g:g + s_].reshape(ssum.shape),
+           flat[g + s_:g + s_ + c].round().to(counts.dtype))
+    if with_layout:
+        out = out + (flat[g + s_ + c:].round().to(counts.dtype).reshape(n, c),)
+    return out
 
 
 def pick_reference(stack_flags, stack_refs):
@@ -270,10 +280,18 @@ class ShardedChain(object):
             ref = t.zeros((self.n_c, self.n_win), dtype=t.float64, device=spt.device)
         return ref, counts > 0
 
-    # 6. partial Gram with the shared reference
+    # 6. partial Gram.  The kernel shifts by a LOCAL reference waveform (conditioning of the
+    #    float32/tf32 products); the result is re-expressed for the zero reference in float64
+    #    - sum (d+r)(d+r)^T = G + S r^T + r S^T + n r r^T - so that shards simply add up
+    #    and no reference has to be agreed on between ranks
     def gram(self, ref):
+        t = self.t
         gram, ssum, _, counts = _ops.pca_gram(self.res.waves, offsets=self.res.offsets, ref=ref)
-        return gram, ssum, counts
+        n = counts.to(t.float64)
+        sr = ssum[:, :, None] * ref[:, None, :]
+        gram0 = gram + sr + sr.transpose(1, 2) + n[:, None, None] * ref[:, :, None] * ref[:, None, :]
+        sum0 = ssum + n[:, None] * ref
+        return gram0, sum0, counts
 
     # 7. replicated eigensolve + local projection
     def project(self, gram, ssum, counts):
@@ -298,18 +316,41 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
         n_total = n_ranks * n
     ch = ShardedChain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize, rank,
                       n_ranks, index_offset, n_total)
+    import os
+    prof = os.environ.get("SS_DIST_PROFILE") and rank == 0
+    marks = []
+
+    def mark(name):
+        if prof:
+            import time
+            t.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
+    mark("start")
     ch.prepare()
+    mark("prepare")
     thr = ch.head_threshold() if rank == 0 else t.empty(x.shape[0], dtype=t.float64,
                                                         device=x.device)
     thr = share_thresholds(thr, 0)
+    mark("threshold+bcast")
     left_slab, right_slab = ch.filter_detect(thr)
+    mark("filter_detect")
     halo_left, halo_right = exchange_with_neighbours(left_slab, right_slab)
+    mark("halo exchange")
     last = ch.align(halo_left, halo_right)
+    mark("align")
     prev_last, _ = exchange_with_neighbours(t.zeros_like(last), last)
-    ref, has = ch.extract(prev_last)
-    ref = share_reference(ref, has)
+    mark("last exchange")
+    ref, _ = ch.extract(prev_last)
+    mark("extract")
     gram, ssum, counts = ch.gram(ref)
-    gram, ssum, counts = merge_gram(gram, ssum, counts)
+    gram, ssum, counts, all_counts = merge_gram(gram, ssum, counts, with_layout=True)
+    mark("gram+allreduce")
     res = ch.project(gram, ssum, counts)
-    res.all_counts = gather_counts(res.offsets)
+    res.all_counts = all_counts
+    mark("project")
+    if prof:
+        print("dist profile (ms): " + ", ".join(
+            "%s %.3f" % (marks[i][0], 1000 * (marks[i][1] - marks[i - 1][1]))
+            for i in range(1, len(marks))), flush=True)
     return res

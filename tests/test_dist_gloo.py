@@ -46,8 +46,9 @@ def _worker(rank, world, port, q):
         gram = torch.full((3, 2, 2), float(rank + 1), dtype=torch.float64)
         ssum = torch.full((3, 2), 10.0 * (rank + 1), dtype=torch.float64)
         counts = torch.tensor([rank, 4, 0], dtype=torch.int64)
-        g, s, c = ssd.merge_gram(gram, ssum, counts)
+        g, s, c, lay = ssd.merge_gram(gram, ssum, counts, with_layout=True)
         out["gram"], out["ssum"], out["counts"] = g[0, 0, 0].item(), s[1, 1].item(), c.tolist()
+        out["layout"] = lay.tolist()
         # shared reference: lowest rank that has a spike on the contact
         ref = torch.full((3, 2), float(rank + 1), dtype=torch.float64)
         has = torch.tensor([rank == 1, True, False])
@@ -73,6 +74,7 @@ def test_exchange_steps_world2():
         assert res[r]["thr"] == [-10.0, -20.0, -30.0]
         assert res[r]["gram"] == 3.0 and res[r]["ssum"] == 30.0 and res[r]["counts"] == [1, 8, 0]
         assert res[r]["ref"] == [2.0, 1.0, 1.0]
+        assert res[r]["layout"] == [[0, 4, 0], [1, 4, 0]]
         assert res[r]["all_counts"] == [[1, 2, 0], [2, 2, 0]]
     # rank 0 sees rank 1's first samples (2,4,6)-25; falling crossing needs last > thr > next
     assert res[0]["nxt"] == [-23.0, -21.0, -19.0] and res[1]["nxt"] == [None, None, None]

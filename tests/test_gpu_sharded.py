@@ -1,7 +1,7 @@
 """GPU tier: the time-sharded chain (spikesort_b200/dist.py) equals the unsharded chain.
 
 The phases of several shards are run in lock-step on ONE GPU, with the exchange steps
-(thresholds, neighbour halos, last aligned times, shared PCA reference, Gram sum) done
+(thresholds, neighbour halos, last aligned times, Gram sum) done
 by hand exactly as run_chain_sharded does them over NCCL.  Concatenated per contact in
 shard order, spike times and waveforms must be bit-identical to pipeline.run_chain on
 the whole recording; PCA scores agree to round-off (the Gram is summed in another order).
@@ -29,9 +29,7 @@ def _run_sharded(torch, dist_mod, x_full, S, FS, flt, sp_win, chunksize, thresh)
         hr = slabs[r + 1][0] if r < S - 1 else None
         lasts.append(c.align(hl, hr))
     refs = [c.extract(lasts[r - 1] if r > 0 else None) for r, c in enumerate(chains)]
-    ref = dist_mod.pick_reference(torch.stack([h for _, h in refs]),   # all-gather + pick
-                                  torch.stack([f for f, _ in refs]))
-    parts = [c.gram(ref) for c in chains]
+    parts = [c.gram(ref) for c, (ref, _) in zip(chains, refs)]       # each shard its own reference
     gram = sum(p[0] for p in parts)                                    # all-reduce
     ssum = sum(p[1] for p in parts)
     counts = sum(p[2] for p in parts)
