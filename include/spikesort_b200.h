@@ -234,6 +234,19 @@ int ss_pca_project(const float *d_waves, int n_win, int64_t n_spk, int n_c,
                    const double *d_evals, const double *d_evecs, int ncomps,
                    double *d_scores, void *stream);
 
+/* ------------------------------------------------------- cheap features (8f)
+ * Replaces fetP2P / fetMin (features.py:473-474, 483-484) on a float32 waveform block
+ * (n_win, n_spk, n_c): d_min[s, c] = min_w, d_p2p[s, c] = max_w - min_w (float32, as
+ * np.ptp on float32).  Either output may be NULL.
+ * ss_normalize_columns replaces normalize (features.py:191-193) on a row-major float64
+ * (n_rows, n_cols) matrix, in place: (x - colmin) / (colmax - colmin).  Both bit-exact.
+ */
+int ss_wave_minmax(const float *d_waves, int n_win, int64_t n_spk, int n_c,
+                   float *d_min, float *d_p2p, void *stream);
+size_t ss_normalize_workspace_bytes(int n_cols);
+int ss_normalize_columns(double *d_x, int64_t n_rows, int n_cols, void *d_ws, size_t ws_bytes,
+                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -356,6 +356,70 @@ def fetPCA(spikes_data, ncomps=2, contacts='all'):
     return out
 
 
+def _select(spikes_data, contacts):
+    spikes = spikes_data['data']
+    if not (isinstance(contacts, str) and contacts == 'all'):
+        try:
+            spikes = spikes[:, :, np.asarray(contacts)]
+        except IndexError:
+            raise IndexError("contacts must be either 'all' or a "
+                             "list of valid contact indices")
+    return spikes
+
+
+def _masked(out, spikes_data):
+    if 'is_valid' in spikes_data:
+        out['is_valid'] = spikes_data['is_valid']
+    return out
+
+
+def fetP2P(spikes_data, contacts='all'):
+    """features.py:445-479: peak-to-peak amplitude per (spike, contact)."""
+    p2p = np.ptp(_select(spikes_data, contacts), axis=0)
+    if p2p.ndim < 2:
+        p2p = p2p[:, np.newaxis]
+    return _masked({'data': p2p, 'names': ["Ch%d:P2P" % i for i in range(p2p.shape[1])]},
+                   spikes_data)
+
+
+def fetMin(spikes_data, contacts='all'):
+    """features.py:481-489."""
+    mn = np.min(_select(spikes_data, contacts), axis=0)
+    return _masked({'data': mn, 'names': ["Ch%d:Min" % i for i in range(mn.shape[1])]},
+                   spikes_data)
+
+
+def normalize(features, copy=True):
+    """features.py:184-197: shift every column to 0, scale to 1."""
+    out = features.copy() if copy else features
+    data = out['data']
+    data = data - data.min(0)[np.newaxis, :]
+    out['data'] = data / data.max(0)[np.newaxis, :]
+    return out
+
+
+def combine(feat_data, norm=True, feat_method_names=None):
+    """features.py:98-139."""
+    names = [list(d['names']) for d in feat_data]
+    masks = [d['is_valid'] for d in feat_data if 'is_valid' in d]
+    try:
+        data = np.hstack([d['data'] for d in feat_data])
+    except ValueError:
+        raise ValueError('all features must contain the same number of spikes')
+    if feat_method_names:
+        for i, method in enumerate(feat_method_names):
+            names[i] = [method + ':' + n for n in names[i]]
+    out = {'data': data, 'names': list(np.concatenate(names))}
+    if masks:
+        m = masks[0]
+        for other in masks[1:]:
+            m = np.logical_and(m, other)
+        out['is_valid'] = m
+    if norm:
+        normalize(out, copy=False)
+    return out
+
+
 # ---------------------------------------------------------------------------
 # the multi-contact chain the bench times (SURVEY.md section 8d)
 # ---------------------------------------------------------------------------

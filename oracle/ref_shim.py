@@ -69,6 +69,9 @@ class _FakeAtom(object):
 def _install_shims():
     if not hasattr(builtins, "basestring"):
         builtins.basestring = str
+    if not hasattr(builtins, "reduce"):          # features.combine, features.py:120
+        import functools
+        builtins.reduce = functools.reduce
     if "tables" not in sys.modules:
         tables = types.ModuleType("tables")
         tables.Atom = _FakeAtom

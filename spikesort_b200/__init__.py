@@ -19,7 +19,8 @@ _HOT_PATH = {
     "filters": ("Filter", "ZeroPhaseFilter", "filter_proxy", "fltLinearIIR", "clean_after_exit"),
     "extract": ("detect_spikes", "filter_spt", "extract_spikes", "align_spikes",
                 "remove_doubles"),
-    "features": ("PCA", "fetPCA", "add_mask"),
+    "features": ("PCA", "fetPCA", "add_mask", "fetP2P", "fetMin", "fetSpIdx", "fetSpTime",
+                 "normalize", "combine"),
 }
 
 

@@ -323,3 +323,31 @@ def pca_project(waves, evals, evecs, ncomps, offsets=None):
     _lib.check(rc, "ss_pca_project")
     _launched(1 if n_spk > 0 else 0)
     return scores
+
+
+# ------------------------------------------------------------- cheap features
+def wave_minmax(waves, want_min=True, want_p2p=True):
+    """(min, max - min) over the time axis of CUDA float32 waves (n_win, n_spk, n_c);
+    each (n_spk, n_c) float32 or None."""
+    lib = _lib.load()
+    t = _lib.torch()
+    n_win, n_spk, n_c = waves.shape
+    mn = t.empty((n_spk, n_c), dtype=t.float32, device=waves.device) if want_min else None
+    pp = t.empty((n_spk, n_c), dtype=t.float32, device=waves.device) if want_p2p else None
+    rc = lib.ss_wave_minmax(_lib.ptr(waves), n_win, n_spk, n_c, _lib.ptr(mn), _lib.ptr(pp),
+                            _lib.stream_ptr())
+    _lib.check(rc, "ss_wave_minmax")
+    _launched(1 if n_spk > 0 else 0)
+    return mn, pp
+
+
+def normalize_columns(x):
+    """In-place (x - colmin) / (colmax - colmin) of a CUDA float64 (n_rows, n_cols) matrix."""
+    lib = _lib.load()
+    n_rows, n_cols = x.shape
+    ws = _lib.workspace(lib.ss_normalize_workspace_bytes(n_cols))
+    rc = lib.ss_normalize_columns(_lib.ptr(x), n_rows, n_cols, _lib.ptr(ws), ws.numel(),
+                                  _lib.stream_ptr())
+    _lib.check(rc, "ss_normalize_columns")
+    _launched(3 if n_rows > 0 and n_cols > 0 else 0)
+    return x

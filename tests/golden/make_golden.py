@@ -113,6 +113,15 @@ def main():
     out['chain_pca0_evecs'] = evecs
     out['chain_pca0_score'] = score
 
+    # --- cheap features and combine/normalize on the same waveforms (features.py:98-197,445-489)
+    p2p = rfe.fetP2P(wv)
+    out['chain_p2p'] = p2p['data']
+    out['chain_min'] = rfe.fetMin(wv)['data']
+    comb = rfe.combine((rfe.fetP2P(wv), rfe.fetPCA(wv, ncomps=2)), norm=True,
+                       feat_method_names=['P2P', 'PCA'])
+    out['chain_combined'] = comb['data']
+    out['chain_combined_names'] = np.array(comb['names'])
+
     # --- band-pass (order 8) on float32 input, single chunk
     x32 = synth.make_recording(1, 20000, 30000, seed=7, rate_hz=30.0, noise=8.0,
                                dtype="float32").numpy()

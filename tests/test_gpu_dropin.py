@@ -190,3 +190,32 @@ def test_install_rebinds_reference_namespace(ss):
     assert fake.filters.fltLinearIIR is ss.filters.fltLinearIIR
     assert fake.features.fetPCA is ss.features.fetPCA
     assert orig[("extract", "detect_spikes")] == 2
+
+
+def test_cheap_features_and_combine(ss, oracle, golden):
+    """fetP2P / fetMin / combine(norm=True), bit-exact."""
+    rng = np.random.default_rng(9)
+    wv = {'data': golden['chain_waves'], 'time': np.arange(25.0), 'FS': 25000,
+          'is_valid': np.arange(golden['chain_waves'].shape[1]) % 7 != 0}
+    p2p = ss.features.fetP2P(wv)
+    assert p2p['data'].dtype == np.float32 and np.array_equal(p2p['data'], golden['chain_p2p'])
+    assert p2p['names'] == ['Ch0:P2P', 'Ch1:P2P'] and np.array_equal(p2p['is_valid'], wv['is_valid'])
+    assert np.array_equal(ss.features.fetMin(wv)['data'], golden['chain_min'])
+    big = {'data': rng.standard_normal((30, 20011, 3)).astype(np.float32)}
+    assert np.array_equal(ss.features.fetP2P(big)['data'], oracle.fetP2P(big)['data'])
+    assert np.array_equal(ss.features.fetMin(big, contacts=[2, 0])['data'],
+                          oracle.fetMin(big, contacts=[2, 0])['data'])
+    # normalize: bit-exact against NumPy on arbitrary float64 columns
+    feats = {'data': rng.standard_normal((50021, 7)) * np.array([1, 1e3, 1e-3, 5, 7, 9, 11.0]) + 3,
+             'names': list("abcdefg")}
+    got = ss.features.normalize(feats)
+    ref = oracle.normalize(feats)
+    assert np.array_equal(got['data'], ref['data']) and feats['data'].max() > 1.5   # copy=True
+    comb = ss.features.combine((ss.features.fetP2P(wv), oracle.fetPCA(wv, ncomps=2)), norm=True,
+                               feat_method_names=['P2P', 'PCA'])
+    refc = oracle.combine((oracle.fetP2P(wv), oracle.fetPCA(wv, ncomps=2)), norm=True,
+                          feat_method_names=['P2P', 'PCA'])
+    assert comb['names'] == refc['names'] and np.array_equal(comb['data'], refc['data'])
+    assert np.array_equal(comb['is_valid'], refc['is_valid'])
+    assert ss.features.fetSpIdx(wv)['data'].shape == (wv['data'].shape[1], 1)
+    assert ss.features.fetSpTime({'data': np.array([1.0, 2.0])})['data'].shape == (2, 1)

@@ -178,3 +178,27 @@ def test_fetpca_mask_and_contacts(oracle):
     assert f['data'].shape == (50, 4) and np.array_equal(f['is_valid'], waves['is_valid'])
     with pytest.raises(IndexError):
         oracle.fetPCA(waves, contacts=[5])
+
+
+def test_cheap_features_and_combine_golden(oracle, golden):
+    wv = {'data': golden['chain_waves'], 'time': np.arange(25.0), 'FS': 25000,
+          'is_valid': np.arange(golden['chain_waves'].shape[1]) % 7 != 0}
+    p2p = oracle.fetP2P(wv)
+    assert p2p['data'].dtype == np.float32 and np.array_equal(p2p['data'], golden['chain_p2p'])
+    assert p2p['names'] == ['Ch0:P2P', 'Ch1:P2P'] and np.array_equal(p2p['is_valid'], wv['is_valid'])
+    assert np.array_equal(oracle.fetMin(wv)['data'], golden['chain_min'])
+    assert oracle.fetP2P(wv, contacts=[1])['data'].shape == (wv['data'].shape[1], 1)
+    comb = oracle.combine((oracle.fetP2P(wv), oracle.fetPCA(wv, ncomps=2)), norm=True,
+                          feat_method_names=['P2P', 'PCA'])
+    assert comb['names'] == list(golden['chain_combined_names'])
+    assert comb['names'][0] == 'P2P:Ch0:P2P' and comb['names'][-1] == 'PCA:Ch1:PC1'
+    # the P2P columns are bit-exact; the PCA columns up to eigenvector sign (x -> 1 - x)
+    g = golden['chain_combined']
+    assert np.array_equal(comb['data'][:, :2], g[:, :2])
+    for j in range(2, 6):
+        d = min(np.abs(comb['data'][:, j] - g[:, j]).max(), np.abs(1 - comb['data'][:, j] - g[:, j]).max())
+        assert d < 1e-9
+    assert comb['data'].min() == 0.0 and comb['data'].max() == 1.0
+    with pytest.raises(ValueError):
+        oracle.combine(({'data': np.zeros((3, 1)), 'names': ['a']},
+                        {'data': np.zeros((4, 1)), 'names': ['b']}))
