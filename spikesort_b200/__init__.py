@@ -11,9 +11,11 @@ no CPU fallback.
 """
 from . import filters, extract, features            # noqa: F401
 from ._signal import DeviceSignal, to_device        # noqa: F401
+from .pipeline import sort_frontend                 # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["filters", "extract", "features", "DeviceSignal", "to_device", "install"]
+__all__ = ["filters", "extract", "features", "DeviceSignal", "to_device", "install",
+           "sort_frontend"]
 
 _HOT_PATH = {
     "filters": ("Filter", "ZeroPhaseFilter", "filter_proxy", "fltLinearIIR", "clean_after_exit"),

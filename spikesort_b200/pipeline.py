@@ -115,3 +115,75 @@ def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='
         res.evals, res.evecs = _ops.pca_eig(gram, ssum, counts)
         res.scores = _ops.pca_project(waves, res.evals, res.evecs, ncomps, offsets=offsets)
     return res
+
+
+_PINNED = {}
+
+
+def _pinned_like(name, tensor):
+    """Grow-only pinned staging buffer (pinned allocation costs milliseconds)."""
+    t = _lib.torch()
+    need = tensor.numel()
+    buf = _PINNED.get((name, tensor.dtype))
+    if buf is None or buf.numel() < need:
+        buf = t.empty(max(need, 1), dtype=tensor.dtype).pin_memory()
+        _PINNED[(name, tensor.dtype)] = buf
+    return buf[:need].view(tensor.shape)
+
+
+def sort_frontend(spike_data, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
+                  thresh='auto', ncomps=2, chunksize=1E6, contacts=None):
+    """The whole front end for a multi-contact recording in ONE call, host in / host out.
+
+    spike_data: the reference's raw-recording dict {'data', 'FS', 'n_contacts'}; 'data' may
+    be a NumPy array, a (pinned) torch CPU tensor or a device-resident signal.  Every
+    contact c gets exactly what the reference's per-contact calls would give
+    (detect_spikes(contact=c) -> align_spikes(contact=c) -> extract_spikes(contacts=c) ->
+    fetPCA), computed by the batched device chain; results come back as NumPy in the
+    reference's dict conventions:
+
+        {'FS', 'n_contacts', 'contacts': [c, ...],
+         'spt':      [ {'data', 'thresh', 'contact'}, ... ],          # detected
+         'spt_aligned': [ {'data'}, ... ],
+         'sp_waves': [ {'data' (n_win, n_spk_c, 1) float32, 'time', 'FS'[, 'is_valid']}, ... ],
+         'features': [ {'data' (n_spk_c, ncomps), 'names'[, 'is_valid']}, ... ]}
+    """
+    t = _lib.require_cuda()
+    FS = spike_data['FS']
+    x = _lib.to_device_2d(spike_data['data'])            # one H2D copy (pinned: ~55 GB/s)
+    if contacts is not None:
+        x = x[t.as_tensor(list(contacts), device=x.device)]
+    res = run_chain(x, FS, filt=filt, sp_win=sp_win, edge=edge, align_type=align_type,
+                    thresh=thresh, ncomps=ncomps, chunksize=chunksize)
+    # one D2H per result array, through pinned staging, then zero-copy per-contact views
+    def host(name, ten):
+        if ten is None:
+            return None
+        buf = _pinned_like(name, ten)
+        buf.copy_(ten, non_blocking=True)
+        return buf
+    h = {k: host(k, getattr(res, k)) for k in ('thresh', 'spt_detected', 'offsets_detected', 'spt',
+                                               'offsets', 'waves', 'valid', 'scores')}
+    t.cuda.current_stream().synchronize()
+    h = {k: (v.numpy() if v is not None else None) for k, v in h.items()}
+    n_rows = x.shape[0]
+    ids = list(range(n_rows)) if contacts is None else list(contacts)
+    out = {'FS': FS, 'n_contacts': n_rows, 'contacts': ids, 'spt': [], 'spt_aligned': [],
+           'sp_waves': [], 'features': []}
+    names = ["Ch0:PC%d" % j for j in range(ncomps)]
+    off, offd = h['offsets'], h['offsets_detected']
+    for r, c in enumerate(ids):
+        lo, hi = int(off[r]), int(off[r + 1])
+        out['spt'].append({'data': h['spt_detected'][int(offd[r]):int(offd[r + 1])].copy(),
+                           'thresh': float(h['thresh'][r]), 'contact': c})
+        out['spt_aligned'].append({'data': h['spt'][lo:hi].copy()})
+        valid = h['valid'][lo:hi].astype(bool)
+        wd = {'data': np.ascontiguousarray(h['waves'][:, lo:hi, :]), 'time': res.time, 'FS': FS}
+        fd = {'data': h['scores'][lo:hi].copy() if h['scores'] is not None else None,
+              'names': list(names)}
+        if not valid.all():
+            wd['is_valid'] = valid
+            fd['is_valid'] = valid
+        out['sp_waves'].append(wd)
+        out['features'].append(fd)
+    return out

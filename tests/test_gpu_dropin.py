@@ -219,3 +219,31 @@ def test_cheap_features_and_combine(ss, oracle, golden):
     assert np.array_equal(comb['is_valid'], refc['is_valid'])
     assert ss.features.fetSpIdx(wv)['data'].shape == (wv['data'].shape[1], 1)
     assert ss.features.fetSpTime({'data': np.array([1.0, 2.0])})['data'].shape == (2, 1)
+
+
+def test_sort_frontend_equals_per_contact_calls(ss, golden):
+    """The one-call front end returns, per contact, what the reference-style calls return."""
+    import torch
+    FS = 25000
+    x = golden['chain_raw']
+    raw = {'data': torch.from_numpy(x).pin_memory(), 'FS': FS, 'n_contacts': 2}
+    flt = ss.filters.Filter(800., 100.)
+    out = ss.sort_frontend(raw, filt=flt, sp_win=[-0.2, 0.8], edge='rising', align_type='max',
+                           thresh='auto', ncomps=2, chunksize=25000)
+    f = ss.filters.filter_proxy({'data': x, 'FS': FS, 'n_contacts': 2}, flt, chunksize=25000)
+    for c in range(2):
+        spt = ss.extract.detect_spikes(f, thresh='auto', edge='rising', contact=c)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            spa = ss.extract.align_spikes(f, spt, [-0.2, 0.8], type='max', contact=c)
+        wv = ss.extract.extract_spikes(f, spa, [-0.2, 0.8], contacts=c)
+        ft = ss.features.fetPCA(wv, ncomps=2)
+        assert np.array_equal(out['spt'][c]['data'], spt['data'])
+        assert out['spt'][c]['thresh'] == spt['thresh'] and out['spt'][c]['contact'] == c
+        assert np.array_equal(out['spt_aligned'][c]['data'], spa['data'])
+        assert np.array_equal(out['sp_waves'][c]['data'], wv['data'])
+        assert np.array_equal(out['sp_waves'][c]['time'], wv['time'])
+        assert ('is_valid' in out['sp_waves'][c]) == ('is_valid' in wv)
+        assert out['features'][c]['names'] == ft['names']
+        assert rel_err(sign_normalise(out['features'][c]['data'], ft['data']), ft['data']) < 1e-9
+    assert np.array_equal(out['spt_aligned'][1]['data'], golden['chain_align'])
