@@ -247,6 +247,24 @@ size_t ss_normalize_workspace_bytes(int n_cols);
 int ss_normalize_columns(double *d_x, int64_t n_rows, int n_cols, void *d_ws, size_t ws_bytes,
                          void *stream);
 
+/* ------------------------------------------------------- spline upsampling (8f)
+ * Replaces resample_spikes (extract.py:187-205) and the resample != 1 branch of
+ * align_spikes (extract.py:245-258).  d_W is the (n_out, n_win) float64 matrix of the
+ * interpolating cubic spline on the two time grids (built on the host with the SciPy
+ * routines the reference calls); d_rtime the n_out upsampled times (ms).
+ *   ss_resample        : d_out (n_out, n_spk, n_c) float64 = W applied along the time axis
+ *                        of d_waves (n_win, n_spk, n_c), element type `dtype`;
+ *   ss_align_resampled : as ss_align, the extremum searched on W y, shift = d_rtime[k].
+ */
+int ss_resample(const void *d_waves, int dtype, int n_win, int64_t n_spk, int n_c,
+                const double *d_W, int n_out, double *d_out, void *stream);
+int ss_align_resampled(const void *d_x, int dtype, int64_t n_samples, int64_t ld, double FS,
+                       const int32_t *d_rows, int64_t n_rows, const int64_t *d_offsets,
+                       int win0, int win1, double t_min, double t_max, double lo, double hi,
+                       int use_min, const double *d_W, int n_out, const double *d_rtime,
+                       double *d_spt, int64_t n_spk, int max_iter, int64_t index_offset,
+                       int64_t halo_before, int64_t halo_after, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

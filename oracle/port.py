@@ -235,11 +235,10 @@ def _window(sp_win, FS):
 
 
 def extract_spikes(spike_data, spt_dict, sp_win, resample=1, contacts='all'):
-    """extract.py:114-184 (resample == 1 only).  float32 (n_win, n_spk, n_c);
-    windows that leave the recording are clipped, zero-filled and flagged
-    through 'is_valid' (present only when at least one spike is clipped)."""
-    if resample != 1:
-        raise NotImplementedError("oracle covers resample=1 only")
+    """extract.py:114-184.  float32 (n_win, n_spk, n_c); windows that leave the
+    recording are clipped, zero-filled and flagged through 'is_valid' (present only
+    when at least one spike is clipped).  resample != 1 hands the result to
+    resample_spikes (:179-183), which drops 'is_valid'."""
     sp_data = spike_data['data']
     if isinstance(contacts, str) and contacts == 'all':
         contacts = np.arange(spike_data['n_contacts'])
@@ -270,7 +269,27 @@ def extract_spikes(spike_data, spt_dict, sp_win, resample=1, contacts='all'):
     out = {'data': waves, 'time': time, 'FS': FS}
     if not inner.all():
         out['is_valid'] = inner
+    if resample != 1:
+        warnings.warn("resample argument is deprecated."
+                      "Please update your code to use function"
+                      "resample_spikes", DeprecationWarning)
+        out = resample_spikes(out, FS * resample)
     return out
+
+
+def resample_spikes(spikes_dict, FS_new):
+    """extract.py:187-205: every (spike, contact) waveform is interpolated by the cubic
+    B-spline splrep(time, wave, s=0) (SciPy/FITPACK, not-a-knot ends) and evaluated on
+    arange(time[0], time[-1], 1000/FS_new); float64 out, 'FS' stays the ORIGINAL rate."""
+    from scipy import interpolate
+    waves, time = spikes_dict['data'], spikes_dict['time']
+    fine = np.arange(time[0], time[-1], 1000.0 / FS_new)
+    n_spk, n_c = waves.shape[1], waves.shape[2]
+    up = np.empty((len(fine), n_spk, n_c))
+    for s in range(n_spk):
+        for c in range(n_c):
+            up[:, s, c] = interpolate.splev(fine, interpolate.splrep(time, waves[:, s, c], s=0), der=0)
+    return {'data': up, 'time': fine, 'FS': spikes_dict['FS']}
 
 
 def remove_doubles(spt_dict, tol):
@@ -289,8 +308,8 @@ def remove_doubles(spt_dict, tol):
 
 def align_spikes(spike_data, spt_dict, sp_win, type="max", resample=1,
                  contact=0, remove=True):
-    """extract.py:208-274 (resample == 1).  Each in-bounds spike is moved to the
-    first extremum of its float32 window on `contact`; spikes whose extremum sat
+    """extract.py:208-274.  Each in-bounds spike is moved to the first extremum of its
+    float32 window on `contact` (of the spline-upsampled float64 window for resample != 1); spikes whose extremum sat
     within 0.1 ms of a window edge are re-examined from the new position until
     none is left.  Out-of-bounds spikes are kept unmoved."""
     tol = 0.1
@@ -303,7 +322,9 @@ def align_spikes(spike_data, spt_dict, sp_win, type="max", resample=1,
         cand = {'data': spt[todo]}
         ok = filter_spt(spike_data, cand, sp_win)
         todo = todo[ok]
-        waves = extract_spikes(spike_data, cand, sp_win, contacts=contact)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore', DeprecationWarning)
+            waves = extract_spikes(spike_data, cand, sp_win, resample=resample, contacts=contact)
         w = waves['data'][:, ok, 0]
         where = w.argmax(0) if type == "max" else w.argmin(0)
         shift = waves['time'][where]

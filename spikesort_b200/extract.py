@@ -1,6 +1,6 @@
 """Drop-in for the hot-path functions of ``spike_sort.core.extract`` (reference
 ``src/spike_sort/core/extract.py``): ``detect_spikes``, ``filter_spt``,
-``extract_spikes``, ``align_spikes``, ``remove_doubles``.  Same arguments, same
+``extract_spikes``, ``resample_spikes``, ``align_spikes``, ``remove_doubles``.  Same arguments, same
 dict keys and dtypes; spike times and waveforms are bit-identical to the
 reference given the same input signal.
 """
@@ -70,9 +70,6 @@ def filter_spt(spike_data, spt_dict, sp_win):
 def extract_spikes(spike_data, spt_dict, sp_win, resample=1, contacts='all'):
     """``extract.py:114-184``: float32 waveforms (n_win, n_spikes, n_contacts),
     'time' (ms) and 'FS'; 'is_valid' only when some window was clipped."""
-    if resample != 1:
-        raise NotImplementedError("resample != 1 (spline upsampling) is not on the CUDA "
-                                  "path yet; use resample=1")
     n_contacts = spike_data['n_contacts']
     if isinstance(contacts, str) and contacts == "all":
         contacts = np.arange(n_contacts)
@@ -91,10 +88,31 @@ def extract_spikes(spike_data, spt_dict, sp_win, resample=1, contacts='all'):
     cdev = t.as_tensor(np.ascontiguousarray(rows, dtype=np.int32)).to(x.device)
     _, _, time = _ops.window_params(sp_win, FS)
     waves, valid, n_invalid = _ops.extract(x, spt, FS, sp_win, contacts=cdev)
+    if resample != 1:
+        warn("resample argument is deprecated."
+             "Please update your code to use function"
+             "resample_spikes", DeprecationWarning)
+        # extract.py:183 returns resample_spikes' fresh dict: no 'is_valid'
+        W, rtime = _ops.spline_matrix(time, FS * resample)
+        return {"data": _ops.resample(waves, W).cpu().numpy(), "time": rtime, "FS": FS}
     wavedict = {"data": waves.cpu().numpy(), "time": time, "FS": FS}
     if int(n_invalid.item()) != 0:
         wavedict['is_valid'] = valid.cpu().numpy().astype(bool)
     return wavedict
+
+
+def resample_spikes(spikes_dict, FS_new):
+    """``extract.py:187-205``: cubic-spline upsampling of every (spike, contact)
+    waveform to `FS_new`; float64 'data', new 'time', 'FS' unchanged."""
+    t = _lib.require_cuda()
+    sp_waves = np.asarray(spikes_dict['data'])
+    if sp_waves.dtype not in (np.int16, np.float32, np.float64):
+        sp_waves = sp_waves.astype(np.float64)
+    time = np.asarray(spikes_dict['time'], dtype=np.float64)
+    W, rtime = _ops.spline_matrix(time, FS_new)
+    waves = t.as_tensor(np.ascontiguousarray(sp_waves)).to(_lib.device())
+    return {"data": _ops.resample(waves, W).cpu().numpy(), "time": rtime,
+            "FS": spikes_dict['FS']}
 
 
 def remove_doubles(spt_dict, tol):
@@ -118,9 +136,6 @@ def align_spikes(spike_data, spt_dict, sp_win, type="max", resample=1,
     if (sp_win[0] > -tol) or (sp_win[1] < tol):
         warn('You are using very short sp_win. '
              'This may lead to alignment problems.')
-    if resample != 1:
-        raise NotImplementedError("resample != 1 (spline upsampling) is not on the CUDA "
-                                  "path yet; use resample=1")
     if type not in ("max", "min"):
         raise ValueError("type must be 'max' or 'min'")
     t = _lib.require_cuda()
@@ -128,7 +143,10 @@ def align_spikes(spike_data, spt_dict, sp_win, type="max", resample=1,
     x, remap = _rows_on_device(spike_data, [contact])
     row = x[(remap[int(contact)] if remap else contact):][:1]
     spt = t.as_tensor(np.array(spt_dict['data'], dtype=np.float64, copy=True)).to(row.device)
-    _ops.align(row, spt, None, None, FS, sp_win, type == "min")
+    if resample != 1:
+        _ops.align_resampled(row, spt, None, None, FS, sp_win, type == "min", resample)
+    else:
+        _ops.align(row, spt, None, None, FS, sp_win, type == "min")
     if remove:
         spt, _ = _ops.remove_doubles(spt, None, 1000.0 / FS) if spt.numel() > 0 else (spt, None)
     return {'data': spt.cpu().numpy()}

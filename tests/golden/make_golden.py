@@ -122,6 +122,27 @@ def main():
     out['chain_combined'] = comb['data']
     out['chain_combined_names'] = np.array(comb['names'])
 
+    # --- spline upsampling (extract.py:179-205,245-258): the tutorial's resample=10
+    # alignment, the deprecated extract(resample=) branch and resample_spikes itself
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        al_rs = re_.align_spikes(fd, det, [-0.2, 0.8], type='max', contact=1, resample=10)
+        out['chain_align_rs10'] = al_rs['data']
+        al_rs_min = re_.align_spikes(fd, det, [-0.2, 0.8], type='min', contact=0, resample=4,
+                                     remove=False)
+        out['chain_align_rs4_min'] = al_rs_min['data']
+        wv_rs = re_.extract_spikes(fd, al_rs, [-0.2, 0.8], resample=3)
+    out['chain_waves_rs3'] = wv_rs['data']
+    out['chain_waves_rs3_time'] = wv_rs['time']
+    out['chain_waves_rs3_keys'] = np.array(sorted(wv_rs.keys()))
+    sp3, period, _ = sine_fixture()                      # tests/test_core.py:138-146
+    zc = period * np.arange(100) + 1000.0 / sp3['FS'] / 2.0
+    sw = re_.extract_spikes(sp3, {'data': zc}, [0, period])
+    sr = re_.resample_spikes(sw, sp3['FS'] * 2)
+    out['sine_resample_spt'] = zc
+    out['sine_resample'] = sr['data']
+    out['sine_resample_time'] = sr['time']
+
     # --- band-pass (order 8) on float32 input, single chunk
     x32 = synth.make_recording(1, 20000, 30000, seed=7, rate_hz=30.0, noise=8.0,
                                dtype="float32").numpy()

@@ -92,6 +92,17 @@ def check_extract(ex):                                  # test_core.py:118-125
     assert (np.abs(ref_sp[:, np.newaxis] - sp_waves['data'][:, :, 0]) < 1E-6).all()
 
 
+def check_extract_and_resample(ex):                     # test_core.py:138-146
+    c = SineCase()
+    zero_crossing = c.period * np.arange(c.n_spikes)
+    zero_crossing += 1000.0 / c.FS / 2.0
+    sp_win = [0, c.period]
+    sp_waves = ex.extract_spikes(c.spk_data, {"data": zero_crossing}, sp_win)
+    sp_resamp = ex.resample_spikes(sp_waves, c.FS * 2)
+    ref_sp = np.sin(2 * np.pi / c.period * sp_resamp['time'])
+    assert (np.abs(ref_sp[:, np.newaxis] - sp_resamp['data'][:, :, 0]) < 1E-6).all()
+
+
 def check_mask_of_truncated_spikes(ex):                 # test_core.py:148-174
     c = SineCase()
     sp_win = [0, c.period]
@@ -178,5 +189,5 @@ def check_fetpca_multichannel_labels(fet):              # test_features.py:72-10
 
 EXTRACT_CASES = [check_detect, check_align, check_align_short_win, check_align_edge,
                  check_align_double_spikes, check_remove_doubles_roundoff, check_extract,
-                 check_mask_of_truncated_spikes, check_filter_spt]
+                 check_extract_and_resample, check_mask_of_truncated_spikes, check_filter_spt]
 FEATURE_CASES = [check_pca_whitening, check_fetpca_separates, check_fetpca_multichannel_labels]

@@ -123,6 +123,46 @@ def test_chain_golden(ss, golden):
     assert mism == 0
 
 
+def test_resample_golden(ss, golden):
+    """8f rank 1: spline upsampling.  The spline is applied as a precomputed matrix, so
+    upsampled waveforms agree with FITPACK's per-waveform solve to round-off (asserted
+    1e-12 of the waveform scale; bar 1e-5) and aligned times are compared exactly, with
+    mismatches counted (an exact tie between two upsampled points could flip)."""
+    FS = 25000
+    fd = {'data': golden['chain_filtered'], 'FS': FS, 'n_contacts': 2}
+    det = {'data': golden['chain_detect']}
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter('always')
+        al = ss.extract.align_spikes(fd, det, [-0.2, 0.8], type='max', contact=1, resample=10)
+        al4 = ss.extract.align_spikes(fd, det, [-0.2, 0.8], type='min', contact=0, resample=4,
+                                      remove=False)
+        wv = ss.extract.extract_spikes(fd, {'data': golden['chain_align_rs10']}, [-0.2, 0.8],
+                                       resample=3)
+        assert any(issubclass(x.category, DeprecationWarning) for x in w)
+    for got, key in ((al, 'chain_align_rs10'), (al4, 'chain_align_rs4_min')):
+        assert got['data'].shape == golden[key].shape
+        mism = int(np.sum(got['data'] != golden[key]))
+        print("%s: %d of %d aligned times differ" % (key, mism, len(golden[key])))
+        assert mism == 0
+    assert wv['data'].dtype == np.float64 and wv['data'].shape == golden['chain_waves_rs3'].shape
+    assert rel_err(wv['data'], golden['chain_waves_rs3']) < 1e-12
+    assert np.array_equal(wv['time'], golden['chain_waves_rs3_time'])
+    assert sorted(wv.keys()) == list(golden['chain_waves_rs3_keys'])      # no 'is_valid'
+    sp, period, _ = sine_fixture()
+    sw = ss.extract.extract_spikes(sp, {'data': golden['sine_resample_spt']}, [0, period])
+    sr = ss.extract.resample_spikes(sw, sp['FS'] * 2)
+    assert rel_err(sr['data'], golden['sine_resample']) < 1e-12
+    assert np.array_equal(sr['time'], golden['sine_resample_time'])
+    assert sr['FS'] == sp['FS']
+    # float64 waveforms in (a user-built dict) take the same route
+    sr64 = ss.extract.resample_spikes({'data': sw['data'].astype(np.float64), 'time': sw['time'],
+                                       'FS': sw['FS']}, sp['FS'] * 2)
+    assert np.array_equal(sr64['data'], sr['data'])
+    empty = ss.extract.resample_spikes({'data': np.zeros((len(sw['time']), 0, 1), np.float32),
+                                        'time': sw['time'], 'FS': sw['FS']}, sp['FS'] * 2)
+    assert empty['data'].shape == (len(sr['time']), 0, 1)
+
+
 def test_bandpass_float32_golden(ss, golden):
     raw = {'data': golden['bp_raw'], 'FS': 30000, 'n_contacts': 1}
     f = ss.filters.filter_proxy(raw, ss.filters.Filter(np.array([300., 6000.]),

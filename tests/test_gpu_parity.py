@@ -173,6 +173,41 @@ def test_align_extract_bit_exact_burst(env, oracle, align_type):
             assert np.array_equal(wg['data'], wr['data'])
 
 
+@pytest.mark.parametrize("align_type,resample", [("min", 10), ("max", 3)])
+def test_align_resampled_burst(env, oracle, align_type, resample):
+    """Alignment on the spline-upsampled window (extract.py:245-258, resample != 1) on a
+    burst recording with edge re-examinations; aligned times compared exactly, mismatches
+    counted (the matrix form of the spline differs from FITPACK at round-off)."""
+    x, FS = _burst_recording(env, n_c=2, n=60000)
+    raw = {'data': x.astype(np.float64) * 0.37, 'FS': FS, 'n_contacts': x.shape[0]}
+    sp_win = [-0.6, 0.8]
+    total = mism = 0
+    for c in range(x.shape[0]):
+        edge = 'falling' if align_type == 'min' else 'rising'
+        thr = -30.0 if align_type == 'min' else 12.0
+        det = oracle.detect_spikes(raw, thresh=thr, edge=edge, contact=c)
+        assert len(det['data']) > 100
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ref = oracle.align_spikes(raw, det, sp_win, type=align_type, contact=c,
+                                      resample=resample, remove=False)
+            got = env['ss'].extract.align_spikes(raw, det, sp_win, type=align_type, contact=c,
+                                                 resample=resample, remove=False)
+            plain = oracle.align_spikes(raw, det, sp_win, type=align_type, contact=c, remove=False)
+        assert got['data'].shape == ref['data'].shape
+        total += len(ref['data'])
+        mism += int(np.sum(got['data'] != ref['data']))
+        assert not np.array_equal(ref['data'], plain['data'])     # sub-sample shifts happened
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            wr = oracle.extract_spikes(raw, ref, sp_win, resample=resample, contacts=[c])
+            wg = env['ss'].extract.extract_spikes(raw, ref, sp_win, resample=resample, contacts=[c])
+        assert rel_err(wg['data'], wr['data']) < 1e-12                # bar 1e-5
+        assert np.array_equal(wg['time'], wr['time'])
+    print("resample=%d %s: %d of %d aligned times differ" % (resample, align_type, mism, total))
+    assert mism == 0
+
+
 def test_align_ties_and_plateaus(env, oracle):
     # flat tops: argmax must return the FIRST maximum, also after float32 rounding
     FS = 10000

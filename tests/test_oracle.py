@@ -144,6 +144,31 @@ def test_filter_chain_golden(oracle, golden):
     assert np.allclose(ev, golden['chain_pca0_evals'], rtol=1e-10, atol=1e-12 * ev.max())
 
 
+def test_resample_golden(oracle, golden):
+    """Spline upsampling (extract.py:179-205,245-258) - bit-exact: the port calls the same
+    SciPy splrep/splev as the reference."""
+    FS = 25000
+    fd = {'data': golden['chain_filtered'], 'FS': FS, 'n_contacts': 2}
+    det = {'data': golden['chain_detect']}
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        al = oracle.align_spikes(fd, det, [-0.2, 0.8], type='max', contact=1, resample=10)
+        al4 = oracle.align_spikes(fd, det, [-0.2, 0.8], type='min', contact=0, resample=4,
+                                  remove=False)
+        wv = oracle.extract_spikes(fd, al, [-0.2, 0.8], resample=3)
+    assert np.array_equal(al['data'], golden['chain_align_rs10'])
+    assert np.array_equal(al4['data'], golden['chain_align_rs4_min'])
+    assert np.array_equal(wv['data'], golden['chain_waves_rs3'])
+    assert np.array_equal(wv['time'], golden['chain_waves_rs3_time'])
+    assert sorted(wv.keys()) == list(golden['chain_waves_rs3_keys'])
+    sp, period, _ = sine_fixture()
+    sw = oracle.extract_spikes(sp, {'data': golden['sine_resample_spt']}, [0, period])
+    sr = oracle.resample_spikes(sw, sp['FS'] * 2)
+    assert np.array_equal(sr['data'], golden['sine_resample'])
+    assert np.array_equal(sr['time'], golden['sine_resample_time'])
+    assert sr['FS'] == sp['FS']
+
+
 def test_bandpass_float32_golden(oracle, golden):
     raw = {'data': golden['bp_raw'], 'FS': 30000, 'n_contacts': 1}
     f = oracle.filter_proxy(raw, oracle.Filter(np.array([300., 6000.]), np.array([100., 8000.])))
