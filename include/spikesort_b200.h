@@ -249,21 +249,30 @@ int ss_normalize_columns(double *d_x, int64_t n_rows, int n_cols, void *d_ws, si
 
 /* ------------------------------------------------------- spline upsampling (8f)
  * Replaces resample_spikes (extract.py:187-205) and the resample != 1 branch of
- * align_spikes (extract.py:245-258).  d_W is the (n_out, n_win) float64 matrix of the
- * interpolating cubic spline on the two time grids (built on the host with the SciPy
- * routines the reference calls); d_rtime the n_out upsampled times (ms).
- *   ss_resample        : d_out (n_out, n_spk, n_c) float64 = W applied along the time axis
- *                        of d_waves (n_win, n_spk, n_c), element type `dtype`;
- *   ss_align_resampled : as ss_align, the extremum searched on W y, shift = d_rtime[k].
+ * align_spikes (extract.py:245-258): splrep(time, wave, s=0) + splev per waveform, i.e.
+ * FITPACK's fpcurf/fpback/splev.  The waveform-independent part is a "plan" built by the
+ * host in FITPACK's operation order (spikesort_b200/_spline.py), m = n_win:
+ *   d_plan_f64 = [rot_cos (4m) | rot_sin (4m) | tri (4m, row-major m x 4) | ev_h (4 n_out)]
+ *   d_plan_i32 = [rot_j (4m, -1 = no rotation) | ev_l (n_out)]
+ * rot_*[4 it + q] is the q-th Givens rotation of data row `it` against coefficient rot_j;
+ * tri the triangularised banded matrix; ev_l / ev_h the first coefficient and the four
+ * B-spline values of every new abscissa.  The kernels replay the right-hand-side
+ * operations unfused and in order: results are bit-identical to SciPy's.
+ *   ss_resample        : d_out (n_out, n_spk, n_c) float64 from d_waves (n_win, n_spk, n_c)
+ *                        of element type `dtype`;
+ *   ss_align_resampled : as ss_align, the FIRST extremum searched on the upsampled
+ *                        float64 window, shift = d_rtime[k] (the n_out new times, ms).
  */
 int ss_resample(const void *d_waves, int dtype, int n_win, int64_t n_spk, int n_c,
-                const double *d_W, int n_out, double *d_out, void *stream);
+                const double *d_plan_f64, const int32_t *d_plan_i32, int n_out,
+                double *d_out, void *stream);
 int ss_align_resampled(const void *d_x, int dtype, int64_t n_samples, int64_t ld, double FS,
                        const int32_t *d_rows, int64_t n_rows, const int64_t *d_offsets,
                        int win0, int win1, double t_min, double t_max, double lo, double hi,
-                       int use_min, const double *d_W, int n_out, const double *d_rtime,
-                       double *d_spt, int64_t n_spk, int max_iter, int64_t index_offset,
-                       int64_t halo_before, int64_t halo_after, void *stream);
+                       int use_min, const double *d_plan_f64, const int32_t *d_plan_i32,
+                       int n_out, const double *d_rtime, double *d_spt, int64_t n_spk,
+                       int max_iter, int64_t index_offset, int64_t halo_before,
+                       int64_t halo_after, void *stream);
 
 #ifdef __cplusplus
 }

@@ -56,10 +56,10 @@ SIGNATURES = {
     "ss_wave_minmax": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp]),
     "ss_normalize_workspace_bytes": (_sz, [_int]),
     "ss_normalize_columns": (_int, [_vp, _i64, _int, _vp, _sz, _vp]),
-    "ss_resample": (_int, [_vp, _int, _int, _i64, _int, _vp, _int, _vp, _vp]),
+    "ss_resample": (_int, [_vp, _int, _int, _i64, _int, _vp, _vp, _int, _vp, _vp]),
     "ss_align_resampled": (_int, [_vp, _int, _i64, _i64, _dbl, _vp, _i64, _vp, _int, _int, _dbl,
-                                  _dbl, _dbl, _dbl, _int, _vp, _int, _vp, _vp, _i64, _int, _i64,
-                                  _i64, _i64, _vp]),
+                                  _dbl, _dbl, _dbl, _int, _vp, _vp, _int, _vp, _vp, _i64, _int,
+                                  _i64, _i64, _i64, _vp]),
 }
 
 _lib = None

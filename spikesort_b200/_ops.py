@@ -354,59 +354,50 @@ def normalize_columns(x):
 
 
 # ----------------------------------------------------------- spline upsampling
-_SPLINE_CACHE = {}
+def _plan_on_device(plan, device):
+    t = _lib.torch()
+    key = str(device)
+    cache = plan.__dict__.setdefault("_dev", {})
+    if key not in cache:
+        cache[key] = (t.from_numpy(plan.f64).to(device), t.from_numpy(plan.i32).to(device),
+                      t.from_numpy(plan.new_time).to(device))
+    return cache[key]
 
 
-def spline_matrix(time, FS_new):
-    """(W, resamp_time): the interpolating cubic spline of extract.py:194-203 as a matrix.
-    Column j of W is the reference's own splrep/splev applied to the j-th unit vector."""
-    key = (time.tobytes(), float(FS_new))
-    if key not in _SPLINE_CACHE:
-        from scipy import interpolate
-        rt = np.arange(time[0], time[-1], 1000.0 / FS_new)
-        W = np.empty((len(rt), len(time)))
-        for j in range(len(time)):
-            e = np.zeros(len(time))
-            e[j] = 1.0
-            W[:, j] = interpolate.splev(rt, interpolate.splrep(time, e, s=0), der=0)
-        if len(_SPLINE_CACHE) > 32:
-            _SPLINE_CACHE.clear()
-        _SPLINE_CACHE[key] = (np.ascontiguousarray(W), rt)
-    return _SPLINE_CACHE[key]
-
-
-def resample(waves, W):
-    """CUDA waves (n_win, n_spk, n_c), any ss dtype -> CUDA float64 (n_out, n_spk, n_c)."""
+def resample(waves, plan):
+    """CUDA waves (n_win, n_spk, n_c), any ss dtype -> CUDA float64 (n_out, n_spk, n_c);
+    `plan` = _spline.spline_plan(time, FS_new)."""
     lib = _lib.load()
     t = _lib.torch()
     n_win, n_spk, n_c = waves.shape
-    n_out = W.shape[0]
-    Wd = t.from_numpy(W).to(waves.device)
-    out = t.empty((n_out, n_spk, n_c), dtype=t.float64, device=waves.device)
-    rc = lib.ss_resample(_lib.ptr(waves), _lib.ss_dtype_of(waves), n_win, n_spk, n_c, _lib.ptr(Wd), n_out, _lib.ptr(out),
-                         _lib.stream_ptr())
+    if n_win != plan.m:
+        raise ValueError("waveforms have %d samples, the spline plan %d" % (n_win, plan.m))
+    pf, pi, _ = _plan_on_device(plan, waves.device)
+    out = t.empty((plan.n_out, n_spk, n_c), dtype=t.float64, device=waves.device)
+    rc = lib.ss_resample(_lib.ptr(waves), _lib.ss_dtype_of(waves), n_win, n_spk, n_c, _lib.ptr(pf),
+                         _lib.ptr(pi), plan.n_out, _lib.ptr(out), _lib.stream_ptr())
     _lib.check(rc, "ss_resample")
-    _launched(1 if n_spk > 0 else 0)
+    _launched(1 if n_spk > 0 and n_c > 0 and plan.n_out > 0 else 0)
     return out
 
 
 def align_resampled(x, spt, offsets, rows, FS, sp_win, use_min, resample_factor, shard=_WHOLE):
-    """align() with the extremum searched on the spline-upsampled window."""
+    """align() with the extremum searched on the spline-upsampled window
+    (extract.py:245-258 with resample != 1)."""
+    from ._spline import spline_plan
     lib = _lib.load()
-    t = _lib.torch()
     n = x.shape[1]
     win0, win1, time = window_params(sp_win, FS)
     t_min, t_max = time_bounds(n if shard.n_total is None else shard.n_total, FS, sp_win)
     tol = 0.1
     lo, hi = sp_win[0] + tol, sp_win[1] - tol
-    W, rt = spline_matrix(time, FS * resample_factor)
-    Wd = t.from_numpy(W).to(x.device)
-    rtd = t.from_numpy(np.ascontiguousarray(rt)).to(x.device)
+    plan = spline_plan(time, FS * resample_factor)
+    pf, pi, rt = _plan_on_device(plan, x.device)
     n_rows = 1 if offsets is None else offsets.numel() - 1
     rc = lib.ss_align_resampled(_lib.ptr(x), _lib.ss_dtype_of(x), n, x.stride(0), float(FS),
                                 _lib.ptr(rows), n_rows, _lib.ptr(offsets), win0, win1, t_min, t_max,
-                                float(lo), float(hi), int(bool(use_min)), _lib.ptr(Wd), W.shape[0],
-                                _lib.ptr(rtd), _lib.ptr(spt), spt.numel(), MAX_ALIGN_ITER,
+                                float(lo), float(hi), int(bool(use_min)), _lib.ptr(pf), _lib.ptr(pi),
+                                plan.n_out, _lib.ptr(rt), _lib.ptr(spt), spt.numel(), MAX_ALIGN_ITER,
                                 shard.index_offset, shard.halo_before, shard.halo_after,
                                 _lib.stream_ptr())
     _lib.check(rc, "ss_align_resampled")

@@ -8,7 +8,7 @@ from warnings import warn
 
 import numpy as np
 
-from . import _lib, _ops
+from . import _lib, _ops, _spline
 
 _EDGES = ('rising', 'max', 'falling', 'min')
 
@@ -93,8 +93,9 @@ def extract_spikes(spike_data, spt_dict, sp_win, resample=1, contacts='all'):
              "Please update your code to use function"
              "resample_spikes", DeprecationWarning)
         # extract.py:183 returns resample_spikes' fresh dict: no 'is_valid'
-        W, rtime = _ops.spline_matrix(time, FS * resample)
-        return {"data": _ops.resample(waves, W).cpu().numpy(), "time": rtime, "FS": FS}
+        plan = _spline.spline_plan(time, FS * resample)
+        return {"data": _ops.resample(waves, plan).cpu().numpy(), "time": plan.new_time.copy(),
+                "FS": FS}
     wavedict = {"data": waves.cpu().numpy(), "time": time, "FS": FS}
     if int(n_invalid.item()) != 0:
         wavedict['is_valid'] = valid.cpu().numpy().astype(bool)
@@ -109,9 +110,9 @@ def resample_spikes(spikes_dict, FS_new):
     if sp_waves.dtype not in (np.int16, np.float32, np.float64):
         sp_waves = sp_waves.astype(np.float64)
     time = np.asarray(spikes_dict['time'], dtype=np.float64)
-    W, rtime = _ops.spline_matrix(time, FS_new)
+    plan = _spline.spline_plan(time, FS_new)
     waves = t.as_tensor(np.ascontiguousarray(sp_waves)).to(_lib.device())
-    return {"data": _ops.resample(waves, W).cpu().numpy(), "time": rtime,
+    return {"data": _ops.resample(waves, plan).cpu().numpy(), "time": plan.new_time.copy(),
             "FS": spikes_dict['FS']}
 
 

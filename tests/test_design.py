@@ -68,3 +68,29 @@ def test_known_truncation_quirks():
     # sp_win=[-0.6, 0.8] at 25 kHz gives win=[-14, 20], not [-15, 20]
     assert _ops.window_params([-0.6, 0.8], 25000)[:2] == (-14, 20)
     assert _ops.window_params([-0.2, 0.8], 25000)[:2] == (-5, 20)
+
+
+@pytest.mark.parametrize("FS,sp_win,resample", [(25000, [-0.2, 0.8], 10), (30000, [-0.6, 0.8], 3),
+                                                (25000, [0, 4.0], 2), (10000, [-0.2, 0.2], 7)])
+def test_spline_plan_bit_exact_vs_scipy(FS, sp_win, resample):
+    """Host half of the spline upsampling (spikesort_b200/_spline.py): the plan, replayed in
+    plain Python in the order the kernels use, reproduces scipy splrep(s=0)/splev - what
+    resample_spikes (extract.py:199-203) calls - bit for bit."""
+    from scipy import interpolate
+    from spikesort_b200._spline import spline_plan
+    win = (np.asarray(sp_win) / 1000.0 * FS).astype(np.int32)
+    time = np.arange(win[1] - win[0]) * 1000.0 / FS + sp_win[0]
+    plan = spline_plan(time, FS * resample)
+    assert np.array_equal(plan.new_time, np.arange(time[0], time[-1], 1000.0 / (FS * resample)))
+    rng = np.random.default_rng(11)
+    for trial in range(20):
+        y = (rng.standard_normal(len(time)) * 10.0 ** rng.integers(-3, 4)).astype(np.float32)
+        if trial == 0:
+            y[:] = 0
+        if trial == 1:
+            y = np.round(y)                                  # many exact ties
+        tck = interpolate.splrep(time, y, s=0)
+        assert np.array_equal(tck[0], plan.knots)
+        assert np.array_equal(plan.apply(y), interpolate.splev(plan.new_time, tck, der=0))
+    with pytest.raises(TypeError):
+        spline_plan(time[:3], FS * resample)                # splrep: m > k must hold

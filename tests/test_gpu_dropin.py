@@ -124,10 +124,8 @@ def test_chain_golden(ss, golden):
 
 
 def test_resample_golden(ss, golden):
-    """8f rank 1: spline upsampling.  The spline is applied as a precomputed matrix, so
-    upsampled waveforms agree with FITPACK's per-waveform solve to round-off (asserted
-    1e-12 of the waveform scale; bar 1e-5) and aligned times are compared exactly, with
-    mismatches counted (an exact tie between two upsampled points could flip)."""
+    """8f rank 1: spline upsampling.  The kernels replay FITPACK's operations in order and
+    unfused: upsampled waveforms and the times aligned on them are BIT-exact."""
     FS = 25000
     fd = {'data': golden['chain_filtered'], 'FS': FS, 'n_contacts': 2}
     det = {'data': golden['chain_detect']}
@@ -145,13 +143,13 @@ def test_resample_golden(ss, golden):
         print("%s: %d of %d aligned times differ" % (key, mism, len(golden[key])))
         assert mism == 0
     assert wv['data'].dtype == np.float64 and wv['data'].shape == golden['chain_waves_rs3'].shape
-    assert rel_err(wv['data'], golden['chain_waves_rs3']) < 1e-12
+    assert np.array_equal(wv['data'], golden['chain_waves_rs3'])
     assert np.array_equal(wv['time'], golden['chain_waves_rs3_time'])
     assert sorted(wv.keys()) == list(golden['chain_waves_rs3_keys'])      # no 'is_valid'
     sp, period, _ = sine_fixture()
     sw = ss.extract.extract_spikes(sp, {'data': golden['sine_resample_spt']}, [0, period])
     sr = ss.extract.resample_spikes(sw, sp['FS'] * 2)
-    assert rel_err(sr['data'], golden['sine_resample']) < 1e-12
+    assert np.array_equal(sr['data'], golden['sine_resample'])
     assert np.array_equal(sr['time'], golden['sine_resample_time'])
     assert sr['FS'] == sp['FS']
     # float64 waveforms in (a user-built dict) take the same route

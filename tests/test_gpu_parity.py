@@ -176,8 +176,8 @@ def test_align_extract_bit_exact_burst(env, oracle, align_type):
 @pytest.mark.parametrize("align_type,resample", [("min", 10), ("max", 3)])
 def test_align_resampled_burst(env, oracle, align_type, resample):
     """Alignment on the spline-upsampled window (extract.py:245-258, resample != 1) on a
-    burst recording with edge re-examinations; aligned times compared exactly, mismatches
-    counted (the matrix form of the spline differs from FITPACK at round-off)."""
+    burst recording with edge re-examinations and many exact ties (quantised samples):
+    aligned times and upsampled waveforms bit-exact."""
     x, FS = _burst_recording(env, n_c=2, n=60000)
     raw = {'data': x.astype(np.float64) * 0.37, 'FS': FS, 'n_contacts': x.shape[0]}
     sp_win = [-0.6, 0.8]
@@ -202,7 +202,7 @@ def test_align_resampled_burst(env, oracle, align_type, resample):
             warnings.simplefilter('ignore')
             wr = oracle.extract_spikes(raw, ref, sp_win, resample=resample, contacts=[c])
             wg = env['ss'].extract.extract_spikes(raw, ref, sp_win, resample=resample, contacts=[c])
-        assert rel_err(wg['data'], wr['data']) < 1e-12                # bar 1e-5
+        assert np.array_equal(wg['data'], wr['data'])
         assert np.array_equal(wg['time'], wr['time'])
     print("resample=%d %s: %d of %d aligned times differ" % (resample, align_type, mism, total))
     assert mism == 0
