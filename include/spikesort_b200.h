@@ -274,6 +274,63 @@ int ss_align_resampled(const void *d_x, int dtype, int64_t n_samples, int64_t ld
                        int max_iter, int64_t index_offset, int64_t halo_before,
                        int64_t halo_after, void *stream);
 
+/* ------------------------------------------- time shards over peer memory (8e)
+ * Exchange steps of a recording sharded by time across GPUs (one process per GPU).  The
+ * reference has no such step: its filter_proxy walks (contact, chunk) units in one process
+ * (filters.py:135-141) and detect/align/extract see the whole recording.  What crosses a
+ * shard boundary (extract.py:79,86-91,160-163,245,281; features.py:224-231) travels through
+ * one small ARENA per rank in peer-addressable device memory: `arenas` is a HOST array of
+ * `world` device pointers, arenas[r] = base of rank r's arena as seen from THIS process
+ * (torch symmetric memory, cudaIpc, or plain allocations when all shards sit on one GPU).
+ * Producers store directly into the peers' arenas (NVLink), ss_peer_barrier orders them
+ * with the consumers; nothing here synchronises with the host.
+ *   ss_shard_arena_bytes / _offsets : size and layout {flags, thr, from_left, from_right,
+ *                                     prev_last, slots, slot_stride}; zero the arena once.
+ *   ss_peer_barrier        : all ranks reached `epoch` (1, 2, 3, ... per arena set) and the
+ *                            peer stores issued before it on this stream are visible;
+ *                            bounded spin (timeout_s, default 10 s), traps instead of hanging.
+ *   ss_shard_put_thresholds: thresholds of the rank owning the first 10 s -> every arena.
+ *   ss_shard_put_halos     : first/last H filtered samples of every contact -> neighbours.
+ *   ss_shard_install_halos : neighbours' samples into the margins d_sig[-H..0) and
+ *                            d_sig[n..n+H) of the shard's buffer; d_flags[c] = 1 where the
+ *                            shard's last sample and the next shard's first form a crossing.
+ *   ss_shard_append_boundary: appends t_last to the spike list of every flagged contact
+ *                            (d_spt_out needs room for n_spk_in + n_c times).
+ *   ss_shard_put_last      : last aligned time per contact (NaN: none) -> right neighbour,
+ *                            read there as d_prev_last of ss_remove_doubles_mark.
+ *   ss_shard_gram_put      : Gram/sums of ss_pca_gram re-expressed for the zero reference
+ *                            -> slot `rank` of every arena;
+ *   ss_shard_gram_reduce   : sum of the slots in rank order (bit-identical on every rank),
+ *                            per-contact counts of every rank in d_all_counts (world, n_c).
+ * Kernels that take (d_spt, n_spk, d_offsets) ignore entries at or beyond
+ * d_offsets[n_rows], so a list with spare capacity can be passed without a host sync.
+ */
+#define SS_MAX_PEERS 16
+size_t ss_shard_arena_bytes(int n_c, int H, int n_win, int world);
+int ss_shard_arena_offsets(int n_c, int H, int n_win, int world, size_t *out7);
+int ss_peer_barrier(void *const *arenas, int rank, int world, uint64_t epoch, double timeout_s,
+                    void *stream);
+int ss_shard_put_thresholds(const double *d_thr, int n_c, int H, int n_win, void *const *arenas,
+                            int world, void *stream);
+int ss_shard_put_halos(const double *d_sig, int64_t ld, int n_c, int64_t n, int H, int n_win,
+                       void *const *arenas, int rank, int world, void *stream);
+int ss_shard_install_halos(double *d_sig, int64_t ld, int n_c, int64_t n, int H, int n_win,
+                           const void *arena, int rank, int world, const double *d_thr,
+                           int falling, int32_t *d_flags, void *stream);
+int ss_shard_append_boundary(const double *d_spt_in, const int64_t *d_offsets_in, int n_c,
+                             int64_t n_spk_in, const int32_t *d_flags, double t_last,
+                             double *d_spt_out, int64_t *d_offsets_out, void *stream);
+int ss_shard_put_last(const double *d_spt, const int64_t *d_offsets, int n_c, int H, int n_win,
+                      void *const *arenas, int rank, int world, void *stream);
+int ss_shard_gram_put(const double *d_gram, const double *d_sum, const double *d_ref,
+                      const int64_t *d_offsets, int n_c, int H, int n_win, void *const *arenas,
+                      int rank, int world, void *stream);
+int ss_shard_gram_reduce(const void *arena, int n_c, int H, int n_win, int world, double *d_gram,
+                         double *d_sum, int64_t *d_counts, int64_t *d_all_counts, void *stream);
+/* reference waveform for the Gram shift of ss_pca_gram: the first spike of every group */
+int ss_pca_first_wave(const float *d_waves, int n_win, int64_t n_spk, int n_c,
+                      const int64_t *d_offsets, int64_t n_groups, double *d_ref, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

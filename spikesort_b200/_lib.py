@@ -56,6 +56,18 @@ SIGNATURES = {
     "ss_wave_minmax": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp]),
     "ss_normalize_workspace_bytes": (_sz, [_int]),
     "ss_normalize_columns": (_int, [_vp, _i64, _int, _vp, _sz, _vp]),
+    "ss_shard_arena_bytes": (_sz, [_int, _int, _int, _int]),
+    "ss_shard_arena_offsets": (_int, [_int, _int, _int, _int, _vp]),
+    "ss_peer_barrier": (_int, [_vp, _int, _int, _c.c_uint64, _dbl, _vp]),
+    "ss_shard_put_thresholds": (_int, [_vp, _int, _int, _int, _vp, _int, _vp]),
+    "ss_shard_put_halos": (_int, [_vp, _i64, _int, _i64, _int, _int, _vp, _int, _int, _vp]),
+    "ss_shard_install_halos": (_int, [_vp, _i64, _int, _i64, _int, _int, _vp, _int, _int, _vp, _int,
+                                      _vp, _vp]),
+    "ss_shard_append_boundary": (_int, [_vp, _vp, _int, _i64, _vp, _dbl, _vp, _vp, _vp]),
+    "ss_shard_put_last": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _vp]),
+    "ss_shard_gram_put": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _vp, _int, _int, _vp]),
+    "ss_shard_gram_reduce": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    "ss_pca_first_wave": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp]),
     "ss_resample": (_int, [_vp, _int, _int, _i64, _int, _vp, _vp, _int, _vp, _vp]),
     "ss_align_resampled": (_int, [_vp, _int, _i64, _i64, _dbl, _vp, _i64, _vp, _int, _int, _dbl,
                                   _dbl, _dbl, _dbl, _int, _vp, _vp, _int, _vp, _vp, _i64, _int,

@@ -214,8 +214,10 @@ def align(x, spt, offsets, rows, FS, sp_win, use_min, shard=_WHOLE):
     return spt
 
 
-def remove_doubles(spt, offsets, tol, prev_last=None):
-    """Returns (kept times, new offsets); offsets None = one row."""
+def remove_doubles(spt, offsets, tol, prev_last=None, also=None):
+    """Returns (kept times, new offsets); offsets None = one row.  `spt` may have spare
+    capacity beyond offsets[-1].  also: optional CUDA int64 scalar fetched in the same host
+    synchronisation that sizes the result; its value is then returned as a third item."""
     lib = _lib.load()
     t = _lib.torch()
     n_spk = spt.numel()
@@ -230,12 +232,17 @@ def remove_doubles(spt, offsets, tol, prev_last=None):
                                     _lib.stream_ptr())
     _lib.check(rc, "ss_remove_doubles_mark")
     _launched(3)          # mark, scan, row offsets
-    total = int(new_off[-1].item())
+    if also is None:
+        total = int(new_off[-1].item())
+    else:
+        total, extra = (int(v) for v in t.stack((new_off[-1], also.reshape(()))).tolist())
     out = t.empty(total, dtype=t.float64, device=spt.device)
     rc = lib.ss_remove_doubles_emit(_lib.ptr(spt), n_spk, _lib.ptr(ws), ws.numel(), _lib.ptr(out),
                                     total, _lib.stream_ptr())
     _lib.check(rc, "ss_remove_doubles_emit")
     _launched(1 if (n_spk > 0 and total > 0) else 0)
+    if also is not None:
+        return out, (None if single else new_off), extra
     return out, (None if single else new_off)
 
 
@@ -265,6 +272,21 @@ def extract(x, spt, FS, sp_win, contacts=None, offsets=None, rows=None, shard=_W
 
 
 # ------------------------------------------------------------------------ PCA
+def pca_first_wave(waves, offsets=None):
+    """Reference waveform (float64 (G, n_win)) for the Gram shift: the first spike of every
+    group (contact c's first spike without offsets)."""
+    lib = _lib.load()
+    t = _lib.torch()
+    n_win, n_spk, n_c = waves.shape
+    n_groups = n_c if offsets is None else offsets.numel() - 1
+    ref = t.empty((n_groups, n_win), dtype=t.float64, device=waves.device)
+    rc = lib.ss_pca_first_wave(_lib.ptr(waves), n_win, n_spk, n_c, _lib.ptr(offsets), n_groups,
+                               _lib.ptr(ref), _lib.stream_ptr())
+    _lib.check(rc, "ss_pca_first_wave")
+    _launched(1)
+    return ref
+
+
 def pca_gram(waves, offsets=None, ref=None):
     """Gram / sums of CUDA float32 waves (n_win, n_spk, n_c) per group.
     Returns (gram (G, n_win, n_win), sum (G, n_win), ref (G, n_win), counts (G,))."""
@@ -274,18 +296,11 @@ def pca_gram(waves, offsets=None, ref=None):
     if offsets is None:
         n_groups = n_c
         counts = t.full((n_groups,), n_spk, dtype=t.int64, device=waves.device)
-        if ref is None:
-            ref = (waves[:, 0, :].t().to(t.float64).contiguous() if n_spk > 0
-                   else t.zeros((n_groups, n_win), dtype=t.float64, device=waves.device))
     else:
         n_groups = offsets.numel() - 1
-        counts = (offsets[1:] - offsets[:-1]).contiguous()
-        if ref is None:
-            if n_spk > 0:
-                first = offsets[:-1].clamp(max=n_spk - 1)
-                ref = waves[:, first, 0].t().to(t.float64).contiguous()
-            else:
-                ref = t.zeros((n_groups, n_win), dtype=t.float64, device=waves.device)
+        counts = offsets[1:] - offsets[:-1]
+    if ref is None:
+        ref = pca_first_wave(waves, offsets)
     gram = t.empty((n_groups, n_win, n_win), dtype=t.float64, device=waves.device)
     ssum = t.empty((n_groups, n_win), dtype=t.float64, device=waves.device)
     ws = _lib.workspace(lib.ss_pca_workspace_bytes(n_win, n_groups))

@@ -41,7 +41,7 @@ align_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t l
 {
     const int lane = threadIdx.x & 31;
     const int64_t s = (int64_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
-    if (s >= n_spk) return;
+    if (s >= n_spk || (offsets && s >= __ldg(offsets + n_rows))) return;   // spare capacity
     int64_t r = n_rows > 1 ? find_row(offsets, n_rows, s) : 0;
     if (rows) r = rows[r];
     const int64_t row0 = r * ld;
@@ -89,7 +89,8 @@ rd_mark_kernel(const double *__restrict__ spt, int64_t n_spk, const int64_t *__r
     __shared__ int warp_cnt[RD_BLOCK / 32];
     const int64_t k = (int64_t)blockIdx.x * RD_BLOCK + threadIdx.x;
     bool kp = false;
-    if (k < n_spk) {
+    if (k < n_spk && k >= __ldg(offsets + n_rows)) keep[k] = 0;            // spare capacity
+    if (k < n_spk && k < __ldg(offsets + n_rows)) {
         const int64_t r = n_rows > 1 ? find_row(offsets, n_rows, k) : 0;
         if (k == __ldg(offsets + r)) {
             // first of its row: kept, unless the previous time shard ended within tol

@@ -142,7 +142,7 @@ align_resampled_kernel(const void *__restrict__ x, int dtype, int64_t n_samples,
     const int64_t s = (int64_t)blockIdx.x * RA_BLOCK + threadIdx.x;
     double t = 0.0;
     int64_t row0 = 0;
-    bool active = s < n_spk, moved = false;
+    bool active = s < n_spk && !(offsets && s >= __ldg(offsets + n_rows)), moved = false;
     if (active) {
         int64_t r = n_rows > 1 ? rs_find_row(offsets, n_rows, s) : 0;
         if (rows) r = rows[r];

@@ -30,10 +30,22 @@ rank order is, per contact, exactly the list the single-GPU chain produces
 (``tests/test_gpu_sharded.py`` checks this bit for bit by running the phases of
 several shards on one GPU).
 
-``ShardedChain`` splits the chain into phases separated by exactly those exchanges, so
-the same code runs under NCCL (``run_chain_sharded``), under gloo on CPU tensors (the
-helpers, ``tests/test_dist_gloo.py``) and in the single-GPU emulation.
+``ShardedChain`` splits the chain into phases separated by exactly those exchanges.  Two
+transports carry them:
+
+* **peer memory** (default under NCCL worlds; ``PeerFabric``): every rank owns a small arena
+  in torch symmetric memory; the library's own kernels (``csrc/exchange.cu``) store
+  thresholds, halos, last spike times and Gram partials straight into the neighbours'
+  arenas over NVLink and order themselves with a flag barrier kernel - no NCCL call, no
+  torch op and no extra host sync between the stages.  ``LocalFabric`` gives the same
+  kernels plain arenas on ONE device, which is how the tests (and a slab-pipelined
+  single-GPU run) drive several shards in lock-step;
+* **collectives** (``transport='nccl'``, and gloo on CPU tensors for the helpers,
+  ``tests/test_dist_gloo.py``): broadcast / send-recv / all-reduce through
+  ``torch.distributed``.
 """
+import ctypes
+
 from . import _lib, _ops
 from .pipeline import ChainResult
 
@@ -183,13 +195,102 @@ def gather_counts(offsets):
     return t.stack(allc)
 
 
+
+# ------------------------------------------------------------------ peer memory
+class _Fabric(object):
+    """Arenas of all shards as seen from this process (include/spikesort_b200.h, "time
+    shards over peer memory")."""
+
+    def __init__(self, n_c, H, n_win, world):
+        lib = _lib.load()
+        self.n_c, self.H, self.n_win, self.world = int(n_c), int(H), int(n_win), int(world)
+        self.nbytes = int(lib.ss_shard_arena_bytes(self.n_c, self.H, self.n_win, self.world))
+        off = (ctypes.c_size_t * 7)()
+        _lib.check(lib.ss_shard_arena_offsets(self.n_c, self.H, self.n_win, self.world, off),
+                   "ss_shard_arena_offsets")
+        (self.off_flags, self.off_thr, self.off_from_left, self.off_from_right,
+         self.off_prev_last, self.off_slots, self.slot_stride) = (int(v) for v in off)
+        self.epoch = 0
+
+    def _set_ptrs(self, ptrs):
+        self.ptrs = (ctypes.c_void_p * self.world)(*[int(p) for p in ptrs])
+
+    def local(self, rank, offset, count):
+        """float64 view of `count` values at byte `offset` of rank's arena (own arenas only)."""
+        a = self.arena(rank)
+        return a[offset // 8:offset // 8 + count]
+
+    def key(self):
+        return (self.n_c, self.H, self.n_win, self.world)
+
+
+class LocalFabric(_Fabric):
+    """All shards on one device and one stream: plain allocations, stream order is the barrier."""
+
+    def __init__(self, n_c, H, n_win, world, device=None):
+        _Fabric.__init__(self, n_c, H, n_win, world)
+        t = _lib.require_cuda()
+        dev = device if device is not None else _lib.device()
+        self._arenas = [t.zeros(self.nbytes // 8, dtype=t.float64, device=dev)
+                        for _ in range(self.world)]
+        self._set_ptrs([a.data_ptr() for a in self._arenas])
+
+    def arena(self, rank):
+        return self._arenas[rank]
+
+    def barrier(self, rank):
+        pass
+
+
+class PeerFabric(_Fabric):
+    """One process per GPU: the arena lives in torch symmetric memory, peers store into it
+    over NVLink; ss_peer_barrier (flags in the arena itself) orders the steps."""
+
+    def __init__(self, n_c, H, n_win, group=None):
+        t = _lib.require_cuda()
+        d = _dist()
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else d.group.WORLD
+        self.rank, world = d.get_rank(group), d.get_world_size(group)
+        _Fabric.__init__(self, n_c, H, n_win, world)
+        self._arena = symm.empty(self.nbytes // 8, dtype=t.float64, device=_lib.device())
+        self._arena.zero_()
+        self._hdl = symm.rendezvous(self._arena, group)
+        self._set_ptrs(self._hdl.buffer_ptrs)
+        t.cuda.synchronize()
+        d.barrier(group)                       # every arena is zeroed before anyone signals
+
+    def arena(self, rank):
+        if rank != self.rank:
+            raise ValueError("only the local arena is addressable from the host side")
+        return self._arena
+
+    def barrier(self, rank):
+        self.epoch += 1
+        rc = _lib.load().ss_peer_barrier(self.ptrs, rank, self.world, self.epoch, 10.0,
+                                         _lib.stream_ptr())
+        _lib.check(rc, "ss_peer_barrier")
+        _ops._launched(1)
+
+
+_FABRICS = {}
+
+
+def peer_fabric(n_c, H, n_win):
+    """Cached PeerFabric of the default process group (the rendezvous costs milliseconds)."""
+    key = (int(n_c), int(H), int(n_win), world()[1], int(_lib.torch().cuda.current_device()))
+    if key not in _FABRICS:
+        _FABRICS[key] = PeerFabric(n_c, H, n_win)
+    return _FABRICS[key]
+
+
 # ---------------------------------------------------------------- phased chain
 class ShardedChain(object):
     """One time shard of the chain, as phases separated by the exchange steps."""
 
     def __init__(self, x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
                  thresh='auto', ncomps=2, chunksize=1E6, rank=0, n_ranks=1, index_offset=0,
-                 n_total=None, halo=None):
+                 n_total=None, halo=None, fabric=None):
         t = _lib.require_cuda()
         self.t = t
         self.x, self.FS, self.filt = x, FS, filt
@@ -209,6 +310,10 @@ class ShardedChain(object):
         # filtered signal with room for the neighbours' samples on both sides
         self.buf = t.empty((self.n_c, self.n + 2 * self.H), dtype=t.float64, device=x.device)
         self.sig = self.buf[:, self.H:self.H + self.n]
+        self.fabric = fabric
+        if fabric is not None and fabric.key() != (self.n_c, self.H, self.n_win, n_ranks):
+            raise ValueError("fabric %r does not match the shard %r"
+                             % (fabric.key(), (self.n_c, self.H, self.n_win, n_ranks)))
 
     # 1. sweep 1 of the filter (needs nothing from other ranks)
     def prepare(self):
@@ -225,7 +330,7 @@ class ShardedChain(object):
                                             -frac if self.falling else frac)
 
     # 3. sweep 2 with fused crossing marks; returns what the neighbours need
-    def filter_detect(self, thr):
+    def filter_detect(self, thr, slabs=True):
         r = self.res
         r.thresh = thr
         _, _, spt, offsets = _ops.filtfilt_detect(
@@ -233,6 +338,8 @@ class ShardedChain(object):
             out=self.sig, ws=self.ws, shard=self.shard)
         r.filtered = self.sig
         self._spt, self._offsets = spt, offsets
+        if not slabs:
+            return None
         H = self.H
         left_slab = self.sig[:, :H].contiguous()            # becomes rank-1's right halo
         right_slab = self.sig[:, self.n - H:].contiguous()  # becomes rank+1's left halo
@@ -300,13 +407,120 @@ class ShardedChain(object):
         r.scores = _ops.pca_project(r.waves, r.evals, r.evecs, self.ncomps, offsets=r.offsets)
         return r
 
+    # ---- the same phases over a fabric (peer memory): no torch op, no extra host sync
+    def _xargs(self):
+        f = self.fabric
+        return self.n_c, self.H, self.n_win, f.ptrs
+
+    def fab_put_thresholds(self, thr):
+        """Rank owning the first 10 s: thresholds into every arena (then barrier)."""
+        n_c, H, n_win, ptrs = self._xargs()
+        rc = _lib.load().ss_shard_put_thresholds(_lib.ptr(thr), n_c, H, n_win, ptrs, self.n_ranks,
+                                                 _lib.stream_ptr())
+        _lib.check(rc, "ss_shard_put_thresholds")
+        _ops._launched(1)
+
+    def fab_thresholds(self):
+        f = self.fabric
+        return f.local(self.rank, f.off_thr, self.n_c).clone()
+
+    def fab_filter_detect(self, thr):
+        """Sweep 2 with fused crossing marks, then the boundary slabs into the neighbours'
+        arenas (then barrier)."""
+        self.filter_detect(thr, slabs=False)
+        n_c, H, n_win, ptrs = self._xargs()
+        rc = _lib.load().ss_shard_put_halos(_lib.ptr(self.sig), self.sig.stride(0), n_c, self.n, H,
+                                            n_win, ptrs, self.rank, self.n_ranks, _lib.stream_ptr())
+        _lib.check(rc, "ss_shard_put_halos")
+        _ops._launched(1 if self.n_ranks > 1 and H > 0 else 0)
+
+    def fab_align(self):
+        """Halos into the margins, boundary crossing appended, alignment, last aligned time of
+        every contact into the right neighbour's arena (then barrier)."""
+        t, r, f, lib = self.t, self.res, self.fabric, _lib.load()
+        n_c, H, n_win, ptrs = self._xargs()
+        dev = self.sig.device
+        flags = t.empty(n_c, dtype=t.int32, device=dev)
+        rc = lib.ss_shard_install_halos(_lib.ptr(self.sig), self.sig.stride(0), n_c, self.n, H, n_win,
+                                        _lib.ptr(f.arena(self.rank)), self.rank, self.n_ranks,
+                                        _lib.ptr(r.thresh), int(self.falling), _lib.ptr(flags),
+                                        _lib.stream_ptr())
+        _lib.check(rc, "ss_shard_install_halos")
+        _ops._launched(1)
+        self._cap_detected = None
+        if self.rank < self.n_ranks - 1:
+            n_old = self._spt.numel()
+            spt = t.empty(n_old + n_c, dtype=t.float64, device=dev)     # spare capacity
+            offsets = t.empty(n_c + 1, dtype=t.int64, device=dev)
+            t_last = (self.shard.index_offset + self.n - 1) * 1000.0 / self.FS
+            rc = lib.ss_shard_append_boundary(_lib.ptr(self._spt), _lib.ptr(self._offsets), n_c,
+                                              n_old, _lib.ptr(flags), float(t_last), _lib.ptr(spt),
+                                              _lib.ptr(offsets), _lib.stream_ptr())
+            _lib.check(rc, "ss_shard_append_boundary")
+            _ops._launched(1)
+            self._spt, self._offsets = spt, offsets
+            self._cap_detected = offsets[-1]       # true length, read with remove_doubles' sync
+        r.spt_detected, r.offsets_detected = self._spt, self._offsets
+        spt = self._spt.clone()
+        _ops.align(self.sig, spt, self._offsets, None, self.FS, self.sp_win, self.use_min,
+                   shard=self.shard)
+        self._aligned = spt
+        rc = lib.ss_shard_put_last(_lib.ptr(spt), _lib.ptr(self._offsets), n_c, H, n_win, ptrs,
+                                   self.rank, self.n_ranks, _lib.stream_ptr())
+        _lib.check(rc, "ss_shard_put_last")
+        _ops._launched(1 if self.rank < self.n_ranks - 1 else 0)
+
+    def fab_extract_gram(self):
+        """Duplicate removal (left neighbour's last times from the arena), extraction, partial
+        Gram re-expressed for the zero reference into slot `rank` of every arena (then
+        barrier)."""
+        t, r, f, lib = self.t, self.res, self.fabric, _lib.load()
+        n_c, H, n_win, ptrs = self._xargs()
+        prev_last = f.local(self.rank, f.off_prev_last, n_c) if self.rank > 0 else None
+        if self._cap_detected is not None:
+            spt, offsets, n_det = _ops.remove_doubles(self._aligned, self._offsets, 1000.0 / self.FS,
+                                                      prev_last=prev_last, also=self._cap_detected)
+            r.spt_detected = r.spt_detected[:n_det]
+        else:
+            spt, offsets = _ops.remove_doubles(self._aligned, self._offsets, 1000.0 / self.FS,
+                                               prev_last=prev_last)
+        r.spt, r.offsets = spt, offsets
+        waves, valid, n_invalid = _ops.extract(self.sig, spt, self.FS, self.sp_win, contacts=None,
+                                               offsets=offsets, shard=self.shard)
+        r.waves, r.valid, r.n_invalid, r.time = waves, valid, n_invalid, self.time
+        gram, ssum, ref, _ = _ops.pca_gram(waves, offsets=offsets)
+        rc = lib.ss_shard_gram_put(_lib.ptr(gram), _lib.ptr(ssum), _lib.ptr(ref), _lib.ptr(offsets),
+                                   n_c, H, n_win, ptrs, self.rank, self.n_ranks, _lib.stream_ptr())
+        _lib.check(rc, "ss_shard_gram_put")
+        _ops._launched(1)
+
+    def fab_project(self):
+        """Sum of all shards' partials in rank order, replicated eigensolve, local projection."""
+        t, r, f, lib = self.t, self.res, self.fabric, _lib.load()
+        n_c, H, n_win, _ = self._xargs()
+        dev = self.sig.device
+        gram = t.empty((n_c, n_win, n_win), dtype=t.float64, device=dev)
+        ssum = t.empty((n_c, n_win), dtype=t.float64, device=dev)
+        counts = t.empty(n_c, dtype=t.int64, device=dev)
+        all_counts = t.empty((self.n_ranks, n_c), dtype=t.int64, device=dev)
+        rc = lib.ss_shard_gram_reduce(_lib.ptr(f.arena(self.rank)), n_c, H, n_win, self.n_ranks,
+                                      _lib.ptr(gram), _lib.ptr(ssum), _lib.ptr(counts),
+                                      _lib.ptr(all_counts), _lib.stream_ptr())
+        _lib.check(rc, "ss_shard_gram_reduce")
+        _ops._launched(1)
+        r.all_counts = all_counts
+        return self.project(gram, ssum, counts)
+
 
 def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
-                      thresh='auto', ncomps=2, chunksize=1E6, index_offset=None, n_total=None):
+                      thresh='auto', ncomps=2, chunksize=1E6, index_offset=None, n_total=None,
+                      transport=None):
     """The chain on this rank's time shard `x` (CUDA tensor, every rank the same number
     of samples unless index_offset/n_total say otherwise), with the exchange steps of
     the module docstring.  Spike times are global; `all_counts` gives the layout of the
-    concatenated list."""
+    concatenated list.  transport: 'peer' (NVLink peer memory, default) or 'nccl'
+    (torch.distributed collectives); SS_TRANSPORT overrides the default."""
+    import os
     t = _lib.require_cuda()
     rank, n_ranks = world()
     n = x.shape[1]
@@ -314,9 +528,16 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
         index_offset = rank * n
     if n_total is None:
         n_total = n_ranks * n
+    if transport is None:
+        transport = os.environ.get("SS_TRANSPORT", "peer")
+    if transport not in ("peer", "nccl"):
+        raise ValueError("transport must be 'peer' or 'nccl'")
+    fabric = None
+    if transport == "peer" and n_ranks > 1:
+        win0, win1, _ = _ops.window_params(list(sp_win), FS)
+        fabric = peer_fabric(x.shape[0], min(4 * (win1 - win0), n), win1 - win0)
     ch = ShardedChain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize, rank,
-                      n_ranks, index_offset, n_total)
-    import os
+                      n_ranks, index_offset, n_total, fabric=fabric)
     prof = os.environ.get("SS_DIST_PROFILE") and rank == 0
     marks = []
 
@@ -329,26 +550,46 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
     mark("start")
     ch.prepare()
     mark("prepare")
-    thr = ch.head_threshold() if rank == 0 else t.empty(x.shape[0], dtype=t.float64,
-                                                        device=x.device)
-    thr = share_thresholds(thr, 0)
-    mark("threshold+bcast")
-    left_slab, right_slab = ch.filter_detect(thr)
-    mark("filter_detect")
-    halo_left, halo_right = exchange_with_neighbours(left_slab, right_slab)
-    mark("halo exchange")
-    last = ch.align(halo_left, halo_right)
-    mark("align")
-    prev_last, _ = exchange_with_neighbours(t.zeros_like(last), last)
-    mark("last exchange")
-    ref, _ = ch.extract(prev_last)
-    mark("extract")
-    gram, ssum, counts = ch.gram(ref)
-    gram, ssum, counts, all_counts = merge_gram(gram, ssum, counts, with_layout=True)
-    mark("gram+allreduce")
-    res = ch.project(gram, ssum, counts)
-    res.all_counts = all_counts
-    mark("project")
+    if fabric is not None:
+        if rank == 0:
+            thr = ch.head_threshold()
+            ch.fab_put_thresholds(thr)
+        fabric.barrier(rank)
+        if rank != 0:
+            thr = ch.fab_thresholds()
+        mark("threshold+put")
+        ch.fab_filter_detect(thr)
+        fabric.barrier(rank)
+        mark("filter_detect+halo put")
+        ch.fab_align()
+        fabric.barrier(rank)
+        mark("align+last put")
+        ch.fab_extract_gram()
+        fabric.barrier(rank)
+        mark("extract+gram put")
+        res = ch.fab_project()
+        mark("reduce+project")
+    else:
+        thr = ch.head_threshold() if rank == 0 else t.empty(x.shape[0], dtype=t.float64,
+                                                            device=x.device)
+        thr = share_thresholds(thr, 0)
+        mark("threshold+bcast")
+        left_slab, right_slab = ch.filter_detect(thr)
+        mark("filter_detect")
+        halo_left, halo_right = exchange_with_neighbours(left_slab, right_slab)
+        mark("halo exchange")
+        last = ch.align(halo_left, halo_right)
+        mark("align")
+        prev_last, _ = exchange_with_neighbours(t.zeros_like(last), last)
+        mark("last exchange")
+        ref, _ = ch.extract(prev_last)
+        mark("extract")
+        gram, ssum, counts = ch.gram(ref)
+        gram, ssum, counts, all_counts = merge_gram(gram, ssum, counts, with_layout=True)
+        mark("gram+allreduce")
+        res = ch.project(gram, ssum, counts)
+        res.all_counts = all_counts
+        mark("project")
     if prof:
         print("dist profile (ms): " + ", ".join(
             "%s %.3f" % (marks[i][0], 1000 * (marks[i][1] - marks[i - 1][1]))

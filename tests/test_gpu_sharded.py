@@ -36,8 +36,35 @@ def _run_sharded(torch, dist_mod, x_full, S, FS, flt, sp_win, chunksize, thresh)
     return [c.project(gram, ssum, counts) for c in chains], thr
 
 
+def _run_sharded_fabric(torch, dist_mod, x_full, S, FS, flt, sp_win, chunksize, thresh):
+    """The peer-memory transport (csrc/exchange.cu) with all arenas on one device: the same
+    kernels and call order as run_chain_sharded(transport='peer'), stream order standing in
+    for the NVLink flag barrier."""
+    from spikesort_b200 import _ops
+    n = x_full.shape[1] // S
+    win0, win1, _ = _ops.window_params(list(sp_win), FS)
+    fab = dist_mod.LocalFabric(x_full.shape[0], min(4 * (win1 - win0), n), win1 - win0, S)
+    chains = [dist_mod.ShardedChain(x_full[:, r * n:(r + 1) * n], FS, flt, sp_win, 'falling',
+                                    'min', thresh, 2, chunksize, rank=r, n_ranks=S,
+                                    index_offset=r * n, n_total=S * n, fabric=fab)
+              for r in range(S)]
+    for c in chains:
+        c.prepare()
+    thr0 = chains[0].head_threshold()
+    chains[0].fab_put_thresholds(thr0)
+    thrs = [thr0] + [c.fab_thresholds() for c in chains[1:]]
+    for c, thr in zip(chains, thrs):
+        c.fab_filter_detect(thr)
+    for c in chains:
+        c.fab_align()
+    for c in chains:
+        c.fab_extract_gram()
+    return [c.fab_project() for c in chains], thr0
+
+
+@pytest.mark.parametrize("transport", ["collective", "fabric"])
 @pytest.mark.parametrize("S,chunksize", [(2, 20000), (3, 10000), (4, 30000)])
-def test_sharded_chain_equals_whole(cuda, S, chunksize):
+def test_sharded_chain_equals_whole(cuda, S, chunksize, transport):
     import torch
     from spikesort_b200 import dist as ssd, filters, pipeline, synth
     FS, n_c = 3000, 5
@@ -56,7 +83,8 @@ def test_sharded_chain_equals_whole(cuda, S, chunksize):
     sp_win = [-1.0, 2.0]                                               # 3 + 6 samples at 3 kHz
     whole = pipeline.run_chain(x, FS, filt=flt, sp_win=sp_win, edge='falling', align_type='min',
                                thresh='4', ncomps=2, chunksize=chunksize)
-    shards, thr = _run_sharded(torch, ssd, x, S, FS, flt, sp_win, chunksize, '4')
+    run = _run_sharded if transport == "collective" else _run_sharded_fabric
+    shards, thr = run(torch, ssd, x, S, FS, flt, sp_win, chunksize, '4')
     assert torch.equal(thr, whole.thresh)
     assert torch.equal(torch.cat([s.filtered for s in shards], dim=1), whole.filtered)
     tot = 0
@@ -74,6 +102,12 @@ def test_sharded_chain_equals_whole(cuda, S, chunksize):
         assert rel_err(sign_normalise(sc, w['scores']), w['scores']) < 1e-9, c
         tot += len(spt)
     assert tot > 200
+    if transport == "fabric":
+        # layout of the concatenated list, identical on every shard
+        layout = torch.stack([s.offsets[1:] - s.offsets[:-1] for s in shards])
+        for s in shards:
+            assert torch.equal(s.all_counts, layout)
+        assert torch.equal(shards[0].evecs, shards[-1].evecs)          # bit-identical replicas
     # something really happened at the boundaries
     t_edges = [r * n * 1000.0 / FS for r in range(1, S)]
     near = sum(int(((whole.spt > te - 3.0) & (whole.spt < te + 3.0)).sum()) for te in t_edges)
