@@ -18,9 +18,11 @@ extract -> per-contact PCA, all 32 contacts) over the recording.
   cpu_baseline: the oracle port (CPU restatement of the reference, oracle/) timed on a
                bounded sample of the same workload, on rank 0
 
-With N > 1 every rank owns one recording-sized time shard (weak scaling): thresholds
-come from the rank owning the first 10 s (broadcast), per-contact Gram matrices and
-spike counts are all-reduced / all-gathered over NCCL (spikesort_b200/dist.py).
+With N > 1 every rank owns one recording-sized time shard (weak scaling): thresholds come
+from the rank owning the first 10 s, window halos and last spike times from the neighbours,
+per-contact Gram partials from everyone - stored by the library's own kernels straight into
+the peers' arenas over NVLink (spikesort_b200/dist.py, csrc/exchange.cu; SS_TRANSPORT=nccl
+selects torch.distributed collectives instead).
 
 --impl reference times the CPU oracle port itself (all host cores, process pool over
 contacts) on bounded samples of the same workload: the reference is pure Python and
@@ -298,8 +300,9 @@ def run_gpu(args):
 
     # ---- e2e: public API, host buffers in, NumPy out (rank-local, then max over ranks)
     if args.no_e2e:
-        print(json.dumps({"profiling_run": True, "ms_per_step": ms_step,
-                          "ms_filter": ms_filter, "gpu_launches": launches}))
+        if rank == 0:
+            print(json.dumps({"profiling_run": True, "n_gpus": world, "ms_per_step": ms_step,
+                              "ms_filter": ms_filter, "gpu_launches": launches}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -416,7 +419,10 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dict(CONFIG, parallelism="time-sharded x%d" % world if world > 1 else "1 GPU",
+        "config": dict(CONFIG, parallelism=("time-sharded x%d, exchanges over %s" % (
+                           world, "NVLink peer memory (own kernels)"
+                           if os.environ.get("SS_TRANSPORT", "peer") == "peer" else "NCCL")
+                           if world > 1 else "1 GPU"),
                        spikes_detected_rank0=n_det, spikes_kept_rank0=n_spk),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT,
