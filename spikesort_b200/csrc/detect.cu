@@ -93,9 +93,16 @@ detect_emit_kernel(const uint32_t *__restrict__ mask, const int64_t *__restrict_
     if (offsets[blk + 1] == first) return;
     const int64_t b = blk % blocks_per_row;
     int64_t pos = first;
-#pragma unroll 1
+    // all 8 words of a lane are loaded up front; groups of 32 words without a crossing (most
+    // of them: a block holds a handful of spikes) cost one ballot
+    uint32_t mw[DT_BLOCK_WORDS / 32];
+#pragma unroll
+    for (int j = 0; j < DT_BLOCK_WORDS / 32; ++j) mw[j] = mask[blk * DT_BLOCK_WORDS + 32 * j + lane];
+#pragma unroll
     for (int j = 0; j < DT_BLOCK_WORDS / 32; ++j) {
-        uint32_t m = mask[blk * DT_BLOCK_WORDS + 32 * j + lane];
+        uint32_t m = mw[j];
+        const unsigned any = __ballot_sync(SS_FULL, m != 0);
+        if (any == 0) continue;
         const int c = __popc(m);
         int inc = c;
 #pragma unroll
@@ -118,21 +125,21 @@ detect_emit_kernel(const uint32_t *__restrict__ mask, const int64_t *__restrict_
 // counts[blk] = number of set bits in the block's 256 mask words (fused path: the mask
 // is filled by atomicOr from the filter kernel, counts are derived afterwards)
 __global__ void __launch_bounds__(32 * DT_WARPS)
-detect_count_kernel(const uint32_t *__restrict__ mask, int32_t *__restrict__ counts)
+detect_count_kernel(const uint32_t *__restrict__ mask, int32_t *__restrict__ counts, int64_t n_blocks)
 {
-    __shared__ int warp_cnt[DT_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int c = __popc(mask[(int64_t)blockIdx.x * DT_BLOCK_WORDS + threadIdx.x]);
+    const int64_t blk = (int64_t)blockIdx.x * DT_WARPS + warp;       // one warp per block
+    if (blk >= n_blocks) return;
+    const uint4 *m4 = reinterpret_cast<const uint4 *>(mask + blk * DT_BLOCK_WORDS);
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < DT_BLOCK_WORDS / 128; ++k) {
+        const uint4 v = __ldg(m4 + 32 * k + lane);
+        c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(SS_FULL, c, d);
-    if (lane == 0) warp_cnt[warp] = c;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int s = 0;
-#pragma unroll
-        for (int w = 0; w < DT_WARPS; ++w) s += warp_cnt[w];
-        counts[blockIdx.x] = s;
-    }
+    if (lane == 0) counts[blk] = c;
 }
 
 // ---- auto threshold: shifted sums over the first n0 samples of each row ----
@@ -257,8 +264,8 @@ int ssi::count_and_scan(int64_t n_rows, int64_t n_samples, void *d_ws, int64_t *
     const DetLayout L = det_layout(n_rows, n_samples);
     char *ws = reinterpret_cast<char *>(d_ws);
     int32_t *counts = reinterpret_cast<int32_t *>(ws + L.off_counts);
-    detect_count_kernel<<<(unsigned)L.n_blocks, 32 * DT_WARPS, 0, st>>>(
-        reinterpret_cast<const uint32_t *>(ws + L.off_mask), counts);
+    detect_count_kernel<<<(unsigned)ss_cdiv(L.n_blocks, DT_WARPS), 32 * DT_WARPS, 0, st>>>(
+        reinterpret_cast<const uint32_t *>(ws + L.off_mask), counts, L.n_blocks);
     SS_LAUNCH_CHECK("detect_count_kernel");
     ssb::scan_counts_kernel<<<1, ssb::SCAN_THREADS, 0, st>>>(
         counts, L.n_blocks, reinterpret_cast<int64_t *>(ws + L.off_offsets), L.blocks_per_row,

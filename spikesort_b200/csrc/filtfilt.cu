@@ -314,18 +314,24 @@ __device__ __forceinline__ void summary_group_fast(const T *__restrict__ p, int 
 // 128-bit weight reads - half the L1 requests of the scalar path (ncu: L1 at 68 % with
 // 2-byte loads while DRAM sat at 32 %)
 template <int NS>
-__device__ __forceinline__ void summary_group_fast_i16x2(const int16_t *__restrict__ p, int lane,
-                                                         const double *tab_s,
-                                                         double (&acc)[sm_r(NS)][2 * NS + 1])
+__device__ __forceinline__ void summary_load_i16x2(const int16_t *__restrict__ p, int lane,
+                                                   unsigned (&raw)[sm_r(NS)][FS_S / 2])
 {
-    constexpr int NQ = 2 * NS + 1;
     constexpr int SM_R = sm_r(NS);
     const unsigned *p32 = reinterpret_cast<const unsigned *>(p);
-    unsigned raw[SM_R][FS_S / 2];
 #pragma unroll
     for (int r = 0; r < SM_R; ++r)
 #pragma unroll
         for (int k = 0; k < FS_S / 2; ++k) raw[r][k] = __ldg(p32 + r * (FS_T / 2) + 32 * k + lane);
+}
+
+template <int NS>
+__device__ __forceinline__ void summary_compute_i16x2(const unsigned (&raw)[sm_r(NS)][FS_S / 2], int lane,
+                                                      const double *tab_s,
+                                                      double (&acc)[sm_r(NS)][2 * NS + 1])
+{
+    constexpr int NQ = 2 * NS + 1;
+    constexpr int SM_R = sm_r(NS);
 #pragma unroll
     for (int k = 0; k < FS_S / 2; ++k) {
         double2 w[NQ];                                      // weights of samples 64k + 2*lane, +1
@@ -334,16 +340,79 @@ __device__ __forceinline__ void summary_group_fast_i16x2(const int16_t *__restri
             w[q] = *reinterpret_cast<const double2 *>(tab_s + q * FS_T + 64 * k + 2 * lane);
 #pragma unroll
         for (int r = 0; r < SM_R; ++r) {
-            const double x0 = ss_to_f64((int16_t)(raw[r][k] & 0xffffu));
-            const double x1 = ss_to_f64((int16_t)(raw[r][k] >> 16));
+            // two int16 -> float64, exact: offset binary (v + 2^15) in the low mantissa word
+            // of 2^52, one XOR for both halves, then one full-rate DADD each
+            const unsigned ob = raw[r][k] ^ 0x80008000u;
+            const double x0 = __hiloint2double(0x43300000, (int)(ob & 0xffffu)) - 4503599627403264.0;
+            const double x1 = __hiloint2double(0x43300000, (int)(ob >> 16)) - 4503599627403264.0;
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) acc[r][q] += w[q].x * x0 + w[q].y * x1;
+            for (int q = 0; q < NQ; ++q) acc[r][q] = fma(w[q].y, x1, fma(w[q].x, x0, acc[r][q]));
         }
     }
 }
 
+// Sum each of V per-lane values over the 32 lanes with V-ish exchanges instead of 5V: at
+// every butterfly step the lanes whose `off` bit is set keep the upper half of the values and
+// hand the lower half over (and vice versa), so the number of live values halves with the
+// lane distance.  On return v[0] of lane l is the total of value index id (multi_reduce_id);
+// several lanes may hold the same id, `owner` marks one of them.
+template <int N, int OFF, int V>
+__device__ __forceinline__ void multi_reduce_step(double (&v)[V], int lane)
+{
+    constexpr int H = (N + 1) / 2;
+    const bool upper = (lane & OFF) != 0;
+#pragma unroll
+    for (int i = 0; i < H; ++i) {
+        if (i + H < N) {
+            const double a = v[i], b = v[i + H];
+            const double send = upper ? a : b, keep = upper ? b : a;
+            v[i] = keep + __shfl_xor_sync(SS_FULL, send, OFF);
+        } else {
+            v[i] += __shfl_xor_sync(SS_FULL, v[i], OFF);
+        }
+    }
+    if constexpr (OFF > 1) multi_reduce_step<H, OFF / 2, V>(v, lane);
+}
+
+template <int V>
+__device__ __forceinline__ void multi_reduce(double (&v)[V], int lane)
+{
+    multi_reduce_step<V, 16, V>(v, lane);
+}
+
+// value index held in v[0] of `lane` after multi_reduce<V>: trace v[0] back, last step first
+template <int N, int OFF>
+__device__ __forceinline__ int multi_reduce_trace(int lane, bool &owner)
+{
+    constexpr int H = (N + 1) / 2;
+    int id = 0;
+    if constexpr (OFF > 1) id = multi_reduce_trace<H, OFF / 2>(lane, owner);
+    if (lane & OFF) {
+        if (id + H < N) id += H; else owner = false;      // a replica of the lower lane
+    }
+    return id;
+}
+
+template <int V>
+__device__ __forceinline__ int multi_reduce_id(int lane, bool &owner)
+{
+    owner = true;
+    return multi_reduce_trace<V, 16>(lane, owner);
+}
+
+// chunk-relative start of the group of SM_R tiles beginning at tile t0, and whether all of
+// it lies inside the chunk proper (no padding, no odd extension, no ragged end)
 template <int NS>
-__global__ void __launch_bounds__(32 * SM_WPB, NS <= 2 ? 4 : 1)
+__device__ __forceinline__ bool summary_group_interior(const FiltGeom &g, const TileInfo &ti, int64_t t0,
+                                                       int64_t &r0)
+{
+    constexpr int SM_R = sm_r(NS);
+    r0 = t0 * FS_T - ti.pad - g.edge;
+    return t0 + SM_R <= ti.nt && r0 >= 0 && r0 + SM_R * FS_T <= ti.L;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32 * SM_WPB, NS <= 2 ? 2 : 1)
 filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *__restrict__ tab,
                     double *__restrict__ F, double *__restrict__ Bz, double *__restrict__ ylast)
 {
@@ -356,6 +425,21 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *
     TileInfo ti = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
     const int64_t t_first = ((int64_t)blockIdx.x * SM_WPB + warp) * SM_TPW;
     const int64_t row0 = ti.c * g.ld_in;
+    bool red_owner;
+    const int red_id = multi_reduce_id<SM_R * NQ>(lane, red_owner);
+    const int red_r = red_id / NQ, red_q = red_id - red_r * NQ;
+    // int16 groups are software-pipelined: the 32-bit loads of group it+1 are issued before
+    // the dot products of group it, so every warp always has one group (128 B per lane) in
+    // flight (ncu r01_c: the unpipelined loop sat at 32 % of DRAM peak on long_scoreboard)
+    unsigned nxt[SM_R][FS_S / 2];
+    bool nxt_ok = false;
+    if (g.dtype == SS_I16 && t_first < ti.nt) {
+        int64_t r0;
+        if (summary_group_interior<NS>(g, ti, t_first, r0) && ((row0 + ti.cs0 + r0) & 1) == 0) {
+            summary_load_i16x2<NS>(reinterpret_cast<const int16_t *>(x) + row0 + ti.cs0 + r0, lane, nxt);
+            nxt_ok = true;
+        }
+    }
 #pragma unroll 1
     for (int it = 0; it < SM_TPW; it += SM_R) {
         const int64_t t0 = t_first + it;
@@ -366,48 +450,66 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *
         for (int r = 0; r < SM_R; ++r)
 #pragma unroll
             for (int q = 0; q < NQ; ++q) acc[r][q] = 0.0;
-        const int64_t r0 = t0 * FS_T - ti.pad - g.edge;     // chunk-relative start of the group
-        if (nr == SM_R && r0 >= 0 && r0 + SM_R * FS_T <= ti.L) {
-            const int64_t base = row0 + ti.cs0 + r0;
-            if (g.dtype == SS_I16 && (base & 1) == 0)
-                summary_group_fast_i16x2<NS>(reinterpret_cast<const int16_t *>(x) + base, lane, tab_s, acc);
-            else if (g.dtype == SS_I16)
-                summary_group_fast<int16_t, NS>(reinterpret_cast<const int16_t *>(x) + base, lane, tab_s, acc);
-            else if (g.dtype == SS_F32)
-                summary_group_fast<float, NS>(reinterpret_cast<const float *>(x) + base, lane, tab_s, acc);
-            else
-                summary_group_fast<double, NS>(reinterpret_cast<const double *>(x) + base, lane, tab_s, acc);
+        int64_t r0;
+        const bool interior = summary_group_interior<NS>(g, ti, t0, r0);
+        if (nxt_ok) {
+            unsigned raw[SM_R][FS_S / 2];
+#pragma unroll
+            for (int r = 0; r < SM_R; ++r)
+#pragma unroll
+                for (int k = 0; k < FS_S / 2; ++k) raw[r][k] = nxt[r][k];
+            nxt_ok = false;
+            int64_t rn;
+            if (it + SM_R < SM_TPW && summary_group_interior<NS>(g, ti, t0 + SM_R, rn) &&
+                ((row0 + ti.cs0 + rn) & 1) == 0) {
+                summary_load_i16x2<NS>(reinterpret_cast<const int16_t *>(x) + row0 + ti.cs0 + rn, lane, nxt);
+                nxt_ok = true;
+            }
+            summary_compute_i16x2<NS>(raw, lane, tab_s, acc);
         } else {
-            // group touching the padding / odd extension / end of the unit: one tile at a time
+            // prefetch for the next group also from the unpipelined paths
+            int64_t rn;
+            if (g.dtype == SS_I16 && it + SM_R < SM_TPW &&
+                summary_group_interior<NS>(g, ti, t0 + SM_R, rn) && ((row0 + ti.cs0 + rn) & 1) == 0) {
+                summary_load_i16x2<NS>(reinterpret_cast<const int16_t *>(x) + row0 + ti.cs0 + rn, lane, nxt);
+                nxt_ok = true;
+            }
+            if (interior) {
+                const int64_t base = row0 + ti.cs0 + r0;
+                if (g.dtype == SS_I16)
+                    summary_group_fast<int16_t, NS>(reinterpret_cast<const int16_t *>(x) + base, lane, tab_s, acc);
+                else if (g.dtype == SS_F32)
+                    summary_group_fast<float, NS>(reinterpret_cast<const float *>(x) + base, lane, tab_s, acc);
+                else
+                    summary_group_fast<double, NS>(reinterpret_cast<const double *>(x) + base, lane, tab_s, acc);
+            } else {
+                // group touching the padding / odd extension / end of the unit: one tile at a time
 #pragma unroll
-            for (int r = 0; r < SM_R; ++r) {
-                if (r < nr) {
-                    ti.t = t0 + r;
-                    const int64_t e0 = ti.t * FS_T - ti.pad;
+                for (int r = 0; r < SM_R; ++r) {
+                    if (r < nr) {
+                        ti.t = t0 + r;
+                        const int64_t e0 = ti.t * FS_T - ti.pad;
 #pragma unroll 1
-                    for (int k = 0; k < FS_S; ++k) {
-                        const double xv = ext_value(x, g.dtype, row0, ti, g.edge, e0 + 32 * k + lane);
+                        for (int k = 0; k < FS_S; ++k) {
+                            const double xv = ext_value(x, g.dtype, row0, ti, g.edge, e0 + 32 * k + lane);
 #pragma unroll
-                        for (int q = 0; q < NQ; ++q) acc[r][q] += tab_s[q * FS_T + 32 * k + lane] * xv;
+                            for (int q = 0; q < NQ; ++q) acc[r][q] += tab_s[q * FS_T + 32 * k + lane] * xv;
+                        }
                     }
                 }
             }
         }
+        double flat[SM_R * NQ];
 #pragma unroll
-        for (int r = 0; r < SM_R; ++r) {
+        for (int r = 0; r < SM_R; ++r)
 #pragma unroll
-            for (int q = 0; q < NQ; ++q)
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) acc[r][q] += __shfl_xor_sync(SS_FULL, acc[r][q], d);
-            if (lane == 0 && r < nr) {
-                const int64_t tile = ti.g0 + t0 + r;
-#pragma unroll
-                for (int i = 0; i < NS; ++i) {
-                    F[tile * NS + i] = acc[r][i];
-                    Bz[tile * NS + i] = acc[r][NS + i];
-                }
-                ylast[tile] = acc[r][2 * NS];
-            }
+            for (int q = 0; q < NQ; ++q) flat[r * NQ + q] = acc[r][q];
+        multi_reduce<SM_R * NQ>(flat, lane);
+        if (red_owner && red_r < nr) {
+            const int64_t tile = ti.g0 + t0 + red_r;
+            if (red_q < NS) F[tile * NS + red_q] = flat[0];
+            else if (red_q < 2 * NS) Bz[tile * NS + red_q - NS] = flat[0];
+            else ylast[tile] = flat[0];
         }
     }
 }

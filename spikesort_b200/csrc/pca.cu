@@ -152,8 +152,9 @@ pca_gram_reduce_kernel(const double *__restrict__ ws_gram, const double *__restr
 }
 
 // One CTA per group.  smem: A[ne*ld], V[ne*ld] (row stride ld odd: column sweeps are
-// bank-conflict free), rotation (c, s) per pair, reduction scratch.  Warps take pairs,
-// lanes take the row/column index: no integer division in the sweeps.
+// bank-conflict free), rotation (c, s) per pair, reduction scratch.  A round is two phases:
+// the ne/2 disjoint rotations, then A by 2x2 blocks (thread = (row pair, column pair)) and
+// the columns of V (warp = pair, lane = row) - no integer division in the sweeps.
 __global__ void __launch_bounds__(PC_THREADS)
 pca_eig_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
                const int64_t *__restrict__ counts, int n, double *__restrict__ evals,
@@ -228,31 +229,37 @@ pca_eig_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
                 s_p[k] = p; s_q[k] = q; rc[k] = c; rs[k] = s;
             }
             __syncthreads();
-            // columns of A and V
+            // A <- J^T A J by 2x2 blocks: the block of row pair bi and column pair bj only
+            // needs the two rotations, so one pass (and one barrier) updates all of A;
+            // column rotation first, then row rotation (B' = J1^T (B J2)).
+            for (int bi = tid >> 4; bi < half; bi += PC_THREADS / 16) {
+                const int p1 = s_p[bi], q1 = s_q[bi];
+                const double c1 = rc[bi], s1 = rs[bi];
+                for (int bj = tid & 15; bj < half; bj += 16) {
+                    const double c2 = rc[bj], s2 = rs[bj];
+                    if (s1 == 0.0 && s2 == 0.0) continue;
+                    const int p2 = s_p[bj], q2 = s_q[bj];
+                    const double b00 = A[p1 * ld + p2], b01 = A[p1 * ld + q2];
+                    const double b10 = A[q1 * ld + p2], b11 = A[q1 * ld + q2];
+                    const double t00 = c2 * b00 - s2 * b01, t01 = s2 * b00 + c2 * b01;
+                    const double t10 = c2 * b10 - s2 * b11, t11 = s2 * b10 + c2 * b11;
+                    A[p1 * ld + p2] = c1 * t00 - s1 * t10;
+                    A[p1 * ld + q2] = c1 * t01 - s1 * t11;
+                    A[q1 * ld + p2] = s1 * t00 + c1 * t10;
+                    A[q1 * ld + q2] = s1 * t01 + c1 * t11;
+                }
+            }
+            // V <- V J (columns only)
             for (int k = warp; k < half; k += nwarps) {
-                const int p = s_p[k], q = s_q[k];
                 const double c = rc[k], s = rs[k];
-                if (s != 0.0)
+                if (s != 0.0) {
+                    const int p = s_p[k], q = s_q[k];
                     for (int i = lane; i < ne; i += 32) {
-                        const double aip = A[i * ld + p], aiq = A[i * ld + q];
-                        A[i * ld + p] = c * aip - s * aiq;
-                        A[i * ld + q] = s * aip + c * aiq;
                         const double vip = V[i * ld + p], viq = V[i * ld + q];
                         V[i * ld + p] = c * vip - s * viq;
                         V[i * ld + q] = s * vip + c * viq;
                     }
-            }
-            __syncthreads();
-            // rows of A
-            for (int k = warp; k < half; k += nwarps) {
-                const int p = s_p[k], q = s_q[k];
-                const double c = rc[k], s = rs[k];
-                if (s != 0.0)
-                    for (int j = lane; j < ne; j += 32) {
-                        const double apj = A[p * ld + j], aqj = A[q * ld + j];
-                        A[p * ld + j] = c * apj - s * aqj;
-                        A[q * ld + j] = s * apj + c * aqj;
-                    }
+                }
             }
             __syncthreads();
         }

@@ -13,43 +13,52 @@ static __global__ void __launch_bounds__(SCAN_THREADS)
 scan_counts_kernel(const int32_t *__restrict__ counts, int64_t n, int64_t *__restrict__ offsets,
                    int64_t per_row, int64_t n_rows, int64_t *__restrict__ row_offsets)
 {
-    __shared__ int64_t warp_tot[32];
+    // warp w owns the contiguous segment [w*seg, (w+1)*seg), seg a multiple of 32; lanes
+    // read consecutive elements (coalesced), two passes: segment totals, then the scan
+    __shared__ int64_t warp_base[32];
     __shared__ int64_t grand;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t per = (n + SCAN_THREADS - 1) / SCAN_THREADS;
-    const int64_t lo = min((int64_t)tid * per, n), hi = min(lo + per, n);
+    const int64_t seg = ((n + 32 * 32 - 1) / (32 * 32)) * 32;
+    const int64_t lo = min((int64_t)warp * seg, n), hi = min(lo + seg, n);
     int64_t s = 0;
-    for (int64_t i = lo; i < hi; ++i) s += counts[i];
-    // inclusive warp scan
-    int64_t inc = s;
+    for (int64_t i = lo + lane; i < hi; i += 32) s += counts[i];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int64_t o = __shfl_up_sync(SS_FULL, inc, d);
-        if (lane >= d) inc += o;
-    }
-    if (lane == 31) warp_tot[warp] = inc;
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(SS_FULL, s, d);
+    if (lane == 0) warp_base[warp] = s;
     __syncthreads();
     if (warp == 0) {
-        int64_t w = warp_tot[lane];
+        const int64_t w = warp_base[lane];
         int64_t winc = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const int64_t o = __shfl_up_sync(SS_FULL, winc, d);
             if (lane >= d) winc += o;
         }
-        warp_tot[lane] = winc - w;           // exclusive over warps
+        warp_base[lane] = winc - w;          // exclusive over warps
         if (lane == 31) grand = winc;
     }
     __syncthreads();
-    int64_t run = warp_tot[warp] + inc - s;  // exclusive prefix of this thread's chunk
-    for (int64_t i = lo; i < hi; ++i) {
-        offsets[i] = run;
-        if (row_offsets && per_row > 0 && i % per_row == 0) row_offsets[i / per_row] = run;
-        run += counts[i];
+    int64_t run = warp_base[warp];
+    for (int64_t i0 = lo; i0 < hi; i0 += 32) {
+        const int64_t i = i0 + lane;
+        const int64_t c = i < hi ? (int64_t)counts[i] : 0;
+        int64_t inc = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t o = __shfl_up_sync(SS_FULL, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (i < hi) {
+            const int64_t ex = run + inc - c;
+            offsets[i] = ex;
+        }
+        run += __shfl_sync(SS_FULL, inc, 31);
     }
-    if (tid == 0) {
-        offsets[n] = grand;
-        if (row_offsets) row_offsets[n_rows] = grand;
+    if (tid == 0) offsets[n] = grand;
+    if (row_offsets) {
+        __syncthreads();                     // offsets[] of the other warps (same CTA)
+        for (int64_t r = tid; r <= n_rows; r += SCAN_THREADS)
+            row_offsets[r] = r < n_rows && r * per_row < n ? offsets[r * per_row] : grand;
     }
 }
 
