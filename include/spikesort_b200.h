@@ -274,6 +274,16 @@ int ss_align_resampled(const void *d_x, int dtype, int64_t n_samples, int64_t ld
                        int max_iter, int64_t index_offset, int64_t halo_before,
                        int64_t halo_after, void *stream);
 
+/* ------------------------------------------------------- zero-phase FIR (8f)
+ * Replaces FilterFir.__call__ = scipy.signal.filtfilt(b, [1], x) (filters.py:41-74) for
+ * every (contact, chunk) unit of filter_proxy (filters.py:135-141); b = remez taps designed
+ * on the host.  Same chunking, odd padding (3*n_taps, in the input dtype) and error
+ * (SS_ERR_PADLEN when a chunk is not longer than the padding) as ss_filtfilt_sos.
+ */
+int ss_filtfilt_fir(const void *d_x, int dtype, int64_t n_contacts, int64_t n_samples,
+                    int64_t ld_in, const double *d_b, int n_taps, int64_t chunksize,
+                    double *d_out, int64_t ld_out, void *stream);
+
 /* ------------------------------------------- time shards over peer memory (8e)
  * Exchange steps of a recording sharded by time across GPUs (one process per GPU).  The
  * reference has no such step: its filter_proxy walks (contact, chunk) units in one process

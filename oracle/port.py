@@ -102,6 +102,8 @@ def filtfilt(b, a, x):
     filters.py:38,74,101 (defaults: odd padding, padlen 3*ntaps)."""
     bb, aa, ntaps = _pad_ba(b, a)
     x = _supported(x)
+    if np.atleast_1d(a).size == 1:
+        return _filtfilt_fir(np.atleast_1d(np.asarray(b, dtype=np.float64)) / np.atleast_1d(a)[0], x)
     out = np.empty(x.shape[0], dtype=np.float64)
     zi = np.ascontiguousarray(lfilter_zi(bb, aa))
     rc = _clib().orc_filtfilt(_as_dp(bb), _as_dp(aa), _as_dp(zi), ntaps, x.ctypes.data,
@@ -112,6 +114,79 @@ def filtfilt(b, a, x):
     if rc:
         raise RuntimeError("oracle filtfilt failed (%d)" % rc)
     return out
+
+
+def _odd_ext(x, n):
+    """scipy.signal._arraytools.odd_ext, evaluated in the dtype of x as NumPy does."""
+    left = 2 * x[0] - x[n:0:-1]
+    right = 2 * x[-1] - x[-2:-(n + 2):-1]
+    return np.concatenate((left, x, right))
+
+
+def _lfilter_fir(b, x, zi):
+    """scipy.signal.lfilter with a == [1]: SciPy special-cases FIR filters and evaluates
+    them as np.convolve(b, x), adding zi to the first len(b)-1 outputs."""
+    full = np.convolve(b, x)
+    full[:len(zi)] += zi
+    return full[:len(x)]
+
+
+def _filtfilt_fir(b, x):
+    """filtfilt(b, [1], x) as called at filters.py:74: odd padding by 3*len(b), forward
+    pass from zi*ext[0], backward pass over the reversed output from zi*y[-1]."""
+    ntaps = len(b)
+    edge = 3 * ntaps
+    if x.shape[0] <= edge:
+        raise ValueError("The length of the input vector x must be greater "
+                         "than padlen, which is %d." % edge)
+    ext = _odd_ext(x, edge)
+    zi = lfilter_zi(b, np.ones(1))
+    y = _lfilter_fir(b, ext, zi * ext[0])
+    y = _lfilter_fir(b, y[::-1], zi * y[-1])[::-1]
+    return np.ascontiguousarray(y[edge:-edge], dtype=np.float64)
+
+
+class FilterFir(object):
+    """filters.py:41-74 - remez FIR of `order` taps + filtfilt.  The reference passes the
+    sampling rate as remez(..., Hz=FS); SciPy renamed that keyword to fs (same meaning)."""
+
+    def __init__(self, f_pass, f_stop, order):
+        self.fp, self.fs, self.order = f_pass, f_stop, order
+        self._coefs = {}
+
+    def coefficients(self, FS):
+        if FS not in self._coefs:
+            from scipy import signal
+            bands = [0, min(self.fs, self.fp), max(self.fs, self.fp), FS / 2]
+            gains = [int(self.fp < self.fs), int(self.fp > self.fs)]
+            self._coefs[FS] = (signal.remez(self.order, bands, gains, fs=FS), [1])
+        return self._coefs[FS]
+
+    def __call__(self, x, FS):
+        b, a = self.coefficients(FS)
+        return filtfilt(b, a, x)
+
+
+class ZeroPhaseFilter(object):
+    """filters.py:10-38 - iirdesign from a band and a transition width, then filtfilt."""
+
+    def __init__(self, ftype, fband, tw=200., stop=20):
+        self.ftype, self.fband, self.tw, self.gstop, self.gpass = ftype, fband, tw, stop, 1
+        self._coefs = {}
+
+    def coefficients(self, FS):
+        if FS not in self._coefs:
+            from scipy import signal
+            wp = np.array(self.fband)
+            ws = wp + np.array([-self.tw, self.tw])
+            self._coefs[FS] = signal.iirdesign(wp=wp * 2.0 / FS, ws=ws * 2.0 / FS,
+                                               gstop=self.gstop, gpass=self.gpass,
+                                               ftype=self.ftype)
+        return self._coefs[FS]
+
+    def __call__(self, x, FS):
+        b, a = self.coefficients(FS)
+        return filtfilt(b, a, x)
 
 
 class Filter(object):

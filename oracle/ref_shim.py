@@ -107,7 +107,25 @@ def load(name):
 
 
 def filters():
-    return load("filters")
+    """core/filters.py.  FilterFir calls signal.remez(..., Hz=FS) (filters.py:66); SciPy
+    renamed that keyword to fs, so the module's `signal.remez` is wrapped to translate it -
+    same routine, same arguments."""
+    mod = load("filters")
+    if not getattr(mod, "_remez_shimmed", False):
+        import scipy.signal as _sig
+        _orig = _sig.remez
+
+        def remez(numtaps, bands, desired, *args, **kw):
+            if "Hz" in kw:
+                kw["fs"] = kw.pop("Hz")
+            return _orig(numtaps, bands, desired, *args, **kw)
+
+        shim = types.ModuleType("scipy_signal_shim")
+        shim.__dict__.update(_sig.__dict__)
+        shim.remez = remez
+        mod.signal = shim
+        mod._remez_shimmed = True
+    return mod
 
 
 def extract():

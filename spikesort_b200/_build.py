@@ -17,7 +17,7 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libspikesort_b200.so")
 
-SOURCES = ["lib.cu", "filtfilt.cu", "detect.cu", "align.cu", "extract.cu", "pca.cu", "pca_tc.cu", "features.cu", "resample.cu", "exchange.cu"]
+SOURCES = ["lib.cu", "filtfilt.cu", "detect.cu", "align.cu", "extract.cu", "pca.cu", "pca_tc.cu", "features.cu", "resample.cu", "exchange.cu", "fir.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "scan.cuh"), os.path.join(CSRC, "internal.cuh"),
            os.path.join(INCLUDE, "spikesort_b200.h")]
 

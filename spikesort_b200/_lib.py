@@ -56,6 +56,7 @@ SIGNATURES = {
     "ss_wave_minmax": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp]),
     "ss_normalize_workspace_bytes": (_sz, [_int]),
     "ss_normalize_columns": (_int, [_vp, _i64, _int, _vp, _sz, _vp]),
+    "ss_filtfilt_fir": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _i64, _vp, _i64, _vp]),
     "ss_shard_arena_bytes": (_sz, [_int, _int, _int, _int]),
     "ss_shard_arena_offsets": (_int, [_int, _int, _int, _int, _vp]),
     "ss_peer_barrier": (_int, [_vp, _int, _int, _c.c_uint64, _dbl, _vp]),

@@ -77,6 +77,23 @@ def filtfilt_sos(x, sos, padlen, chunksize, out=None):
     return out
 
 
+def filtfilt_fir(x, b, chunksize, out=None):
+    """Zero-phase FIR filter (taps b, host float64) of every (contact, chunk) unit."""
+    lib = _lib.load()
+    t = _lib.torch()
+    n_c, n = x.shape
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    bd = t.from_numpy(b).to(x.device)
+    if out is None:
+        out = t.empty((n_c, n), dtype=t.float64, device=x.device)
+    rc = lib.ss_filtfilt_fir(_lib.ptr(x), _lib.ss_dtype_of(x), n_c, n, x.stride(0), _lib.ptr(bd),
+                             int(b.shape[0]), int(chunksize), _lib.ptr(out), out.stride(0),
+                             _lib.stream_ptr())
+    _lib.check(rc, "ss_filtfilt_fir")
+    _launched(1)
+    return out
+
+
 def filtfilt_detect(x, sos, padlen, chunksize, FS, falling, thr=None, n0=None, factor=None,
                     out=None, ws=None, shard=_WHOLE):
     """Fused filter + (auto threshold) + crossing marking + emit.

@@ -5,7 +5,7 @@ the arithmetic on the B200.
 ``filter_proxy`` keeps the reference's semantics - every contact is filtered in
 independent chunks of ``chunksize`` samples, each with its own odd padding and
 steady-state initial conditions (``filters.py:135-141``) - but runs all
-(contact, chunk) units in three kernel launches and leaves the float64 result in
+(contact, chunk) units in three kernel launches (one for the FIR filter) and leaves the float64 result in
 HBM inside a :class:`DeviceSignal` (the reference leaves it in an HDF5 CArray).
 """
 import numpy as np
@@ -28,15 +28,18 @@ class _IIRBase(object):
             self._sos_cache[FS] = tf2sos_exact(b, a)
         return self._sos_cache[FS]
 
+    def apply(self, x, FS, chunksize):
+        """CUDA recording (n_contacts, n_samples) -> CUDA float64, chunk by chunk."""
+        sos, padlen = self.sections(FS)
+        return _ops.filtfilt_sos(x, sos, padlen, chunksize)
+
     def __call__(self, x, FS):
         """filtfilt of one 1-D signal; returns a float64 ndarray (``filters.py:99-101``)."""
         arr = np.asarray(x)
         if arr.ndim != 1:
             raise ValueError("expected a 1-D signal")
-        sos, padlen = self.sections(FS)
         dev = _lib.to_device_2d(arr)
-        out = _ops.filtfilt_sos(dev, sos, padlen, max(dev.shape[1], 1))
-        return out[0].cpu().numpy()
+        return self.apply(dev, FS, max(dev.shape[1], 1))[0].cpu().numpy()
 
 
 class Filter(_IIRBase):
@@ -84,11 +87,33 @@ class ZeroPhaseFilter(_IIRBase):
 
 
 class FilterFir(object):
-    """``filters.py:41-74`` (remez FIR + filtfilt): not on the CUDA path yet
-    (SURVEY.md section 8f, rank 4)."""
+    """``filters.py:41-74``: remez FIR of `order` taps, applied forwards and backwards.
+    (The reference passes the rate to remez as ``Hz=FS``; SciPy now calls it ``fs``.)"""
 
     def __init__(self, f_pass, f_stop, order):
-        raise NotImplementedError("FilterFir is not implemented on the CUDA path yet")
+        self._coefs_cache = {}
+        self.fp = f_pass
+        self.fs = f_stop
+        self.order = order
+
+    def _design_filter(self, FS):
+        if FS not in self._coefs_cache:
+            from scipy import signal
+            bands = [0, min(self.fs, self.fp), max(self.fs, self.fp), FS / 2]
+            gains = [int(self.fp < self.fs), int(self.fp > self.fs)]
+            self._coefs_cache[FS] = (signal.remez(self.order, bands, gains, fs=FS), [1])
+        return self._coefs_cache[FS]
+
+    def apply(self, x, FS, chunksize):
+        b, _ = self._design_filter(FS)
+        return _ops.filtfilt_fir(x, b, chunksize)
+
+    def __call__(self, x, FS):
+        arr = np.asarray(x)
+        if arr.ndim != 1:
+            raise ValueError("expected a 1-D signal")
+        dev = _lib.to_device_2d(arr)
+        return self.apply(dev, FS, max(dev.shape[1], 1))[0].cpu().numpy()
 
 
 def filter_proxy(spikes, filter_obj, chunksize=1E6):
@@ -96,14 +121,13 @@ def filter_proxy(spikes, filter_obj, chunksize=1E6):
     float64 filtered recording, resident on the GPU."""
     if filter_obj is None:
         return spikes
-    if not hasattr(filter_obj, "sections"):
+    if not hasattr(filter_obj, "apply"):
         raise TypeError("filter_proxy on the CUDA path needs a spikesort_b200 filter object "
-                        "(Filter / ZeroPhaseFilter); arbitrary Python callables cannot run on "
-                        "the GPU and there is no CPU fallback")
+                        "(Filter / ZeroPhaseFilter / FilterFir); arbitrary Python callables "
+                        "cannot run on the GPU and there is no CPU fallback")
     sp_dict = spikes.copy()
-    sos, padlen = filter_obj.sections(sp_dict['FS'])
     x = _lib.to_device_2d(spikes['data'])
-    out = _ops.filtfilt_sos(x, sos, padlen, int(chunksize))
+    out = filter_obj.apply(x, sp_dict['FS'], int(chunksize))
     sp_dict['data'] = DeviceSignal(out)
     return sp_dict
 

@@ -73,7 +73,7 @@ def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='
     falling = edge in _FALLING
     auto = thr_override is None and isinstance(thresh, str)
     frac = (8.0 if thresh == 'auto' else float(thresh)) if auto else None
-    if filt is not None and fused:
+    if filt is not None and fused and hasattr(filt, "sections"):
         # filter with the threshold and the crossing marks produced in the same sweep
         sos, padlen = filt.sections(FS)
         if auto:
@@ -88,8 +88,7 @@ def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='
         res.filtered, res.thresh = sig, thr
     else:
         if filt is not None:
-            sos, padlen = filt.sections(FS)
-            sig = _ops.filtfilt_sos(x, sos, padlen, int(chunksize))
+            sig = filt.apply(x, FS, int(chunksize))      # unfused IIR, or the FIR stencil
         else:
             sig = x
         res.filtered = sig

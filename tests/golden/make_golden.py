@@ -143,6 +143,19 @@ def main():
     out['sine_resample'] = sr['data']
     out['sine_resample_time'] = sr['time']
 
+    # --- FilterFir (remez, filters.py:41-74) and ZeroPhaseFilter (filters.py:10-38) through
+    # filter_proxy, int16 input, three chunks with a short last one
+    xf = synth.make_recording(2, 14000, FS, seed=99, rate_hz=40.0, noise=12.0,
+                              amp=(120.0, 300.0), negative=True, drift_amp=60.0).numpy()
+    rawf = {'data': xf, 'FS': FS, 'n_contacts': 2}
+    out['fir_raw'] = xf
+    out['fir_hp_filtered'] = np.asarray(rf.filter_proxy(rawf, rf.FilterFir(300., 100., 101),
+                                                        chunksize=6000)['data'])
+    out['fir_lp_filtered'] = np.asarray(rf.filter_proxy(rawf, rf.FilterFir(3000., 5000., 64),
+                                                        chunksize=6000)['data'])
+    out['zpf_filtered'] = np.asarray(rf.filter_proxy(rawf, rf.ZeroPhaseFilter('ellip', [300., 3000.]),
+                                                     chunksize=6000)['data'])
+
     # --- band-pass (order 8) on float32 input, single chunk
     x32 = synth.make_recording(1, 20000, 30000, seed=7, rate_hz=30.0, noise=8.0,
                                dtype="float32").numpy()

@@ -161,6 +161,42 @@ def test_resample_golden(ss, golden):
     assert empty['data'].shape == (len(sr['time']), 0, 1)
 
 
+def test_fir_and_zerophase_golden(ss, golden):
+    """8f rank 4: FilterFir (two-stage FIR stencil) and ZeroPhaseFilter (the IIR scan) through
+    filter_proxy against the reference's output; bar rel 1e-5, asserted far tighter (the
+    elliptic band-pass is limited by the round-off of the REFERENCE's (b, a)-form recursion,
+    as for the high orders of test_filtfilt_vs_oracle)."""
+    raw = {'data': golden['fir_raw'], 'FS': 25000, 'n_contacts': 2}
+    for key, flt, tol in (('fir_hp_filtered', ss.filters.FilterFir(300., 100., 101), 1e-13),
+                          ('fir_lp_filtered', ss.filters.FilterFir(3000., 5000., 64), 1e-13),
+                          ('zpf_filtered', ss.filters.ZeroPhaseFilter('ellip', [300., 3000.]), 1e-6)):
+        f = ss.filters.filter_proxy(raw, flt, chunksize=6000)
+        got = np.asarray(f['data'])
+        assert got.shape == golden[key].shape and got.dtype == np.float64
+        err = rel_err(got, golden[key])
+        print("%s: rel err %.2e" % (key, err))
+        assert err < tol, key
+    fir = ss.filters.FilterFir(300., 100., 101)
+    one = fir(golden['fir_raw'][0, :6000], 25000)                   # the callable form
+    assert rel_err(one, golden['fir_hp_filtered'][0, :6000]) < 1e-13
+    with pytest.raises(ValueError):
+        fir(golden['fir_raw'][0, :303], 25000)                      # len <= padlen, as SciPy
+    # float32 / float64 recordings and the chain on an FIR-filtered signal
+    for dt in (np.float32, np.float64):
+        rawd = {'data': golden['fir_raw'].astype(dt) * 0.5, 'FS': 25000, 'n_contacts': 2}
+        import oracle.port as port
+        ref = port.filter_proxy(rawd, port.FilterFir(300., 100., 101), chunksize=6000)['data']
+        got = np.asarray(ss.filters.filter_proxy(rawd, fir, chunksize=6000)['data'])
+        assert rel_err(got, ref) < 1e-13
+    out = ss.sort_frontend(raw, filt=fir, sp_win=[-0.2, 0.8], edge='falling', align_type='min',
+                           thresh='4', ncomps=2, chunksize=6000)
+    f = ss.filters.filter_proxy(raw, fir, chunksize=6000)
+    for c in range(2):
+        spt = ss.extract.detect_spikes(f, thresh='4', edge='falling', contact=c)
+        assert np.array_equal(out['spt'][c]['data'], spt['data'])
+        assert len(spt['data']) > 5
+
+
 def test_bandpass_float32_golden(ss, golden):
     raw = {'data': golden['bp_raw'], 'FS': 30000, 'n_contacts': 1}
     f = ss.filters.filter_proxy(raw, ss.filters.Filter(np.array([300., 6000.]),

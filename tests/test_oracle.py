@@ -169,6 +169,19 @@ def test_resample_golden(oracle, golden):
     assert sr['FS'] == sp['FS']
 
 
+def test_fir_and_zerophase_golden(oracle, golden):
+    """FilterFir (filters.py:41-74) and ZeroPhaseFilter (filters.py:10-38) through
+    filter_proxy, bit-exact against the reference's output."""
+    raw = {'data': golden['fir_raw'], 'FS': 25000, 'n_contacts': 2}
+    for key, flt in (('fir_hp_filtered', oracle.FilterFir(300., 100., 101)),
+                     ('fir_lp_filtered', oracle.FilterFir(3000., 5000., 64)),
+                     ('zpf_filtered', oracle.ZeroPhaseFilter('ellip', [300., 3000.]))):
+        f = oracle.filter_proxy(raw, flt, chunksize=6000)
+        assert np.array_equal(f['data'], golden[key]), key
+    with pytest.raises(ValueError):
+        oracle.FilterFir(300., 100., 101)(golden['fir_raw'][0, :303], 25000)   # len <= padlen
+
+
 def test_bandpass_float32_golden(oracle, golden):
     raw = {'data': golden['bp_raw'], 'FS': 30000, 'n_contacts': 1}
     f = oracle.filter_proxy(raw, oracle.Filter(np.array([300., 6000.]), np.array([100., 8000.])))
