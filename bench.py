@@ -301,8 +301,16 @@ def run_gpu(args):
     # ---- e2e: public API, host buffers in, NumPy out (rank-local, then max over ranks)
     if args.no_e2e:
         if rank == 0:
+            fm = statistics.mean(ms_filter) if ms_filter else float("nan")
+            ab = N_CONTACTS * N_SAMPLES * (2 + 8) + N_CONTACTS * min(N_SAMPLES, 10 * FS) * 8 + \
+                N_CONTACTS * N_SAMPLES * 8 + n_det * 8
             print(json.dumps({"profiling_run": True, "n_gpus": world, "ms_per_step": ms_step,
-                              "ms_filter": ms_filter, "gpu_launches": launches}), flush=True)
+                              "value": value, "workload": CONFIG["workload"],
+                              "ms_filter_stage": fm,
+                              "filter_stage_frac_of_hbm_peak": ab / (fm / 1000.0) / 1e9 / measured_peak()[0],
+                              "ms_pca": statistics.mean(ms_pca) if ms_pca else None,
+                              "spikes_detected_rank0": n_det, "spikes_kept_rank0": n_spk,
+                              "clocks": clocks, "gpu_launches": launches}), flush=True)
         if world > 1:
             dist.destroy_process_group()
         return
@@ -442,6 +450,20 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def select_workload(name):
+    """--workload c3: one GPU's time shard of configs[2] (Neuropixels scale, 384 contacts x
+    1 h at 30 kHz sharded over 8 GPUs = 384 x 13,500,000 per GPU).  Device numbers only
+    (a 10.4 GB pinned recording per rank is not staged): not the driver's bench line."""
+    global N_CONTACTS, N_SAMPLES, SEED, CONFIG
+    if name == "c2":
+        return
+    N_CONTACTS, N_SAMPLES, SEED = 384, 13500000, 3
+    CONFIG = dict(CONFIG, n_contacts=N_CONTACTS, n_samples=N_SAMPLES, seed=SEED,
+                  workload="configs[2] shard: 384-channel 30 kHz recording, 450 s per GPU "
+                           "(1 h over 8 GPUs), int16 (384 x 13,500,000 per GPU), same chain",
+                  l2="inputs larger than L2 (10.4 GB in, 41.5 GB filtered per step and GPU)")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -450,7 +472,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
     args = ap.parse_args()
+    select_workload(args.workload)
+    if args.workload != "c2":
+        args.no_e2e = args.no_cpu_baseline = True
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
