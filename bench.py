@@ -326,9 +326,14 @@ def run_gpu(args):
     def e2e_step():
         # ONE public call for the whole recording: pinned host recording in (the H2D copy of
         # all 1.15 GB is inside), NumPy results out (spike times, waveforms, PCA scores)
-        out = spikesort_b200.sort_frontend(raw, filt=flt, sp_win=SP_WIN, edge='falling',
-                                           align_type='min', thresh='auto', ncomps=2,
-                                           chunksize=CHUNK)
+        if world > 1:
+            # this rank's shard of the (world x 10 min) recording, exchanges over NVLink
+            out = ssdist.sort_frontend_sharded(raw, flt, SP_WIN, edge='falling', align_type='min',
+                                               thresh='auto', ncomps=2, chunksize=CHUNK)
+        else:
+            out = spikesort_b200.sort_frontend(raw, filt=flt, sp_win=SP_WIN, edge='falling',
+                                               align_type='min', thresh='auto', ncomps=2,
+                                               chunksize=CHUNK)
         d2h = 0
         for c in range(N_CONTACTS):
             d2h += out['spt'][c]['data'].nbytes + out['spt_aligned'][c]['data'].nbytes + \
@@ -436,8 +441,11 @@ def run_gpu(args):
         "e2e": {"value": e2e_value, "unit": UNIT,
                 "h2d_bytes_per_step": int(host.numel() * 2), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps, "ms_per_step": e2e_s * 1000.0,
-                "api": "spikesort_b200.sort_frontend(raw_dict, filt, ...): one call, pinned host "
-                       "recording in, per-contact NumPy dicts (spt, sp_waves, features) out",
+                "api": ("spikesort_b200.dist.sort_frontend_sharded(raw_shard_dict, filt, ...) on every "
+                        "rank: pinned host shard in, sharded chain with NVLink exchanges, "
+                        "per-contact NumPy dicts out" if world > 1 else
+                        "spikesort_b200.sort_frontend(raw_dict, filt, ...): one call, pinned host "
+                        "recording in, per-contact NumPy dicts (spt, sp_waves, features) out"),
                 "per_contact_api": {
                     "value": N_CONTACTS * N_SAMPLES / e2e_pc_s, "ms_per_step": e2e_pc_s * 1000.0,
                     "api": "filters.fltLinearIIR + 32 x (extract.detect_spikes, align_spikes, "

@@ -17,7 +17,9 @@
  * Conventions
  *   - plain C: pointers and sizes only, no C++/torch types;
  *   - every pointer named d_* is DEVICE memory owned by the caller, everything
- *     else is host memory; the library never allocates device memory;
+ *     else is host memory; the library never allocates device memory, with one
+ *     exception: the weight table of each distinct filter (<= 100 KB) is cached on every
+ *     device that uses it, for the life of the process;
  *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); all
  *     work is enqueued on it and NO call synchronises the host;
  *   - return value: 0 on success, negative ss_status on failure, message via
@@ -52,6 +54,11 @@ typedef enum {
 
 int         ss_version(void);
 const char *ss_last_error(void);
+
+/* Time slab of every contact between a (pinned) host recording and HBM as one asynchronous
+ * 2-D DMA (rows = contacts, pitches in bytes); to_device 1 = host -> device, 0 = back. */
+int ss_copy_2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch,
+                     size_t width_bytes, size_t rows, int to_device, void *stream);
 /* limits compiled into the library */
 int         ss_max_filter_order(void);      /* total number of delay states     */
 int         ss_max_window(void);            /* largest n_win for align/extract  */
@@ -337,6 +344,15 @@ int ss_shard_gram_put(const double *d_gram, const double *d_sum, const double *d
                       int rank, int world, void *stream);
 int ss_shard_gram_reduce(const void *arena, int n_c, int H, int n_win, int world, double *d_gram,
                          double *d_sum, int64_t *d_counts, int64_t *d_all_counts, void *stream);
+/* Results of one time shard into the whole recording's host layout: lists contact-major
+ * across shards (position d_dst_row_base[c] + rank inside the shard's row), waveforms as one
+ * contiguous (n_win, d_n_tot[c], 1) block per contact starting at d_block_base[c]*n_win.
+ * Any input/output pair may be NULL. */
+int ss_merge_shard(const double *d_spt, const uint8_t *d_valid, const double *d_scores,
+                   int ncomps, const float *d_waves, int n_win, int64_t n_src,
+                   const int64_t *d_src_offsets, int n_c, const int64_t *d_dst_row_base,
+                   const int64_t *d_block_base, const int64_t *d_n_tot, double *d_spt_out,
+                   uint8_t *d_valid_out, double *d_scores_out, float *d_waves_out, void *stream);
 /* reference waveform for the Gram shift of ss_pca_gram: the first spike of every group */
 int ss_pca_first_wave(const float *d_waves, int n_win, int64_t n_spk, int n_c,
                       const int64_t *d_offsets, int64_t n_groups, double *d_ref, void *stream);

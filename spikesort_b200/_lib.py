@@ -56,6 +56,7 @@ SIGNATURES = {
     "ss_wave_minmax": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp]),
     "ss_normalize_workspace_bytes": (_sz, [_int]),
     "ss_normalize_columns": (_int, [_vp, _i64, _int, _vp, _sz, _vp]),
+    "ss_copy_2d_async": (_int, [_vp, _sz, _vp, _sz, _sz, _sz, _int, _vp]),
     "ss_filtfilt_fir": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _i64, _vp, _i64, _vp]),
     "ss_shard_arena_bytes": (_sz, [_int, _int, _int, _int]),
     "ss_shard_arena_offsets": (_int, [_int, _int, _int, _int, _vp]),
@@ -68,6 +69,8 @@ SIGNATURES = {
     "ss_shard_put_last": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _vp]),
     "ss_shard_gram_put": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _vp, _int, _int, _vp]),
     "ss_shard_gram_reduce": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    "ss_merge_shard": (_int, [_vp, _vp, _vp, _int, _vp, _int, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp,
+                              _vp, _vp, _vp]),
     "ss_pca_first_wave": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp]),
     "ss_resample": (_int, [_vp, _int, _int, _i64, _int, _vp, _vp, _int, _vp, _vp]),
     "ss_align_resampled": (_int, [_vp, _int, _i64, _i64, _dbl, _vp, _i64, _vp, _int, _int, _dbl,
@@ -164,6 +167,13 @@ def ss_dtype_of(tensor):
 def np_dtype_of(tensor):
     t = torch()
     return {t.int16: np.int16, t.float32: np.float32, t.float64: np.float64}[tensor.dtype]
+
+
+def np_dtype_full(torch_dtype):
+    """NumPy dtype of any torch dtype this package moves to the host."""
+    t = torch()
+    return np.dtype({t.int16: np.int16, t.float32: np.float32, t.float64: np.float64,
+                     t.int64: np.int64, t.int32: np.int32, t.uint8: np.uint8}[torch_dtype])
 
 
 def to_device_2d(data):

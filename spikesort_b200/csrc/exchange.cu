@@ -249,6 +249,35 @@ __global__ void first_wave_kernel(const float *__restrict__ waves, int n_win, in
     ref[i] = v;
 }
 
+// Results of one time shard (contact-major inside the shard) into the layout the host wants
+// for the WHOLE recording: every list contact-major across shards, waveforms as one
+// contiguous (n_win, n_tot[c], 1) block per contact - so that the host side of
+// extract_spikes' result (extract.py:154-177) is a plain slice per contact.
+// blockIdx.y == 0: times / valid flags / scores; blockIdx.y == 1 + w: waveform row w.
+__global__ void __launch_bounds__(XC_THREADS)
+merge_shard_kernel(const double *__restrict__ spt, const uint8_t *__restrict__ valid,
+                   const double *__restrict__ scores, int ncomps, const float *__restrict__ waves,
+                   int64_t n_src, const int64_t *__restrict__ src_off, int n_c,
+                   const int64_t *__restrict__ dst_row_base, const int64_t *__restrict__ block_base,
+                   const int64_t *__restrict__ n_tot, double *__restrict__ spt_out,
+                   uint8_t *__restrict__ valid_out, double *__restrict__ scores_out,
+                   float *__restrict__ waves_out, int n_win)
+{
+    const int64_t k = (int64_t)blockIdx.x * XC_THREADS + threadIdx.x;
+    if (k >= n_src) return;
+    const int64_t r = xc_find_row(src_off, n_c, k);
+    const int64_t p = dst_row_base[r] + (k - src_off[r]);
+    if (blockIdx.y == 0) {
+        if (spt_out) spt_out[p] = spt[k];
+        if (valid_out) valid_out[p] = valid[k];
+        if (scores_out)
+            for (int j = 0; j < ncomps; ++j) scores_out[p * ncomps + j] = scores[k * ncomps + j];
+    } else {
+        const int64_t w = blockIdx.y - 1, bb = block_base[r];
+        waves_out[bb * n_win + w * n_tot[r] + (p - bb)] = waves[w * n_src + k];
+    }
+}
+
 PeerPtrs peer_ptrs(void *const *bases, int world, size_t offset)
 {
     PeerPtrs P;
@@ -391,5 +420,26 @@ extern "C" int ss_pca_first_wave(const float *d_waves, int n_win, int64_t n_spk,
     first_wave_kernel<<<(unsigned)ss_cdiv(n_groups * n_win, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         d_waves, n_win, n_spk, n_c, d_offsets, n_groups, d_ref);
     SS_LAUNCH_CHECK("first_wave_kernel");
+    return SS_OK;
+}
+
+extern "C" int ss_merge_shard(const double *d_spt, const uint8_t *d_valid, const double *d_scores,
+                              int ncomps, const float *d_waves, int n_win, int64_t n_src,
+                              const int64_t *d_src_offsets, int n_c, const int64_t *d_dst_row_base,
+                              const int64_t *d_block_base, const int64_t *d_n_tot,
+                              double *d_spt_out, uint8_t *d_valid_out, double *d_scores_out,
+                              float *d_waves_out, void *stream)
+{
+    if (n_src == 0) return SS_OK;
+    SS_REQUIRE(d_src_offsets && d_dst_row_base && n_c >= 1, SS_ERR_ARG, "merge_shard: null layout");
+    SS_REQUIRE((!d_spt_out || d_spt) && (!d_valid_out || d_valid) && (!d_scores_out || d_scores) &&
+               (!d_waves_out || (d_waves && d_block_base && d_n_tot)), SS_ERR_ARG,
+               "merge_shard: output without input");
+    SS_REQUIRE(n_win >= 0 && n_win < 65535 && ncomps >= 0, SS_ERR_ARG, "merge_shard: bad shape");
+    const dim3 grid((unsigned)ss_cdiv(n_src, XC_THREADS), d_waves_out ? 1 + n_win : 1);
+    merge_shard_kernel<<<grid, XC_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        d_spt, d_valid, d_scores, ncomps, d_waves, n_src, d_src_offsets, n_c, d_dst_row_base,
+        d_block_base, d_n_tot, d_spt_out, d_valid_out, d_scores_out, d_waves_out, n_win);
+    SS_LAUNCH_CHECK("merge_shard_kernel");
     return SS_OK;
 }

@@ -804,6 +804,19 @@ struct HostTables {
     double *dot;
 };
 
+// Device-resident copies of the summary weights, one per (filter, device), made on first
+// use and kept for the life of the process (12 KB for order 1).  A per-call H2D copy would
+// queue on the copy engine BEHIND a recording upload that overlaps the filter
+// (sort_frontend's slab pipeline) and stall the first kernel until the upload ends.
+struct DeviceTabKey {
+    const double *host;
+    int device;
+    bool operator<(const DeviceTabKey &o) const
+    {
+        return host != o.host ? host < o.host : device < o.device;
+    }
+};
+
 static int build_tables(const QSections &S, HostTables &T)
 {
     const int n = S.ns;
@@ -970,6 +983,25 @@ static int get_tables(const double *sos, int n_sections, bool fo, const QSection
     return rc;
 }
 
+static std::map<DeviceTabKey, double *> g_device_tabs;
+
+static int device_table(const HostTables &T, size_t bytes, const double **d_tab)
+{
+    DeviceTabKey key;
+    key.host = T.dot;
+    SS_CUDA_CHECK(cudaGetDevice(&key.device));
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    auto it = g_device_tabs.find(key);
+    if (it == g_device_tabs.end()) {
+        double *d = nullptr;
+        SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void **>(&d), bytes));
+        SS_CUDA_CHECK(cudaMemcpy(d, T.dot, bytes, cudaMemcpyHostToDevice));   // once per filter and device
+        it = g_device_tabs.emplace(key, d).first;
+    }
+    *d_tab = it->second;
+    return SS_OK;
+}
+
 static int make_geom(FiltGeom &g, int dtype, int64_t n_contacts, int64_t n_samples, int64_t ld_in,
                      int64_t ld_out, int64_t chunksize, int padlen)
 {
@@ -1048,8 +1080,7 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
     double *Zf = Bz + g.total_tiles * NS;
     double *Zb = Zf + g.total_tiles * NS;
     double *yl = Zb + g.total_tiles * NS;
-    double *d_tab = yl + g.total_tiles;                     // (2*NS+1) * FS_T weights
-    const size_t tab_bytes = (size_t)(2 * NS + 1) * FS_T * sizeof(double);
+    const size_t tab_bytes = (size_t)(2 * NS + 1) * FS_T * sizeof(double);   // (2*NS+1) * FS_T weights
     // tiles per unit in this range: full chunks and/or the trailing short one
     const bool has_full = j_begin < g.n_full;
     const bool has_last = g.len_last > 0 && j_begin + j_count > g.n_full;
@@ -1060,7 +1091,8 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
     if (phases & PH_SUMMARY) {
         const dim3 sum_blocks((unsigned)ss_cdiv(nt_max, SM_WPB * SM_TPW), (unsigned)j_count,
                               (unsigned)g.n_contacts);
-        SS_CUDA_CHECK(cudaMemcpyAsync(d_tab, T.dot, tab_bytes, cudaMemcpyHostToDevice, st));
+        const double *d_tab = nullptr;
+        { const int rc_tab = device_table(T, tab_bytes, &d_tab); if (rc_tab) return rc_tab; }
         SS_CUDA_CHECK(cudaFuncSetAttribute(filt_summary_kernel<NS>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)tab_bytes));

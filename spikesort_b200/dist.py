@@ -595,3 +595,21 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
             "%s %.3f" % (marks[i][0], 1000 * (marks[i][1] - marks[i - 1][1]))
             for i in range(1, len(marks))), flush=True)
     return res
+
+
+def sort_frontend_sharded(spike_data, filt, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
+                          thresh='auto', ncomps=2, chunksize=1E6, transport=None):
+    """Host in / host out on one rank of a time-sharded recording: `spike_data['data']` is
+    THIS rank's shard (n_contacts, n_samples_per_rank) on the host (pinned for full PCIe
+    speed).  Uploads it, runs run_chain_sharded (exchanges over NVLink) and returns this
+    shard's part of every contact's results as the reference's dicts, spike times global -
+    concatenating the ranks' lists in rank order gives the whole recording's lists
+    ('all_counts' holds every rank's per-contact counts)."""
+    from .pipeline import results_to_host
+    x = _lib.to_device_2d(spike_data['data'])
+    FS = spike_data['FS']
+    res = run_chain_sharded(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
+                            transport=transport)
+    out = results_to_host(res, list(range(x.shape[0])), FS, ncomps)
+    out['all_counts'] = res.all_counts.cpu().numpy()
+    return out

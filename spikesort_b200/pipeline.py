@@ -131,7 +131,7 @@ def _pinned_like(name, tensor):
 
 
 def sort_frontend(spike_data, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
-                  thresh='auto', ncomps=2, chunksize=1E6, contacts=None):
+                  thresh='auto', ncomps=2, chunksize=1E6, contacts=None, slabs='auto'):
     """The whole front end for a multi-contact recording in ONE call, host in / host out.
 
     spike_data: the reference's raw-recording dict {'data', 'FS', 'n_contacts'}; 'data' may
@@ -146,43 +146,278 @@ def sort_frontend(spike_data, filt=None, sp_win=(-0.2, 0.8), edge='falling', ali
          'spt_aligned': [ {'data'}, ... ],
          'sp_waves': [ {'data' (n_win, n_spk_c, 1) float32, 'time', 'FS'[, 'is_valid']}, ... ],
          'features': [ {'data' (n_spk_c, ncomps), 'names'[, 'is_valid']}, ... ]}
+
+    slabs: a host-resident recording is cut into time slabs (multiples of `chunksize`) whose
+    upload overlaps the chain on the previous slab ('auto': up to 6 slabs; 1: one upload, one
+    chain).  Slabs are time shards on one GPU (dist.ShardedChain over a LocalFabric): spike
+    times and waveforms are identical to the unsliced chain, PCA scores to round-off.
     """
     t = _lib.require_cuda()
     FS = spike_data['FS']
+    if contacts is None and slabs != 1:
+        piped = _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, ncomps,
+                                     chunksize, slabs)
+        if piped is not None:
+            return piped
     x = _lib.to_device_2d(spike_data['data'])            # one H2D copy (pinned: ~55 GB/s)
     if contacts is not None:
         x = x[t.as_tensor(list(contacts), device=x.device)]
     res = run_chain(x, FS, filt=filt, sp_win=sp_win, edge=edge, align_type=align_type,
                     thresh=thresh, ncomps=ncomps, chunksize=chunksize)
-    # one D2H per result array, through pinned staging, then zero-copy per-contact views
-    def host(name, ten):
-        if ten is None:
-            return None
-        buf = _pinned_like(name, ten)
-        buf.copy_(ten, non_blocking=True)
-        return buf
-    h = {k: host(k, getattr(res, k)) for k in ('thresh', 'spt_detected', 'offsets_detected', 'spt',
-                                               'offsets', 'waves', 'valid', 'scores')}
-    t.cuda.current_stream().synchronize()
-    h = {k: (v.numpy() if v is not None else None) for k, v in h.items()}
     n_rows = x.shape[0]
     ids = list(range(n_rows)) if contacts is None else list(contacts)
-    out = {'FS': FS, 'n_contacts': n_rows, 'contacts': ids, 'spt': [], 'spt_aligned': [],
-           'sp_waves': [], 'features': []}
+    return results_to_host(res, ids, FS, ncomps)
+
+
+def _merge_and_fetch(results, ids, FS, ncomps, time):
+    """ChainResults of one or more time slabs/shards (in time order) -> the reference's
+    per-contact dicts on the host.  The device first brings everything into the host's
+    layout (ss_merge_shard: lists contact-major across slabs, one contiguous waveform block
+    per contact), one D2H per array through pinned staging follows, and what is left for the
+    host is one contiguous copy per contact and array."""
+    t = _lib.torch()
+    lib = _lib.load()
+    n_c = len(ids)
+    r0 = results[0]
+    dev = r0.spt.device
+    n_win = int(r0.waves.shape[0])
+    have_scores = all(r.scores is not None for r in results)
+    n_kept = sum(int(r.spt.numel()) for r in results)
+    n_det = sum(int(r.spt_detected.numel()) for r in results)
+
+    def layout(offs):
+        counts = t.stack([o[1:] - o[:-1] for o in offs])           # (S, n_c)
+        n_tot = counts.sum(0)
+        block = t.cumsum(n_tot, 0) - n_tot
+        before = t.cumsum(counts, 0) - counts
+        ends = t.cat((block, n_tot.sum(0, keepdim=True)))          # host-side offsets [n_c+1]
+        return (block[None, :] + before).contiguous(), block.contiguous(), n_tot.contiguous(), ends
+
+    base_k, block_k, ntot_k, ends_k = layout([r.offsets for r in results])
+    base_d, _, _, ends_d = layout([r.offsets_detected for r in results])
+    spt_all = t.empty(n_kept, dtype=t.float64, device=dev)
+    det_all = t.empty(n_det, dtype=t.float64, device=dev)
+    val_all = t.empty(n_kept, dtype=t.uint8, device=dev)
+    sc_all = t.empty((n_kept, ncomps), dtype=t.float64, device=dev) if have_scores else None
+    wav_all = t.empty(n_kept * n_win, dtype=t.float32, device=dev)
+    st = _lib.stream_ptr()
+    for k, r in enumerate(results):
+        rc = lib.ss_merge_shard(_lib.ptr(r.spt), _lib.ptr(r.valid),
+                                _lib.ptr(r.scores if have_scores else None), int(ncomps),
+                                _lib.ptr(r.waves), n_win, int(r.spt.numel()), _lib.ptr(r.offsets), n_c,
+                                _lib.ptr(base_k[k]), _lib.ptr(block_k), _lib.ptr(ntot_k),
+                                _lib.ptr(spt_all), _lib.ptr(val_all), _lib.ptr(sc_all),
+                                _lib.ptr(wav_all), st)
+        _lib.check(rc, "ss_merge_shard")
+        rc = lib.ss_merge_shard(_lib.ptr(r.spt_detected), None, None, 0, None, 0,
+                                int(r.spt_detected.numel()), _lib.ptr(r.offsets_detected), n_c,
+                                _lib.ptr(base_d[k]), None, None, _lib.ptr(det_all), None, None, None, st)
+        _lib.check(rc, "ss_merge_shard")
+        _ops._launched((1 if r.spt.numel() else 0) + (1 if r.spt_detected.numel() else 0))
+    dev_arrays = {'thresh': r0.thresh, 'det': det_all, 'spt': spt_all, 'valid': val_all,
+                  'scores': sc_all, 'waves': wav_all, 'ends_k': ends_k, 'ends_d': ends_d}
+    # One pinned host block per call, leased from a pool and handed out as the result arrays
+    # themselves (views): no second host copy, no page faults on fresh memory.  A block
+    # returns to the pool when the caller has dropped every array that points into it.
+    spans, total = {}, 0
+    for name, ten in dev_arrays.items():
+        if ten is not None:
+            spans[name] = (total, ten.numel() * ten.element_size())
+            total = (total + spans[name][1] + 63) // 64 * 64
+    pinned, block = _lease_host_block(max(total, 64))
+    h = {}
+    for name, ten in dev_arrays.items():
+        if ten is None:
+            h[name] = None
+            continue
+        off, nbytes = spans[name]
+        if nbytes:
+            pinned[off:off + nbytes].view(ten.dtype).copy_(ten.reshape(-1), non_blocking=True)
+        h[name] = block[off:off + nbytes].view(_lib.np_dtype_full(ten.dtype))
+    t.cuda.current_stream().synchronize()
+    out = {'FS': FS, 'n_contacts': n_c, 'contacts': ids, 'spt': [None] * n_c,
+           'spt_aligned': [None] * n_c, 'sp_waves': [None] * n_c, 'features': [None] * n_c}
     names = ["Ch0:PC%d" % j for j in range(ncomps)]
-    off, offd = h['offsets'], h['offsets_detected']
-    for r, c in enumerate(ids):
-        lo, hi = int(off[r]), int(off[r + 1])
-        out['spt'].append({'data': h['spt_detected'][int(offd[r]):int(offd[r + 1])].copy(),
-                           'thresh': float(h['thresh'][r]), 'contact': c})
-        out['spt_aligned'].append({'data': h['spt'][lo:hi].copy()})
-        valid = h['valid'][lo:hi].astype(bool)
-        wd = {'data': np.ascontiguousarray(h['waves'][:, lo:hi, :]), 'time': res.time, 'FS': FS}
-        fd = {'data': h['scores'][lo:hi].copy() if h['scores'] is not None else None,
-              'names': list(names)}
+    ok, od = h['ends_k'], h['ends_d']
+    valid_all = h['valid'].view(np.bool_)                 # uint8 0/1 -> bool, same bytes
+    scores_all = h['scores'].reshape(-1, ncomps) if have_scores else None
+    for r in range(n_c):
+        lo, hi = int(ok[r]), int(ok[r + 1])
+        out['spt'][r] = {'data': h['det'][int(od[r]):int(od[r + 1])],
+                         'thresh': float(h['thresh'][r]), 'contact': ids[r]}
+        out['spt_aligned'][r] = {'data': h['spt'][lo:hi]}
+        valid = valid_all[lo:hi]
+        wd = {'data': h['waves'][lo * n_win:hi * n_win].reshape(n_win, hi - lo, 1),
+              'time': time, 'FS': FS}
+        fd = {'data': scores_all[lo:hi] if have_scores else None, 'names': list(names)}
         if not valid.all():
             wd['is_valid'] = valid
             fd['is_valid'] = valid
-        out['sp_waves'].append(wd)
-        out['features'].append(fd)
+        out['sp_waves'][r] = wd
+        out['features'][r] = fd
     return out
+
+
+_HOST_BLOCKS = []                  # [(pinned uint8 tensor, its ndarray)]
+_MAX_HOST_BLOCKS = 6
+
+
+def _lease_host_block(nbytes):
+    """(pinned uint8 tensor, ndarray over the same memory) of at least nbytes.  A pooled block
+    is free when nothing but the pool refers to its ndarray (result arrays are views of it,
+    so they keep it busy for as long as the caller holds them)."""
+    import sys
+    t = _lib.torch()
+    for i, (ten, arr) in enumerate(_HOST_BLOCKS):
+        if arr.nbytes >= nbytes and sys.getrefcount(arr) <= 3:     # pool tuple, loop variable, argument
+            return ten, arr
+    for i, (ten, arr) in enumerate(_HOST_BLOCKS):                  # free but too small: replace
+        if sys.getrefcount(arr) <= 3:
+            del _HOST_BLOCKS[i]
+            break
+    if len(_HOST_BLOCKS) >= _MAX_HOST_BLOCKS:
+        # the caller keeps many results alive: plain (pageable) memory, owned by the arrays
+        arr = np.empty(nbytes, dtype=np.uint8)
+        return t.from_numpy(arr), arr
+    ten = t.empty(int(nbytes * 1.25) + 4096, dtype=t.uint8).pin_memory()
+    arr = ten.numpy()
+    _HOST_BLOCKS.append((ten, arr))
+    return ten, arr
+
+
+def results_to_host(res, ids, FS, ncomps):
+    """ChainResult -> the reference's per-contact dicts on the host."""
+    return _merge_and_fetch([res], ids, FS, ncomps, res.time)
+
+
+def _slab_bounds(n, chunksize, n0, want):
+    """Time slabs in whole chunks: [(a, b), ...]; the first one holds the n0 threshold
+    samples, a short trailing chunk joins the last slab.  None if slicing is pointless."""
+    cs = int(chunksize)
+    n_chunks = -(-n // cs)
+    full = n // cs                                        # chunks of full length
+    if full < 2:
+        return None
+    S = min(int(want), full)
+    per = -(-full // S)
+    first = max(per, -(-min(n0, n) // cs))
+    edges = [0]
+    k = first
+    while k < full:
+        edges.append(k * cs)
+        k += per
+    edges.append(n)
+    if len(edges) < 3:
+        return None
+    del n_chunks
+    return list(zip(edges[:-1], edges[1:]))
+
+
+def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
+                         slabs):
+    """sort_frontend with the upload of slab s+1 overlapping the chain on slab s.  Returns
+    None when the input does not qualify (device-resident, FIR / no filter, too short)."""
+    t = _lib.torch()
+    data = spike_data['data']
+    if hasattr(data, "device_tensor") or filt is None or not hasattr(filt, "sections"):
+        return None
+    if isinstance(data, t.Tensor):
+        if data.is_cuda or data.dim() != 2:
+            return None
+        host = data
+    else:
+        arr = np.asarray(data)
+        if arr.ndim != 2 or arr.dtype not in (np.int16, np.float32, np.float64):
+            return None
+        host = t.from_numpy(np.ascontiguousarray(arr))
+    if host.dtype not in (t.int16, t.float32, t.float64) or host.stride(1) != 1:
+        return None
+    FS = spike_data['FS']
+    n_c, n = host.shape
+    win0, win1, time = _ops.window_params(list(sp_win), FS)
+    n_win = win1 - win0
+    H = 4 * n_win
+    bounds = _slab_bounds(n, chunksize, int(10 * FS) if isinstance(thresh, str) else 0,
+                          6 if slabs == 'auto' else slabs)
+    if bounds is None or min(b - a for a, b in bounds) < max(H, 1):
+        return None
+    from . import dist as ssd
+    import os
+    import time as _time
+    prof = [] if os.environ.get("SS_E2E_PROFILE") else None
+
+    def mark(name):
+        if prof is not None:
+            prof.append((name, _time.perf_counter()))
+
+    mark("start")
+    S = len(bounds)
+    dev = _lib.device()
+    cur = t.cuda.current_stream()
+    up, _ = _side_streams()
+    up.wait_stream(cur)
+    xdev = t.empty((n_c, n), dtype=host.dtype, device=dev)
+    arrived = []
+    lib = _lib.load()
+    esz = host.element_size()
+    with t.cuda.stream(up):                               # all uploads queued up front
+        for a, b in bounds:
+            # one strided DMA per slab (torch's copy_ would stage a non-contiguous slice
+            # through pageable memory)
+            rc = lib.ss_copy_2d_async(xdev.data_ptr() + a * esz, xdev.stride(0) * esz,
+                                      host.data_ptr() + a * esz, host.stride(0) * esz,
+                                      (b - a) * esz, n_c, 1, up.cuda_stream)
+            _lib.check(rc, "ss_copy_2d_async")
+            ev = t.cuda.Event()
+            ev.record(up)
+            arrived.append(ev)
+    mark("uploads queued")
+    key = (n_c, H, n_win, S, str(dev))
+    if key not in _SLAB_FABRICS:
+        _SLAB_FABRICS[key] = ssd.LocalFabric(n_c, H, n_win, S, dev)
+    fab = _SLAB_FABRICS[key]
+    chains = [ssd.ShardedChain(xdev[:, a:b], FS, filt, sp_win, edge, align_type, thresh, ncomps,
+                               chunksize, rank=k, n_ranks=S, index_offset=a, n_total=n, fabric=fab)
+              for k, (a, b) in enumerate(bounds)]
+
+    def finish(k):
+        # slab k's neighbours are filtered: align, remove doubles, extract, partial Gram
+        chains[k].fab_align()
+        chains[k].fab_extract_gram()
+
+    thr = None
+    for k in range(S):
+        cur.wait_event(arrived[k])
+        chains[k].prepare()
+        if k == 0:
+            thr = chains[0].head_threshold()
+        chains[k].fab_filter_detect(thr)
+        mark("filter %d" % k)
+        if k > 0:
+            finish(k - 1)
+            mark("finish %d" % (k - 1))
+    finish(S - 1)
+    mark("finish last")
+    res0 = chains[0].fab_project()                        # Gram of all slabs, ONE eigensolve
+    for k in range(1, S):
+        r = chains[k].res
+        r.scores = _ops.pca_project(r.waves, res0.evals, res0.evecs, ncomps, offsets=r.offsets)
+    mark("project queued")
+    out = _merge_and_fetch([c.res for c in chains], list(range(n_c)), FS, ncomps, time)
+    mark("merged, fetched, assembled")
+    if prof is not None:
+        print("e2e profile (ms): " + ", ".join("%s %.2f" % (prof[i][0], 1e3 * (prof[i][1] - prof[i - 1][1]))
+                                               for i in range(1, len(prof))), flush=True)
+    return out
+
+
+_SLAB_FABRICS = {}
+_STREAMS = {}
+
+
+def _side_streams():
+    t = _lib.torch()
+    dev = t.cuda.current_device()
+    if dev not in _STREAMS:
+        _STREAMS[dev] = (t.cuda.Stream(), t.cuda.Stream())
+    return _STREAMS[dev]

@@ -321,3 +321,35 @@ def test_sort_frontend_equals_per_contact_calls(ss, golden):
         assert out['features'][c]['names'] == ft['names']
         assert rel_err(sign_normalise(out['features'][c]['data'], ft['data']), ft['data']) < 1e-9
     assert np.array_equal(out['spt_aligned'][1]['data'], golden['chain_align'])
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_sort_frontend_slab_pipeline_equals_single_upload(ss, pinned):
+    """The upload-overlapped path (time slabs = shards on one GPU over a LocalFabric) returns
+    what the single-upload chain returns: spike times and waveforms bit for bit, PCA scores
+    to round-off (the Gram is summed slab by slab)."""
+    import torch
+    from spikesort_b200 import synth, pipeline
+    FS, n_c, n, cs = 3000, 5, 170500, 10000          # 17 full chunks + a short one
+    x = synth.make_recording(n_c, n, FS, seed=77, rate_hz=30.0, noise=6.0, amp=(70.0, 160.0),
+                             burst=True, negative=True)
+    assert pipeline._slab_bounds(n, cs, 10 * FS, 6) is not None
+    data = x.pin_memory() if pinned else x.numpy()
+    raw = {'data': data, 'FS': FS, 'n_contacts': n_c}
+    flt = ss.filters.Filter(300., 40.)
+    kw = dict(filt=flt, sp_win=[-1.0, 2.0], edge='falling', align_type='min', thresh='4', ncomps=2,
+              chunksize=cs)
+    one = ss.sort_frontend(raw, slabs=1, **kw)
+    for slabs in ('auto', 3):
+        got = ss.sort_frontend(raw, slabs=slabs, **kw)
+        tot = 0
+        for c in range(n_c):
+            assert np.array_equal(got['spt'][c]['data'], one['spt'][c]['data']), c
+            assert got['spt'][c]['thresh'] == one['spt'][c]['thresh']
+            assert np.array_equal(got['spt_aligned'][c]['data'], one['spt_aligned'][c]['data']), c
+            assert np.array_equal(got['sp_waves'][c]['data'], one['sp_waves'][c]['data']), c
+            assert ('is_valid' in got['sp_waves'][c]) == ('is_valid' in one['sp_waves'][c])
+            a, b = got['features'][c]['data'], one['features'][c]['data']
+            assert rel_err(sign_normalise(a, b), b) < 1e-9, c
+            tot += len(one['spt_aligned'][c]['data'])
+        assert tot > 300
