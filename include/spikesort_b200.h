@@ -347,9 +347,9 @@ int ss_shard_gram_reduce(const void *arena, int n_c, int H, int n_win, int world
 /* Results of one time shard into the whole recording's host layout: lists contact-major
  * across shards (position d_dst_row_base[c] + rank inside the shard's row), waveforms as one
  * contiguous (n_win, d_n_tot[c], 1) block per contact starting at d_block_base[c]*n_win.
- * Any input/output pair may be NULL. */
+ * Any input/output pair may be NULL; wave_stride = row stride of d_waves in elements. */
 int ss_merge_shard(const double *d_spt, const uint8_t *d_valid, const double *d_scores,
-                   int ncomps, const float *d_waves, int n_win, int64_t n_src,
+                   int ncomps, const float *d_waves, int n_win, int64_t wave_stride, int64_t n_src,
                    const int64_t *d_src_offsets, int n_c, const int64_t *d_dst_row_base,
                    const int64_t *d_block_base, const int64_t *d_n_tot, double *d_spt_out,
                    uint8_t *d_valid_out, double *d_scores_out, float *d_waves_out, void *stream);

@@ -69,7 +69,7 @@ SIGNATURES = {
     "ss_shard_put_last": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _vp]),
     "ss_shard_gram_put": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _vp, _int, _int, _vp]),
     "ss_shard_gram_reduce": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
-    "ss_merge_shard": (_int, [_vp, _vp, _vp, _int, _vp, _int, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp,
+    "ss_merge_shard": (_int, [_vp, _vp, _vp, _int, _vp, _int, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp,
                               _vp, _vp, _vp]),
     "ss_pca_first_wave": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp]),
     "ss_resample": (_int, [_vp, _int, _int, _i64, _int, _vp, _vp, _int, _vp, _vp]),

@@ -95,10 +95,13 @@ def filtfilt_fir(x, b, chunksize, out=None):
 
 
 def filtfilt_detect(x, sos, padlen, chunksize, FS, falling, thr=None, n0=None, factor=None,
-                    out=None, ws=None, shard=_WHOLE):
+                    out=None, ws=None, shard=_WHOLE, cap=None):
     """Fused filter + (auto threshold) + crossing marking + emit.
     thr: CUDA float64 (n_contacts,) thresholds, or None to derive them from the first
-    n0 filtered samples (factor carries the sign).  Returns (out, thr, spt, offsets)."""
+    n0 filtered samples (factor carries the sign).  Returns (out, thr, spt, offsets).
+    cap: size the spike list by this capacity instead of synchronising with the host to
+    learn the count; the true count is offsets[-1] (more than cap: the list is truncated and
+    the caller must redo the call without cap)."""
     lib = _lib.load()
     t = _lib.torch()
     n_c, n = x.shape
@@ -125,7 +128,7 @@ def filtfilt_detect(x, sos, padlen, chunksize, FS, falling, thr=None, n0=None, f
     _lib.check(rc, "ss_filtfilt_detect_sos")
     # summary, tilescan | apply(head), 2 threshold, mark(head), edge | apply+marks, edge | count, scan
     _launched((0 if prepared else 2) + (5 if auto else 0) + 4)
-    total = int(offsets[-1].item())
+    total = int(offsets[-1].item()) if cap is None else int(cap)
     spt = t.empty(total, dtype=t.float64, device=x.device)
     rc = lib.ss_detect_emit(n_c, n, float(FS), shard.index_offset, _lib.ptr(dws), dws.numel(),
                             _lib.ptr(spt), total, _lib.stream_ptr())
@@ -188,7 +191,7 @@ def var_threshold(x, n0, factor):
 
 
 # --------------------------------------------------------------------- detect
-def detect(x, thr, falling, FS, shard=_WHOLE):
+def detect(x, thr, falling, FS, shard=_WHOLE, cap=None):
     """Threshold crossings of every row.  Returns (spt, offsets): CUDA float64 times
     (ms) concatenated row by row and CUDA int64 offsets[n_rows+1]."""
     lib = _lib.load()
@@ -201,7 +204,7 @@ def detect(x, thr, falling, FS, shard=_WHOLE):
                             _lib.ptr(offsets), _lib.stream_ptr())
     _lib.check(rc, "ss_detect_mark")
     _launched(2)          # mark, scan
-    total = int(offsets[-1].item())                 # the one sync: size of the result
+    total = int(offsets[-1].item()) if cap is None else int(cap)   # the one sync: size of the result
     spt = t.empty(total, dtype=t.float64, device=x.device)
     rc = lib.ss_detect_emit(n_rows, n, float(FS), shard.index_offset, _lib.ptr(ws), ws.numel(),
                             _lib.ptr(spt), total, _lib.stream_ptr())
@@ -231,7 +234,7 @@ def align(x, spt, offsets, rows, FS, sp_win, use_min, shard=_WHOLE):
     return spt
 
 
-def remove_doubles(spt, offsets, tol, prev_last=None, also=None):
+def remove_doubles(spt, offsets, tol, prev_last=None, also=None, cap=None):
     """Returns (kept times, new offsets); offsets None = one row.  `spt` may have spare
     capacity beyond offsets[-1].  also: optional CUDA int64 scalar fetched in the same host
     synchronisation that sizes the result; its value is then returned as a third item."""
@@ -249,7 +252,9 @@ def remove_doubles(spt, offsets, tol, prev_last=None, also=None):
                                     _lib.stream_ptr())
     _lib.check(rc, "ss_remove_doubles_mark")
     _launched(3)          # mark, scan, row offsets
-    if also is None:
+    if cap is not None:
+        total = int(cap)                            # no host sync; true count = new_off[-1]
+    elif also is None:
         total = int(new_off[-1].item())
     else:
         total, extra = (int(v) for v in t.stack((new_off[-1], also.reshape(()))).tolist())

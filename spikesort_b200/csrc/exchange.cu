@@ -261,10 +261,10 @@ merge_shard_kernel(const double *__restrict__ spt, const uint8_t *__restrict__ v
                    const int64_t *__restrict__ dst_row_base, const int64_t *__restrict__ block_base,
                    const int64_t *__restrict__ n_tot, double *__restrict__ spt_out,
                    uint8_t *__restrict__ valid_out, double *__restrict__ scores_out,
-                   float *__restrict__ waves_out, int n_win)
+                   float *__restrict__ waves_out, int n_win, int64_t wave_stride)
 {
     const int64_t k = (int64_t)blockIdx.x * XC_THREADS + threadIdx.x;
-    if (k >= n_src) return;
+    if (k >= n_src || k >= __ldg(src_off + n_c)) return;     // spare capacity
     const int64_t r = xc_find_row(src_off, n_c, k);
     const int64_t p = dst_row_base[r] + (k - src_off[r]);
     if (blockIdx.y == 0) {
@@ -274,7 +274,7 @@ merge_shard_kernel(const double *__restrict__ spt, const uint8_t *__restrict__ v
             for (int j = 0; j < ncomps; ++j) scores_out[p * ncomps + j] = scores[k * ncomps + j];
     } else {
         const int64_t w = blockIdx.y - 1, bb = block_base[r];
-        waves_out[bb * n_win + w * n_tot[r] + (p - bb)] = waves[w * n_src + k];
+        waves_out[bb * n_win + w * n_tot[r] + (p - bb)] = waves[w * wave_stride + k];
     }
 }
 
@@ -424,8 +424,8 @@ extern "C" int ss_pca_first_wave(const float *d_waves, int n_win, int64_t n_spk,
 }
 
 extern "C" int ss_merge_shard(const double *d_spt, const uint8_t *d_valid, const double *d_scores,
-                              int ncomps, const float *d_waves, int n_win, int64_t n_src,
-                              const int64_t *d_src_offsets, int n_c, const int64_t *d_dst_row_base,
+                              int ncomps, const float *d_waves, int n_win, int64_t wave_stride,
+                              int64_t n_src, const int64_t *d_src_offsets, int n_c, const int64_t *d_dst_row_base,
                               const int64_t *d_block_base, const int64_t *d_n_tot,
                               double *d_spt_out, uint8_t *d_valid_out, double *d_scores_out,
                               float *d_waves_out, void *stream)
@@ -439,7 +439,7 @@ extern "C" int ss_merge_shard(const double *d_spt, const uint8_t *d_valid, const
     const dim3 grid((unsigned)ss_cdiv(n_src, XC_THREADS), d_waves_out ? 1 + n_win : 1);
     merge_shard_kernel<<<grid, XC_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         d_spt, d_valid, d_scores, ncomps, d_waves, n_src, d_src_offsets, n_c, d_dst_row_base,
-        d_block_base, d_n_tot, d_spt_out, d_valid_out, d_scores_out, d_waves_out, n_win);
+        d_block_base, d_n_tot, d_spt_out, d_valid_out, d_scores_out, d_waves_out, n_win, wave_stride);
     SS_LAUNCH_CHECK("merge_shard_kernel");
     return SS_OK;
 }

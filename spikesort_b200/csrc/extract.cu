@@ -48,11 +48,15 @@ extract_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t
     const int64_t s0 = (int64_t)blockIdx.x * SB;
     const int c0 = blockIdx.y * CB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // the list may have spare capacity: entries at or beyond offsets[n_rows] are not spikes
+    // (their waveforms are written as zeros, their valid flag as 0)
+    const int64_t n_live = (!contacts && offsets) ? min(n_spk, __ldg(offsets + n_rows)) : n_spk;
 
     if (tid < SB) {
         const int64_t s = s0 + tid;
         int64_t first = 0, row0 = 0;
-        if (s < n_spk) {
+        if (s >= n_live && s < n_spk && blockIdx.y == 0) valid[s] = 0;
+        if (s < n_live) {
             const double t = spt[s];
             const int centre = __double2int_rz(__dmul_rn(__ddiv_rn(t, 1000.0), FS));
             first = (int64_t)centre + win0 - index_offset;          // local index
@@ -77,7 +81,7 @@ extract_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t
         const int sl = p / CB, cl = p - sl * CB;
         const int64_t s = s0 + sl;
         const int c = c0 + cl;
-        const bool live = s < n_spk && c < n_c;
+        const bool live = s < n_live && c < n_c;
         int64_t base = 0;
         if (live) base = contacts ? (int64_t)__ldg(contacts + c) * ld : s_row0[sl];
         const int64_t first = s_first[sl];

@@ -295,6 +295,7 @@ pca_project_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
             if (__ldg(offsets + mid) <= s) lo = mid; else hi = mid;
         }
         g = lo;
+        if (s >= __ldg(offsets + n_groups)) return;          // spare capacity, not a spike
     }
     double acc[PC_MAX_COMPS];
 #pragma unroll

@@ -58,15 +58,48 @@ class ChainResult(object):
         return out
 
 
+_CAPACITY_HINTS = {}
+
+
 def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
-              thresh='auto', ncomps=2, chunksize=1E6, pca=True, thr_override=None, fused=True):
+              thresh='auto', ncomps=2, chunksize=1E6, pca=True, thr_override=None, fused=True,
+              speculate=True):
     """x: CUDA tensor (n_contacts, n_samples), int16/float32/float64.
     filt: a spikesort_b200.filters filter object or None.
     thresh: 'auto' / numeric string (multiple of the std of the first 10 s) or a number.
     thr_override: optional CUDA float64 (n_contacts,) thresholds (e.g. broadcast from the
     rank owning the first 10 s when the recording is time-sharded).
     fused: mark the crossings in the filter's second sweep (default) instead of a
-    separate pass over the filtered signal; the results are identical."""
+    separate pass over the filtered signal; the results are identical.
+    speculate: the chain needs the number of detected / kept spikes on the HOST twice, to
+    size arrays - two synchronisations that leave the GPU waiting for the launches of every
+    kernel behind them.  When a call with the same shape has been seen before, the arrays
+    are sized by that call's count + 25 % instead, every kernel bounds its work by the
+    device-side offsets, and the counts are read once at the end; if the capacity turns out
+    too small the chain is simply run again with exact sizes.  Results are identical."""
+    key = (tuple(x.shape), x.dtype, float(FS), tuple(sp_win), edge, align_type, str(thresh),
+           id(type(filt)), int(chunksize), bool(fused))
+    hint = _CAPACITY_HINTS.get(key) if speculate else None
+    if hint is not None:
+        cap = int(hint * 1.25) + 1024
+        res, n_det, n_kept = _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps,
+                                        chunksize, pca, thr_override, fused, cap)
+        if n_det <= cap:
+            _CAPACITY_HINTS[key] = n_det
+            return res
+    res, n_det, n_kept = _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
+                                    pca, thr_override, fused, None)
+    if speculate:
+        if len(_CAPACITY_HINTS) > 64:
+            _CAPACITY_HINTS.clear()
+        _CAPACITY_HINTS[key] = n_det
+    return res
+
+
+def _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize, pca, thr_override,
+               fused, cap):
+    """The chain; cap=None: exact sizes (two host syncs), else capacity-sized arrays and one
+    sync at the end.  Returns (ChainResult, n_detected, n_kept)."""
     t = _lib.require_cuda()
     res = ChainResult()
     sp_win = list(sp_win)
@@ -84,7 +117,7 @@ def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='
             thr = t.full((x.shape[0],), float(thresh), dtype=t.float64, device=x.device)
         sig, thr, spt, offsets = _ops.filtfilt_detect(
             x, sos, padlen, int(chunksize), FS, falling, thr=thr, n0=int(10 * FS),
-            factor=(-frac if falling else frac) if auto else None)
+            factor=(-frac if falling else frac) if auto else None, cap=cap)
         res.filtered, res.thresh = sig, thr
     else:
         if filt is not None:
@@ -100,20 +133,33 @@ def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='
         else:
             thr = t.full((n_rows,), float(thresh), dtype=t.float64, device=sig.device)
         res.thresh = thr
-        spt, offsets = _ops.detect(sig, thr, falling, FS)
+        spt, offsets = _ops.detect(sig, thr, falling, FS, cap=cap)
     res.spt_detected, res.offsets_detected = spt, offsets
     spt = spt.clone()
     _ops.align(sig, spt, offsets, None, FS, sp_win, align_type == 'min')
-    spt, offsets = _ops.remove_doubles(spt, offsets, 1000.0 / FS)
+    spt, offsets = _ops.remove_doubles(spt, offsets, 1000.0 / FS, cap=cap)
     res.spt, res.offsets = spt, offsets
     waves, valid, n_invalid = _ops.extract(sig, spt, FS, sp_win, contacts=None, offsets=offsets)
     res.waves, res.valid, res.n_invalid = waves, valid, n_invalid
     res.time = _ops.window_params(sp_win, FS)[2]
-    if pca and spt.numel() > 0:
+    if pca and (cap is not None or spt.numel() > 0):
         gram, ssum, _, counts = _ops.pca_gram(waves, offsets=offsets)
         res.evals, res.evecs = _ops.pca_eig(gram, ssum, counts)
         res.scores = _ops.pca_project(waves, res.evals, res.evecs, ncomps, offsets=offsets)
-    return res
+    if cap is None:
+        return res, int(res.spt_detected.numel()), int(res.spt.numel())
+    # the one host sync of the speculative chain: both counts at once, then trim (views)
+    n_det, n_kept = (int(v) for v in t.stack((res.offsets_detected[-1], res.offsets[-1])).tolist())
+    if n_det <= cap:
+        res.spt_detected = res.spt_detected[:n_det]
+        res.spt, res.valid = res.spt[:n_kept], res.valid[:n_kept]
+        res.waves = res.waves[:, :n_kept, :]
+        if res.scores is not None:
+            if n_kept == 0:
+                res.scores = res.evals = res.evecs = None
+            else:
+                res.scores = res.scores[:n_kept]
+    return res, n_det, n_kept
 
 
 _PINNED = {}
@@ -204,12 +250,13 @@ def _merge_and_fetch(results, ids, FS, ncomps, time):
     for k, r in enumerate(results):
         rc = lib.ss_merge_shard(_lib.ptr(r.spt), _lib.ptr(r.valid),
                                 _lib.ptr(r.scores if have_scores else None), int(ncomps),
-                                _lib.ptr(r.waves), n_win, int(r.spt.numel()), _lib.ptr(r.offsets), n_c,
+                                _lib.ptr(r.waves), n_win, int(r.waves.stride(0)), int(r.spt.numel()),
+                                _lib.ptr(r.offsets), n_c,
                                 _lib.ptr(base_k[k]), _lib.ptr(block_k), _lib.ptr(ntot_k),
                                 _lib.ptr(spt_all), _lib.ptr(val_all), _lib.ptr(sc_all),
                                 _lib.ptr(wav_all), st)
         _lib.check(rc, "ss_merge_shard")
-        rc = lib.ss_merge_shard(_lib.ptr(r.spt_detected), None, None, 0, None, 0,
+        rc = lib.ss_merge_shard(_lib.ptr(r.spt_detected), None, None, 0, None, 0, 0,
                                 int(r.spt_detected.numel()), _lib.ptr(r.offsets_detected), n_c,
                                 _lib.ptr(base_d[k]), None, None, _lib.ptr(det_all), None, None, None, st)
         _lib.check(rc, "ss_merge_shard")

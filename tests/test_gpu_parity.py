@@ -462,3 +462,43 @@ def test_fetpca_ten_million_waveforms_properties(env):
         mine = (gram[c] - torch.outer(ssum[c], ssum[c]) / n_spk) / (n_spk - 1)
         # 10 M spikes take the tensor-core Gram (3xTF32, truncating float32 accumulation)
         assert float((mine - full).abs().max()) < 5e-6 * float(full.abs().max())
+
+
+def test_speculative_chain_equals_exact_chain(env):
+    """run_chain sized by the previous call's spike count (+25 %), one host sync at the end,
+    returns what the exact-size chain returns - bit for bit - and falls back to exact sizes
+    when the capacity is too small."""
+    torch, pipeline = env['torch'], env['pipeline']
+    FS = 30000
+    x = env['synth'].make_recording(6, 400000, FS, seed=21, rate_hz=60.0, noise=8.0,
+                                    amp=(80.0, 200.0), negative=True, burst=True).to(env['dev'])
+    flt = env['ss'].filters.Filter(800., 100.)
+    kw = dict(filt=flt, sp_win=[-0.2, 0.8], edge='falling', align_type='min', thresh='auto',
+              ncomps=2, chunksize=100000)
+    pipeline._CAPACITY_HINTS.clear()
+    exact = pipeline.run_chain(x, FS, speculate=False, **kw)
+    assert not pipeline._CAPACITY_HINTS
+    first = pipeline.run_chain(x, FS, **kw)                   # learns the count (exact sizes)
+    assert len(pipeline._CAPACITY_HINTS) == 1
+    spec = pipeline.run_chain(x, FS, **kw)                    # capacity-sized
+    key = next(iter(pipeline._CAPACITY_HINTS))
+    pipeline._CAPACITY_HINTS[key] = 10                        # far too small: must fall back
+    small = pipeline.run_chain(x, FS, **kw)
+    assert pipeline._CAPACITY_HINTS[key] == exact.spt_detected.numel()
+    assert exact.spt.numel() > 500
+    for r in (first, spec, small):
+        for name in ('thresh', 'spt_detected', 'offsets_detected', 'spt', 'offsets', 'valid',
+                     'evals', 'evecs', 'scores'):
+            assert torch.equal(getattr(r, name), getattr(exact, name)), name
+        assert torch.equal(r.waves, exact.waves)
+        assert int(r.n_invalid) == int(exact.n_invalid)
+    for c in (0, 5):
+        a, b = spec.per_contact(c), exact.per_contact(c)
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    # unfused path too
+    pipeline._CAPACITY_HINTS.clear()
+    u1 = pipeline.run_chain(x, FS, fused=False, **kw)
+    u2 = pipeline.run_chain(x, FS, fused=False, **kw)
+    assert torch.equal(u1.spt, u2.spt) and torch.equal(u1.waves, u2.waves)
+    assert torch.equal(u1.spt, exact.spt)
