@@ -319,6 +319,9 @@ int ss_filtfilt_fir(const void *d_x, int dtype, int64_t n_contacts, int64_t n_sa
  *                            -> slot `rank` of every arena;
  *   ss_shard_gram_reduce   : sum of the slots in rank order (bit-identical on every rank),
  *                            per-contact counts of every rank in d_all_counts (world, n_c).
+ *                            A status word (*d_status, may be NULL = 0) travels with every
+ *                            partial; *d_status_max is its maximum over the ranks - how all
+ *                            ranks learn that one of them overflowed a capacity-sized list.
  * Kernels that take (d_spt, n_spk, d_offsets) ignore entries at or beyond
  * d_offsets[n_rows], so a list with spare capacity can be passed without a host sync.
  */
@@ -341,9 +344,10 @@ int ss_shard_put_last(const double *d_spt, const int64_t *d_offsets, int n_c, in
                       void *const *arenas, int rank, int world, void *stream);
 int ss_shard_gram_put(const double *d_gram, const double *d_sum, const double *d_ref,
                       const int64_t *d_offsets, int n_c, int H, int n_win, void *const *arenas,
-                      int rank, int world, void *stream);
+                      int rank, int world, const int64_t *d_status, void *stream);
 int ss_shard_gram_reduce(const void *arena, int n_c, int H, int n_win, int world, double *d_gram,
-                         double *d_sum, int64_t *d_counts, int64_t *d_all_counts, void *stream);
+                         double *d_sum, int64_t *d_counts, int64_t *d_all_counts,
+                         int64_t *d_status_max, void *stream);
 /* Results of one time shard into the whole recording's host layout: lists contact-major
  * across shards (position d_dst_row_base[c] + rank inside the shard's row), waveforms as one
  * contiguous (n_win, d_n_tot[c], 1) block per contact starting at d_block_base[c]*n_win.

@@ -67,8 +67,8 @@ SIGNATURES = {
                                       _vp, _vp]),
     "ss_shard_append_boundary": (_int, [_vp, _vp, _int, _i64, _vp, _dbl, _vp, _vp, _vp]),
     "ss_shard_put_last": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _vp]),
-    "ss_shard_gram_put": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _vp, _int, _int, _vp]),
-    "ss_shard_gram_reduce": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
+    "ss_shard_gram_put": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _vp, _int, _int, _vp, _vp]),
+    "ss_shard_gram_reduce": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ss_merge_shard": (_int, [_vp, _vp, _vp, _int, _vp, _int, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp,
                               _vp, _vp, _vp]),
     "ss_pca_first_wave": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp]),

@@ -17,7 +17,7 @@
 //   from_left  [n_c][H]               last H filtered samples of the left neighbour
 //   from_right [n_c][H]               first H filtered samples of the right neighbour
 //   prev_last  [n_c]                  last aligned spike time of the left neighbour (NaN: none)
-//   slots      [world][n_c*n_win^2 + n_c*n_win + n_c]   Gram | sums | counts of every rank
+//   slots      [world][n_c*n_win^2 + n_c*n_win + n_c + 1]   Gram | sums | counts | status of every rank
 #include "common.cuh"
 #include "internal.cuh"
 
@@ -38,7 +38,7 @@ ArenaLayout arena_layout(int64_t n_c, int64_t H, int64_t n_win, int64_t world)
     L.from_left = o;   o = ss_align_up(o + (size_t)n_c * H * 8, 256);
     L.from_right = o;  o = ss_align_up(o + (size_t)n_c * H * 8, 256);
     L.prev_last = o;   o = ss_align_up(o + (size_t)n_c * 8, 256);
-    L.slot_stride = ss_align_up((size_t)n_c * (n_win * n_win + n_win + 1) * 8, 256);
+    L.slot_stride = ss_align_up(((size_t)n_c * (n_win * n_win + n_win + 1) + 1) * 8, 256);   // + status
     L.slots = o;       o += L.slot_stride * (size_t)world;
     L.total = o;
     return L;
@@ -133,7 +133,7 @@ __device__ __forceinline__ int64_t xc_find_row(const int64_t *__restrict__ offse
 __global__ void __launch_bounds__(XC_THREADS)
 append_boundary_kernel(const double *__restrict__ spt_in, const int64_t *__restrict__ off_in, int n_c,
                        const int32_t *__restrict__ flags, double t_last,
-                       double *__restrict__ spt_out, int64_t *__restrict__ off_out)
+                       double *__restrict__ spt_out, int64_t *__restrict__ off_out, int64_t cap_in)
 {
     extern __shared__ int shift[];                        // [n_c + 1] exclusive scan of flags
     __shared__ int warp_tot[XC_THREADS / 32];
@@ -158,14 +158,17 @@ append_boundary_kernel(const double *__restrict__ spt_in, const int64_t *__restr
     __syncthreads();
 
     const int64_t k = (int64_t)blockIdx.x * XC_THREADS + tid;
-    const int64_t total = off_in[n_c];
+    // off_in[n_c] > cap_in: the capacity-sized input list was truncated (the caller learns it
+    // from the offsets and redoes the step); stay inside both buffers meanwhile
+    const int64_t total = min(off_in[n_c], cap_in);
     if (k < total) {
         const int64_t r = xc_find_row(off_in, n_c, k);
         spt_out[k + shift[r]] = spt_in[k];
     }
     if (k < n_c) {
         off_out[k] = off_in[k] + shift[k];
-        if (flags[k]) spt_out[off_in[k + 1] + shift[k]] = t_last;
+        const int64_t pos = off_in[k + 1] + shift[k];
+        if (flags[k] && pos < cap_in + n_c) spt_out[pos] = t_last;
     }
     if (k == 0) off_out[n_c] = total + shift[n_c];
 }
@@ -187,9 +190,14 @@ __global__ void put_last_kernel(const double *__restrict__ spt, const int64_t *_
 __global__ void __launch_bounds__(XC_THREADS)
 gram_put_kernel(const double *__restrict__ gram, const double *__restrict__ ssum,
                 const double *__restrict__ ref, const int64_t *__restrict__ offsets, int n_c,
-                int n_win, PeerPtrs slots, int world)
+                int n_win, PeerPtrs slots, int world, const int64_t *__restrict__ status)
 {
     const int64_t c = blockIdx.x;
+    if (c == 0 && threadIdx.x == 0) {
+        const double st = status ? (double)*status : 0.0;
+        const size_t at = (size_t)n_c * (n_win * n_win + n_win + 1);
+        for (int p = 0; p < world; ++p) reinterpret_cast<double *>(slots.p[p])[at] = st;
+    }
     const int nn = n_win * n_win;
     const double n = (double)(offsets[c + 1] - offsets[c]);
     const double *G = gram + c * nn, *S = ssum + c * n_win, *r = ref + c * n_win;
@@ -216,10 +224,17 @@ gram_put_kernel(const double *__restrict__ gram, const double *__restrict__ ssum
 __global__ void __launch_bounds__(XC_THREADS)
 gram_reduce_kernel(const double *__restrict__ slots, size_t slot_stride_f64, int world, int n_c,
                    int n_win, double *__restrict__ gram, double *__restrict__ ssum,
-                   int64_t *__restrict__ counts, int64_t *__restrict__ all_counts)
+                   int64_t *__restrict__ counts, int64_t *__restrict__ all_counts,
+                   int64_t *__restrict__ status_max)
 {
     const int64_t e = (int64_t)blockIdx.x * XC_THREADS + threadIdx.x;
     const int64_t ng = (int64_t)n_c * n_win * n_win, ns = (int64_t)n_c * n_win;
+    if (e == ng + ns + n_c) {                              // status word: maximum over the ranks
+        double m = 0.0;
+        for (int p = 0; p < world; ++p) m = fmax(m, slots[(size_t)p * slot_stride_f64 + e]);
+        if (status_max) *status_max = __double2ll_rn(m);
+        return;
+    }
     if (e >= ng + ns + n_c) return;
     double acc = 0.0;
     for (int p = 0; p < world; ++p) {
@@ -367,7 +382,7 @@ extern "C" int ss_shard_append_boundary(const double *d_spt_in, const int64_t *d
     const int64_t work = n_spk_in > n_c + 1 ? n_spk_in : n_c + 1;
     append_boundary_kernel<<<(unsigned)ss_cdiv(work, XC_THREADS), XC_THREADS, (n_c + 1) * sizeof(int),
                              reinterpret_cast<cudaStream_t>(stream)>>>(
-        d_spt_in, d_offsets_in, n_c, d_flags, t_last, d_spt_out, d_offsets_out);
+        d_spt_in, d_offsets_in, n_c, d_flags, t_last, d_spt_out, d_offsets_out, n_spk_in);
     SS_LAUNCH_CHECK("append_boundary_kernel");
     return SS_OK;
 }
@@ -386,28 +401,30 @@ extern "C" int ss_shard_put_last(const double *d_spt, const int64_t *d_offsets, 
 
 extern "C" int ss_shard_gram_put(const double *d_gram, const double *d_sum, const double *d_ref,
                                  const int64_t *d_offsets, int n_c, int H, int n_win,
-                                 void *const *arenas, int rank, int world, void *stream)
+                                 void *const *arenas, int rank, int world,
+                                 const int64_t *d_status, void *stream)
 {
     SS_REQUIRE(d_gram && d_sum && d_ref && d_offsets && arenas && rank >= 0 && rank < world &&
                world <= SS_MAX_PEERS, SS_ERR_ARG, "gram_put: bad argument");
     const ArenaLayout L = arena_layout(n_c, H, n_win, world);
     gram_put_kernel<<<n_c, XC_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         d_gram, d_sum, d_ref, d_offsets, n_c, n_win,
-        peer_ptrs(arenas, world, L.slots + L.slot_stride * (size_t)rank), world);
+        peer_ptrs(arenas, world, L.slots + L.slot_stride * (size_t)rank), world, d_status);
     SS_LAUNCH_CHECK("gram_put_kernel");
     return SS_OK;
 }
 
 extern "C" int ss_shard_gram_reduce(const void *arena, int n_c, int H, int n_win, int world,
                                     double *d_gram, double *d_sum, int64_t *d_counts,
-                                    int64_t *d_all_counts, void *stream)
+                                    int64_t *d_all_counts, int64_t *d_status_max, void *stream)
 {
     SS_REQUIRE(arena && d_gram && d_sum && d_counts && d_all_counts, SS_ERR_ARG, "gram_reduce: null pointer");
     const ArenaLayout L = arena_layout(n_c, H, n_win, world);
-    const int64_t total = (int64_t)n_c * (n_win * n_win + n_win + 1);
+    const int64_t total = (int64_t)n_c * (n_win * n_win + n_win + 1) + 1;
     gram_reduce_kernel<<<(unsigned)ss_cdiv(total, XC_THREADS), XC_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const double *>(reinterpret_cast<const char *>(arena) + L.slots),
-        L.slot_stride / sizeof(double), world, n_c, n_win, d_gram, d_sum, d_counts, d_all_counts);
+        L.slot_stride / sizeof(double), world, n_c, n_win, d_gram, d_sum, d_counts, d_all_counts,
+        d_status_max);
     SS_LAUNCH_CHECK("gram_reduce_kernel");
     return SS_OK;
 }

@@ -274,6 +274,7 @@ class PeerFabric(_Fabric):
 
 
 _FABRICS = {}
+_CAPACITY_HINTS = {}
 
 
 def peer_fabric(n_c, H, n_win):
@@ -330,12 +331,12 @@ class ShardedChain(object):
                                             -frac if self.falling else frac)
 
     # 3. sweep 2 with fused crossing marks; returns what the neighbours need
-    def filter_detect(self, thr, slabs=True):
+    def filter_detect(self, thr, slabs=True, cap=None):
         r = self.res
         r.thresh = thr
         _, _, spt, offsets = _ops.filtfilt_detect(
             self.x, self.sos, self.padlen, self.chunksize, self.FS, self.falling, thr=thr,
-            out=self.sig, ws=self.ws, shard=self.shard)
+            out=self.sig, ws=self.ws, shard=self.shard, cap=cap)
         r.filtered = self.sig
         self._spt, self._offsets = spt, offsets
         if not slabs:
@@ -424,10 +425,17 @@ class ShardedChain(object):
         f = self.fabric
         return f.local(self.rank, f.off_thr, self.n_c).clone()
 
-    def fab_filter_detect(self, thr):
+    def fab_filter_detect(self, thr, cap=None):
         """Sweep 2 with fused crossing marks, then the boundary slabs into the neighbours'
-        arenas (then barrier)."""
-        self.filter_detect(thr, slabs=False)
+        arenas (then barrier).  cap: capacity of the detected-spike list (no host sync; see
+        pipeline.run_chain `speculate`)."""
+        self.cap = cap
+        self._overflow = None
+        if cap is not None:
+            self.filter_detect(thr, slabs=False, cap=cap)
+            self._overflow = (self._offsets[-1] > cap).to(self.t.int64)     # device flag
+        else:
+            self.filter_detect(thr, slabs=False)
         n_c, H, n_win, ptrs = self._xargs()
         rc = _lib.load().ss_shard_put_halos(_lib.ptr(self.sig), self.sig.stride(0), n_c, self.n, H,
                                             n_win, ptrs, self.rank, self.n_ranks, _lib.stream_ptr())
@@ -477,7 +485,11 @@ class ShardedChain(object):
         t, r, f, lib = self.t, self.res, self.fabric, _lib.load()
         n_c, H, n_win, ptrs = self._xargs()
         prev_last = f.local(self.rank, f.off_prev_last, n_c) if self.rank > 0 else None
-        if self._cap_detected is not None:
+        if self.cap is not None:
+            # capacity mode: no host sync here, lists keep their spare room until finalize()
+            spt, offsets = _ops.remove_doubles(self._aligned, self._offsets, 1000.0 / self.FS,
+                                               prev_last=prev_last, cap=self._aligned.numel())
+        elif self._cap_detected is not None:
             spt, offsets, n_det = _ops.remove_doubles(self._aligned, self._offsets, 1000.0 / self.FS,
                                                       prev_last=prev_last, also=self._cap_detected)
             r.spt_detected = r.spt_detected[:n_det]
@@ -490,7 +502,8 @@ class ShardedChain(object):
         r.waves, r.valid, r.n_invalid, r.time = waves, valid, n_invalid, self.time
         gram, ssum, ref, _ = _ops.pca_gram(waves, offsets=offsets)
         rc = lib.ss_shard_gram_put(_lib.ptr(gram), _lib.ptr(ssum), _lib.ptr(ref), _lib.ptr(offsets),
-                                   n_c, H, n_win, ptrs, self.rank, self.n_ranks, _lib.stream_ptr())
+                                   n_c, H, n_win, ptrs, self.rank, self.n_ranks,
+                                   _lib.ptr(self._overflow), _lib.stream_ptr())
         _lib.check(rc, "ss_shard_gram_put")
         _ops._launched(1)
 
@@ -503,23 +516,43 @@ class ShardedChain(object):
         ssum = t.empty((n_c, n_win), dtype=t.float64, device=dev)
         counts = t.empty(n_c, dtype=t.int64, device=dev)
         all_counts = t.empty((self.n_ranks, n_c), dtype=t.int64, device=dev)
+        self._status = t.empty(1, dtype=t.int64, device=dev)
         rc = lib.ss_shard_gram_reduce(_lib.ptr(f.arena(self.rank)), n_c, H, n_win, self.n_ranks,
                                       _lib.ptr(gram), _lib.ptr(ssum), _lib.ptr(counts),
-                                      _lib.ptr(all_counts), _lib.stream_ptr())
+                                      _lib.ptr(all_counts), _lib.ptr(self._status),
+                                      _lib.stream_ptr())
         _lib.check(rc, "ss_shard_gram_reduce")
         _ops._launched(1)
         r.all_counts = all_counts
         return self.project(gram, ssum, counts)
 
+    def finalize(self):
+        """Capacity mode: the one host sync of the step - true list lengths and whether ANY
+        shard overflowed its capacity (the status word that travelled with the Gram partials).
+        Trims the results to views of their true length.  Returns (ok, n_detected)."""
+        t, r = self.t, self.res
+        n_det, n_kept, bad = (int(v) for v in t.stack(
+            (r.offsets_detected[-1], r.offsets[-1], self._status[0])).tolist())
+        if bad:
+            return False, n_det
+        r.spt_detected = r.spt_detected[:n_det]
+        r.spt, r.valid = r.spt[:n_kept], r.valid[:n_kept]
+        r.waves = r.waves[:, :n_kept, :]
+        if r.scores is not None:
+            r.scores = r.scores[:n_kept]
+        return True, n_det
+
 
 def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
                       thresh='auto', ncomps=2, chunksize=1E6, index_offset=None, n_total=None,
-                      transport=None):
+                      transport=None, speculate=True):
     """The chain on this rank's time shard `x` (CUDA tensor, every rank the same number
     of samples unless index_offset/n_total say otherwise), with the exchange steps of
     the module docstring.  Spike times are global; `all_counts` gives the layout of the
     concatenated list.  transport: 'peer' (NVLink peer memory, default) or 'nccl'
-    (torch.distributed collectives); SS_TRANSPORT overrides the default."""
+    (torch.distributed collectives); SS_TRANSPORT overrides the default.  speculate: as
+    pipeline.run_chain - capacity-sized lists from the previous call's count, one host sync
+    at the end, exact rerun (agreed on by all ranks) if any shard overflowed."""
     import os
     t = _lib.require_cuda()
     rank, n_ranks = world()
@@ -536,8 +569,6 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
     if transport == "peer" and n_ranks > 1:
         win0, win1, _ = _ops.window_params(list(sp_win), FS)
         fabric = peer_fabric(x.shape[0], min(4 * (win1 - win0), n), win1 - win0)
-    ch = ShardedChain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize, rank,
-                      n_ranks, index_offset, n_total, fabric=fabric)
     prof = os.environ.get("SS_DIST_PROFILE") and rank == 0
     marks = []
 
@@ -547,10 +578,15 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
             t.cuda.synchronize()
             marks.append((name, time.perf_counter()))
 
-    mark("start")
-    ch.prepare()
-    mark("prepare")
-    if fabric is not None:
+    def new_chain():
+        return ShardedChain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize, rank,
+                            n_ranks, index_offset, n_total, fabric=fabric)
+
+    def fabric_pass(cap):
+        ch = new_chain()
+        mark("start")
+        ch.prepare()
+        mark("prepare")
         if rank == 0:
             thr = ch.head_threshold()
             ch.fab_put_thresholds(thr)
@@ -558,7 +594,7 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
         if rank != 0:
             thr = ch.fab_thresholds()
         mark("threshold+put")
-        ch.fab_filter_detect(thr)
+        ch.fab_filter_detect(thr, cap=cap)
         fabric.barrier(rank)
         mark("filter_detect+halo put")
         ch.fab_align()
@@ -569,7 +605,31 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
         mark("extract+gram put")
         res = ch.fab_project()
         mark("reduce+project")
+        if cap is None:
+            return True, res, int(res.spt_detected.numel())
+        ok, n_det = ch.finalize()
+        return ok, res, n_det
+
+    if fabric is not None:
+        # all ranks decide alike: the hint exists on every rank or on none (same call
+        # history), an overflow on any rank is seen by all (status word of the Gram slots)
+        key = (tuple(x.shape), x.dtype, float(FS), tuple(sp_win), edge, align_type, str(thresh),
+               id(type(filt)), int(chunksize), n_ranks, rank)
+        hint = _CAPACITY_HINTS.get(key) if speculate else None
+        cap = None if hint is None else int(hint * 1.25) + 1024 + x.shape[0]
+        ok, res, n_det = fabric_pass(cap)
+        if not ok:
+            marks[:] = []
+            ok, res, n_det = fabric_pass(None)
+        if speculate:
+            if len(_CAPACITY_HINTS) > 64:
+                _CAPACITY_HINTS.clear()
+            _CAPACITY_HINTS[key] = n_det
     else:
+        ch = new_chain()
+        mark("start")
+        ch.prepare()
+        mark("prepare")
         thr = ch.head_threshold() if rank == 0 else t.empty(x.shape[0], dtype=t.float64,
                                                             device=x.device)
         thr = share_thresholds(thr, 0)

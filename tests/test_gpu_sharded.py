@@ -36,7 +36,7 @@ def _run_sharded(torch, dist_mod, x_full, S, FS, flt, sp_win, chunksize, thresh)
     return [c.project(gram, ssum, counts) for c in chains], thr
 
 
-def _run_sharded_fabric(torch, dist_mod, x_full, S, FS, flt, sp_win, chunksize, thresh):
+def _run_sharded_fabric(torch, dist_mod, x_full, S, FS, flt, sp_win, chunksize, thresh, cap=None):
     """The peer-memory transport (csrc/exchange.cu) with all arenas on one device: the same
     kernels and call order as run_chain_sharded(transport='peer'), stream order standing in
     for the NVLink flag barrier."""
@@ -54,15 +54,23 @@ def _run_sharded_fabric(torch, dist_mod, x_full, S, FS, flt, sp_win, chunksize, 
     chains[0].fab_put_thresholds(thr0)
     thrs = [thr0] + [c.fab_thresholds() for c in chains[1:]]
     for c, thr in zip(chains, thrs):
-        c.fab_filter_detect(thr)
+        c.fab_filter_detect(thr, cap=cap)
     for c in chains:
         c.fab_align()
     for c in chains:
         c.fab_extract_gram()
-    return [c.fab_project() for c in chains], thr0
+    out = [c.fab_project() for c in chains]
+    if cap is not None:
+        # capacity mode: lists carry spare room until the one host sync at the end; a capacity
+        # that is too small on ANY shard is reported to ALL of them
+        oks = [c.finalize()[0] for c in chains]
+        assert all(oks) or not any(oks)
+        if not all(oks):
+            return None, thr0
+    return out, thr0
 
 
-@pytest.mark.parametrize("transport", ["collective", "fabric"])
+@pytest.mark.parametrize("transport", ["collective", "fabric", "fabric-capacity"])
 @pytest.mark.parametrize("S,chunksize", [(2, 20000), (3, 10000), (4, 30000)])
 def test_sharded_chain_equals_whole(cuda, S, chunksize, transport):
     import torch
@@ -84,7 +92,13 @@ def test_sharded_chain_equals_whole(cuda, S, chunksize, transport):
     whole = pipeline.run_chain(x, FS, filt=flt, sp_win=sp_win, edge='falling', align_type='min',
                                thresh='4', ncomps=2, chunksize=chunksize)
     run = _run_sharded if transport == "collective" else _run_sharded_fabric
-    shards, thr = run(torch, ssd, x, S, FS, flt, sp_win, chunksize, '4')
+    if transport == "fabric-capacity":
+        # far too small on every shard -> all report overflow; then with room to spare
+        none, _ = run(torch, ssd, x, S, FS, flt, sp_win, chunksize, '4', cap=7)
+        assert none is None
+        shards, thr = run(torch, ssd, x, S, FS, flt, sp_win, chunksize, '4', cap=4000)
+    else:
+        shards, thr = run(torch, ssd, x, S, FS, flt, sp_win, chunksize, '4')
     assert torch.equal(thr, whole.thresh)
     assert torch.equal(torch.cat([s.filtered for s in shards], dim=1), whole.filtered)
     tot = 0
@@ -102,7 +116,7 @@ def test_sharded_chain_equals_whole(cuda, S, chunksize, transport):
         assert rel_err(sign_normalise(sc, w['scores']), w['scores']) < 1e-9, c
         tot += len(spt)
     assert tot > 200
-    if transport == "fabric":
+    if transport.startswith("fabric"):
         # layout of the concatenated list, identical on every shard
         layout = torch.stack([s.offsets[1:] - s.offsets[:-1] for s in shards])
         for s in shards:
