@@ -78,18 +78,23 @@ def _cpu_chain_one(args):
         warnings.simplefilter("ignore")
         _, res = port.chain_per_contact(raw, port.Filter(800., 100.), SP_WIN, edge='falling',
                                         align_type='min', ncomps=2, chunksize=CHUNK)
-    return c, len(res[0][1]['data'])
+    return c, len(res[0][1]['data']), res[0][1]['data'], res[0][3]['data'] if res[0][3] else None
 
 
-def cpu_chain(x, pool=None):
-    """Oracle chain over all contacts of host array x; returns (seconds, n_spikes)."""
+def cpu_chain(x, pool=None, keep=None):
+    """Oracle chain over all contacts of host array x; returns (seconds, n_spikes).
+    keep: dict filled with {contact: (aligned spike times, PCA scores)} of the oracle."""
     t0 = time.perf_counter()
     jobs = [(x[c:c + 1], c) for c in range(x.shape[0])]
     if pool is None:
         out = [_cpu_chain_one(j) for j in jobs]
     else:
         out = list(pool.map(_cpu_chain_one, jobs))
-    return time.perf_counter() - t0, sum(n for _, n in out)
+    dt = time.perf_counter() - t0
+    if keep is not None:
+        for c, _, spt, sc in out:
+            keep[c] = (spt, sc)
+    return dt, sum(o[1] for o in out)
 
 
 def run_reference(args):
@@ -416,13 +421,31 @@ def run_gpu(args):
         return
 
     # ---- CPU baseline on a bounded sample (oracle port, 1 core as the reference runs)
-    cpu = None
+    cpu = parity = None
     if not args.no_cpu_baseline:
         from oracle import port
         port.build()
         n_sample = N_SAMPLES                      # the whole recording: ~8 s on one core
         xs = x[:, :n_sample].cpu().numpy()
-        dt, _ = cpu_chain(xs, None)
+        oracle_out = {}
+        dt, _ = cpu_chain(xs, None, keep=oracle_out)
+        # north_star: end-to-end spike-time mismatches are counted and reported - the GPU
+        # chain (own filter) against the CPU oracle chain on the same recording
+        mism, total, worst = 0, 0, 0.0
+        for c in range(N_CONTACTS):
+            g = res.per_contact(c)
+            o_spt, o_sc = oracle_out[c]
+            total += len(o_spt)
+            if len(o_spt) == len(g['spt']) and np.array_equal(o_spt, g['spt']):
+                if o_sc is not None and 'scores' in g:
+                    sgn = np.sign(np.sum(g['scores'] * o_sc, axis=0))
+                    worst = max(worst, float(np.abs(g['scores'] * sgn - o_sc).max() /
+                                             np.abs(o_sc).max()))
+            else:
+                mism += len(np.setxor1d(o_spt, g['spt']))
+        parity = {"spike_times_compared": total, "spike_time_mismatches": mism,
+                  "pca_score_max_rel_err": worst,
+                  "against": "oracle/port.py chain on the whole recording, every contact"}
         cpu = {"value": N_CONTACTS * n_sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
                "sample": "all %d samples (600 s) of all %d contacts of the same recording, "
                          "oracle/port.py chain (C filtfilt + NumPy), 1 core as the reference "
@@ -452,6 +475,7 @@ def run_gpu(args):
                            "extract_spikes, features.fetPCA), rank-local"}},
         "gpu_launches": launches,
         "roofline": roofline, "chain_roofline": chain, "cpu_baseline": cpu,
+        "parity": parity,
     }
     print(json.dumps(line))
     if world > 1:
