@@ -5,10 +5,10 @@
 //   :277-288  remove_doubles
 //
 // Alignment: every spike is independent (the reference's "queue" is only a way
-// to vectorise), so one warp walks one spike to its fixed point: lanes read the
-// sp_win neighbourhood of the current position coalesced, round to float32 as
-// extract_spikes does (extract.py:157-163), and a warp arg-max/min with
-// first-occurrence tie-break (NumPy argmax/argmin) gives the shift.  Every
+// to vectorise), so one thread walks one spike to its fixed point: it scans the
+// sp_win neighbourhood of the current position, rounded to float32 as
+// extract_spikes does (extract.py:157-163); the strict comparison in scan order is
+// NumPy's first-occurrence arg-max/min.  Every
 // float64 expression is evaluated in the reference's order with explicit
 // IEEE round-to-nearest intrinsics (no FMA contraction), the sample index by a
 // truncating cast, so the spike times are bit-identical.
@@ -32,6 +32,11 @@ __device__ __forceinline__ int64_t find_row(const int64_t *__restrict__ offsets,
     return lo;
 }
 
+// One THREAD per spike.  (A warp per spike - lanes along the window, shuffle arg-max - made
+// every lane repeat the scalar float64 work: two IEEE divisions and the index conversion per
+// pass; ncu showed the kernel issue-bound on exactly that, 70 us for 166 k spikes.  Here the
+// scalar work is done once per spike, the n_win loads of a thread are independent and hit the
+// 2-3 cache lines of its window, and the first extremum falls out of the scan order.)
 __global__ void __launch_bounds__(32 * AL_WARPS)
 align_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t ld, double FS,
              const int32_t *__restrict__ rows, int64_t n_rows, const int64_t *__restrict__ offsets,
@@ -39,8 +44,7 @@ align_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t l
              int use_min, double *__restrict__ spt, int64_t n_spk, int max_iter,
              int64_t index_offset, int64_t halo_before, int64_t halo_after)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t s = (int64_t)blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
+    const int64_t s = (int64_t)blockIdx.x * (32 * AL_WARPS) + threadIdx.x;
     if (s >= n_spk || (offsets && s >= __ldg(offsets + n_rows))) return;   // spare capacity
     int64_t r = n_rows > 1 ? find_row(offsets, n_rows, s) : 0;
     if (rows) r = rows[r];
@@ -53,22 +57,31 @@ align_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t l
         const int centre = __double2int_rz(__dmul_rn(__ddiv_rn(t, 1000.0), FS));   // :150
         const int64_t first = (int64_t)centre + win0 - index_offset;   // local index
         float best = 0.f;
-        int best_k = AL_NONE;
-        for (int k = lane; k < n_win; k += 32) {
-            const int64_t i = first + k;
-            float v = 0.f;
-            if (i >= -halo_before && i < n_samples + halo_after) v = ss_load_f32(x, dtype, row0 + i);
-            if (use_min) v = -v;                                // argmin(v) == argmax(-v), ties alike
-            if (best_k == AL_NONE || v > best) { best = v; best_k = k; }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const float ov = __shfl_xor_sync(SS_FULL, best, d);
-            const int ok = __shfl_xor_sync(SS_FULL, best_k, d);
-            if (ok != AL_NONE &&
-                (best_k == AL_NONE || ov > best || (ov == best && ok < best_k))) {
-                best = ov;
-                best_k = ok;
+        int best_k = 0;
+        if (first >= -halo_before && first + n_win <= n_samples + halo_after) {
+            // whole window inside the stored samples (all spikes but those at the very ends)
+            const int64_t base = row0 + first;
+            if (dtype == SS_F64) {
+                const double *p = reinterpret_cast<const double *>(x) + base;
+                for (int k = 0; k < n_win; ++k) {
+                    float v = __double2float_rn(__ldg(p + k));
+                    if (use_min) v = -v;                        // argmin(v) == argmax(-v), ties alike
+                    if (k == 0 || v > best) { best = v; best_k = k; }
+                }
+            } else {
+                for (int k = 0; k < n_win; ++k) {
+                    float v = ss_load_f32(x, dtype, base + k);
+                    if (use_min) v = -v;
+                    if (k == 0 || v > best) { best = v; best_k = k; }
+                }
+            }
+        } else {
+            for (int k = 0; k < n_win; ++k) {
+                const int64_t i = first + k;
+                float v = 0.f;
+                if (i >= -halo_before && i < n_samples + halo_after) v = ss_load_f32(x, dtype, row0 + i);
+                if (use_min) v = -v;
+                if (k == 0 || v > best) { best = v; best_k = k; }
             }
         }
         // time[k] = k*1000.0/FS + sp_win[0]  (extract.py:152), spt += shift (:258)
@@ -77,7 +90,7 @@ align_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t l
         moved = true;
         if (!(shift < lo || shift > hi)) break;                 // :263-264
     }
-    if (moved && lane == 0) spt[s] = t;
+    if (moved) spt[s] = t;
 }
 
 // keep[k] = first of its row, or (int64)((t[k]-t[k-1])/tol) > 1
@@ -196,7 +209,7 @@ extern "C" int ss_align(const void *d_x, int dtype, int64_t n_samples, int64_t l
     SS_REQUIRE(n_spk > 0 && max_iter > 0, SS_ERR_ARG, "align: bad n_spk/max_iter");
     SS_REQUIRE(halo_before >= 0 && halo_after >= 0, SS_ERR_ARG, "align: negative halo");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    align_kernel<<<(unsigned)ss_cdiv(n_spk, AL_WARPS), 32 * AL_WARPS, 0, st>>>(
+    align_kernel<<<(unsigned)ss_cdiv(n_spk, 32 * AL_WARPS), 32 * AL_WARPS, 0, st>>>(
         d_x, dtype, n_samples, ld, FS, d_rows, n_rows, d_offsets, sp_win0, win0, win1, t_min,
         t_max, lo, hi, use_min, d_spt, n_spk, max_iter, index_offset, halo_before, halo_after);
     SS_LAUNCH_CHECK("align_kernel");

@@ -106,6 +106,54 @@ extract_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t
     }
 }
 
+// Row mode (one contact per spike list, n_c == 1): one THREAD per spike.  The n_win loads of
+// a thread are independent and stay inside the 2-3 cache lines of its window; for every time
+// step the threads of a warp store 32 consecutive floats of the output row - coalesced
+// without a shared-memory transposition.
+__global__ void __launch_bounds__(256)
+extract_rows_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t ld, double FS,
+                    const int32_t *__restrict__ rows, int64_t n_rows, const int64_t *__restrict__ offsets,
+                    int win0, int n_win, double t_min, double t_max,
+                    const double *__restrict__ spt, int64_t n_spk,
+                    float *__restrict__ waves, uint8_t *__restrict__ valid, int32_t *__restrict__ n_invalid,
+                    int64_t index_offset, int64_t halo_before, int64_t halo_after)
+{
+    const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (s >= n_spk) return;
+    const int64_t n_live = offsets ? min(n_spk, __ldg(offsets + n_rows)) : n_spk;
+    float *dst = waves + s;
+    if (s >= n_live) {                                  // spare capacity: zeros, not a spike
+        valid[s] = 0;
+        for (int w = 0; w < n_win; ++w) dst[(int64_t)w * n_spk] = 0.f;
+        return;
+    }
+    const double t = spt[s];
+    const int centre = __double2int_rz(__dmul_rn(__ddiv_rn(t, 1000.0), FS));
+    const int64_t first = (int64_t)centre + win0 - index_offset;          // local index
+    int64_t r = n_rows > 1 ? ex_find_row(offsets, n_rows, s) : 0;
+    if (rows) r = rows[r];
+    const int64_t row0 = r * ld;
+    const bool ok = (t >= t_min) && (t <= t_max);
+    valid[s] = ok ? 1 : 0;
+    if (!ok) atomicAdd(n_invalid, 1);
+    if (first >= -halo_before && first + n_win <= n_samples + halo_after) {
+        const int64_t base = row0 + first;
+        if (dtype == SS_F64) {
+            const double *p = reinterpret_cast<const double *>(x) + base;
+            for (int w = 0; w < n_win; ++w) dst[(int64_t)w * n_spk] = __double2float_rn(__ldg(p + w));
+        } else {
+            for (int w = 0; w < n_win; ++w) dst[(int64_t)w * n_spk] = ss_load_f32(x, dtype, base + w);
+        }
+    } else {
+        for (int w = 0; w < n_win; ++w) {
+            const int64_t i = first + w;
+            float v = 0.f;
+            if (i >= -halo_before && i < n_samples + halo_after) v = ss_load_f32(x, dtype, row0 + i);
+            dst[(int64_t)w * n_spk] = v;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int ss_max_window(void) { return EX_MAX_WIN; }
@@ -132,6 +180,13 @@ extern "C" int ss_extract(const void *d_x, int dtype, int64_t n_samples, int64_t
         SS_REQUIRE(n_c == 1, SS_ERR_ARG, "extract: row mode needs n_c == 1");
         SS_REQUIRE(n_rows >= 1 && (n_rows == 1 || d_offsets), SS_ERR_ARG,
                    "extract: offsets required for %lld rows", (long long)n_rows);
+    }
+    if (!d_contacts) {
+        extract_rows_kernel<<<(unsigned)ss_cdiv(n_spk, 256), 256, 0, st>>>(
+            d_x, dtype, n_samples, ld, FS, d_rows, n_rows, d_offsets, win0, n_win, t_min, t_max,
+            d_spt, n_spk, d_waves, d_valid, d_n_invalid, index_offset, halo_before, halo_after);
+        SS_LAUNCH_CHECK("extract_rows_kernel");
+        return SS_OK;
     }
     int CB = 1;
     while (CB < n_c && CB < 16) CB <<= 1;           // contacts per CTA: 1, 2, 4, 8 or 16
