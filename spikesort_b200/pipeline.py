@@ -162,20 +162,6 @@ def _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
     return res, n_det, n_kept
 
 
-_PINNED = {}
-
-
-def _pinned_like(name, tensor):
-    """Grow-only pinned staging buffer (pinned allocation costs milliseconds)."""
-    t = _lib.torch()
-    need = tensor.numel()
-    buf = _PINNED.get((name, tensor.dtype))
-    if buf is None or buf.numel() < need:
-        buf = t.empty(max(need, 1), dtype=tensor.dtype).pin_memory()
-        _PINNED[(name, tensor.dtype)] = buf
-    return buf[:need].view(tensor.shape)
-
-
 def sort_frontend(spike_data, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
                   thresh='auto', ncomps=2, chunksize=1E6, contacts=None, slabs='auto'):
     """The whole front end for a multi-contact recording in ONE call, host in / host out.
