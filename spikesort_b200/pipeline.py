@@ -213,8 +213,8 @@ def _merge_and_fetch(results, ids, FS, ncomps, time):
     r0 = results[0]
     dev = r0.spt.device
     n_win = int(r0.waves.shape[0])
-    have_scores = all(r.scores is not None for r in results)
     n_kept = sum(int(r.spt.numel()) for r in results)
+    have_scores = n_kept > 0 and all(r.scores is not None for r in results)
     n_det = sum(int(r.spt_detected.numel()) for r in results)
 
     def layout(offs):

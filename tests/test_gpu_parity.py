@@ -502,3 +502,81 @@ def test_speculative_chain_equals_exact_chain(env):
     u2 = pipeline.run_chain(x, FS, fused=False, **kw)
     assert torch.equal(u1.spt, u2.spt) and torch.equal(u1.waves, u2.waves)
     assert torch.equal(u1.spt, exact.spt)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_small_cases_bit_exact(env, oracle, seed):
+    """Randomised sweep of shapes, dtypes, rates, windows and edges at sizes the oracle does
+    in milliseconds: detect -> align -> extract per contact must be bit-identical given the
+    same signal (includes lengths that are no multiple of 32 / 8192, windows wider than a
+    warp, spikes at both ends of the recording, thresholds nothing crosses)."""
+    rng = np.random.default_rng(1000 + seed)
+    FS = int(rng.choice([1000, 8000, 25000, 30000, 44100]))
+    n_c = int(rng.integers(1, 5))
+    n = int(rng.integers(40, 30000))
+    dtype = [np.int16, np.float32, np.float64][seed % 3]
+    x = rng.standard_normal((n_c, n)) * 40.0
+    for c in range(n_c):                                   # spikes, some at the very edges
+        for pos in rng.integers(0, n, size=max(n // 400, 2)):
+            w = int(rng.integers(2, 12))
+            a, b = max(pos - w, 0), min(pos + w, n)
+            x[c, a:b] -= rng.uniform(100, 400) * np.hanning(b - a + 2)[1:-1]
+    x = np.round(x).astype(dtype) if dtype is np.int16 else x.astype(dtype)
+    raw = {'data': x, 'FS': FS, 'n_contacts': n_c}
+    lo = float(rng.choice([-0.2, -0.6, -1.0, -2.5]))
+    hi = float(rng.choice([0.4, 0.8, 2.0]))
+    sp_win = [lo, hi]
+    edge, typ = [('falling', 'min'), ('rising', 'max'), ('min', 'min'), ('max', 'max')][seed % 4]
+    thr = float(rng.choice([-90.0, -150.0, -1e9])) if edge in ('falling', 'min') else \
+        float(rng.choice([60.0, 90.0, 1e9]))
+    ex = env['ss'].extract
+    total = 0
+    for c in range(n_c):
+        ref = oracle.detect_spikes(raw, thresh=thr, edge=edge, contact=c)
+        got = ex.detect_spikes(raw, thresh=thr, edge=edge, contact=c)
+        assert np.array_equal(got['data'], ref['data']), (seed, c)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ra = oracle.align_spikes(raw, ref, sp_win, type=typ, contact=c)
+            ga = ex.align_spikes(raw, ref, sp_win, type=typ, contact=c)
+        assert np.array_equal(ga['data'], ra['data']), (seed, c)
+        rw = oracle.extract_spikes(raw, ra, sp_win)
+        gw = ex.extract_spikes(raw, ra, sp_win)
+        assert gw['data'].shape == rw['data'].shape and np.array_equal(gw['data'], rw['data'])
+        assert ('is_valid' in gw) == ('is_valid' in rw)
+        if 'is_valid' in rw:
+            assert np.array_equal(gw['is_valid'], rw['is_valid'])
+        total += len(ra['data'])
+    # the batched chain on the same signal (no filter) agrees with the per-contact calls
+    res = env['pipeline'].run_chain(_dev(env, x), FS, filt=None, sp_win=sp_win, edge=edge,
+                                    align_type=typ, thresh=thr, ncomps=2, pca=False)
+    for c in range(n_c):
+        ref = oracle.detect_spikes(raw, thresh=thr, edge=edge, contact=c)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            ra = oracle.align_spikes(raw, ref, sp_win, type=typ, contact=c)
+        assert np.array_equal(res.per_contact(c)['spt'], ra['data']), (seed, c)
+
+
+def test_chain_without_spikes(env):
+    """Nothing crosses the threshold: every path returns empty, well-shaped results - exact
+    sizes, capacity-sized (second call) and the host-in/host-out front ends."""
+    torch, pipeline, ss = env['torch'], env['pipeline'], env['ss']
+    FS, n_c, n = 30000, 3, 90000
+    x = torch.zeros((n_c, n), dtype=torch.int16)
+    x[:, ::7] = 1
+    flt = ss.filters.Filter(800., 100.)
+    kw = dict(filt=flt, sp_win=[-0.2, 0.8], edge='falling', align_type='min', thresh=-1e6,
+              ncomps=2, chunksize=30000)
+    pipeline._CAPACITY_HINTS.clear()
+    for _ in range(2):
+        res = pipeline.run_chain(x.to(env['dev']), FS, **kw)
+        assert res.spt.numel() == 0 and res.spt_detected.numel() == 0
+        assert tuple(res.waves.shape) == (30, 0, 1) and res.scores is None
+        assert res.offsets.tolist() == [0] * (n_c + 1)
+    for slabs in (1, 'auto'):
+        out = ss.sort_frontend({'data': x.numpy(), 'FS': FS, 'n_contacts': n_c}, slabs=slabs, **kw)
+        for c in range(n_c):
+            assert out['spt'][c]['data'].shape == (0,) and out['spt_aligned'][c]['data'].shape == (0,)
+            assert out['sp_waves'][c]['data'].shape == (30, 0, 1)
+            assert out['features'][c]['data'] is None
