@@ -390,10 +390,13 @@ def run_gpu(args):
     achieved = alg_bytes / (filt_ms / 1000.0) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of this stage
-                # from the ncu --set full capture of this command (profiles/README.md):
-                # sweep 1 1.18 GB + sweep 2 5.68 GB + head marks/count/emit ~0.4 GB
-                "traffic": 7.25e9, "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_c_filter_fused.txt)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of this stage from
+                # the ncu --set full capture of this command (profiles/README.md, state e):
+                # sweep 1 1.18 GB + sweep 2 5.42 + head 0.26 GB + head marks / threshold / count /
+                # emit 0.47 GB
+                "traffic": 7.33e9,
+                "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_g_chain_kernels_final.txt "
+                                "+ r01_ncu_f_chain_kernels.txt for the bookkeeping kernels)",
                 "kernel": "ss_filtfilt_detect_sos + ss_detect_emit = filter (summary, tilescan, "
                           "apply with fused crossing marks) + auto threshold + count/scan/emit: "
                           "the filter, threshold and detect stages of the chain",

@@ -94,3 +94,22 @@ def test_spline_plan_bit_exact_vs_scipy(FS, sp_win, resample):
         assert np.array_equal(plan.apply(y), interpolate.splev(plan.new_time, tck, der=0))
     with pytest.raises(TypeError):
         spline_plan(time[:3], FS * resample)                # splrep: m > k must hold
+
+
+def test_slab_bounds_host_logic():
+    """Time slabs of the upload-overlapped front end (pipeline._slab_bounds): whole chunks, in
+    order, covering the recording once; the first slab holds the auto-threshold samples; a
+    short trailing chunk joins the last slab; nothing to slice -> None."""
+    from spikesort_b200.pipeline import _slab_bounds
+    b = _slab_bounds(18000000, 1e6, 300000, 6)
+    assert b == [(k * 3000000, (k + 1) * 3000000) for k in range(6)]
+    for n, cs, n0, want in [(170500, 10000, 30000, 6), (70001, 30000, 0, 6), (3000000, 1e6, 300000, 6),
+                            (999999, 1000, 5000, 9), (10 ** 7 + 1, 10 ** 6, 0, 3)]:
+        b = _slab_bounds(n, cs, n0, want)
+        assert b[0][0] == 0 and b[-1][1] == n and len(b) <= want + 1
+        assert all(x[1] == y[0] for x, y in zip(b, b[1:]))
+        assert all(a % int(cs) == 0 for a, _ in b)
+        assert b[0][1] >= min(n0, n)
+    assert _slab_bounds(60000, 25000, 250000, 6) is None       # threshold needs everything
+    assert _slab_bounds(1500000, 1e6, 300000, 6) is None       # one full chunk only
+    assert _slab_bounds(500, 1000, 0, 6) is None
