@@ -411,6 +411,13 @@ __device__ __forceinline__ bool summary_group_interior(const FiltGeom &g, const 
     return t0 + SM_R <= ti.nt && r0 >= 0 && r0 + SM_R * FS_T <= ti.L;
 }
 
+// 32-bit loads of int16 pairs need a 4-byte aligned ADDRESS (the recording may be a view
+// that starts at an odd sample of its parent, e.g. a time slab cut at an odd chunk size)
+__device__ __forceinline__ bool i16_pair_aligned(const void *x, int64_t index)
+{
+    return ((reinterpret_cast<uintptr_t>(x) + 2 * (uintptr_t)index) & 3u) == 0;
+}
+
 template <int NS>
 __global__ void __launch_bounds__(32 * SM_WPB, NS <= 2 ? 2 : 1)
 filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *__restrict__ tab,
@@ -435,7 +442,7 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *
     bool nxt_ok = false;
     if (g.dtype == SS_I16 && t_first < ti.nt) {
         int64_t r0;
-        if (summary_group_interior<NS>(g, ti, t_first, r0) && ((row0 + ti.cs0 + r0) & 1) == 0) {
+        if (summary_group_interior<NS>(g, ti, t_first, r0) && i16_pair_aligned(x, row0 + ti.cs0 + r0)) {
             summary_load_i16x2<NS>(reinterpret_cast<const int16_t *>(x) + row0 + ti.cs0 + r0, lane, nxt);
             nxt_ok = true;
         }
@@ -461,7 +468,7 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *
             nxt_ok = false;
             int64_t rn;
             if (it + SM_R < SM_TPW && summary_group_interior<NS>(g, ti, t0 + SM_R, rn) &&
-                ((row0 + ti.cs0 + rn) & 1) == 0) {
+                i16_pair_aligned(x, row0 + ti.cs0 + rn)) {
                 summary_load_i16x2<NS>(reinterpret_cast<const int16_t *>(x) + row0 + ti.cs0 + rn, lane, nxt);
                 nxt_ok = true;
             }
@@ -470,7 +477,7 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *
             // prefetch for the next group also from the unpipelined paths
             int64_t rn;
             if (g.dtype == SS_I16 && it + SM_R < SM_TPW &&
-                summary_group_interior<NS>(g, ti, t0 + SM_R, rn) && ((row0 + ti.cs0 + rn) & 1) == 0) {
+                summary_group_interior<NS>(g, ti, t0 + SM_R, rn) && i16_pair_aligned(x, row0 + ti.cs0 + rn)) {
                 summary_load_i16x2<NS>(reinterpret_cast<const int16_t *>(x) + row0 + ti.cs0 + rn, lane, nxt);
                 nxt_ok = true;
             }

@@ -29,6 +29,48 @@ _DATASET = ("^/(?P<subject>[a-zA-z]+)"
             "/?(?P<type>[a-zA-Z]+)?(?P<cell_id>[0-9]+)?$")
 
 
+class LazyRecording(object):
+    """A raw recording that still lives in its per-contact files: shape/dtype like an array,
+    `read_slab(a, b, out)` fills a (n_contacts, b-a) buffer with samples [a, b) of every
+    contact.  `sort_frontend` pulls time slabs out of it while earlier slabs are already on
+    the GPU (files -> pinned buffers -> HBM -> chain, all overlapped); anything else that
+    needs the whole array (`np.asarray`, slicing) reads it."""
+
+    dtype = np.dtype(np.int16)
+    ndim = 2
+
+    def __init__(self, names, npts):
+        self.names = list(names)
+        self.shape = (len(self.names), int(npts))
+        self._lens = [min(os.path.getsize(n) // 2, int(npts)) for n in self.names]
+
+    def read_slab(self, a, b, out):
+        """out: int16 (n_contacts, b-a) torch CPU tensor or ndarray view, rows unit-stride."""
+        for i, name in enumerate(self.names):
+            row = out[i]
+            arr = row.numpy() if hasattr(row, "numpy") else row
+            hi = min(b, self._lens[i])
+            if hi < b:
+                arr[max(hi - a, 0):] = 0                    # shorter file: zeros, as read_sp
+            if hi > a:
+                with open(name, 'rb', buffering=0) as fid:
+                    fid.seek(2 * a)
+                    view = memoryview(arr[:hi - a]).cast('B')
+                    if fid.readinto(view) != 2 * (hi - a):
+                        raise IOError("short read from %s" % name)
+
+    def __array__(self, dtype=None, copy=None):
+        out = np.empty(self.shape, dtype=np.int16)
+        self.read_slab(0, self.shape[1], out)
+        return out.astype(dtype) if dtype is not None else out
+
+    def __getitem__(self, key):
+        return np.asarray(self)[key]
+
+    def __len__(self):
+        return self.shape[0]
+
+
 class BakerlabFilter(object):
     """Reader/writer of raw recordings in the Bakerlab layout (int16 file per contact)."""
 
@@ -59,14 +101,18 @@ class BakerlabFilter(object):
         return names
 
     # ------------------------------------------------------------------- read
-    def read_sp(self, dataset, memmap=None, host=False):
+    def read_sp(self, dataset, memmap=None, host=False, lazy=False):
         """``io/filters.py:72-129``.  `memmap` is accepted for compatibility (the recording
         goes to HBM, not to a host array).  host=True returns the plain NumPy array the
-        reference returns instead (no GPU involved: plain file reads)."""
+        reference returns instead (no GPU involved: plain file reads).  lazy=True reads
+        nothing yet: 'data' is a LazyRecording that `sort_frontend` streams slab by slab
+        while the chain already runs on the earlier slabs."""
         conf = self.conf_dict
         names = self.contact_files(dataset)
         n_contacts = len(names)
         npts = os.path.getsize(names[0]) // 2
+        if lazy:
+            return {'data': LazyRecording(names, npts), 'FS': conf['FS'], 'n_contacts': n_contacts}
         if host:
             data = np.empty((n_contacts, npts), dtype=np.int16)
             for i, name in enumerate(names):

@@ -354,7 +354,15 @@ def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, nco
     data = spike_data['data']
     if hasattr(data, "device_tensor") or filt is None or not hasattr(filt, "sections"):
         return None
-    if isinstance(data, t.Tensor):
+    lazy = hasattr(data, "read_slab")                     # io.LazyRecording: slabs come from files
+    if lazy:
+        host = None
+        shape, tdtype = tuple(data.shape), {np.dtype(np.int16): t.int16,
+                                            np.dtype(np.float32): t.float32,
+                                            np.dtype(np.float64): t.float64}.get(np.dtype(data.dtype))
+        if tdtype is None or len(shape) != 2:
+            return None
+    elif isinstance(data, t.Tensor):
         if data.is_cuda or data.dim() != 2:
             return None
         host = data
@@ -363,10 +371,12 @@ def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, nco
         if arr.ndim != 2 or arr.dtype not in (np.int16, np.float32, np.float64):
             return None
         host = t.from_numpy(np.ascontiguousarray(arr))
-    if host.dtype not in (t.int16, t.float32, t.float64) or host.stride(1) != 1:
-        return None
+    if not lazy:
+        if host.dtype not in (t.int16, t.float32, t.float64) or host.stride(1) != 1:
+            return None
+        shape, tdtype = tuple(host.shape), host.dtype
     FS = spike_data['FS']
-    n_c, n = host.shape
+    n_c, n = shape
     win0, win1, time = _ops.window_params(list(sp_win), FS)
     n_win = win1 - win0
     H = 4 * n_win
@@ -389,21 +399,29 @@ def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, nco
     cur = t.cuda.current_stream()
     up, _ = _side_streams()
     up.wait_stream(cur)
-    xdev = t.empty((n_c, n), dtype=host.dtype, device=dev)
+    xdev = t.empty((n_c, n), dtype=tdtype, device=dev)
     arrived = []
     lib = _lib.load()
-    esz = host.element_size()
-    with t.cuda.stream(up):                               # all uploads queued up front
-        for a, b in bounds:
-            # one strided DMA per slab (torch's copy_ would stage a non-contiguous slice
-            # through pageable memory)
-            rc = lib.ss_copy_2d_async(xdev.data_ptr() + a * esz, xdev.stride(0) * esz,
-                                      host.data_ptr() + a * esz, host.stride(0) * esz,
-                                      (b - a) * esz, n_c, 1, up.cuda_stream)
+    esz = xdev.element_size()
+
+    def upload(src_ptr, src_pitch, a, b):
+        # one strided DMA per slab (torch's copy_ would stage a non-contiguous slice
+        # through pageable memory)
+        with t.cuda.stream(up):
+            rc = lib.ss_copy_2d_async(xdev.data_ptr() + a * esz, xdev.stride(0) * esz, src_ptr,
+                                      src_pitch, (b - a) * esz, n_c, 1, up.cuda_stream)
             _lib.check(rc, "ss_copy_2d_async")
             ev = t.cuda.Event()
             ev.record(up)
-            arrived.append(ev)
+        return ev
+
+    feeder = None
+    if lazy:
+        # files -> two pinned slab buffers (reader thread, one slab ahead) -> HBM
+        feeder = _SlabFeeder(data, bounds, n_c, tdtype)
+    else:
+        for a, b in bounds:                               # all uploads queued up front
+            arrived.append(upload(host.data_ptr() + a * esz, host.stride(0) * esz, a, b))
     mark("uploads queued")
     key = (n_c, H, n_win, S, str(dev))
     if key not in _SLAB_FABRICS:
@@ -420,6 +438,12 @@ def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, nco
 
     thr = None
     for k in range(S):
+        if feeder is not None:
+            a, b = bounds[k]
+            buf = feeder.get(k)                           # blocks until slab k is read
+            ev = upload(buf.data_ptr(), buf.stride(0) * esz, a, b)
+            feeder.release_after(k, ev)
+            arrived.append(ev)
         cur.wait_event(arrived[k])
         chains[k].prepare()
         if k == 0:
@@ -437,6 +461,8 @@ def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, nco
         r.scores = _ops.pca_project(r.waves, res0.evals, res0.evecs, ncomps, offsets=r.offsets)
     mark("project queued")
     out = _merge_and_fetch([c.res for c in chains], list(range(n_c)), FS, ncomps, time)
+    if feeder is not None:
+        feeder.close()
     mark("merged, fetched, assembled")
     if prof is not None:
         print("e2e profile (ms): " + ", ".join("%s %.2f" % (prof[i][0], 1e3 * (prof[i][1] - prof[i - 1][1]))
@@ -444,6 +470,60 @@ def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, nco
     return out
 
 
+class _SlabFeeder(object):
+    """Reads the time slabs of a lazy (file-backed) recording into two pinned buffers on a
+    background thread, one slab ahead of the upload: disk, PCIe and the kernels overlap."""
+
+    def __init__(self, source, bounds, n_c, tdtype):
+        import queue
+        import threading
+        t = _lib.torch()
+        self.source, self.bounds = source, bounds
+        width = max(b - a for a, b in bounds)
+        key = (n_c, width, tdtype)
+        if key not in _FEEDER_BUFS:                        # pinned allocation costs milliseconds
+            if len(_FEEDER_BUFS) > 2:
+                _FEEDER_BUFS.clear()
+            _FEEDER_BUFS[key] = [t.empty((n_c, width), dtype=tdtype).pin_memory() for _ in range(2)]
+        self.bufs = _FEEDER_BUFS[key]
+        self.free = [threading.Event(), threading.Event()]
+        for f in self.free:
+            f.set()
+        self.uploaded = [None, None]
+        self.ready = queue.Queue()
+        self.error = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        try:
+            for k, (a, b) in enumerate(self.bounds):
+                slot = k & 1
+                self.free[slot].wait()
+                self.free[slot].clear()
+                if self.uploaded[slot] is not None:
+                    self.uploaded[slot].synchronize()      # the DMA out of this buffer is done
+                self.source.read_slab(a, b, self.bufs[slot][:, :b - a])
+                self.ready.put(k)
+        except Exception as exc:                           # surfaced by get()
+            self.error = exc
+            self.ready.put(-1)
+
+    def get(self, k):
+        got = self.ready.get()
+        if got != k:
+            raise self.error if self.error is not None else RuntimeError("slab feeder out of order")
+        return self.bufs[k & 1]
+
+    def release_after(self, k, event):
+        self.uploaded[k & 1] = event
+        self.free[k & 1].set()
+
+    def close(self):
+        self.thread.join(timeout=10)
+
+
+_FEEDER_BUFS = {}
 _SLAB_FABRICS = {}
 _STREAMS = {}
 

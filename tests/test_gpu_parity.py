@@ -580,3 +580,25 @@ def test_chain_without_spikes(env):
             assert out['spt'][c]['data'].shape == (0,) and out['spt_aligned'][c]['data'].shape == (0,)
             assert out['sp_waves'][c]['data'].shape == (30, 0, 1)
             assert out['features'][c]['data'] is None
+
+
+def test_filtfilt_on_odd_offset_int16_view(env, oracle):
+    """A recording that is a VIEW starting at an odd int16 sample of its parent (2-byte aligned
+    address, e.g. a time slab cut at an odd chunk size): the paired 32-bit loads of the
+    summary sweep must fall back to scalar loads; results as for a fresh array."""
+    rng = np.random.default_rng(8)
+    parent = np.round(rng.standard_normal((3, 40001)) * 200).astype(np.int16)
+    b, a = signal.iirdesign(800 * 2 / 25000, 100 * 2 / 25000, 1, 10, ftype='butter')
+    from spikesort_b200._design import tf2sos_exact
+    sos, padlen = tf2sos_exact(b, a)
+    dev_parent = _dev(env, parent)
+    for start in (1, 3, 2):
+        view = dev_parent[:, start:]
+        assert view.data_ptr() % 4 == (2 if start % 2 else 0)
+        got = env['ops'].filtfilt_sos(view, sos, padlen, 10007).cpu().numpy()
+        fresh = env['ops'].filtfilt_sos(_dev(env, parent[:, start:]), sos, padlen, 10007).cpu().numpy()
+        assert np.array_equal(got, fresh) or rel_err(got, fresh) < 1e-13     # other summation order
+        ref = np.stack([np.concatenate([oracle.filtfilt(b, a, parent[c, start:][lo:lo + 10007])
+                                        for lo in range(0, parent.shape[1] - start, 10007)])
+                        for c in range(3)])
+        assert rel_err(got, ref) < 1e-12

@@ -87,6 +87,19 @@ def test_read_sp_streams_to_device(cuda, tmp_path):
     for c in range(4):
         assert np.array_equal(a['spt_aligned'][c]['data'], b['spt_aligned'][c]['data'])
         assert len(a['spt_aligned'][c]['data']) > 10
+    # lazy source: the slabs are read from the files while earlier slabs are on the GPU
+    lazy = flt.read_sp("/Gollum/s5gollum01/el3", lazy=True)
+    assert lazy['data'].shape == (4, n) and np.array_equal(np.asarray(lazy['data']), x)
+    from spikesort_b200 import pipeline
+    assert pipeline._slab_bounds(n, 10007, 10 * FS, 6) is None      # 'auto'-style threshold needs 250000 samples
+    assert len(pipeline._slab_bounds(n, 10007, 0, 6)) == 6          # numeric threshold: 6 slabs
+    for kw in (dict(thresh=-150.0, chunksize=10007), dict(thresh='4', chunksize=30000)):
+        c_l = ss.sort_frontend(lazy, filt=hp, **kw)
+        c_h = ss.sort_frontend({'data': x, 'FS': FS, 'n_contacts': 4}, filt=hp, slabs=1, **kw)
+        for c in range(4):
+            assert np.array_equal(c_l['spt'][c]['data'], c_h['spt'][c]['data'])
+            assert np.array_equal(c_l['spt_aligned'][c]['data'], c_h['spt_aligned'][c]['data'])
+            assert np.array_equal(c_l['sp_waves'][c]['data'], c_h['sp_waves'][c]['data'])
     flt.write_sp(sp, "/Gollum/s5gollum01/el4")
     for c in range(4):
         assert filecmp.cmp(str(tmp_path / ("Gollum_5gollum01_el3_c%d.sp" % (c + 1))),
