@@ -602,3 +602,35 @@ def test_filtfilt_on_odd_offset_int16_view(env, oracle):
                                         for lo in range(0, parent.shape[1] - start, 10007)])
                         for c in range(3)])
         assert rel_err(got, ref) < 1e-12
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_filter_geometry(env, oracle, seed):
+    """Randomised chunk geometry for the filter: odd and even chunk sizes, short last chunks,
+    chunks barely longer than the padding, row-strided views with odd offsets, all dtypes,
+    orders 1-8 - against the oracle's per-(contact, chunk) filtfilt."""
+    rng = np.random.default_rng(500 + seed)
+    name = ['hp1_butter', 'bp2', 'lp3', 'ellip_hp3', 'bp4', 'bp8'][seed % 6]
+    b, a = DESIGNS[name]()
+    from spikesort_b200._design import tf2sos_exact
+    sos, padlen = tf2sos_exact(b, a)
+    dtype = [np.int16, np.float32, np.float64][seed % 3]
+    n_c = int(rng.integers(1, 5))
+    cs = int(rng.integers(padlen + 2, 6000))
+    n_chunks = int(rng.integers(1, 6))
+    last = int(rng.integers(padlen + 1, cs + 1))
+    n = (n_chunks - 1) * cs + last
+    off = int(rng.integers(0, 4))
+    parent = rng.standard_normal((n_c, n + off + 5)) * 300.0
+    parent = np.round(parent).astype(dtype) if dtype is np.int16 else parent.astype(dtype)
+    view = _dev(env, parent)[:, off:off + n]                      # strided rows, odd/even start
+    got = env['ops'].filtfilt_sos(view, sos, padlen, cs).cpu().numpy()
+    x = parent[:, off:off + n]
+    ref = np.stack([np.concatenate([oracle.filtfilt(b, a, x[c, lo:min(lo + cs, n)])
+                                    for lo in range(0, n, cs)]) for c in range(n_c)])
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < TIGHT[name] * 10, (name, dtype, n_c, cs, n_chunks, last, off)
+    # a chunk that is not longer than the padding raises what SciPy raises
+    if n > padlen + 1:
+        with pytest.raises(ValueError):
+            env['ops'].filtfilt_sos(view, sos, padlen, padlen)
