@@ -13,8 +13,9 @@ extract -> per-contact PCA, all 32 contacts) over the recording.
   value      : chain throughput with the recording resident in HBM (CUDA events)
   e2e        : the same chain through the spike_sort.core-compatible public API with
                HOST buffers (pinned raw recording in, NumPy results out)
-  roofline   : the filter stage (the three launches of ss_filtfilt_sos, ~all of the
-               step) against the measured HBM peak
+  roofline   : the fused filter + auto-threshold + detect stage (ss_filtfilt_detect_sos +
+               ss_detect_emit, ~80 % of the step) against the measured HBM peak
+  parity     : end-to-end spike-time mismatches / PCA error against the CPU oracle chain
   cpu_baseline: the oracle port (CPU restatement of the reference, oracle/) timed on a
                bounded sample of the same workload, on rank 0
 
