@@ -291,6 +291,19 @@ int ss_filtfilt_fir(const void *d_x, int dtype, int64_t n_contacts, int64_t n_sa
                     int64_t ld_in, const double *d_b, int n_taps, int64_t chunksize,
                     double *d_out, int64_t ld_out, void *stream);
 
+/* ss_filtfilt_detect_sos for one time shard with the halo exchange FUSED into sweep 2: the
+ * tiles that produce the shard's first / last H filtered samples of every contact store them,
+ * besides d_out, straight into the left neighbour's `from_right` / the right neighbour's
+ * `from_left` arena region (peer memory; NULL = no neighbour on that side).  Follow with
+ * ss_peer_barrier; ss_shard_put_halos is then not needed. */
+int ss_filtfilt_detect_sos_peer(const void *d_x, int dtype, int64_t n_contacts, int64_t n_samples,
+                                int64_t ld_in, const double *sos, int n_sections, int padlen,
+                                int64_t chunksize, double *d_out, int64_t ld_out, void *d_ws,
+                                size_t ws_bytes, int auto_thr, int64_t n0, double factor,
+                                double *d_thr, int falling, void *d_det_ws, size_t det_ws_bytes,
+                                int64_t *d_offsets, int prepared, double *d_left_from_right,
+                                double *d_right_from_left, int H, void *stream);
+
 /* ------------------------------------------- time shards over peer memory (8e)
  * Exchange steps of a recording sharded by time across GPUs (one process per GPU).  The
  * reference has no such step: its filter_proxy walks (contact, chunk) units in one process

@@ -33,6 +33,9 @@ SIGNATURES = {
     "ss_filtfilt_detect_sos": (_int, [_vp, _int, _i64, _i64, _i64, _dp, _int, _int, _i64, _vp, _i64,
                                       _vp, _sz, _int, _i64, _dbl, _vp, _int, _vp, _sz, _vp, _int,
                                       _vp]),
+    "ss_filtfilt_detect_sos_peer": (_int, [_vp, _int, _i64, _i64, _i64, _dp, _int, _int, _i64, _vp, _i64,
+                                           _vp, _sz, _int, _i64, _dbl, _vp, _int, _vp, _sz, _vp, _int,
+                                           _vp, _vp, _int, _vp]),
     "ss_filtfilt_prepare_sos": (_int, [_vp, _int, _i64, _i64, _i64, _dp, _int, _int, _i64, _vp, _sz,
                                        _vp]),
     "ss_filtfilt_head_threshold_sos": (_int, [_vp, _int, _i64, _i64, _i64, _dp, _int, _int, _i64,

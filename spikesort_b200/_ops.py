@@ -95,13 +95,16 @@ def filtfilt_fir(x, b, chunksize, out=None):
 
 
 def filtfilt_detect(x, sos, padlen, chunksize, FS, falling, thr=None, n0=None, factor=None,
-                    out=None, ws=None, shard=_WHOLE, cap=None):
+                    out=None, ws=None, shard=_WHOLE, cap=None, peer=None):
     """Fused filter + (auto threshold) + crossing marking + emit.
     thr: CUDA float64 (n_contacts,) thresholds, or None to derive them from the first
     n0 filtered samples (factor carries the sign).  Returns (out, thr, spt, offsets).
     cap: size the spike list by this capacity instead of synchronising with the host to
     learn the count; the true count is offsets[-1] (more than cap: the list is truncated and
-    the caller must redo the call without cap)."""
+    the caller must redo the call without cap).
+    peer: (left_from_right_ptr, right_from_left_ptr, H) - integer device addresses in the
+    neighbour shards' arenas (0 = no neighbour): the tiles of sweep 2 that produce the first /
+    last H samples store them there as well (halo exchange fused into the filter)."""
     lib = _lib.load()
     t = _lib.torch()
     n_c, n = x.shape
@@ -118,13 +121,19 @@ def filtfilt_detect(x, sos, padlen, chunksize, FS, falling, thr=None, n0=None, f
     auto = thr is None
     if auto:
         thr = t.empty(n_c, dtype=t.float64, device=x.device)
-    rc = lib.ss_filtfilt_detect_sos(_lib.ptr(x), _lib.ss_dtype_of(x), n_c, n, x.stride(0),
-                                    sos.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_sec,
-                                    int(padlen), int(chunksize), _lib.ptr(out), out.stride(0),
-                                    _lib.ptr(ws), ws.numel(), int(auto),
-                                    int(n0) if auto else 0, float(factor) if auto else 0.0,
-                                    _lib.ptr(thr), int(bool(falling)), _lib.ptr(dws), dws.numel(),
-                                    _lib.ptr(offsets), int(prepared), _lib.stream_ptr())
+    args = (_lib.ptr(x), _lib.ss_dtype_of(x), n_c, n, x.stride(0),
+            sos.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n_sec,
+            int(padlen), int(chunksize), _lib.ptr(out), out.stride(0),
+            _lib.ptr(ws), ws.numel(), int(auto),
+            int(n0) if auto else 0, float(factor) if auto else 0.0,
+            _lib.ptr(thr), int(bool(falling)), _lib.ptr(dws), dws.numel(),
+            _lib.ptr(offsets), int(prepared))
+    if peer is None:
+        rc = lib.ss_filtfilt_detect_sos(*(args + (_lib.stream_ptr(),)))
+    else:
+        rc = lib.ss_filtfilt_detect_sos_peer(*(args + (ctypes.c_void_p(int(peer[0])),
+                                                       ctypes.c_void_p(int(peer[1])), int(peer[2]),
+                                                       _lib.stream_ptr())))
     _lib.check(rc, "ss_filtfilt_detect_sos")
     # summary, tilescan | apply(head), 2 threshold, mark(head), edge | apply+marks, edge | count, scan
     _launched((0 if prepared else 2) + (5 if auto else 0) + 4)

@@ -65,7 +65,17 @@ struct MarkParams {
     int64_t words_per_row;
     int64_t n_samples;
     int falling;
+    // time shards: the first / last halo_H filtered samples of every contact are ALSO stored
+    // straight into the neighbour ranks' arenas (NVLink peer memory) by the tiles that
+    // produce them - the halo exchange is the epilogue of sweep 2, not a separate step
+    double *peer_left;           // left neighbour's from_right  [n_contacts][halo_H], or null
+    double *peer_right;          // right neighbour's from_left  [n_contacts][halo_H], or null
+    int halo_H;
+    int64_t shard_n;             // samples per contact of this shard
 };
+
+struct PeerHalo { double *left, *right; int H; };
+static thread_local PeerHalo g_peer_halo = {nullptr, nullptr, 0};
 
 struct TileInfo {
     int64_t c, cs0, L, nt, t, pad, g0;   // contact, chunk start, chunk length, tiles in unit,
@@ -601,6 +611,21 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
             if (r >= 0 && r < ti.L) __stcs(orow + r, sm[34 * k + base]);
         }
     }
+    if (mk.peer_left || mk.peer_right) {
+        // tiles that hold one of the shard's first / last halo_H samples (warp-uniform test)
+        const int64_t s_lo = ti.cs0 + r0, H = mk.halo_H, n = mk.shard_n;
+        if (s_lo < H || s_lo + FS_T > n - H) {
+#pragma unroll 1
+            for (int k = 0; k < FS_S; ++k) {
+                const int64_t r = r0 + 32 * k + lane;
+                if (r < 0 || r >= ti.L) continue;
+                const int64_t sidx = ti.cs0 + r;
+                const double val = sm[34 * k + base];
+                if (mk.peer_left && sidx < H) mk.peer_left[ti.c * H + sidx] = val;
+                if (mk.peer_right && sidx >= n - H) mk.peer_right[ti.c * H + (sidx - (n - H))] = val;
+            }
+        }
+    }
 }
 
 // One thread per tile: the crossing whose first sample is the last chunk sample of the
@@ -1110,13 +1135,19 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
     }
     if (!(phases & PH_APPLY)) return SS_OK;
     if (mk) {
-        filt_apply_kernel<NB, FO, true><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, *mk);
+        MarkParams mkp = *mk;
+        mkp.peer_left = g_peer_halo.left;
+        mkp.peer_right = g_peer_halo.right;
+        mkp.halo_H = g_peer_halo.H;
+        mkp.shard_n = g.n_samples;
+        filt_apply_kernel<NB, FO, true><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, mkp);
         SS_LAUNCH_CHECK("filt_apply_kernel<mark>");
         const dim3 bgrid((unsigned)ss_cdiv(nt_max, 256), (unsigned)j_count, (unsigned)g.n_contacts);
         filt_boundary_mark_kernel<<<bgrid, 256, 0, st>>>(d_out, g, *mk);
         SS_LAUNCH_CHECK("filt_boundary_mark_kernel");
     } else {
-        MarkParams none = {nullptr, nullptr, 0, 0, 0};
+        MarkParams none = {nullptr, nullptr, 0, 0, 0, g_peer_halo.left, g_peer_halo.right,
+                           g_peer_halo.H, g.n_samples};
         filt_apply_kernel<NB, FO, false><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, none);
         SS_LAUNCH_CHECK("filt_apply_kernel");
     }
@@ -1256,6 +1287,9 @@ extern "C" int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_cont
     mk.words_per_row = L.words_per_row;
     mk.n_samples = n_samples;
     mk.falling = falling;
+    mk.peer_left = mk.peer_right = nullptr;
+    mk.halo_H = 0;
+    mk.shard_n = n_samples;
     SS_CUDA_CHECK(cudaMemsetAsync(mk.mask, 0, (size_t)L.words_per_row * n_contacts * 4, st));
     int64_t j0 = 0;
     if (auto_thr) {
@@ -1336,4 +1370,29 @@ extern "C" int ss_filtfilt_head_threshold_sos(const void *d_x, int dtype, int64_
     if (rc) return rc;
     return ss_var_threshold(d_out, SS_F64, n_contacts, ld_out, n0, factor, d_thr, d_thr_ws,
                             thr_ws_bytes, stream);
+}
+
+// ss_filtfilt_detect_sos with the halo exchange fused into sweep 2: the tiles that produce the
+// shard's first / last H samples also store them into the neighbours' arenas (peer memory).
+extern "C" int ss_filtfilt_detect_sos_peer(const void *d_x, int dtype, int64_t n_contacts,
+                                           int64_t n_samples, int64_t ld_in, const double *sos,
+                                           int n_sections, int padlen, int64_t chunksize,
+                                           double *d_out, int64_t ld_out, void *d_ws,
+                                           size_t ws_bytes, int auto_thr, int64_t n0, double factor,
+                                           double *d_thr, int falling, void *d_det_ws,
+                                           size_t det_ws_bytes, int64_t *d_offsets, int prepared,
+                                           double *d_left_from_right, double *d_right_from_left,
+                                           int H, void *stream)
+{
+    SS_REQUIRE(H >= 0 && H <= n_samples, SS_ERR_ARG, "filtfilt_detect_peer: halo %d larger than the shard", H);
+    g_peer_halo.left = H > 0 ? d_left_from_right : nullptr;
+    g_peer_halo.right = H > 0 ? d_right_from_left : nullptr;
+    g_peer_halo.H = H;
+    const int rc = ss_filtfilt_detect_sos(d_x, dtype, n_contacts, n_samples, ld_in, sos, n_sections,
+                                          padlen, chunksize, d_out, ld_out, d_ws, ws_bytes, auto_thr,
+                                          n0, factor, d_thr, falling, d_det_ws, det_ws_bytes,
+                                          d_offsets, prepared, stream);
+    g_peer_halo.left = g_peer_halo.right = nullptr;
+    g_peer_halo.H = 0;
+    return rc;
 }

@@ -331,12 +331,12 @@ class ShardedChain(object):
                                             -frac if self.falling else frac)
 
     # 3. sweep 2 with fused crossing marks; returns what the neighbours need
-    def filter_detect(self, thr, slabs=True, cap=None):
+    def filter_detect(self, thr, slabs=True, cap=None, peer=None):
         r = self.res
         r.thresh = thr
         _, _, spt, offsets = _ops.filtfilt_detect(
             self.x, self.sos, self.padlen, self.chunksize, self.FS, self.falling, thr=thr,
-            out=self.sig, ws=self.ws, shard=self.shard, cap=cap)
+            out=self.sig, ws=self.ws, shard=self.shard, cap=cap, peer=peer)
         r.filtered = self.sig
         self._spt, self._offsets = spt, offsets
         if not slabs:
@@ -426,21 +426,20 @@ class ShardedChain(object):
         return f.local(self.rank, f.off_thr, self.n_c).clone()
 
     def fab_filter_detect(self, thr, cap=None):
-        """Sweep 2 with fused crossing marks, then the boundary slabs into the neighbours'
-        arenas (then barrier).  cap: capacity of the detected-spike list (no host sync; see
+        """Sweep 2 with fused crossing marks AND fused halo put: the boundary samples go
+        into the neighbours' arenas from the filter kernel itself (then barrier).  cap: capacity of the detected-spike list (no host sync; see
         pipeline.run_chain `speculate`)."""
         self.cap = cap
         self._overflow = None
+        # the halo exchange is fused into sweep 2: its edge tiles store the first / last H
+        # samples into the neighbours' arenas as they write them to HBM
+        f = self.fabric
+        left = int(f.ptrs[self.rank - 1]) + f.off_from_right if self.rank > 0 else 0
+        right = int(f.ptrs[self.rank + 1]) + f.off_from_left if self.rank < self.n_ranks - 1 else 0
+        peer = (left, right, self.H) if self.H > 0 and self.n_ranks > 1 else None
+        self.filter_detect(thr, slabs=False, cap=cap, peer=peer)
         if cap is not None:
-            self.filter_detect(thr, slabs=False, cap=cap)
             self._overflow = (self._offsets[-1] > cap).to(self.t.int64)     # device flag
-        else:
-            self.filter_detect(thr, slabs=False)
-        n_c, H, n_win, ptrs = self._xargs()
-        rc = _lib.load().ss_shard_put_halos(_lib.ptr(self.sig), self.sig.stride(0), n_c, self.n, H,
-                                            n_win, ptrs, self.rank, self.n_ranks, _lib.stream_ptr())
-        _lib.check(rc, "ss_shard_put_halos")
-        _ops._launched(1 if self.n_ranks > 1 and H > 0 else 0)
 
     def fab_align(self):
         """Halos into the margins, boundary crossing appended, alignment, last aligned time of
