@@ -291,7 +291,7 @@ class ShardedChain(object):
 
     def __init__(self, x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
                  thresh='auto', ncomps=2, chunksize=1E6, rank=0, n_ranks=1, index_offset=0,
-                 n_total=None, halo=None, fabric=None):
+                 n_total=None, halo=None, fabric=None, resample=1):
         t = _lib.require_cuda()
         self.t = t
         self.x, self.FS, self.filt = x, FS, filt
@@ -299,6 +299,7 @@ class ShardedChain(object):
         self.falling = edge in _FALLING
         self.use_min = align_type == 'min'
         self.thresh, self.ncomps, self.chunksize = thresh, ncomps, int(chunksize)
+        self.resample = int(resample)
         self.rank, self.n_ranks = rank, n_ranks
         self.n_c, self.n = x.shape
         win0, win1, self.time = _ops.window_params(self.sp_win, FS)
@@ -315,6 +316,14 @@ class ShardedChain(object):
         if fabric is not None and fabric.key() != (self.n_c, self.H, self.n_win, n_ranks):
             raise ValueError("fabric %r does not match the shard %r"
                              % (fabric.key(), (self.n_c, self.H, self.n_win, n_ranks)))
+
+    def _align(self, spt):
+        if self.resample != 1:
+            _ops.align_resampled(self.sig, spt, self._offsets, None, self.FS, self.sp_win,
+                                 self.use_min, self.resample, shard=self.shard)
+        else:
+            _ops.align(self.sig, spt, self._offsets, None, self.FS, self.sp_win, self.use_min,
+                       shard=self.shard)
 
     # 1. sweep 1 of the filter (needs nothing from other ranks)
     def prepare(self):
@@ -361,8 +370,7 @@ class ShardedChain(object):
                                                               t_last)
         r.spt_detected, r.offsets_detected = self._spt, self._offsets
         spt = self._spt.clone()
-        _ops.align(self.sig, spt, self._offsets, None, self.FS, self.sp_win, self.use_min,
-                   shard=self.shard)
+        self._align(spt)
         self._aligned = spt
         off = self._offsets
         last = t.full((self.n_c,), float('nan'), dtype=t.float64, device=spt.device)
@@ -469,8 +477,7 @@ class ShardedChain(object):
             self._cap_detected = offsets[-1]       # true length, read with remove_doubles' sync
         r.spt_detected, r.offsets_detected = self._spt, self._offsets
         spt = self._spt.clone()
-        _ops.align(self.sig, spt, self._offsets, None, self.FS, self.sp_win, self.use_min,
-                   shard=self.shard)
+        self._align(spt)
         self._aligned = spt
         rc = lib.ss_shard_put_last(_lib.ptr(spt), _lib.ptr(self._offsets), n_c, H, n_win, ptrs,
                                    self.rank, self.n_ranks, _lib.stream_ptr())

@@ -63,7 +63,7 @@ _CAPACITY_HINTS = {}
 
 def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
               thresh='auto', ncomps=2, chunksize=1E6, pca=True, thr_override=None, fused=True,
-              speculate=True):
+              speculate=True, resample=1):
     """x: CUDA tensor (n_contacts, n_samples), int16/float32/float64.
     filt: a spikesort_b200.filters filter object or None.
     thresh: 'auto' / numeric string (multiple of the std of the first 10 s) or a number.
@@ -76,19 +76,21 @@ def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='
     kernel behind them.  When a call with the same shape has been seen before, the arrays
     are sized by that call's count + 25 % instead, every kernel bounds its work by the
     device-side offsets, and the counts are read once at the end; if the capacity turns out
-    too small the chain is simply run again with exact sizes.  Results are identical."""
+    too small the chain is simply run again with exact sizes.  Results are identical.
+    resample: align on the cubic-spline upsampled window (align_spikes(resample=...),
+    extract.py:245-258; the tutorial uses 10); waveforms are extracted at the original rate."""
     key = (tuple(x.shape), x.dtype, float(FS), tuple(sp_win), edge, align_type, str(thresh),
-           id(type(filt)), int(chunksize), bool(fused))
+           id(type(filt)), int(chunksize), bool(fused), int(resample))
     hint = _CAPACITY_HINTS.get(key) if speculate else None
     if hint is not None:
         cap = int(hint * 1.25) + 1024
         res, n_det, n_kept = _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps,
-                                        chunksize, pca, thr_override, fused, cap)
+                                        chunksize, pca, thr_override, fused, cap, resample)
         if n_det <= cap:
             _CAPACITY_HINTS[key] = n_det
             return res
     res, n_det, n_kept = _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
-                                    pca, thr_override, fused, None)
+                                    pca, thr_override, fused, None, resample)
     if speculate:
         if len(_CAPACITY_HINTS) > 64:
             _CAPACITY_HINTS.clear()
@@ -97,7 +99,7 @@ def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='
 
 
 def _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize, pca, thr_override,
-               fused, cap):
+               fused, cap, resample=1):
     """The chain; cap=None: exact sizes (two host syncs), else capacity-sized arrays and one
     sync at the end.  Returns (ChainResult, n_detected, n_kept)."""
     t = _lib.require_cuda()
@@ -136,7 +138,10 @@ def _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
         spt, offsets = _ops.detect(sig, thr, falling, FS, cap=cap)
     res.spt_detected, res.offsets_detected = spt, offsets
     spt = spt.clone()
-    _ops.align(sig, spt, offsets, None, FS, sp_win, align_type == 'min')
+    if resample != 1:
+        _ops.align_resampled(sig, spt, offsets, None, FS, sp_win, align_type == 'min', resample)
+    else:
+        _ops.align(sig, spt, offsets, None, FS, sp_win, align_type == 'min')
     spt, offsets = _ops.remove_doubles(spt, offsets, 1000.0 / FS, cap=cap)
     res.spt, res.offsets = spt, offsets
     waves, valid, n_invalid = _ops.extract(sig, spt, FS, sp_win, contacts=None, offsets=offsets)
@@ -163,7 +168,7 @@ def _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
 
 
 def sort_frontend(spike_data, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
-                  thresh='auto', ncomps=2, chunksize=1E6, contacts=None, slabs='auto'):
+                  thresh='auto', ncomps=2, chunksize=1E6, contacts=None, slabs='auto', resample=1):
     """The whole front end for a multi-contact recording in ONE call, host in / host out.
 
     spike_data: the reference's raw-recording dict {'data', 'FS', 'n_contacts'}; 'data' may
@@ -188,14 +193,14 @@ def sort_frontend(spike_data, filt=None, sp_win=(-0.2, 0.8), edge='falling', ali
     FS = spike_data['FS']
     if contacts is None and slabs != 1:
         piped = _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, ncomps,
-                                     chunksize, slabs)
+                                     chunksize, slabs, resample)
         if piped is not None:
             return piped
     x = _lib.to_device_2d(spike_data['data'])            # one H2D copy (pinned: ~55 GB/s)
     if contacts is not None:
         x = x[t.as_tensor(list(contacts), device=x.device)]
     res = run_chain(x, FS, filt=filt, sp_win=sp_win, edge=edge, align_type=align_type,
-                    thresh=thresh, ncomps=ncomps, chunksize=chunksize)
+                    thresh=thresh, ncomps=ncomps, chunksize=chunksize, resample=resample)
     n_rows = x.shape[0]
     ids = list(range(n_rows)) if contacts is None else list(contacts)
     return results_to_host(res, ids, FS, ncomps)
@@ -347,7 +352,7 @@ def _slab_bounds(n, chunksize, n0, want):
 
 
 def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
-                         slabs):
+                         slabs, resample=1):
     """sort_frontend with the upload of slab s+1 overlapping the chain on slab s.  Returns
     None when the input does not qualify (device-resident, FIR / no filter, too short)."""
     t = _lib.torch()
@@ -428,7 +433,8 @@ def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, nco
         _SLAB_FABRICS[key] = ssd.LocalFabric(n_c, H, n_win, S, dev)
     fab = _SLAB_FABRICS[key]
     chains = [ssd.ShardedChain(xdev[:, a:b], FS, filt, sp_win, edge, align_type, thresh, ncomps,
-                               chunksize, rank=k, n_ranks=S, index_offset=a, n_total=n, fabric=fab)
+                               chunksize, rank=k, n_ranks=S, index_offset=a, n_total=n, fabric=fab,
+                               resample=resample)
               for k, (a, b) in enumerate(bounds)]
 
     def finish(k):

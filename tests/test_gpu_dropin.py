@@ -353,3 +353,29 @@ def test_sort_frontend_slab_pipeline_equals_single_upload(ss, pinned):
             assert rel_err(sign_normalise(a, b), b) < 1e-9, c
             tot += len(one['spt_aligned'][c]['data'])
         assert tot > 300
+
+
+def test_chain_with_resampled_alignment(ss, golden):
+    """The batched chain with align_spikes(resample=r) (the tutorial aligns with resample=10):
+    per contact identical to the per-contact drop-in calls, which are bit-exact against the
+    reference (test_resample_golden); monolithic and slab-pipelined front ends agree."""
+    FS = 25000
+    x = golden['chain_raw']
+    flt = ss.filters.Filter(800., 100.)
+    f = ss.filters.filter_proxy({'data': x, 'FS': FS, 'n_contacts': 2}, flt, chunksize=25000)
+    kw = dict(filt=flt, sp_win=[-0.2, 0.8], edge='rising', align_type='max', thresh='4', ncomps=2,
+              chunksize=10000, resample=10)
+    outs = [ss.sort_frontend({'data': x, 'FS': FS, 'n_contacts': 2}, slabs=s, **kw) for s in (1, 'auto')]
+    f10 = ss.filters.filter_proxy({'data': x, 'FS': FS, 'n_contacts': 2}, flt, chunksize=10000)
+    for c in range(2):
+        spt = ss.extract.detect_spikes(f10, thresh='4', edge='rising', contact=c)
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            spa = ss.extract.align_spikes(f10, spt, [-0.2, 0.8], type='max', contact=c, resample=10)
+            plain = ss.extract.align_spikes(f10, spt, [-0.2, 0.8], type='max', contact=c)
+        assert not np.array_equal(spa['data'], plain['data'])          # sub-sample shifts happened
+        for out in outs:
+            assert np.array_equal(out['spt_aligned'][c]['data'], spa['data']), c
+        wv = ss.extract.extract_spikes(f10, spa, [-0.2, 0.8], contacts=c)
+        assert np.array_equal(outs[0]['sp_waves'][c]['data'], wv['data'])
+        assert np.array_equal(outs[1]['sp_waves'][c]['data'], wv['data'])
