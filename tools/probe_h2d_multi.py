@@ -1,6 +1,6 @@
 """Concurrent pinned H2D bandwidth per rank, with and without binding the process to the
 CPUs NVML reports as local to its GPU (run under torchrun)."""
-import os, sys, time
+import os, time
 import torch, torch.distributed as dist
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
