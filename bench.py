@@ -51,6 +51,7 @@ SP_WIN = [-0.2, 0.8]
 CHUNK = 1000000
 SEED = 2
 RATE_HZ = 10.0
+FILTER_ARGS = (800., 100.)          # fltLinearIIR(800, 100): order-1 Butterworth high-pass
 CONFIG = {
     "workload": "configs[1]: 32-channel 30 kHz 10-minute synthetic int16 recording "
                 "(32 x 18,000,000), fltLinearIIR(800,100) -> auto threshold -> detect(falling) "
@@ -77,7 +78,7 @@ def _cpu_chain_one(args):
     raw = {'data': x, 'FS': FS, 'n_contacts': 1}
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        _, res = port.chain_per_contact(raw, port.Filter(800., 100.), SP_WIN, edge='falling',
+        _, res = port.chain_per_contact(raw, port.Filter(*FILTER_ARGS), SP_WIN, edge='falling',
                                         align_type='min', ncomps=2, chunksize=CHUNK)
     return c, len(res[0][1]['data']), res[0][1]['data'], res[0][3]['data'] if res[0][3] else None
 
@@ -208,7 +209,7 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    flt = filters.Filter(800., 100.)
+    flt = filters.Filter(*FILTER_ARGS)
     # shard r of a 10*world-minute recording: same statistics, seed + rank
     x = synth.make_recording(N_CONTACTS, N_SAMPLES, FS, seed=SEED + rank, device=dev,
                              rate_hz=RATE_HZ, noise=10.0)
@@ -351,7 +352,7 @@ def run_gpu(args):
         d2h = 0
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            f = filters.fltLinearIIR(raw, 800., 100.)          # H2D of the raw recording inside
+            f = filters.fltLinearIIR(raw, *FILTER_ARGS)        # H2D of the raw recording inside
             for c in range(N_CONTACTS):
                 spt = extract.detect_spikes(f, thresh='auto', edge='falling', contact=c)
                 spa = extract.align_spikes(f, spt, SP_WIN, type='min', contact=c)
@@ -491,8 +492,15 @@ def select_workload(name):
     """--workload c3: one GPU's time shard of configs[2] (Neuropixels scale, 384 contacts x
     1 h at 30 kHz sharded over 8 GPUs = 384 x 13,500,000 per GPU).  Device numbers only
     (a 10.4 GB pinned recording per rank is not staged): not the driver's bench line."""
-    global N_CONTACTS, N_SAMPLES, SEED, CONFIG
+    global N_CONTACTS, N_SAMPLES, SEED, CONFIG, FILTER_ARGS
     if name == "c2":
+        return
+    if name == "c2-bp8":
+        # configs[1] with the band-pass SURVEY.md 8d names next to the order-1 high-pass:
+        # Filter([300, 6000], [100, 8000]) -> Butterworth order 8 (4 biquads); extra data point
+        FILTER_ARGS = (np.array([300., 6000.]), np.array([100., 8000.]))
+        CONFIG = dict(CONFIG, workload=CONFIG["workload"].replace(
+            "fltLinearIIR(800,100)", "Filter([300,6000],[100,8000]) (order-8 band-pass)"))
         return
     N_CONTACTS, N_SAMPLES, SEED = 384, 13500000, 3
     CONFIG = dict(CONFIG, n_contacts=N_CONTACTS, n_samples=N_SAMPLES, seed=SEED,
@@ -509,10 +517,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c2-bp8"])
     args = ap.parse_args()
     select_workload(args.workload)
-    if args.workload != "c2":
+    if args.workload == "c3":
         args.no_e2e = args.no_cpu_baseline = True
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

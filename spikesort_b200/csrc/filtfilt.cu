@@ -143,8 +143,12 @@ struct FiltParams {
     static constexpr int NS = 2 * NB + (FO ? 1 : 0);
     static constexpr int NSEC = NB + (FO ? 1 : 0);
     double sec[NSEC][5];          // b0 b1 b2 a1 a2 per section (first-order: b2 = a2 = 0)
-    double hrow[FS_S][NS];        // C A^i, i < S
-    double P[5][NS][NS];          // A^(S 2^k)
+    // sweep 2 treats the cascade SECTION BY SECTION (each section is an LTI system of its own
+    // whose input is the finished output of the one before): 2x2 tables per section instead
+    // of NS x NS ones for the whole cascade - the lane scan costs 4 FMAs per step and section
+    // instead of NS^2 per step (order 8: 96 -> 66 FMAs per sample)
+    double hrow[NSEC][FS_S][2];   // C_s A_s^i, i < S   (first-order section: [.][1] unused)
+    double P[NSEC][5][2][2];      // A_s^(S 2^k)
 };
 
 template <int NS>
@@ -155,37 +159,6 @@ struct ScanParams {
     double hlast[NS];             // C A^(T-1)
     double zi[NS];                // steady state for a unit step
 };
-
-// one sample through the cascade; z updated; returns the cascade output
-template <int NB, bool FO>
-__device__ __forceinline__ double cascade_step(const FiltParams<NB, FO> &P,
-                                               double (&z)[FiltParams<NB, FO>::NS], double x)
-{
-#pragma unroll
-    for (int s = 0; s < NB; ++s) {
-        const double y = z[2 * s] + P.sec[s][0] * x;
-        z[2 * s] = z[2 * s + 1] + P.sec[s][1] * x - P.sec[s][3] * y;
-        z[2 * s + 1] = P.sec[s][2] * x - P.sec[s][4] * y;
-        x = y;
-    }
-    if (FO) {
-        const double y = z[2 * NB] + P.sec[NB][0] * x;
-        z[2 * NB] = P.sec[NB][1] * x - P.sec[NB][3] * y;
-        x = y;
-    }
-    return x;
-}
-
-template <int NB, bool FO, bool REV>
-__device__ __forceinline__ void local_pass(const FiltParams<NB, FO> &P, double (&v)[FS_S],
-                                           double (&z)[FiltParams<NB, FO>::NS])
-{
-#pragma unroll
-    for (int ii = 0; ii < FS_S; ++ii) {
-        const int i = REV ? FS_S - 1 - ii : ii;
-        v[i] = cascade_step<NB, FO>(P, z, v[i]);
-    }
-}
 
 // inclusive scan of lane end states in processing order (REV: lane 31 first)
 template <int NS, bool REV>
@@ -210,31 +183,72 @@ __device__ __forceinline__ void warp_scan(double (&e)[NS], const double (&Pm)[5]
     }
 }
 
-// state at the start of each lane's segment (zero for the seeded lane: its
-// local pass already started from the true state)
-template <int NS, bool REV>
-__device__ __forceinline__ void exclusive_prefix(const double (&e)[NS], double (&pre)[NS], int lane)
+// One section over the warp's tile, in place: every lane runs the section over its FS_S
+// samples (the seeded lane from the true tile state (z0, z1), the others from zero), an
+// inclusive warp scan with A_s^(S 2^k) turns the lane end states into true states, and
+// y[i] += (C_s A_s^i) . (state at the lane's start) corrects the local outputs.
+// SO: second-order section (two states); otherwise first-order (z1 unused).
+template <bool SO, bool REV>
+__device__ __forceinline__ void section_pass(const double (&c)[5], const double (&h)[FS_S][2],
+                                             const double (&Pm)[5][2][2], double (&v)[FS_S],
+                                             double z0, double z1, int lane)
 {
-#pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        const double t = REV ? ss_shfl_down(e[i], 1) : ss_shfl_up(e[i], 1);
-        pre[i] = (REV ? lane == 31 : lane == 0) ? 0.0 : t;
-    }
-}
-
-template <int NB, bool FO, bool REV>
-__device__ __forceinline__ void correct(const FiltParams<NB, FO> &P, double (&v)[FS_S],
-                                        const double (&pre)[FiltParams<NB, FO>::NS])
-{
-    constexpr int NS = FiltParams<NB, FO>::NS;
 #pragma unroll
     for (int ii = 0; ii < FS_S; ++ii) {
         const int i = REV ? FS_S - 1 - ii : ii;
-        double acc = v[i];
+        const double x = v[i];
+        const double y = z0 + c[0] * x;
+        if (SO) {
+            z0 = z1 + c[1] * x - c[3] * y;
+            z1 = c[2] * x - c[4] * y;
+        } else {
+            z0 = c[1] * x - c[3] * y;
+        }
+        v[i] = y;
+    }
 #pragma unroll
-        for (int c = 0; c < NS; ++c) acc += P.hrow[ii][c] * pre[c];
+    for (int k = 0; k < 5; ++k) {
+        const int d = 1 << k;
+        const bool act = REV ? (lane + d < 32) : (lane >= d);
+        const double o0 = REV ? ss_shfl_down(z0, d) : ss_shfl_up(z0, d);
+        if (SO) {
+            const double o1 = REV ? ss_shfl_down(z1, d) : ss_shfl_up(z1, d);
+            if (act) {
+                z0 = z0 + Pm[k][0][0] * o0 + Pm[k][0][1] * o1;
+                z1 = z1 + Pm[k][1][0] * o0 + Pm[k][1][1] * o1;
+            }
+        } else if (act) {
+            z0 = z0 + Pm[k][0][0] * o0;
+        }
+    }
+    // state at the start of the lane's segment (zero for the seeded lane: its local pass
+    // already started from the true state)
+    const bool seeded = REV ? lane == 31 : lane == 0;
+    const double t0 = REV ? ss_shfl_down(z0, 1) : ss_shfl_up(z0, 1);
+    const double p0 = seeded ? 0.0 : t0;
+    double p1 = 0.0;
+    if (SO) {
+        const double t1 = REV ? ss_shfl_down(z1, 1) : ss_shfl_up(z1, 1);
+        p1 = seeded ? 0.0 : t1;
+    }
+#pragma unroll
+    for (int ii = 0; ii < FS_S; ++ii) {
+        const int i = REV ? FS_S - 1 - ii : ii;
+        double acc = v[i] + h[ii][0] * p0;
+        if (SO) acc += h[ii][1] * p1;
         v[i] = acc;
     }
+}
+
+// the whole cascade over the tile, one direction; zt = tile state of the seeded lane
+template <int NB, bool FO, bool REV>
+__device__ __forceinline__ void cascade_pass(const FiltParams<NB, FO> &P, double (&v)[FS_S],
+                                             const double (&zt)[FiltParams<NB, FO>::NS], int lane)
+{
+#pragma unroll
+    for (int s = 0; s < NB; ++s)
+        section_pass<true, REV>(P.sec[s], P.hrow[s], P.P[s], v, zt[2 * s], zt[2 * s + 1], lane);
+    if (FO) section_pass<false, REV>(P.sec[NB], P.hrow[NB], P.P[NB], v, zt[2 * NB], 0.0, lane);
 }
 
 // interior tile: all FS_S loads of a lane are issued before the first use (the
@@ -531,6 +545,174 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *
     }
 }
 
+// Sweep 1 for higher orders (NS >= 3, int16 recordings).  filt_summary_kernel maps lanes to
+// sample positions, so every weight a lane needs is its own shared-memory read: 16 B of
+// shared-memory bandwidth per two FMAs and tile, and for NS = 8 (one tile per weight fetch:
+// the accumulators of more do not fit) the kernel is bound by the shared-memory pipe at a
+// quarter of the FP64 rate (ncu launch list, order-8 band-pass: 2.8 ms).  Here the mapping is
+// transposed: a lane owns SW_RL whole TILES, so the weight of (q, sample) is the same address
+// for all 32 lanes - one broadcast read feeds 2*SW_RL FMAs of every lane - and the per-tile
+// sums need no cross-lane reduction at all.  The price is that a lane's samples are 1 KB
+// apart: the int16 tiles are staged slice by slice (SW_SL samples of each of the warp's
+// 64 tiles) through shared memory with 4-byte cp.async copies, double-buffered per warp, as
+// raw sample PAIRS; tiles that start on an odd sample (padlen odd, e.g. 27 for order 8) are
+// staged from the aligned word below and realigned with a funnel shift.
+constexpr int SW_RL = 2;                       // tiles per lane
+constexpr int SW_TPW = 32 * SW_RL;             // tiles per warp
+constexpr int SW_SL = 32;                      // samples per slice
+constexpr int SW_SLW = SW_SL / 2;              // 32-bit words per slice (one more when odd)
+constexpr int SW_STRIDE = SW_SLW + 1;          // row stride in words: odd -> conflict-free
+__host__ __device__ constexpr int sw_wpb(int ns) { return ns <= 8 ? 16 : 12; }   // warps per CTA
+__host__ __device__ constexpr size_t sw_smem_bytes(int ns)
+{
+    return (size_t)(2 * ns + 1) * FS_T * sizeof(double) +
+           (size_t)sw_wpb(ns) * 2 * SW_TPW * SW_STRIDE * sizeof(uint32_t);
+}
+
+__device__ __forceinline__ void cp_async4(unsigned smem_dst, const void *gmem_src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NS>
+__global__ void __launch_bounds__(32 * sw_wpb(NS), 1)
+filt_summary_wide_kernel(const int16_t *__restrict__ x, const FiltGeom g, const double *__restrict__ tab,
+                         double *__restrict__ F, double *__restrict__ Bz, double *__restrict__ ylast)
+{
+    constexpr int NQ = 2 * NS + 1;
+    constexpr int WPB = sw_wpb(NS);
+    extern __shared__ __align__(16) double tab_s[];         // [NQ][FS_T], then the staging buffers
+    for (int i = threadIdx.x; i < NQ * FS_T; i += 32 * WPB) tab_s[i] = tab[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t *stage = reinterpret_cast<uint32_t *>(tab_s + NQ * FS_T) + warp * (2 * SW_TPW * SW_STRIDE);
+    TileInfo ti = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
+    const int64_t t_first = ((int64_t)blockIdx.x * WPB + warp) * SW_TPW;
+    if (t_first >= ti.nt) return;
+    const int64_t row0 = ti.c * g.ld_in;
+    // sample offset from x of the first sample of tile t_first; tiles follow every FS_T samples
+    const int64_t a0 = row0 + ti.cs0 + t_first * FS_T - ti.pad - g.edge;
+    const int odd = (int)((((uintptr_t)x >> 1) + (uintptr_t)a0) & 1);      // tile starts between two words
+    const int sh = odd * 16;
+    // tiles read straight from the recording: whole tile (and the extra word) inside the chunk
+    uint64_t fastmask = 0, validmask = 0;
+#pragma unroll
+    for (int rl = 0; rl < SW_RL; ++rl) {
+        const int64_t t = t_first + lane + 32 * rl;
+        const int64_t r0 = t * FS_T - ti.pad - g.edge;
+        const bool valid = t < ti.nt;
+        const bool fast = valid && r0 - odd >= 0 && r0 + FS_T + odd <= ti.L;
+        fastmask |= (uint64_t)__ballot_sync(SS_FULL, fast) << (32 * rl);
+        validmask |= (uint64_t)__ballot_sync(SS_FULL, valid) << (32 * rl);
+    }
+    const uint64_t slowmask = validmask & ~fastmask;
+    const int16_t *src0 = x + (a0 - odd) + (lane >> 4) * FS_T + 2 * (lane & 15);
+    const int dst0 = (lane >> 4) * SW_STRIDE + (lane & 15);
+
+    const bool all_fast = fastmask == ~0ull;
+    auto issue_slice = [&](int j, uint32_t *buf) {
+        const int16_t *src = src0 + j * SW_SL;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + dst0);
+        if (all_fast) {
+#pragma unroll 8
+            for (int k = 0; k < SW_TPW / 2; ++k)
+                cp_async4(dst + 2 * k * SW_STRIDE * 4, src + (int64_t)k * 2 * FS_T);
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < SW_TPW / 2; ++k)
+                if ((fastmask >> (2 * k + (lane >> 4))) & 1)
+                    cp_async4(dst + 2 * k * SW_STRIDE * 4, src + (int64_t)k * 2 * FS_T);
+        }
+        if (odd) {
+#pragma unroll
+            for (int rl = 0; rl < SW_RL; ++rl) {
+                const int tl = lane + 32 * rl;
+                if ((fastmask >> tl) & 1)
+                    cp_async4((unsigned)__cvta_generic_to_shared(buf + tl * SW_STRIDE + SW_SLW),
+                              x + (a0 - odd) + (int64_t)tl * FS_T + j * SW_SL + SW_SL);
+            }
+        }
+        if (slowmask) {
+            // tiles touching the padding / odd extension / end of the chunk: element by element
+            const int64_t ext_len = ti.L + 2 * (int64_t)g.edge;
+#pragma unroll 1
+            for (int tl = 0; tl < SW_TPW; ++tl) {
+                if (!((slowmask >> tl) & 1)) continue;
+                if (lane <= SW_SLW) {
+                    const int64_t e = (t_first + tl) * FS_T - ti.pad + j * SW_SL + 2 * lane - odd;
+                    const int lo = e < ext_len ? (int)ext_value(x, SS_I16, row0, ti, g.edge, e) : 0;
+                    const int hi = e + 1 < ext_len ? (int)ext_value(x, SS_I16, row0, ti, g.edge, e + 1) : 0;
+                    buf[tl * SW_STRIDE + lane] = ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    double acc[SW_RL][NQ];
+#pragma unroll
+    for (int rl = 0; rl < SW_RL; ++rl)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) acc[rl][q] = 0.0;
+
+    constexpr int NSLICE = FS_T / SW_SL;
+    issue_slice(0, stage);
+#pragma unroll 1
+    for (int j = 0; j < NSLICE; ++j) {
+        uint32_t *buf = stage + (j & 1) * (SW_TPW * SW_STRIDE);
+        if (j + 1 < NSLICE) {
+            issue_slice(j + 1, stage + ((j + 1) & 1) * (SW_TPW * SW_STRIDE));
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncwarp();
+        const double2 *wt = reinterpret_cast<const double2 *>(tab_s) + j * SW_SLW;
+        unsigned cur[SW_RL];
+#pragma unroll
+        for (int rl = 0; rl < SW_RL; ++rl) cur[rl] = buf[(lane + 32 * rl) * SW_STRIDE];
+#pragma unroll 4
+        for (int w = 0; w < SW_SLW; ++w) {
+            double x0[SW_RL], x1[SW_RL];
+#pragma unroll
+            for (int rl = 0; rl < SW_RL; ++rl) {
+                // row stride SW_STRIDE = SW_SLW + 1: word w + 1 always exists (unused when even)
+                const unsigned nxt = buf[(lane + 32 * rl) * SW_STRIDE + w + 1];
+                const unsigned pr = __funnelshift_r(cur[rl], nxt, sh);
+                cur[rl] = nxt;
+                // two int16 -> float64, exact: offset binary in the low mantissa word of 2^52
+                const unsigned ob = pr ^ 0x80008000u;
+                x0[rl] = __hiloint2double(0x43300000, (int)(ob & 0xffffu)) - 4503599627403264.0;
+                x1[rl] = __hiloint2double(0x43300000, (int)(ob >> 16)) - 4503599627403264.0;
+            }
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const double2 c = wt[q * (FS_T / 2) + w];          // same address in every lane
+#pragma unroll
+                for (int rl = 0; rl < SW_RL; ++rl)
+                    acc[rl][q] = fma(c.y, x1[rl], fma(c.x, x0[rl], acc[rl][q]));
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int rl = 0; rl < SW_RL; ++rl) {
+        const int64_t t = t_first + lane + 32 * rl;
+        if (t < ti.nt) {
+            const int64_t tile = ti.g0 + t;
+#pragma unroll
+            for (int q = 0; q < NS; ++q) {
+                F[tile * NS + q] = acc[rl][q];
+                Bz[tile * NS + q] = acc[rl][NS + q];
+            }
+            ylast[tile] = acc[rl][2 * NS];
+        }
+    }
+}
+
 template <int NB, bool FO, bool MARK>
 __global__ void __launch_bounds__(32 * FS_WPB)
 filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
@@ -548,21 +730,14 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
     double v[FS_S];
     load_tile(x, g, ti, sm, lane, v);
 
-    double e[NS], pre[NS];
-    // forward from the true tile state
+    // forward from the true tile state, then backward over the forward output
+    double zt[NS];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) e[i] = (lane == 0) ? Zf[tile * NS + i] : 0.0;
-    local_pass<NB, FO, false>(P, v, e);
-    warp_scan<NS, false>(e, P.P, lane);
-    exclusive_prefix<NS, false>(e, pre, lane);
-    correct<NB, FO, false>(P, v, pre);
-    // backward over the forward output
+    for (int i = 0; i < NS; ++i) zt[i] = (lane == 0) ? Zf[tile * NS + i] : 0.0;
+    cascade_pass<NB, FO, false>(P, v, zt, lane);
 #pragma unroll
-    for (int i = 0; i < NS; ++i) e[i] = (lane == 31) ? Zb[tile * NS + i] : 0.0;
-    local_pass<NB, FO, true>(P, v, e);
-    warp_scan<NS, true>(e, P.P, lane);
-    exclusive_prefix<NS, true>(e, pre, lane);
-    correct<NB, FO, true>(P, v, pre);
+    for (int i = 0; i < NS; ++i) zt[i] = (lane == 31) ? Zb[tile * NS + i] : 0.0;
+    cascade_pass<NB, FO, true>(P, v, zt, lane);
 
     const int64_t r0 = ti.t * FS_T - ti.pad - g.edge;
     if (MARK) {
@@ -589,8 +764,11 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
         if (bits) {
             const int64_t s = ti.cs0 + rl;                    // sample index of bit 0 in the row
             uint32_t *mrow = mk.mask + ti.c * mk.words_per_row;
+            // a lane that straddles the start of the row has s < 0: its kept bits all land in
+            // word (s >> 5) + 1 = 0, and word -1 must not be touched at all (an atomicOr of
+            // zero there faulted when the mask was the first allocation of its segment)
             const uint64_t w = (uint64_t)bits << (int)(s & 31);
-            atomicOr(mrow + (s >> 5), (uint32_t)w);
+            if ((uint32_t)w) atomicOr(mrow + (s >> 5), (uint32_t)w);
             if (w >> 32) atomicOr(mrow + (s >> 5) + 1, (uint32_t)(w >> 32));
         }
     }
@@ -802,7 +980,7 @@ struct QSections {
     q_t c[MAX_NB + 1][5];
 };
 
-// cascade step in binary128 (same structure as cascade_step)
+// cascade step in binary128 (same structure as section_pass's local loop)
 static q_t qstep(const QSections &S, q_t *z, q_t x)
 {
     int p = 0;
@@ -824,8 +1002,8 @@ static q_t qstep(const QSections &S, q_t *z, q_t x)
 
 struct HostTables {
     int ns;
-    double hrow[FS_S][MAX_NS];
-    double P[5][MAX_NS][MAX_NS];
+    double sec_h[MAX_NB + 1][FS_S][2];      // per section: C_s A_s^i, i < S
+    double sec_P[MAX_NB + 1][5][2][2];      // per section: A_s^(S 2^k)
     double Q[5][MAX_NS][MAX_NS];
     double AT[MAX_NS][MAX_NS];
     double M[MAX_NS][MAX_NS];
@@ -884,17 +1062,46 @@ static int build_tables(const QSections &S, HostTables &T)
             for (int i = 0; i < n; ++i) r[i] = nr[i];
         }
     }
-    for (int t = 0; t < FS_S; ++t)
-        for (int i = 0; i < n; ++i) T.hrow[t][i] = (double)rows[(size_t)t * n + i];
     for (int i = 0; i < n; ++i) T.hlast[i] = (double)rows[(size_t)(FS_T - 1) * n + i];
-    // A^S by repeated multiplication, then squarings
+    // sweep 2's tables, section by section: the section alone as a 1- or 2-state system
+    for (int s = 0; s < S.nsec; ++s) {
+        QSections one;
+        one.nsec = 1;
+        one.first_order_last = S.first_order_last && s == S.nsec - 1;
+        one.ns = one.first_order_last ? 1 : 2;
+        for (int k = 0; k < 5; ++k) one.c[0][k] = S.c[s][k];
+        const int m = one.ns;
+        QMat As;
+        As.n = m;
+        q_t Cs[2];
+        for (int k = 0; k < m; ++k) {
+            q_t z[2] = {k == 0 ? (q_t)1 : (q_t)0, k == 1 ? (q_t)1 : (q_t)0};
+            Cs[k] = qstep(one, z, 0);
+            for (int i = 0; i < m; ++i) As.a[i][k] = z[i];
+        }
+        q_t r[2] = {Cs[0], m > 1 ? Cs[1] : (q_t)0};
+        for (int t = 0; t < FS_S; ++t) {
+            T.sec_h[s][t][0] = (double)r[0];
+            T.sec_h[s][t][1] = m > 1 ? (double)r[1] : 0.0;
+            q_t nr[2] = {0, 0};
+            for (int j = 0; j < m; ++j)
+                for (int i = 0; i < m; ++i) nr[j] += r[i] * As.a[i][j];
+            r[0] = nr[0];
+            r[1] = nr[1];
+        }
+        QMat ps = As;
+        for (int i = 1; i < FS_S; ++i) qmul(ps, As, ps);
+        for (int k = 0; k < 5; ++k) {
+            for (int i = 0; i < 2; ++i)
+                for (int j = 0; j < 2; ++j)
+                    T.sec_P[s][k][i][j] = (i < m && j < m) ? (double)ps.a[i][j] : 0.0;
+            qmul(ps, ps, ps);
+        }
+    }
+    // A^S by repeated multiplication, then squarings up to A^(32 S) = A^T
     QMat pw = A;
     for (int i = 1; i < FS_S; ++i) qmul(pw, A, pw);
-    for (int k = 0; k < 5; ++k) {
-        for (int i = 0; i < n; ++i)
-            for (int j = 0; j < n; ++j) T.P[k][i][j] = (double)pw.a[i][j];
-        qmul(pw, pw, pw);
-    }
+    for (int k = 0; k < 5; ++k) qmul(pw, pw, pw);
     // pw is now A^(32 S) = A^T
     for (int k = 0; k < 5; ++k) {
         for (int i = 0; i < n; ++i)
@@ -1090,15 +1297,17 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
         P.sec[s][3] = sos[s * 6 + 4];
         P.sec[s][4] = sos[s * 6 + 5];
     }
-    for (int t = 0; t < FS_S; ++t)
-        for (int i = 0; i < NS; ++i) P.hrow[t][i] = T.hrow[t][i];
+    for (int s = 0; s < NSEC; ++s) {
+        for (int t = 0; t < FS_S; ++t)
+            for (int i = 0; i < 2; ++i) P.hrow[s][t][i] = T.sec_h[s][t][i];
+        for (int k = 0; k < 5; ++k)
+            for (int i = 0; i < 2; ++i)
+                for (int j = 0; j < 2; ++j) P.P[s][k][i][j] = T.sec_P[s][k][i][j];
+    }
     ScanParams<NS> SP;
     for (int k = 0; k < 5; ++k)
         for (int i = 0; i < NS; ++i)
-            for (int j = 0; j < NS; ++j) {
-                P.P[k][i][j] = T.P[k][i][j];
-                SP.Q[k][i][j] = T.Q[k][i][j];
-            }
+            for (int j = 0; j < NS; ++j) SP.Q[k][i][j] = T.Q[k][i][j];
     for (int i = 0; i < NS; ++i) {
         for (int j = 0; j < NS; ++j) {
             SP.AT[i][j] = T.AT[i][j];
@@ -1128,8 +1337,20 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
         SS_CUDA_CHECK(cudaFuncSetAttribute(filt_summary_kernel<NS>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)tab_bytes));
-        filt_summary_kernel<NS><<<sum_blocks, 32 * SM_WPB, tab_bytes, st>>>(d_x, g, d_tab, F, Bz, yl);
-        SS_LAUNCH_CHECK("filt_summary_kernel");
+        if (NS >= 3 && g.dtype == SS_I16) {
+            constexpr int NSW = NS >= 3 ? NS : 3;               // (not instantiated below 3)
+            const dim3 wide_blocks((unsigned)ss_cdiv(nt_max, sw_wpb(NSW) * SW_TPW), (unsigned)j_count,
+                                   (unsigned)g.n_contacts);
+            SS_CUDA_CHECK(cudaFuncSetAttribute(filt_summary_wide_kernel<NSW>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)sw_smem_bytes(NSW)));
+            filt_summary_wide_kernel<NSW><<<wide_blocks, 32 * sw_wpb(NSW), sw_smem_bytes(NSW), st>>>(
+                reinterpret_cast<const int16_t *>(d_x), g, d_tab, F, Bz, yl);
+            SS_LAUNCH_CHECK("filt_summary_wide_kernel");
+        } else {
+            filt_summary_kernel<NS><<<sum_blocks, 32 * SM_WPB, tab_bytes, st>>>(d_x, g, d_tab, F, Bz, yl);
+            SS_LAUNCH_CHECK("filt_summary_kernel");
+        }
         filt_tilescan_kernel<NS><<<unit_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, SP, F, Bz, yl, Zf, Zb);
         SS_LAUNCH_CHECK("filt_tilescan_kernel");
     }

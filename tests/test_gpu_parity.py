@@ -634,3 +634,26 @@ def test_random_filter_geometry(env, oracle, seed):
     if n > padlen + 1:
         with pytest.raises(ValueError):
             env['ops'].filtfilt_sos(view, sos, padlen, padlen)
+
+
+@pytest.mark.parametrize("name", ['lp3', 'bp4', 'bp8', 'butter12'])
+def test_filtfilt_high_order_large_chunks(env, oracle, name):
+    """Orders >= 3 on int16 take the tile-per-lane summary sweep (filt_summary_wide_kernel) and
+    the section-by-section second sweep: chunks long enough for several warps and more than
+    one CTA per unit (> 1024 tiles), a short last chunk, even and odd sample offsets of the
+    view (tile starts on either side of a 32-bit word), against the oracle's filtfilt."""
+    from spikesort_b200._design import tf2sos_exact
+    b, a = DESIGNS[name]()
+    sos, padlen = tf2sos_exact(b, a)
+    rng = np.random.default_rng(21)
+    cs, n = 600000, 600000 + 100001
+    parent = np.round(rng.standard_normal((2, n + 3)) * 400 + 50).astype(np.int16)
+    dev_parent = _dev(env, parent)
+    for start in (0, 1):
+        x = parent[:, start:start + n]
+        got = env['ops'].filtfilt_sos(dev_parent[:, start:start + n], sos, padlen, cs).cpu().numpy()
+        ref = np.stack([np.concatenate([oracle.filtfilt(b, a, x[c, lo:lo + cs])
+                                        for lo in range(0, n, cs)]) for c in range(2)])
+        err = rel_err(got, ref)
+        print("%s start %d rel err %.3g" % (name, start, err))
+        assert err < TIGHT[name], (name, start)
