@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspikesort_b200.so")
+# SPIKESORT_B200_LIB: another build of the same library (kernel A/B runs)
+LIB_PATH = os.environ.get("SPIKESORT_B200_LIB") or os.path.join(_HERE, "libspikesort_b200.so")
 
 SS_I16, SS_F32, SS_F64 = 0, 1, 2
 SS_ERR_PADLEN = -3

@@ -43,6 +43,9 @@ namespace {
 constexpr int FS_S = 16;            // samples per lane
 constexpr int FS_T = 32 * FS_S;     // samples per tile (one warp)
 constexpr int FS_WPB = 4;           // warps per block
+#ifndef APPLY_MIN_CTAS
+#define APPLY_MIN_CTAS 5
+#endif
 constexpr int FS_PADT = FS_T + FS_T / FS_S;   // padded smem tile (bank-conflict free)
 constexpr int MAX_NB = 6;           // up to 6 biquads (+1 first-order) -> 13 states
 constexpr int MAX_NS = 2 * MAX_NB + 1;
@@ -551,22 +554,31 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *
 // the accumulators of more do not fit) the kernel is bound by the shared-memory pipe at a
 // quarter of the FP64 rate (ncu launch list, order-8 band-pass: 2.8 ms).  Here the mapping is
 // transposed: a lane owns SW_RL whole TILES, so the weight of (q, sample) is the same address
-// for all 32 lanes - one broadcast read feeds 2*SW_RL FMAs of every lane - and the per-tile
-// sums need no cross-lane reduction at all.  The price is that a lane's samples are 1 KB
-// apart: the int16 tiles are staged slice by slice (SW_SL samples of each of the warp's
-// 64 tiles) through shared memory with 4-byte cp.async copies, double-buffered per warp, as
-// raw sample PAIRS; tiles that start on an odd sample (padlen odd, e.g. 27 for order 8) are
-// staged from the aligned word below and realigned with a funnel shift.
-constexpr int SW_RL = 2;                       // tiles per lane
-constexpr int SW_TPW = 32 * SW_RL;             // tiles per warp
+// for all 32 lanes - one broadcast read (2 wavefronts for 16 B, ncu) feeds 2*SW_RL FMAs of
+// every lane - and the per-tile sums need no cross-lane reduction at all.  The price is that
+// a lane's samples are 1 KB apart: the int16 tiles are staged slice by slice (SW_SL samples
+// of each of the warp's tiles) through shared memory with 4-byte cp.async copies,
+// double-buffered per warp, as raw sample PAIRS; tiles that start on an odd sample (padlen
+// odd, e.g. 27 for order 8) are staged from the aligned word below and realigned with a
+// funnel shift.  The grid is persistent (one CTA per SM, the 70-110 KB weight table is loaded
+// once) and warps draw (unit, tile group) items from a global counter, the groups that hold
+// a unit's padded / odd-extended ends (staged element by element) first: with a fixed
+// assignment the one slow warp of every CTA kept the other fifteen waiting (ncu: 15 % of the
+// warp slots active instead of 25 %).
+#ifndef SW_RL_LOW
+#define SW_RL_LOW 4
+#define SW_WPB_LOW 8
+#endif
+__host__ __device__ constexpr int sw_rl(int ns) { return ns <= 8 ? SW_RL_LOW : 2; }   // tiles per lane
+__host__ __device__ constexpr int sw_tpw(int ns) { return 32 * sw_rl(ns); }      // tiles per item
+__host__ __device__ constexpr int sw_wpb(int ns) { return ns <= 8 ? SW_WPB_LOW : 8; }   // warps per CTA
 constexpr int SW_SL = 32;                      // samples per slice
 constexpr int SW_SLW = SW_SL / 2;              // 32-bit words per slice (one more when odd)
 constexpr int SW_STRIDE = SW_SLW + 1;          // row stride in words: odd -> conflict-free
-__host__ __device__ constexpr int sw_wpb(int ns) { return ns <= 8 ? 16 : 12; }   // warps per CTA
 __host__ __device__ constexpr size_t sw_smem_bytes(int ns)
 {
     return (size_t)(2 * ns + 1) * FS_T * sizeof(double) +
-           (size_t)sw_wpb(ns) * 2 * SW_TPW * SW_STRIDE * sizeof(uint32_t);
+           (size_t)sw_wpb(ns) * 2 * sw_tpw(ns) * SW_STRIDE * sizeof(uint32_t);
 }
 
 __device__ __forceinline__ void cp_async4(unsigned smem_dst, const void *gmem_src)
@@ -580,141 +592,179 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <int NS>
 __global__ void __launch_bounds__(32 * sw_wpb(NS), 1)
 filt_summary_wide_kernel(const int16_t *__restrict__ x, const FiltGeom g, const double *__restrict__ tab,
-                         double *__restrict__ F, double *__restrict__ Bz, double *__restrict__ ylast)
+                         double *__restrict__ F, double *__restrict__ Bz, double *__restrict__ ylast,
+                         unsigned long long *__restrict__ next_item)
 {
     constexpr int NQ = 2 * NS + 1;
-    constexpr int WPB = sw_wpb(NS);
+    constexpr int RL = sw_rl(NS), TPW = sw_tpw(NS);
     extern __shared__ __align__(16) double tab_s[];         // [NQ][FS_T], then the staging buffers
-    for (int i = threadIdx.x; i < NQ * FS_T; i += 32 * WPB) tab_s[i] = tab[i];
+    for (int i = threadIdx.x; i < NQ * FS_T; i += 32 * sw_wpb(NS)) tab_s[i] = tab[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t *stage = reinterpret_cast<uint32_t *>(tab_s + NQ * FS_T) + warp * (2 * SW_TPW * SW_STRIDE);
-    TileInfo ti = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
-    const int64_t t_first = ((int64_t)blockIdx.x * WPB + warp) * SW_TPW;
-    if (t_first >= ti.nt) return;
-    const int64_t row0 = ti.c * g.ld_in;
-    // sample offset from x of the first sample of tile t_first; tiles follow every FS_T samples
-    const int64_t a0 = row0 + ti.cs0 + t_first * FS_T - ti.pad - g.edge;
-    const int odd = (int)((((uintptr_t)x >> 1) + (uintptr_t)a0) & 1);      // tile starts between two words
-    const int sh = odd * 16;
-    // tiles read straight from the recording: whole tile (and the extra word) inside the chunk
-    uint64_t fastmask = 0, validmask = 0;
-#pragma unroll
-    for (int rl = 0; rl < SW_RL; ++rl) {
-        const int64_t t = t_first + lane + 32 * rl;
-        const int64_t r0 = t * FS_T - ti.pad - g.edge;
-        const bool valid = t < ti.nt;
-        const bool fast = valid && r0 - odd >= 0 && r0 + FS_T + odd <= ti.L;
-        fastmask |= (uint64_t)__ballot_sync(SS_FULL, fast) << (32 * rl);
-        validmask |= (uint64_t)__ballot_sync(SS_FULL, valid) << (32 * rl);
-    }
-    const uint64_t slowmask = validmask & ~fastmask;
-    const int16_t *src0 = x + (a0 - odd) + (lane >> 4) * FS_T + 2 * (lane & 15);
-    const int dst0 = (lane >> 4) * SW_STRIDE + (lane & 15);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(tab_s + NQ * FS_T) + warp * (2 * TPW * SW_STRIDE);
+    // items: (unit, group of TPW tiles); per unit the first and the last group come first
+    const int64_t n_units = g.n_contacts * g.j_count;
+    const bool has_full = g.j_begin < g.n_full;
+    const int64_t nt_max = has_full && g.nt_full >= g.nt_last ? g.nt_full : g.nt_last;
+    const int64_t G = (nt_max + TPW - 1) / TPW;             // groups per unit (upper bound)
+    const int64_t n_items = n_units * G;
+    const int64_t n_edge = G >= 3 ? 2 * n_units : 0;
 
-    const bool all_fast = fastmask == ~0ull;
-    auto issue_slice = [&](int j, uint32_t *buf) {
-        const int16_t *src = src0 + j * SW_SL;
-        const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + dst0);
-        if (all_fast) {
-#pragma unroll 8
-            for (int k = 0; k < SW_TPW / 2; ++k)
-                cp_async4(dst + 2 * k * SW_STRIDE * 4, src + (int64_t)k * 2 * FS_T);
+#pragma unroll 1
+    for (;;) {
+        unsigned long long it0 = 0;
+        if (lane == 0) it0 = atomicAdd(next_item, 1ull);
+        const int64_t item = (int64_t)__shfl_sync(SS_FULL, it0, 0);
+        if (item >= n_items) break;
+        int64_t u, gi;
+        bool last_group = false;
+        if (item < n_edge) {
+            u = item >> 1;
+            last_group = item & 1;
+            gi = 0;
+        } else if (G >= 3) {
+            u = (item - n_edge) / (G - 2);
+            gi = 1 + (item - n_edge) - u * (G - 2);
         } else {
-#pragma unroll 1
-            for (int k = 0; k < SW_TPW / 2; ++k)
-                if ((fastmask >> (2 * k + (lane >> 4))) & 1)
-                    cp_async4(dst + 2 * k * SW_STRIDE * 4, src + (int64_t)k * 2 * FS_T);
+            u = item / G;
+            gi = item - u * G;
         }
-        if (odd) {
+        const int64_t c = u / g.j_count;
+        const TileInfo ti = decode_unit(g, c, g.j_begin + (u - c * g.j_count));
+        const int64_t G_u = (ti.nt + TPW - 1) / TPW;         // groups of this unit
+        if (last_group) {
+            gi = G_u - 1;
+            if (gi == 0) continue;                           // single group: done as the first
+        } else if (item >= n_edge && G >= 3 && gi >= G_u - 1) {
+            continue;                                        // beyond (or the last group of) a short unit
+        }
+        const int64_t t_first = gi * TPW;
+        if (t_first >= ti.nt) continue;
+        const int64_t row0 = ti.c * g.ld_in;
+        // sample offset from x of the first sample of tile t_first; tiles follow every FS_T samples
+        const int64_t a0 = row0 + ti.cs0 + t_first * FS_T - ti.pad - g.edge;
+        const int odd = (int)((((uintptr_t)x >> 1) + (uintptr_t)a0) & 1);  // tile starts between two words
+        const int sh = odd * 16;
+        // tiles read straight from the recording: whole tile (and the extra word) inside the chunk
+        unsigned fastm[RL], slowm[RL];
+        bool all_fast = true;
 #pragma unroll
-            for (int rl = 0; rl < SW_RL; ++rl) {
-                const int tl = lane + 32 * rl;
-                if ((fastmask >> tl) & 1)
-                    cp_async4((unsigned)__cvta_generic_to_shared(buf + tl * SW_STRIDE + SW_SLW),
-                              x + (a0 - odd) + (int64_t)tl * FS_T + j * SW_SL + SW_SL);
-            }
+        for (int rl = 0; rl < RL; ++rl) {
+            const int64_t t = t_first + lane + 32 * rl;
+            const int64_t r0 = t * FS_T - ti.pad - g.edge;
+            const bool valid = t < ti.nt;
+            const bool fast = valid && r0 - odd >= 0 && r0 + FS_T + odd <= ti.L;
+            fastm[rl] = __ballot_sync(SS_FULL, fast);
+            slowm[rl] = __ballot_sync(SS_FULL, valid && !fast);
+            all_fast = all_fast && fastm[rl] == SS_FULL;
         }
-        if (slowmask) {
-            // tiles touching the padding / odd extension / end of the chunk: element by element
-            const int64_t ext_len = ti.L + 2 * (int64_t)g.edge;
+        const int16_t *src0 = x + (a0 - odd) + (lane >> 4) * FS_T + 2 * (lane & 15);
+        const int dst0 = (lane >> 4) * SW_STRIDE + (lane & 15);
+
+        auto issue_slice = [&](int j, uint32_t *buf) {
+            const int16_t *src = src0 + j * SW_SL;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(buf + dst0);
+            if (all_fast) {
+#pragma unroll 8
+                for (int k = 0; k < TPW / 2; ++k)
+                    cp_async4(dst + 2 * k * SW_STRIDE * 4, src + (int64_t)k * 2 * FS_T);
+            } else {
+#pragma unroll
+                for (int rl = 0; rl < RL; ++rl) {
 #pragma unroll 1
-            for (int tl = 0; tl < SW_TPW; ++tl) {
-                if (!((slowmask >> tl) & 1)) continue;
-                if (lane <= SW_SLW) {
-                    const int64_t e = (t_first + tl) * FS_T - ti.pad + j * SW_SL + 2 * lane - odd;
-                    const int lo = e < ext_len ? (int)ext_value(x, SS_I16, row0, ti, g.edge, e) : 0;
-                    const int hi = e + 1 < ext_len ? (int)ext_value(x, SS_I16, row0, ti, g.edge, e + 1) : 0;
-                    buf[tl * SW_STRIDE + lane] = ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16);
+                    for (int k = 0; k < 16; ++k)
+                        if ((fastm[rl] >> (2 * k + (lane >> 4))) & 1)
+                            cp_async4(dst + (32 * rl + 2 * k) * SW_STRIDE * 4,
+                                      src + (int64_t)(32 * rl + 2 * k) * FS_T);
                 }
             }
-        }
-        cp_async_commit();
-    };
-
-    double acc[SW_RL][NQ];
 #pragma unroll
-    for (int rl = 0; rl < SW_RL; ++rl)
-#pragma unroll
-        for (int q = 0; q < NQ; ++q) acc[rl][q] = 0.0;
+            for (int rl = 0; rl < RL; ++rl) {
+                const int tl = lane + 32 * rl;
+                if (odd && ((fastm[rl] >> lane) & 1))
+                    cp_async4((unsigned)__cvta_generic_to_shared(buf + tl * SW_STRIDE + SW_SLW),
+                              x + (a0 - odd) + (int64_t)tl * FS_T + j * SW_SL + SW_SL);
+                // tiles touching the padding / odd extension / end of the chunk: element by element
+                unsigned m = slowm[rl];
+                const int64_t ext_len = ti.L + 2 * (int64_t)g.edge;
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (lane <= SW_SLW) {
+                        const int64_t e = (t_first + 32 * rl + b) * FS_T - ti.pad + j * SW_SL + 2 * lane - odd;
+                        const int lo = e < ext_len ? (int)ext_value(x, SS_I16, row0, ti, g.edge, e) : 0;
+                        const int hi = e + 1 < ext_len ? (int)ext_value(x, SS_I16, row0, ti, g.edge, e + 1) : 0;
+                        buf[(32 * rl + b) * SW_STRIDE + lane] = ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16);
+                    }
+                }
+            }
+            cp_async_commit();
+        };
 
-    constexpr int NSLICE = FS_T / SW_SL;
-    issue_slice(0, stage);
+        double acc[RL][NQ];
+#pragma unroll
+        for (int rl = 0; rl < RL; ++rl)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) acc[rl][q] = 0.0;
+
+        constexpr int NSLICE = FS_T / SW_SL;
+        issue_slice(0, stage);
 #pragma unroll 1
-    for (int j = 0; j < NSLICE; ++j) {
-        uint32_t *buf = stage + (j & 1) * (SW_TPW * SW_STRIDE);
-        if (j + 1 < NSLICE) {
-            issue_slice(j + 1, stage + ((j + 1) & 1) * (SW_TPW * SW_STRIDE));
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
+        for (int j = 0; j < NSLICE; ++j) {
+            uint32_t *buf = stage + (j & 1) * (TPW * SW_STRIDE);
+            if (j + 1 < NSLICE) {
+                issue_slice(j + 1, stage + ((j + 1) & 1) * (TPW * SW_STRIDE));
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const double2 *wt = reinterpret_cast<const double2 *>(tab_s) + j * SW_SLW;
+            unsigned cur[RL];
+#pragma unroll
+            for (int rl = 0; rl < RL; ++rl) cur[rl] = buf[(lane + 32 * rl) * SW_STRIDE];
+#pragma unroll 2
+            for (int w = 0; w < SW_SLW; ++w) {
+                double x0[RL], x1[RL];
+#pragma unroll
+                for (int rl = 0; rl < RL; ++rl) {
+                    // row stride SW_STRIDE = SW_SLW + 1: word w + 1 always exists (unused when even)
+                    const unsigned nxt = buf[(lane + 32 * rl) * SW_STRIDE + w + 1];
+                    const unsigned pr = __funnelshift_r(cur[rl], nxt, sh);
+                    cur[rl] = nxt;
+                    // two int16 -> float64, exact: offset binary in the low mantissa word of 2^52
+                    const unsigned ob = pr ^ 0x80008000u;
+                    x0[rl] = __hiloint2double(0x43300000, (int)(ob & 0xffffu)) - 4503599627403264.0;
+                    x1[rl] = __hiloint2double(0x43300000, (int)(ob >> 16)) - 4503599627403264.0;
+                }
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const double2 cw = wt[q * (FS_T / 2) + w];     // same address in every lane
+#pragma unroll
+                    for (int rl = 0; rl < RL; ++rl)
+                        acc[rl][q] = fma(cw.y, x1[rl], fma(cw.x, x0[rl], acc[rl][q]));
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
-        const double2 *wt = reinterpret_cast<const double2 *>(tab_s) + j * SW_SLW;
-        unsigned cur[SW_RL];
 #pragma unroll
-        for (int rl = 0; rl < SW_RL; ++rl) cur[rl] = buf[(lane + 32 * rl) * SW_STRIDE];
-#pragma unroll 4
-        for (int w = 0; w < SW_SLW; ++w) {
-            double x0[SW_RL], x1[SW_RL];
+        for (int rl = 0; rl < RL; ++rl) {
+            const int64_t t = t_first + lane + 32 * rl;
+            if (t < ti.nt) {
+                const int64_t tile = ti.g0 + t;
 #pragma unroll
-            for (int rl = 0; rl < SW_RL; ++rl) {
-                // row stride SW_STRIDE = SW_SLW + 1: word w + 1 always exists (unused when even)
-                const unsigned nxt = buf[(lane + 32 * rl) * SW_STRIDE + w + 1];
-                const unsigned pr = __funnelshift_r(cur[rl], nxt, sh);
-                cur[rl] = nxt;
-                // two int16 -> float64, exact: offset binary in the low mantissa word of 2^52
-                const unsigned ob = pr ^ 0x80008000u;
-                x0[rl] = __hiloint2double(0x43300000, (int)(ob & 0xffffu)) - 4503599627403264.0;
-                x1[rl] = __hiloint2double(0x43300000, (int)(ob >> 16)) - 4503599627403264.0;
+                for (int q = 0; q < NS; ++q) {
+                    F[tile * NS + q] = acc[rl][q];
+                    Bz[tile * NS + q] = acc[rl][NS + q];
+                }
+                ylast[tile] = acc[rl][2 * NS];
             }
-#pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const double2 c = wt[q * (FS_T / 2) + w];          // same address in every lane
-#pragma unroll
-                for (int rl = 0; rl < SW_RL; ++rl)
-                    acc[rl][q] = fma(c.y, x1[rl], fma(c.x, x0[rl], acc[rl][q]));
-            }
-        }
-        __syncwarp();
-    }
-#pragma unroll
-    for (int rl = 0; rl < SW_RL; ++rl) {
-        const int64_t t = t_first + lane + 32 * rl;
-        if (t < ti.nt) {
-            const int64_t tile = ti.g0 + t;
-#pragma unroll
-            for (int q = 0; q < NS; ++q) {
-                F[tile * NS + q] = acc[rl][q];
-                Bz[tile * NS + q] = acc[rl][NS + q];
-            }
-            ylast[tile] = acc[rl][2 * NS];
         }
     }
 }
 
 template <int NB, bool FO, bool MARK>
-__global__ void __launch_bounds__(32 * FS_WPB)
+__global__ void __launch_bounds__(32 * FS_WPB, (NB + (FO ? 1 : 0) >= 2) ? APPLY_MIN_CTAS : 0)
 filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
                   const __grid_constant__ FiltParams<NB, FO> P,
                   const double *__restrict__ Zf, const double *__restrict__ Zb,
@@ -1339,13 +1389,17 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
                                            (int)tab_bytes));
         if (NS >= 3 && g.dtype == SS_I16) {
             constexpr int NSW = NS >= 3 ? NS : 3;               // (not instantiated below 3)
-            const dim3 wide_blocks((unsigned)ss_cdiv(nt_max, sw_wpb(NSW) * SW_TPW), (unsigned)j_count,
-                                   (unsigned)g.n_contacts);
+            // persistent grid; the item counter lives in the workspace's spare table region
+            unsigned long long *d_next = reinterpret_cast<unsigned long long *>(yl + g.total_tiles);
+            SS_CUDA_CHECK(cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st));
+            const int64_t n_items = g.n_contacts * j_count * ss_cdiv(nt_max, sw_tpw(NSW));
+            const unsigned wide_blocks = (unsigned)(ss_cdiv(n_items, sw_wpb(NSW)) < SS_NUM_SMS
+                                                        ? ss_cdiv(n_items, sw_wpb(NSW)) : SS_NUM_SMS);
             SS_CUDA_CHECK(cudaFuncSetAttribute(filt_summary_wide_kernel<NSW>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)sw_smem_bytes(NSW)));
             filt_summary_wide_kernel<NSW><<<wide_blocks, 32 * sw_wpb(NSW), sw_smem_bytes(NSW), st>>>(
-                reinterpret_cast<const int16_t *>(d_x), g, d_tab, F, Bz, yl);
+                reinterpret_cast<const int16_t *>(d_x), g, d_tab, F, Bz, yl, d_next);
             SS_LAUNCH_CHECK("filt_summary_wide_kernel");
         } else {
             filt_summary_kernel<NS><<<sum_blocks, 32 * SM_WPB, tab_bytes, st>>>(d_x, g, d_tab, F, Bz, yl);

@@ -10,8 +10,8 @@ import json, sys
 try:
     d = json.loads(open("gpurun_out/bench_%s.log" % sys.argv[1]).read().strip().splitlines()[-1])
     print("%s: value %.4g  ms/step %.3f  filter ms %.3f  filter frac %.3f  chain frac %.3f  pca ms %.3f" % (
-        sys.argv[1], d["value"], d["ms_per_step"], d["roofline"]["ms_per_launch"], d["roofline"]["frac"],
-        d["chain_roofline"]["frac"], d["chain_roofline"]["pca_ms"]), d["clocks"]["reasons"])
+        sys.argv[1], d["value"], d["ms_per_step"], d.get("ms_filter_stage", 0), d.get("filter_stage_frac_of_hbm_peak", 0),
+        0, d.get("ms_pca", 0)), d["clocks"]["reasons"])
 except Exception as e:
     print("bench parse failed", e)
 PY
