@@ -51,6 +51,8 @@ SP_WIN = [-0.2, 0.8]
 CHUNK = 1000000
 SEED = 2
 RATE_HZ = 10.0
+SM_COUNT = 148                      # B200
+WORKLOAD = "c2"
 FILTER_ARGS = (800., 100.)          # fltLinearIIR(800, 100): order-1 Butterworth high-pass
 CONFIG = {
     "workload": "configs[1]: 32-channel 30 kHz 10-minute synthetic int16 recording "
@@ -396,7 +398,7 @@ def run_gpu(args):
                 # the ncu --set full capture of this command (profiles/README.md, state e):
                 # sweep 1 1.18 GB + sweep 2 5.42 + head 0.26 GB + head marks / threshold / count /
                 # emit 0.47 GB
-                "traffic": 7.33e9,
+                "traffic": 7.33e9 if WORKLOAD == "c2" else None,   # captured for the headline workload only
                 "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_g_chain_kernels_final.txt "
                                 "+ r01_ncu_f_chain_kernels.txt for the bookkeeping kernels)",
                 "kernel": "ss_filtfilt_detect_sos + ss_detect_emit = filter (summary, tilescan, "
@@ -404,6 +406,24 @@ def run_gpu(args):
                           "the filter, threshold and detect stages of the chain",
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": filt_ms,
                 "share_of_step": filt_ms / ms_step, "peak_source": peak_src}
+    # FP64 side of the same stage: FMAs per sample of the two sweeps - per
+    # second-order section and direction 5 (recurrence) + 2 (correction) + 20/16 (lane scan),
+    # first-order 3 + 1 + 5/16, plus the 2*NS+1 dot products of sweep 1.  Order 1 is far from
+    # this ceiling (HBM-bound); the order-8 band-pass (--workload c2-bp8) is bound by it.
+    sos_b, _ = flt.sections(FS)
+    n_fo = int(sum(1 for r in sos_b if r[2] == 0.0 and r[5] == 0.0))
+    n_so = len(sos_b) - n_fo
+    fma_per_sample = 2 * (n_so * 8.25 + n_fo * 4.3125) + (2 * (2 * n_so + n_fo) + 1)
+    sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+    fp64_peak = SM_COUNT * 64 * sm_mhz * 1e6 / 1e12                 # 64 FP64 FMA lanes per SM and clock
+    fp64_ach = N_CONTACTS * N_SAMPLES * fma_per_sample / (filt_ms / 1000.0) / 1e12
+    roofline["fp64"] = {"fma_per_sample": fma_per_sample, "achieved": fp64_ach, "peak": fp64_peak,
+                        "unit": "TFMA/s", "frac": fp64_ach / fp64_peak,
+                        "peak_source": "148 SMs x 64 FP64 FMA/clk x the SM clock sampled during the run"}
+    if fp64_ach / fp64_peak > achieved / peak:
+        roofline["bound"] = "fp64"
+        roofline["note"] = ("this filter order is bound by the FP64 pipe, not by HBM: frac/achieved/peak "
+                            "above are the HBM view of the same launch, roofline.fp64 the binding one")
     # whole-chain roofline: 18 B + spikes
     n_win = int(res.waves.shape[0])
     chain_bytes = N_CONTACTS * N_SAMPLES * 18 + n_det * 8 + n_det * (n_win * 8 + 16) + \
@@ -492,7 +512,8 @@ def select_workload(name):
     """--workload c3: one GPU's time shard of configs[2] (Neuropixels scale, 384 contacts x
     1 h at 30 kHz sharded over 8 GPUs = 384 x 13,500,000 per GPU).  Device numbers only
     (a 10.4 GB pinned recording per rank is not staged): not the driver's bench line."""
-    global N_CONTACTS, N_SAMPLES, SEED, CONFIG, FILTER_ARGS
+    global N_CONTACTS, N_SAMPLES, SEED, CONFIG, FILTER_ARGS, WORKLOAD
+    WORKLOAD = name
     if name == "c2":
         return
     if name == "c2-bp8":
