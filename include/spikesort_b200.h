@@ -224,6 +224,11 @@ int ss_extract(const void *d_x, int dtype, int64_t n_samples, int64_t ld, double
  * ss_pca_eig     : covariance (ddof=1) from gram/sum/count, symmetric Jacobi
  *                  eigensolve, eigenvalues |.| sorted descending, eigenvectors
  *                  in columns (features.py:225-229).  d_counts[g] = spikes per group.
+ * ss_pca_eig_top : the same covariance, but only the ncomps LEADING eigenpairs (all that
+ *                  fetPCA's scores need, features.py:230-231,335-336): Householder
+ *                  tridiagonalisation, Sturm multisection, inverse iteration, one warp per
+ *                  group.  Columns >= ncomps of d_evecs / entries >= ncomps of d_evals are
+ *                  zero.  PCA()'s full (evals, evecs) still come from ss_pca_eig.
  * ss_pca_project : d_scores[s, g*ncomps + j] = (v_j . x_s) / sqrt(eval_j) on the
  *                  UN-centred data (features.py:230-231); (n_spk, n_groups*ncomps)
  *                  float64 when d_offsets == NULL, else (n_spk, ncomps).
@@ -236,6 +241,9 @@ int ss_pca_gram(const float *d_waves, int n_win, int64_t n_spk, int n_c,
 int ss_pca_eig(const double *d_gram, const double *d_sum,
                const int64_t *d_counts, int n_win, int64_t n_groups,
                double *d_evals, double *d_evecs, void *stream);
+int ss_pca_eig_top(const double *d_gram, const double *d_sum,
+                   const int64_t *d_counts, int n_win, int64_t n_groups, int ncomps,
+                   double *d_evals, double *d_evecs, void *stream);
 int ss_pca_project(const float *d_waves, int n_win, int64_t n_spk, int n_c,
                    const int64_t *d_offsets, int64_t n_groups,
                    const double *d_evals, const double *d_evecs, int ncomps,

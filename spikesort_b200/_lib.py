@@ -56,6 +56,7 @@ SIGNATURES = {
     "ss_pca_workspace_bytes": (_sz, [_int, _i64]),
     "ss_pca_gram": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ss_pca_eig": (_int, [_vp, _vp, _vp, _int, _i64, _vp, _vp, _vp]),
+    "ss_pca_eig_top": (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp]),
     "ss_pca_project": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp, _int, _vp, _vp]),
     "ss_wave_minmax": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp]),
     "ss_normalize_workspace_bytes": (_sz, [_int]),

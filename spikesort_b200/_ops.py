@@ -343,15 +343,23 @@ def pca_gram(waves, offsets=None, ref=None):
     return gram, ssum, ref, counts
 
 
-def pca_eig(gram, ssum, counts):
+def pca_eig(gram, ssum, counts, top=None):
+    """Eigenpairs of the per-group covariance.  top=None: all of them (Jacobi), what PCA()
+    returns; top=k: only the k leading pairs (ss_pca_eig_top; the other columns are zero),
+    all that the scores of fetPCA need."""
     lib = _lib.load()
     t = _lib.torch()
     n_groups, n_win, _ = gram.shape
     evals = t.empty((n_groups, n_win), dtype=t.float64, device=gram.device)
     evecs = t.empty((n_groups, n_win, n_win), dtype=t.float64, device=gram.device)
-    rc = lib.ss_pca_eig(_lib.ptr(gram), _lib.ptr(ssum), _lib.ptr(counts), n_win, n_groups,
-                        _lib.ptr(evals), _lib.ptr(evecs), _lib.stream_ptr())
-    _lib.check(rc, "ss_pca_eig")
+    if top is None:
+        rc = lib.ss_pca_eig(_lib.ptr(gram), _lib.ptr(ssum), _lib.ptr(counts), n_win, n_groups,
+                            _lib.ptr(evals), _lib.ptr(evecs), _lib.stream_ptr())
+        _lib.check(rc, "ss_pca_eig")
+    else:
+        rc = lib.ss_pca_eig_top(_lib.ptr(gram), _lib.ptr(ssum), _lib.ptr(counts), n_win, n_groups,
+                                int(top), _lib.ptr(evals), _lib.ptr(evecs), _lib.stream_ptr())
+        _lib.check(rc, "ss_pca_eig_top")
     _launched(1)
     return evals, evecs
 

@@ -283,6 +283,354 @@ pca_eig_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
     }
 }
 
+// ---- top-k eigenpairs only (what fetPCA needs: the scores of the first ncomps components) ----
+// pca_eig_kernel's Jacobi sweeps are latency-bound (about 230 rounds of ~1 us for n = 30).  When
+// only the k leading pairs are wanted the classical dense path is ~8x shorter: Householder
+// tridiagonalisation (n - 2 steps), Sturm-sequence MULTISECTION for the k largest eigenvalues
+// (32/k shifts per pass in the lanes of the warp, division-free determinant recurrence on the
+// scaled matrix), inverse iteration with a pivoted tridiagonal LU (reciprocal pivots, three
+// iterations, Gram-Schmidt inside clusters as LAPACK's dstein does), back-transformation by
+// the stored reflectors.  One WARP per group, everything in shared memory, __syncwarp only.
+// tools/proto_eig_top.py is the NumPy statement of the same operation order.
+constexpr int ET_MAXK = PC_MAX_COMPS;
+
+__device__ __forceinline__ double et_sum(double v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(SS_FULL, v, d);
+    return v;
+}
+__device__ __forceinline__ double et_max(double v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmax(v, __shfl_xor_sync(SS_FULL, v, d));
+    return v;
+}
+__device__ __forceinline__ double et_min(double v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = fmin(v, __shfl_xor_sync(SS_FULL, v, d));
+    return v;
+}
+
+__host__ __device__ inline size_t et_smem_doubles(int n, int k)
+{
+    return (size_t)n * (n | 1) + 6 * (size_t)n + 2 * ET_MAXK + (size_t)k * n * 5 + (size_t)(k * n + 1) / 2 + 2;
+}
+
+__global__ void __launch_bounds__(32)
+pca_eig_top_kernel(const double *__restrict__ gram, const double *__restrict__ sum,
+                   const int64_t *__restrict__ counts, int n, int k, double *__restrict__ evals,
+                   double *__restrict__ evecs)
+{
+    extern __shared__ double sm[];
+    const int ld = n | 1, lane = threadIdx.x;
+    double *A = sm, *d = A + n * ld, *e = d + n, *e2 = e + n, *tau = e2 + n, *vs = tau + n, *ws = vs + n;
+    double *lam = ws + n, *lamu = lam + ET_MAXK, *Z = lamu + ET_MAXK, *LU = Z + k * n;
+    int *piv = reinterpret_cast<int *>(LU + (size_t)k * 4 * n);
+    const int64_t g = blockIdx.x;
+    const double cnt = (double)counts[g];
+    {
+        const double icnt = 1.0 / cnt, idof = 1.0 / (cnt - 1.0);
+        const double *G = gram + g * n * n, *S = sum + g * n;
+#pragma unroll 4
+        for (int idx = lane; idx < n * n; idx += 32) {
+            const int i = idx / n, j = idx - i * n;
+            A[i * ld + j] = (G[idx] - S[i] * S[j] * icnt) * idof;
+        }
+    }
+    __syncwarp();
+
+    // 1. A = Q T Q^T; reflector kk: v = (0.., 1, A[kk+2.., kk]), kept in column kk of A.
+    //    The single warp lives on instruction-level parallelism: columns are taken eight at a
+    //    time through registers (all loads of a batch before its stores: the compiler cannot
+    //    prove that the row, v and w arrays do not alias)
+    for (int kk = 0; kk < n - 2; ++kk) {
+        const double alpha = A[(kk + 1) * ld + kk];
+        double x2 = 0.0;
+        for (int i = kk + 2 + lane; i < n; i += 32) { const double a = A[i * ld + kk]; x2 += a * a; }
+        x2 = et_sum(x2);
+        if (lane == 0) d[kk] = A[kk * ld + kk];
+        if (!(x2 > 0.0)) {                                   // nothing to annihilate (or NaN)
+            if (lane == 0) { tau[kk] = 0.0; e[kk] = alpha; }
+            __syncwarp();
+            continue;
+        }
+        const double h2 = alpha * alpha + x2, rh = rsqrt(h2);
+        const double beta = -copysign(h2 * rh, alpha);
+        const double tk = (alpha - beta) * copysign(rh, alpha), sc = 1.0 / (alpha - beta);
+        for (int i = lane; i < n; i += 32) {
+            double v = 0.0;
+            if (i == kk + 1) v = 1.0;
+            else if (i > kk + 1) { v = A[i * ld + kk] * sc; A[i * ld + kk] = v; }
+            vs[i] = v;
+        }
+        if (lane == 0) { tau[kk] = tk; e[kk] = beta; }
+        __syncwarp();
+        // p = tau A v (trailing block), w = p - (tau/2)(p.v) v
+        double pv = 0.0;
+        for (int i = kk + 1 + lane; i < n; i += 32) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            const double *row = A + i * ld;
+            for (int j = kk + 1; j < n; j += 8) {
+                double r[8], v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool ok = j + u < n;
+                    r[u] = ok ? row[j + u] : 0.0;
+                    v[u] = ok ? vs[j + u] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u & 3] = fma(r[u], v[u], acc[u & 3]);
+            }
+            const double pi = tk * ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+            ws[i] = pi;
+            pv += pi * vs[i];
+        }
+        pv = et_sum(pv);
+        __syncwarp();
+        const double hk = 0.5 * tk * pv;
+        for (int i = kk + 1 + lane; i < n; i += 32) ws[i] -= hk * vs[i];
+        __syncwarp();
+        for (int i = kk + 1 + lane; i < n; i += 32) {
+            double *row = A + i * ld;
+            const double vi = vs[i], wi = ws[i];
+            for (int j = kk + 1; j < n; j += 8) {
+                double r[8], v[8], w[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const bool ok = j + u < n;
+                    r[u] = ok ? row[j + u] : 0.0;
+                    v[u] = ok ? vs[j + u] : 0.0;
+                    w[u] = ok ? ws[j + u] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) r[u] -= vi * w[u] + wi * v[u];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (j + u < n) row[j + u] = r[u];
+            }
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        if (n >= 2) { d[n - 2] = A[(n - 2) * ld + n - 2]; e[n - 2] = A[(n - 1) * ld + n - 2]; }
+        d[n - 1] = A[(n - 1) * ld + n - 1];
+    }
+    __syncwarp();
+
+    // 2. scale T to unit size; Gershgorin interval
+    double mx = 0.0;
+    for (int i = lane; i < n; i += 32) mx = fmax(mx, fmax(fabs(d[i]), i < n - 1 ? fabs(e[i]) : 0.0));
+    mx = et_max(mx);
+    const double scale = mx > 0.0 ? mx : 1.0, iscale = 1.0 / scale;
+    __syncwarp();
+    for (int i = lane; i < n; i += 32) {
+        d[i] *= iscale;
+        const double ei = i < n - 1 ? e[i] * iscale : 0.0;
+        e[i] = ei;
+        e2[i] = ei * ei;
+    }
+    __syncwarp();
+    double glo = 1e300, ghi = -1e300;
+    for (int i = lane; i < n; i += 32) {
+        const double r = (i > 0 ? fabs(e[i - 1]) : 0.0) + (i < n - 1 ? fabs(e[i]) : 0.0);
+        glo = fmin(glo, d[i] - r);
+        ghi = fmax(ghi, d[i] + r);
+    }
+    glo = et_min(glo);
+    ghi = et_max(ghi);
+    {
+        const double tn = fmax(fabs(glo), fabs(ghi)), pad = 2.0 * 2.220446049250313e-16 * tn * n + 2e-300;
+        glo -= pad;
+        ghi += pad;
+    }
+    // 3. multisection: lane group m (L lanes) brackets the m-th largest eigenvalue.  Sturm count
+    //    = sign changes of the leading-minor determinants p_i = (d_i - x) p_{i-1} - e_{i-1}^2
+    //    p_{i-2}: one dependent FMA per row, no division; the pair (p_i, p_{i-1}) is rescaled
+    //    every eight rows (|d - x| <= 4 and the pair cannot shrink below 1e-136 per block)
+    int kp = 1;
+    while (kp < k) kp <<= 1;
+    const int L = 32 / kp;
+    const int m_of = min(lane / L, k - 1), l_of = lane % L, base = (lane / L) * L;
+    const unsigned gmask = L == 32 ? 0xffffffffu : ((1u << L) - 1u);
+    int passes = 2;
+    { double w = 1.0; while (w < 1.5e17) { w *= (double)(L + 1); ++passes; } }
+    {
+        const int jt = n - 1 - m_of;                          // ascending index wanted
+        double lo = glo, hi = ghi;
+        for (int ps = 0; ps < passes; ++ps) {
+            const double x = lo + (hi - lo) * ((double)(l_of + 1) / (double)(L + 1));
+            int c = 0;
+            double p2 = 0.0, p1 = 1.0;
+            for (int i0 = 0; i0 < n; i0 += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = i0 + u;
+                    if (i < n) {
+                        const double t = (i > 0 ? e2[i - 1] : 0.0) * p2;
+                        double p = fma(d[i] - x, p1, -t);
+                        if (p == 0.0) p = -copysign(1e-300, p1);
+                        c += (unsigned)(__double2hiint(p) ^ __double2hiint(p1)) >> 31;
+                        p2 = p1;
+                        p1 = p;
+                    }
+                }
+                if (fabs(p1) < 1e-120 && fabs(p2) < 1e-120) { p1 *= 1e120; p2 *= 1e120; }
+                else if (fabs(p1) > 1e120) { p1 *= 1e-120; p2 *= 1e-120; }
+            }
+            const unsigned bal = (__ballot_sync(SS_FULL, c > jt) >> base) & gmask;
+            const int f = bal ? __ffs(bal) - 1 : L;
+            const double xl = __shfl_sync(SS_FULL, x, base + (f > 0 ? f - 1 : 0));
+            const double xh = __shfl_sync(SS_FULL, x, base + (f < L ? f : 0));
+            if (f > 0) lo = xl;
+            if (f < L) hi = xh;
+        }
+        if (l_of == 0 && lane / L < k) lam[m_of] = 0.5 * (lo + hi);
+    }
+    __syncwarp();
+    // 4. inverse iteration on the scaled T
+    const double tol = 2.220446049250313e-16;                 // eps * |T|, |T| = 1
+    if (lane == 0)
+        for (int m = 0; m < k; ++m) {
+            double lm = lam[m];
+            if (m > 0 && fabs(lam[m] - lam[m - 1]) <= 10.0 * tol) lm = lamu[m - 1] - 10.0 * tol;
+            lamu[m] = lm;
+        }
+    __syncwarp();
+    if (lane < k) {
+        // T - lam I = P L U (partial pivoting); ra = 1 / pivots (tiny ones perturbed to eps as
+        // dlagts job -1 does), b and d2 = super-diagonals of U, c = multipliers
+        double *ra = LU + (size_t)lane * 4 * n, *b = ra + n, *c = b + n, *d2 = c + n;
+        int *pv = piv + (size_t)lane * n;
+        const double lm = lamu[lane];
+        double ak = d[0] - lm;                                // pivot candidate of row q
+        double bq = e[0];                                     // b[q] (possibly modified by row q-1)
+        for (int q = 0; q < n - 1; ++q) {
+            const double cq = e[q], an0 = d[q + 1] - lm, bn0 = e[q + 1];   // bn0 = 0 at q = n-2
+            double piv_v, mult, anext, bnext = bn0, bstore, d2q = 0.0;
+            int swapped;
+            if (fabs(ak) >= fabs(cq)) {
+                swapped = 0;
+                piv_v = ak;
+                if (fabs(piv_v) < tol) piv_v = piv_v < 0.0 ? -tol : tol;
+                const double r = 1.0 / piv_v;
+                mult = ak != 0.0 ? cq * r : 0.0;
+                anext = an0 - mult * bq;
+                bstore = bq;
+                ra[q] = r;
+            } else {
+                swapped = 1;
+                piv_v = cq;                                   // |cq| > |ak| >= 0: not tiny unless ak is
+                if (fabs(piv_v) < tol) piv_v = piv_v < 0.0 ? -tol : tol;
+                const double r = 1.0 / piv_v;
+                mult = ak * r;
+                anext = bq - mult * an0;
+                d2q = bn0;
+                bnext = -mult * bn0;
+                bstore = an0;
+                ra[q] = r;
+            }
+            pv[q] = swapped;
+            c[q] = mult;
+            b[q] = bstore;
+            d2[q] = d2q;
+            ak = anext;
+            bq = bnext;
+        }
+        if (fabs(ak) < tol) ak = ak < 0.0 ? -tol : tol;
+        ra[n - 1] = 1.0 / ak;
+        b[n - 1] = 0.0;
+        d2[n - 1] = 0.0;
+        // start vectors: a fixed hash of (row, eigenvalue index) - different per eigenvalue, so
+        // that a cluster (or a diagonal T) still yields independent vectors (dstein: random)
+        double *z = Z + (size_t)lane * n;
+        for (int i = 0; i < n; ++i) {
+            unsigned h = (unsigned)(i + 1) * 2654435761u ^ (unsigned)(lane + 1) * 2246822519u;
+            h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+            z[i] = (double)(h >> 8) * (1.0 / 16777216.0) + 0.25;
+        }
+    }
+    __syncwarp();
+    for (int it = 0; it < 3; ++it) {
+        if (lane < k) {
+            const double *ra = LU + (size_t)lane * 4 * n, *b = ra + n, *c = b + n, *d2 = c + n;
+            const int *pv = piv + (size_t)lane * n;
+            double *z = Z + (size_t)lane * n;
+            double zq = z[0];                                 // carried in a register
+            for (int q = 0; q < n - 1; ++q) {
+                const double zn = z[q + 1], cq = c[q];
+                if (pv[q] == 0) { z[q] = zq; zq = zn - cq * zq; }
+                else { z[q] = zn; zq = zq - cq * zn; }
+            }
+            z[n - 1] = zq;
+            double big = 0.0, y1 = 0.0, y2 = 0.0;             // z[q+1], z[q+2] of the back substitution
+            for (int q = n - 1; q >= 0; --q) {
+                const double t = (z[q] - b[q] * y1 - d2[q] * y2) * ra[q];
+                z[q] = t;
+                big = fmax(big, fabs(t));
+                y2 = y1;
+                y1 = t;
+            }
+            const double ib = big > 0.0 ? 1.0 / big : 1.0;
+            for (int q = 0; q < n; ++q) z[q] *= ib;
+        }
+        __syncwarp();
+        for (int m = 0; m < k; ++m) {                         // Gram-Schmidt inside clusters, normalise
+            double *zm = Z + (size_t)m * n;
+            for (int j = 0; j < m; ++j) {
+                if (fabs(lam[m] - lam[j]) < 1e-3) {
+                    const double *zj = Z + (size_t)j * n;
+                    double dot = 0.0;
+                    for (int i = lane; i < n; i += 32) dot += zm[i] * zj[i];
+                    dot = et_sum(dot);
+                    for (int i = lane; i < n; i += 32) zm[i] -= dot * zj[i];
+                    __syncwarp();
+                }
+            }
+            double nn = 0.0;
+            for (int i = lane; i < n; i += 32) nn += zm[i] * zm[i];
+            nn = et_sum(nn);
+            const double inn = nn > 0.0 ? rsqrt(nn) : 0.0;
+            for (int i = lane; i < n; i += 32) zm[i] *= inn;
+            __syncwarp();
+        }
+    }
+    // 5. back-transformation u = H_0 H_1 ... H_{n-3} z, all k vectors per reflector together
+    for (int kk = n - 3; kk >= 0; --kk) {
+        const double tk = tau[kk];
+        if (tk == 0.0) continue;
+        double sd[ET_MAXK];
+#pragma unroll
+        for (int m = 0; m < ET_MAXK; ++m) sd[m] = 0.0;
+        for (int i = kk + 1 + lane; i < n; i += 32) {
+            const double v = i == kk + 1 ? 1.0 : A[i * ld + kk];
+#pragma unroll
+            for (int m = 0; m < ET_MAXK; ++m)
+                if (m < k) sd[m] = fma(v, Z[(size_t)m * n + i], sd[m]);
+        }
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1)
+#pragma unroll
+            for (int m = 0; m < ET_MAXK; ++m)
+                if (m < k) sd[m] += __shfl_xor_sync(SS_FULL, sd[m], dd);
+        for (int i = kk + 1 + lane; i < n; i += 32) {
+            const double v = tk * (i == kk + 1 ? 1.0 : A[i * ld + kk]);
+#pragma unroll
+            for (int m = 0; m < ET_MAXK; ++m)
+                if (m < k) Z[(size_t)m * n + i] -= sd[m] * v;
+        }
+        __syncwarp();
+    }
+    // 6. columns 0..k-1 hold the leading pairs (descending); the rest is zero
+    for (int j = lane; j < n; j += 32) evals[g * n + j] = j < k ? fabs(lam[j] * scale) : 0.0;
+#pragma unroll 4
+    for (int idx = lane; idx < n * n; idx += 32) {
+        const int i = idx / n, j = idx - i * n;
+        evecs[g * n * n + idx] = j < k ? Z[(size_t)j * n + i] : 0.0;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 pca_project_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, int n_c,
                    const int64_t *__restrict__ offsets, int64_t n_groups,
@@ -388,6 +736,24 @@ extern "C" int ss_pca_eig(const double *d_gram, const double *d_sum, const int64
     const int eig_threads = PC_THREADS;
     pca_eig_kernel<<<(unsigned)n_groups, eig_threads, smem, st>>>(d_gram, d_sum, d_counts, n_win, d_evals, d_evecs);
     SS_LAUNCH_CHECK("pca_eig_kernel");
+    return SS_OK;
+}
+
+extern "C" int ss_pca_eig_top(const double *d_gram, const double *d_sum, const int64_t *d_counts,
+                              int n_win, int64_t n_groups, int ncomps, double *d_evals,
+                              double *d_evecs, void *stream)
+{
+    SS_REQUIRE(d_gram && d_sum && d_counts && d_evals && d_evecs, SS_ERR_ARG, "pca_eig_top: null pointer");
+    SS_REQUIRE(n_win >= 1 && n_win <= PC_MAX_WIN, SS_ERR_UNSUPPORTED, "pca_eig_top: n_win %d outside [1, %d]", n_win, PC_MAX_WIN);
+    SS_REQUIRE(ncomps >= 1 && ncomps <= ET_MAXK && ncomps <= n_win, SS_ERR_UNSUPPORTED,
+               "pca_eig_top: ncomps %d outside [1, min(%d, n_win)]", ncomps, ET_MAXK);
+    SS_REQUIRE(n_groups >= 1, SS_ERR_ARG, "pca_eig_top: bad shape");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t smem = et_smem_doubles(n_win, ncomps) * sizeof(double);
+    SS_CUDA_CHECK(cudaFuncSetAttribute(pca_eig_top_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(et_smem_doubles(PC_MAX_WIN, ET_MAXK) * sizeof(double))));
+    pca_eig_top_kernel<<<(unsigned)n_groups, 32, smem, st>>>(d_gram, d_sum, d_counts, n_win, ncomps, d_evals, d_evecs);
+    SS_LAUNCH_CHECK("pca_eig_top_kernel");
     return SS_OK;
 }
 

@@ -412,7 +412,8 @@ class ShardedChain(object):
     # 7. replicated eigensolve + local projection
     def project(self, gram, ssum, counts):
         r = self.res
-        r.evals, r.evecs = _ops.pca_eig(gram.contiguous(), ssum.contiguous(), counts.contiguous())
+        r.evals, r.evecs = _ops.pca_eig(gram.contiguous(), ssum.contiguous(), counts.contiguous(),
+                                        top=self.ncomps)
         r.scores = _ops.pca_project(r.waves, r.evals, r.evecs, self.ncomps, offsets=r.offsets)
         return r
 

@@ -41,9 +41,9 @@ def _waves_on_device(spikes):
     return w.to(_lib.device()).to(t.float32).contiguous()
 
 
-def _pca_device(w, ncomps):
+def _pca_device(w, ncomps, leading_only=False):
     gram, ssum, _, counts = _ops.pca_gram(w)
-    evals, evecs = _ops.pca_eig(gram, ssum, counts)
+    evals, evecs = _ops.pca_eig(gram, ssum, counts, top=ncomps if leading_only else None)
     score = _ops.pca_project(w, evals, evecs, ncomps)
     return evals, evecs, score
 
@@ -76,7 +76,7 @@ def fetPCA(spikes_data, ncomps=2, contacts='all'):
     spikes = _get_data(spikes_data, contacts)
     w = _waves_on_device(spikes)
     n_channels = w.shape[2]
-    _, _, score = _pca_device(w, ncomps)
+    _, _, score = _pca_device(w, ncomps, leading_only=True)
     names = ["Ch%d:PC%d" % (i, j) for i in range(n_channels) for j in range(ncomps)]
     return {'data': score.cpu().numpy(), "names": names}
 

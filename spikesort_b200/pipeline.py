@@ -34,8 +34,8 @@ class ChainResult(object):
         self.waves = None           # float32 (n_win, n_spk, 1)
         self.valid = None           # uint8 (n_spk,)
         self.n_invalid = None
-        self.evals = None           # float64 (n_contacts, n_win)
-        self.evecs = None           # float64 (n_contacts, n_win, n_win)
+        self.evals = None           # float64 (n_contacts, n_win): the ncomps leading eigenvalues, then zeros
+        self.evecs = None           # float64 (n_contacts, n_win, n_win): leading ncomps columns, rest zero
         self.scores = None          # float64 (n_spk, ncomps)
         self.time = None            # host float64 (n_win,)
 
@@ -149,7 +149,7 @@ def _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
     res.time = _ops.window_params(sp_win, FS)[2]
     if pca and (cap is not None or spt.numel() > 0):
         gram, ssum, _, counts = _ops.pca_gram(waves, offsets=offsets)
-        res.evals, res.evecs = _ops.pca_eig(gram, ssum, counts)
+        res.evals, res.evecs = _ops.pca_eig(gram, ssum, counts, top=ncomps)   # leading pairs only
         res.scores = _ops.pca_project(waves, res.evals, res.evecs, ncomps, offsets=offsets)
     if cap is None:
         return res, int(res.spt_detected.numel()), int(res.spt.numel())

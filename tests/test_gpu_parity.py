@@ -657,3 +657,75 @@ def test_filtfilt_high_order_large_chunks(env, oracle, name):
         err = rel_err(got, ref)
         print("%s start %d rel err %.3g" % (name, start, err))
         assert err < TIGHT[name], (name, start)
+
+
+@pytest.mark.parametrize("n_win,k,n_c", [(30, 2, 4), (25, 1, 2), (42, 3, 3), (112, 8, 2), (3, 2, 2), (2, 2, 1),
+                                         (30, 5, 33)])
+def test_pca_eig_top_matches_full_eigensolve(env, n_win, k, n_c):
+    """ss_pca_eig_top (tridiagonalisation + multisection + inverse iteration, what the chain and
+    fetPCA use) against ss_pca_eig (Jacobi) and numpy.linalg.eigh on covariances of spike-like
+    waveforms: the k leading eigenvalues, eigenvectors up to sign, zeros elsewhere; identical
+    scores within round-off."""
+    ops, torch = env['ops'], env['torch']
+    rng = np.random.default_rng(100 + n_win + k)
+    n_spk = 4000
+    tt = np.linspace(0, 1, n_win)
+    templ = np.stack([np.exp(-((tt - 0.3) / 0.08) ** 2) - 0.4 * np.exp(-((tt - 0.5) / 0.15) ** 2),
+                      np.exp(-((tt - 0.35) / 0.05) ** 2), np.sin(6 * tt) * np.exp(-3 * tt)])
+    waves = np.empty((n_win, n_spk, n_c), np.float32)
+    for c in range(n_c):
+        amp = rng.standard_normal((n_spk, 3)) * np.array([120.0, 60.0, 20.0]) * (1 + c % 3)
+        waves[:, :, c] = (amp @ templ + rng.standard_normal((n_spk, n_win)) * 8.0 + 15.0).T
+    w = _dev(env, waves)
+    gram, ssum, _, counts = ops.pca_gram(w)
+    ev_f, vec_f = ops.pca_eig(gram, ssum, counts)
+    ev_t, vec_t = ops.pca_eig(gram, ssum, counts, top=k)
+    ev_f, vec_f, ev_t, vec_t = (a.cpu().numpy() for a in (ev_f, vec_f, ev_t, vec_t))
+    assert np.all(ev_t[:, k:] == 0) and np.all(vec_t[:, :, k:] == 0)
+    for c in range(n_c):
+        cov = np.cov(waves[:, :, c].astype(np.float64))
+        wv, U = np.linalg.eigh(np.atleast_2d(cov))
+        wv, U = wv[::-1], U[:, ::-1]
+        assert np.allclose(ev_t[c, :k], wv[:k], rtol=1e-11, atol=1e-11 * wv[0])
+        assert np.allclose(ev_t[c, :k], ev_f[c, :k], rtol=1e-11, atol=1e-11 * wv[0])
+        for j in range(k):
+            gap = min(abs(wv[j] - wv[i]) for i in range(n_win) if i != j) / wv[0] if n_win > 1 else 1.0
+            tol = 1e-12 / max(gap, 1e-6)
+            z = vec_t[c, :, j]
+            assert abs(np.linalg.norm(z) - 1.0) < 1e-12
+            assert min(np.linalg.norm(z - U[:, j]), np.linalg.norm(z + U[:, j])) < tol, (c, j, gap)
+            assert min(np.linalg.norm(z - vec_f[c, :, j]), np.linalg.norm(z + vec_f[c, :, j])) < tol
+    s_f = ops.pca_project(w, _dev(env, ev_f), _dev(env, vec_f), min(k, 2)).cpu().numpy()
+    s_t = ops.pca_project(w, _dev(env, ev_t), _dev(env, vec_t), min(k, 2)).cpu().numpy()
+    sgn = np.sign(np.sum(s_f * s_t, axis=0))
+    assert np.abs(s_f - s_t * sgn).max() <= 1e-9 * np.abs(s_f).max()
+
+
+def test_pca_eig_top_special_matrices(env):
+    """Degenerate and rank-deficient covariances: the leading pairs are any orthonormal basis of
+    the leading invariant subspace - checked through residuals and orthonormality."""
+    ops, torch = env['ops'], env['torch']
+    rng = np.random.default_rng(3)
+    n = 30
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    mats = [Q @ np.diag([5.0, 5.0] + list(np.linspace(1, 0.01, n - 2))) @ Q.T,
+            Q @ np.diag([5.0, 5.0 - 1e-9] + list(np.linspace(1, 0.01, n - 2))) @ Q.T,
+            7.0 * np.outer(Q[:, 0], Q[:, 0]),
+            np.diag(np.arange(n, 0, -1.0)),
+            np.zeros((n, n)),
+            Q @ np.diag(np.r_[3.0, np.full(n - 1, 1e-14)]) @ Q.T]
+    A = np.stack([0.5 * (m + m.T) for m in mats])
+    cnt = 11
+    gram = _dev(env, A * (cnt - 1.0))                       # sum = 0: covariance = A exactly
+    ssum = _dev(env, np.zeros((len(mats), n)))
+    counts = _dev(env, np.full(len(mats), cnt, np.int64))
+    for k in (1, 2, 4):
+        ev, vec = (a.cpu().numpy() for a in ops.pca_eig(gram, ssum, counts, top=k))
+        for g in range(len(mats)):
+            wv = np.linalg.eigvalsh(A[g])[::-1]
+            scale = max(wv[0], 1e-300)
+            assert np.abs(ev[g, :k] - np.abs(wv[:k])).max() <= 1e-12 * scale + 1e-290, (g, k)
+            Z = vec[g][:, :k]
+            assert np.abs(Z.T @ Z - np.eye(k)).max() < 1e-10, (g, k)
+            res = np.abs(A[g] @ Z - Z * wv[:k]).max()
+            assert res <= 1e-10 * scale + 1e-290, (g, k, res)
