@@ -315,7 +315,7 @@ __device__ __forceinline__ double et_min(double v)
 
 __host__ __device__ inline size_t et_smem_doubles(int n, int k)
 {
-    return (size_t)n * (n | 1) + 6 * (size_t)n + 2 * ET_MAXK + (size_t)k * n * 5 + (size_t)(k * n + 1) / 2 + 2;
+    return (size_t)n * (n | 1) + 6 * (size_t)n + 2 * ET_MAXK + (size_t)k * n * 5 + (size_t)(k * n + 1) / 2 + 2 + 16;
 }
 
 __global__ void __launch_bounds__(32)
@@ -328,6 +328,10 @@ pca_eig_top_kernel(const double *__restrict__ gram, const double *__restrict__ s
     double *A = sm, *d = A + n * ld, *e = d + n, *e2 = e + n, *tau = e2 + n, *vs = tau + n, *ws = vs + n;
     double *lam = ws + n, *lamu = lam + ET_MAXK, *Z = lamu + ET_MAXK, *LU = Z + k * n;
     int *piv = reinterpret_cast<int *>(LU + (size_t)k * 4 * n);
+    // Sturm recurrence operands, padded to a multiple of 8 rows: ds[i] = d[i], es2[i] = e[i-1]^2
+    // (they alias the LU area, which is only filled after the multisection)
+    const int n8 = (n + 7) & ~7;
+    double *ds = LU, *es2 = LU + n8;
     const int64_t g = blockIdx.x;
     const double cnt = (double)counts[g];
     {
@@ -440,6 +444,11 @@ pca_eig_top_kernel(const double *__restrict__ gram, const double *__restrict__ s
     }
     glo = et_min(glo);
     ghi = et_max(ghi);
+    for (int i = lane; i < n8; i += 32) {
+        ds[i] = i < n ? d[i] : 0.0;
+        es2[i] = (i > 0 && i < n) ? e2[i - 1] : 0.0;
+    }
+    __syncwarp();
     {
         const double tn = fmax(fabs(glo), fabs(ghi)), pad = 2.0 * 2.220446049250313e-16 * tn * n + 2e-300;
         glo -= pad;
@@ -463,18 +472,17 @@ pca_eig_top_kernel(const double *__restrict__ gram, const double *__restrict__ s
             const double x = lo + (hi - lo) * ((double)(l_of + 1) / (double)(L + 1));
             int c = 0;
             double p2 = 0.0, p1 = 1.0;
+            // ds / es2 are padded to a multiple of 8 rows (zeros): the recurrence may run on,
+            // only the count is masked
             for (int i0 = 0; i0 < n; i0 += 8) {
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const int i = i0 + u;
-                    if (i < n) {
-                        const double t = (i > 0 ? e2[i - 1] : 0.0) * p2;
-                        double p = fma(d[i] - x, p1, -t);
-                        if (p == 0.0) p = -copysign(1e-300, p1);
-                        c += (unsigned)(__double2hiint(p) ^ __double2hiint(p1)) >> 31;
-                        p2 = p1;
-                        p1 = p;
-                    }
+                    const double t = es2[i0 + u] * p2;
+                    double p = fma(ds[i0 + u] - x, p1, -t);
+                    if (p == 0.0) p = -copysign(1e-300, p1);
+                    c += (i0 + u < n) & ((unsigned)(__double2hiint(p) ^ __double2hiint(p1)) >> 31);
+                    p2 = p1;
+                    p1 = p;
                 }
                 if (fabs(p1) < 1e-120 && fabs(p2) < 1e-120) { p1 *= 1e120; p2 *= 1e120; }
                 else if (fabs(p1) > 1e120) { p1 *= 1e-120; p2 *= 1e-120; }
@@ -596,31 +604,35 @@ pca_eig_top_kernel(const double *__restrict__ gram, const double *__restrict__ s
             __syncwarp();
         }
     }
-    // 5. back-transformation u = H_0 H_1 ... H_{n-3} z, all k vectors per reflector together
-    for (int kk = n - 3; kk >= 0; --kk) {
-        const double tk = tau[kk];
-        if (tk == 0.0) continue;
-        double sd[ET_MAXK];
+    // 5. back-transformation u = H_0 H_1 ... H_{n-3} z, two vectors per pass (their reductions
+    //    interleave)
+    for (int m0 = 0; m0 < k; m0 += 2) {
+        double *za = Z + (size_t)m0 * n, *zb = Z + (size_t)(m0 + 1 < k ? m0 + 1 : m0) * n;
+        const bool two = m0 + 1 < k;
+        for (int kk = n - 3; kk >= 0; --kk) {
+            const double tk = tau[kk];
+            if (tk == 0.0) continue;
+            double sa = 0.0, sb = 0.0;
+            for (int i = kk + 1 + lane; i < n; i += 32) {
+                const double v = i == kk + 1 ? 1.0 : A[i * ld + kk];
+                sa = fma(v, za[i], sa);
+                sb = fma(v, zb[i], sb);
+            }
 #pragma unroll
-        for (int m = 0; m < ET_MAXK; ++m) sd[m] = 0.0;
-        for (int i = kk + 1 + lane; i < n; i += 32) {
-            const double v = i == kk + 1 ? 1.0 : A[i * ld + kk];
-#pragma unroll
-            for (int m = 0; m < ET_MAXK; ++m)
-                if (m < k) sd[m] = fma(v, Z[(size_t)m * n + i], sd[m]);
+            for (int dd = 16; dd > 0; dd >>= 1) {
+                sa += __shfl_xor_sync(SS_FULL, sa, dd);
+                sb += __shfl_xor_sync(SS_FULL, sb, dd);
+            }
+            sa *= tk;
+            sb *= tk;
+            for (int i = kk + 1 + lane; i < n; i += 32) {
+                const double v = i == kk + 1 ? 1.0 : A[i * ld + kk];
+                const double a = za[i] - sa * v, b = zb[i] - sb * v;
+                za[i] = a;
+                if (two) zb[i] = b;
+            }
+            __syncwarp();
         }
-#pragma unroll
-        for (int dd = 16; dd > 0; dd >>= 1)
-#pragma unroll
-            for (int m = 0; m < ET_MAXK; ++m)
-                if (m < k) sd[m] += __shfl_xor_sync(SS_FULL, sd[m], dd);
-        for (int i = kk + 1 + lane; i < n; i += 32) {
-            const double v = tk * (i == kk + 1 ? 1.0 : A[i * ld + kk]);
-#pragma unroll
-            for (int m = 0; m < ET_MAXK; ++m)
-                if (m < k) Z[(size_t)m * n + i] -= sd[m] * v;
-        }
-        __syncwarp();
     }
     // 6. columns 0..k-1 hold the leading pairs (descending); the rest is zero
     for (int j = lane; j < n; j += 32) evals[g * n + j] = j < k ? fabs(lam[j] * scale) : 0.0;
