@@ -43,6 +43,8 @@ namespace {
 constexpr int FS_S = 16;            // samples per lane
 constexpr int FS_T = 32 * FS_S;     // samples per tile (one warp)
 constexpr int FS_WPB = 4;           // warps per block
+// resident CTAs per SM the multi-section sweep-2 kernels are compiled for (A/B on B200:
+// 5 = 96 registers, no spills, fastest; 6-8 spill and lose 2-5 %); -D overrides for A/B builds
 #ifndef APPLY_MIN_CTAS
 #define APPLY_MIN_CTAS 5
 #endif
@@ -565,6 +567,8 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *
 // a unit's padded / odd-extended ends (staged element by element) first: with a fixed
 // assignment the one slow warp of every CTA kept the other fifteen waiting (ncu: 15 % of the
 // warp slots active instead of 25 %).
+// tiles per lane / warps per CTA of the tile-per-lane sweep 1 for NS <= 8 (A/B on B200: 4 / 8
+// = 254 registers, fastest; 2 / 16 equal within 1 %, 3 / 10 slower); -D overrides for A/B builds
 #ifndef SW_RL_LOW
 #define SW_RL_LOW 4
 #define SW_WPB_LOW 8
