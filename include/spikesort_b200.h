@@ -54,6 +54,9 @@ typedef enum {
 
 int         ss_version(void);
 const char *ss_last_error(void);
+/* Kernels of this library launched by the process so far (every launch site counts itself):
+ * bench.py reports the difference over its timed region as gpu_launches. */
+int64_t ss_launch_count(void);
 
 /* Time slab of every contact between a (pinned) host recording and HBM as one asynchronous
  * 2-D DMA (rows = contacts, pitches in bytes); to_device 1 = host -> device, 0 = back. */

@@ -25,6 +25,7 @@ _dp = _c.POINTER(_c.c_double)
 SIGNATURES = {
     "ss_version": (_int, []),
     "ss_last_error": (_c.c_char_p, []),
+    "ss_launch_count": (_i64, []),
     "ss_max_filter_order": (_int, []),
     "ss_max_window": (_int, []),
     "ss_max_pca_window": (_int, []),

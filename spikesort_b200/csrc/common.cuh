@@ -6,6 +6,7 @@
 #include "spikesort_b200.h"
 
 void ss_set_error(const char *fmt, ...);
+void ss_note_launch(void);        // one more kernel of the library launched (ss_launch_count)
 
 #define SS_CUDA_CHECK(expr)                                                          \
     do {                                                                             \
@@ -24,6 +25,7 @@ void ss_set_error(const char *fmt, ...);
             ss_set_error("launch of %s: %s", name, cudaGetErrorString(e__));         \
             return SS_ERR_CUDA;                                                      \
         }                                                                            \
+        ss_note_launch();                                                            \
     } while (0)
 
 #define SS_REQUIRE(cond, code, ...)                                                  \

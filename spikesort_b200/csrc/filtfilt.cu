@@ -60,6 +60,7 @@ struct FiltGeom {
     int64_t tiles_per_contact, total_tiles;
     int64_t units_per_contact, n_units;
     int64_t j_begin, j_count;    // chunk range processed by this launch
+    int64_t t_lo, t_hi;          // sweep 2 only: tiles [t_lo, t_hi) of every unit of the launch
     int edge, dtype;
 };
 
@@ -108,9 +109,9 @@ __device__ __forceinline__ bool decode_tile(const FiltGeom &g, int warp, TileInf
                                             int64_t &tile)
 {
     ti = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
-    ti.t = (int64_t)blockIdx.x * FS_WPB + warp;
+    ti.t = g.t_lo + (int64_t)blockIdx.x * FS_WPB + warp;
     tile = ti.g0 + ti.t;
-    return ti.t < ti.nt;
+    return ti.t < ti.nt && ti.t < g.t_hi;
 }
 
 // 2*x[iend] - x[iin] in the INPUT dtype (scipy.signal._arraytools.odd_ext on a
@@ -1326,6 +1327,8 @@ static int make_geom(FiltGeom &g, int dtype, int64_t n_contacts, int64_t n_sampl
     g.n_units = g.units_per_contact * n_contacts;
     g.j_begin = 0;
     g.j_count = g.units_per_contact;
+    g.t_lo = 0;
+    g.t_hi = INT64_MAX;
     return SS_OK;
 }
 
@@ -1336,13 +1339,16 @@ enum { PH_SUMMARY = 1, PH_APPLY = 2, PH_ALL = 3 };
 template <int NB, bool FO>
 static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j_count,
                          const HostTables &T, const double *sos, double *d_out, void *d_ws,
-                         const MarkParams *mk, int phases, cudaStream_t st)
+                         const MarkParams *mk, int phases, cudaStream_t st,
+                         int64_t t_lo = 0, int64_t t_hi = INT64_MAX)
 {
     constexpr int NS = FiltParams<NB, FO>::NS;
     constexpr int NSEC = FiltParams<NB, FO>::NSEC;
     if (j_count <= 0) return SS_OK;
     g.j_begin = j_begin;
     g.j_count = j_count;
+    g.t_lo = t_lo;
+    g.t_hi = t_hi;
     FiltParams<NB, FO> P;
     for (int s = 0; s < NSEC; ++s) {
         P.sec[s][0] = sos[s * 6 + 0];
@@ -1380,7 +1386,9 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
     const bool has_full = j_begin < g.n_full;
     const bool has_last = g.len_last > 0 && j_begin + j_count > g.n_full;
     const int64_t nt_max = (has_full && (!has_last || g.nt_full >= g.nt_last)) ? g.nt_full : g.nt_last;
-    const dim3 tile_blocks((unsigned)ss_cdiv(nt_max, FS_WPB), (unsigned)j_count,
+    const int64_t nt_hi = nt_max < t_hi ? nt_max : t_hi;
+    if ((phases & PH_APPLY) && !(phases & PH_SUMMARY) && nt_hi <= t_lo) return SS_OK;
+    const dim3 tile_blocks((unsigned)ss_cdiv(nt_hi > t_lo ? nt_hi - t_lo : 1, FS_WPB), (unsigned)j_count,
                            (unsigned)g.n_contacts);
     const unsigned unit_blocks = (unsigned)ss_cdiv(g.n_contacts * j_count, FS_WPB);
     if (phases & PH_SUMMARY) {
@@ -1485,11 +1493,12 @@ static int make_plan(FiltPlan &pl, int dtype, int64_t n_contacts, int64_t n_samp
 
 static int run_plan(const FiltPlan &pl, const void *d_x, int64_t j_begin, int64_t j_count,
                     const double *sos, double *d_out, void *d_ws, const MarkParams *mk,
-                    int phases, cudaStream_t st)
+                    int phases, cudaStream_t st, int64_t t_lo = 0, int64_t t_hi = INT64_MAX)
 {
 #define SS_FILT_CASE(NB_, FO_)                                                        \
     if (pl.nb == NB_ && pl.fo == FO_)                                                 \
-        return launch_filter<NB_, FO_>(d_x, pl.g, j_begin, j_count, pl.T, sos, d_out, d_ws, mk, phases, st);
+        return launch_filter<NB_, FO_>(d_x, pl.g, j_begin, j_count, pl.T, sos, d_out, d_ws, mk, phases, st, \
+                                       t_lo, t_hi);
     SS_FILT_CASE(0, true)
     SS_FILT_CASE(1, false)
     SS_FILT_CASE(1, true)
@@ -1507,6 +1516,29 @@ static int run_plan(const FiltPlan &pl, const void *d_x, int64_t j_begin, int64_
     ss_set_error("filtfilt: unsupported section layout (%d biquads, first-order %d)", pl.nb,
                  (int)pl.fo);
     return SS_ERR_UNSUPPORTED;
+}
+
+// The 'auto' threshold needs the filtered samples [0, n0) only.  Sweep 2 is tile-parallel
+// (every tile has its own start states from the tile scan), so the plain pass before the
+// thresholds stops at the first tile boundary at or behind n0 instead of at the end of the
+// chunk: jh = chunk of sample n0-1, tiles [0, t_cut) of it are needed, head_end = first sample
+// of the recording the plain pass leaves unwritten (config[1]: 0.3 of a 1 M-sample chunk).
+static void head_cut(const FiltGeom &g, int64_t n0, int64_t &jh, int64_t &t_cut, int64_t &nt_jh,
+                     int64_t &head_end)
+{
+    jh = (n0 - 1) / g.chunksize;
+    const bool last = jh >= g.n_full;
+    const int64_t L = last ? g.len_last : g.chunksize;
+    nt_jh = last ? g.nt_last : g.nt_full;
+    const int64_t pad = nt_jh * FS_T - (L + 2 * (int64_t)g.edge);
+    const int64_t cs0 = jh * g.chunksize, r_need = n0 - cs0;
+    t_cut = ss_cdiv(r_need + pad + g.edge, FS_T);          // first tile with r0 >= r_need
+    int64_t r_end = t_cut * FS_T - pad - g.edge;
+    if (t_cut >= nt_jh || r_end >= L) {                    // the whole chunk
+        t_cut = nt_jh;
+        r_end = L;
+    }
+    head_end = cs0 + r_end;
 }
 
 }  // namespace
@@ -1570,40 +1602,49 @@ extern "C" int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_cont
     mk.halo_H = 0;
     mk.shard_n = n_samples;
     SS_CUDA_CHECK(cudaMemsetAsync(mk.mask, 0, (size_t)L.words_per_row * n_contacts * 4, st));
-    int64_t j0 = 0;
-    if (auto_thr) {
-        // the threshold needs the filtered first n0 samples: filter the chunks that hold
-        // them first (plain), derive the thresholds, mark those chunks with the streaming
-        // kernel, then filter the rest with the marking fused into the apply kernel
-        SS_REQUIRE(n0 > 0, SS_ERR_ARG, "filtfilt_detect: n0 must be positive");
-        if (n0 > n_samples) n0 = n_samples;
-        j0 = ss_cdiv(n0, chunksize);
-        if (j0 > pl.g.units_per_contact) j0 = pl.g.units_per_contact;
-        // sweep 1 and the tile scan do not depend on the thresholds: all chunks at once
-        if (!prepared) {
-            rc = run_plan(pl, d_x, 0, pl.g.units_per_contact, sos, d_out, d_ws, nullptr, PH_SUMMARY, st);
-            if (rc) return rc;
-        }
-        rc = run_plan(pl, d_x, 0, j0, sos, d_out, d_ws, nullptr, PH_APPLY, st);
+    const int64_t units = pl.g.units_per_contact;
+    if (!auto_thr) {
+        rc = run_plan(pl, d_x, 0, units, sos, d_out, d_ws, &mk, prepared ? PH_APPLY : PH_ALL, st);
         if (rc) return rc;
-        rc = ss_var_threshold(d_out, SS_F64, n_contacts, ld_out, n0, factor, d_thr,
-                              dws + L.off_scratch, L.total - L.off_scratch, st);
-        if (rc) return rc;
-        int64_t head_end = j0 * chunksize;
-        if (head_end > n_samples) head_end = n_samples;
-        rc = ssi::mark_head(d_out, SS_F64, n_contacts, head_end, n_samples, ld_out, d_thr, falling,
-                            d_det_ws, st);
-        if (rc) return rc;
-        // the pair (head_end-1, head_end) straddles the two passes: mark it once the
-        // second pass has written head_end (boundary kernel of the head range, below)
+        return ssi::count_and_scan(n_contacts, n_samples, d_det_ws, d_offsets, st);
     }
-    rc = run_plan(pl, d_x, j0, pl.g.units_per_contact - j0, sos, d_out, d_ws, &mk,
-                  (auto_thr || prepared) ? PH_APPLY : PH_ALL, st);
+    // the threshold needs the filtered first n0 samples: filter the tiles that hold them
+    // first (plain), derive the thresholds, mark that range with the streaming kernel, then
+    // filter the rest with the marking fused into the apply kernel
+    SS_REQUIRE(n0 > 0, SS_ERR_ARG, "filtfilt_detect: n0 must be positive");
+    if (n0 > n_samples) n0 = n_samples;
+    int64_t jh, t_cut, nt_jh, head_end;
+    head_cut(pl.g, n0, jh, t_cut, nt_jh, head_end);
+    // sweep 1 and the tile scan do not depend on the thresholds: all chunks at once
+    if (!prepared) {
+        rc = run_plan(pl, d_x, 0, units, sos, d_out, d_ws, nullptr, PH_SUMMARY, st);
+        if (rc) return rc;
+    }
+    rc = run_plan(pl, d_x, 0, jh, sos, d_out, d_ws, nullptr, PH_APPLY, st);
     if (rc) return rc;
-    if (j0 > 0 && j0 < pl.g.units_per_contact) {
-        // chunk-end pair of the last head chunk of every contact
+    rc = run_plan(pl, d_x, jh, 1, sos, d_out, d_ws, nullptr, PH_APPLY, st, 0, t_cut);
+    if (rc) return rc;
+    rc = ss_var_threshold(d_out, SS_F64, n_contacts, ld_out, n0, factor, d_thr,
+                          dws + L.off_scratch, L.total - L.off_scratch, st);
+    if (rc) return rc;
+    rc = ssi::mark_head(d_out, SS_F64, n_contacts, head_end, n_samples, ld_out, d_thr, falling,
+                        d_det_ws, st);
+    if (rc) return rc;
+    // the pair (head_end-1, head_end) straddles the two passes: it is the tile-end (or
+    // chunk-end) pair of the last plain tile, marked by the boundary kernel once the second
+    // pass has written head_end
+    // (later chunks first: the boundary kernel behind the rest of chunk jh also evaluates that
+    //  chunk's END pair, whose second sample belongs to chunk jh + 1)
+    rc = run_plan(pl, d_x, jh + 1, units - jh - 1, sos, d_out, d_ws, &mk, PH_APPLY, st);
+    if (rc) return rc;
+    if (t_cut < nt_jh) {
+        rc = run_plan(pl, d_x, jh, 1, sos, d_out, d_ws, &mk, PH_APPLY, st, t_cut, INT64_MAX);
+        if (rc) return rc;
+    }
+    if (t_cut >= nt_jh && jh + 1 < units) {
+        // the whole chunk jh was filtered plain: its chunk-end pair
         FiltGeom g = pl.g;
-        g.j_begin = j0 - 1;
+        g.j_begin = jh;
         g.j_count = 1;
         const int64_t nt = g.nt_full;
         filt_boundary_mark_kernel<<<dim3((unsigned)ss_cdiv(nt, 256), 1, (unsigned)n_contacts), 256, 0, st>>>(d_out, g, mk);
@@ -1643,9 +1684,11 @@ extern "C" int ss_filtfilt_head_threshold_sos(const void *d_x, int dtype, int64_
     if (rc) return rc;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if (n0 > n_samples) n0 = n_samples;
-    int64_t j0 = ss_cdiv(n0, chunksize);
-    if (j0 > pl.g.units_per_contact) j0 = pl.g.units_per_contact;
-    rc = run_plan(pl, d_x, 0, j0, sos, d_out, d_ws, nullptr, PH_APPLY, st);
+    int64_t jh, t_cut, nt_jh, head_end;
+    head_cut(pl.g, n0, jh, t_cut, nt_jh, head_end);
+    rc = run_plan(pl, d_x, 0, jh, sos, d_out, d_ws, nullptr, PH_APPLY, st);
+    if (rc) return rc;
+    rc = run_plan(pl, d_x, jh, 1, sos, d_out, d_ws, nullptr, PH_APPLY, st, 0, t_cut);
     if (rc) return rc;
     return ss_var_threshold(d_out, SS_F64, n_contacts, ld_out, n0, factor, d_thr, d_thr_ws,
                             thr_ws_bytes, stream);

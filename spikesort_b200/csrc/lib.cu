@@ -1,11 +1,16 @@
 // Error reporting and version of the spikesort_b200 C ABI.
 #include "common.cuh"
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
 namespace {
 thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
 }
+
+void ss_note_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" int64_t ss_launch_count(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
 void ss_set_error(const char *fmt, ...)
 {
