@@ -906,18 +906,28 @@ filt_tilescan_kernel(const void *__restrict__ x, const FiltGeom g,
     for (int i = 0; i < NS; ++i) carry[i] = P.zi[i] * x0;
 
     double y_last = 0.0;
-    // the loads of row+1 are issued before the (latency-bound) scan of row
-    double nxt[NS];
+    // the summaries of the next PD rows are in flight while a row is scanned: a row's scan is
+    // ~300 cycles of dependent shuffles and FMAs, an L2 hit ~400 (one row ahead left the loop
+    // at ~900 cycles per row)
+    constexpr int PD = NS <= 2 ? 3 : (NS <= 4 ? 2 : 1);
+    double nxt[PD][NS];
 #pragma unroll
-    for (int i = 0; i < NS; ++i) nxt[i] = lane < nt ? F[(g0 + lane) * NS + i] : 0.0;
+    for (int p = 0; p < PD; ++p)
+#pragma unroll
+        for (int i = 0; i < NS; ++i) nxt[p][i] = 32 * p + lane < nt ? F[(g0 + 32 * p + lane) * NS + i] : 0.0;
     for (int64_t row = 0; row < nrows; ++row) {
         const int64_t t = row * 32 + lane;
         const bool valid = t < nt;
 #pragma unroll
-        for (int i = 0; i < NS; ++i) e[i] = nxt[i];
-        if (row + 1 < nrows) {
+        for (int i = 0; i < NS; ++i) e[i] = nxt[0][i];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) nxt[i] = t + 32 < nt ? F[(g0 + t + 32) * NS + i] : 0.0;
+        for (int p = 0; p + 1 < PD; ++p)
+#pragma unroll
+            for (int i = 0; i < NS; ++i) nxt[p][i] = nxt[p + 1][i];
+        {
+            const int64_t tn = t + 32 * PD;
+#pragma unroll
+            for (int i = 0; i < NS; ++i) nxt[PD - 1][i] = tn < nt ? F[(g0 + tn) * NS + i] : 0.0;
         }
         if (lane == 0) {
 #pragma unroll
@@ -953,13 +963,15 @@ filt_tilescan_kernel(const void *__restrict__ x, const FiltGeom g,
 
 #pragma unroll
     for (int i = 0; i < NS; ++i) carry[i] = P.zi[i] * y_last;
-    double nzf[NS], nbz[NS];
-    {
-        const int64_t t = (nrows - 1) * 32 + lane;
+    double nzf[PD][NS], nbz[PD][NS];
+#pragma unroll
+    for (int p = 0; p < PD; ++p) {
+        const int64_t t = (nrows - 1 - p) * 32 + lane;
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            nzf[i] = t < nt ? Zf[(g0 + t) * NS + i] : 0.0;
-            nbz[i] = t < nt ? Bz[(g0 + t) * NS + i] : 0.0;
+            const bool ok = t >= 0 && t < nt;
+            nzf[p][i] = ok ? Zf[(g0 + t) * NS + i] : 0.0;
+            nbz[p][i] = ok ? Bz[(g0 + t) * NS + i] : 0.0;
         }
     }
     for (int64_t row = nrows - 1; row >= 0; --row) {
@@ -967,19 +979,24 @@ filt_tilescan_kernel(const void *__restrict__ x, const FiltGeom g,
         const bool valid = t < nt;
         const int64_t left = nt - row * 32;
         const int seed = (int)(left < 32 ? left : 32) - 1;
-        // e = Bz + M Zf of this row (invalid lanes hold zeros), then prefetch row-1
+        // e = Bz + M Zf of this row (invalid lanes hold zeros), then prefetch row - PD
 #pragma unroll
         for (int r = 0; r < NS; ++r) {
-            double acc = nbz[r];
+            double acc = nbz[0][r];
 #pragma unroll
-            for (int q = 0; q < NS; ++q) acc += P.M[r][q] * nzf[q];
+            for (int q = 0; q < NS; ++q) acc += P.M[r][q] * nzf[0][q];
             e[r] = acc;
         }
-        if (row > 0) {
+#pragma unroll
+        for (int p = 0; p + 1 < PD; ++p)
+#pragma unroll
+            for (int i = 0; i < NS; ++i) { nzf[p][i] = nzf[p + 1][i]; nbz[p][i] = nbz[p + 1][i]; }
+        {
+            const int64_t tp = t - 32 * PD;
 #pragma unroll
             for (int i = 0; i < NS; ++i) {
-                nzf[i] = Zf[(g0 + t - 32) * NS + i];
-                nbz[i] = Bz[(g0 + t - 32) * NS + i];
+                nzf[PD - 1][i] = tp >= 0 ? Zf[(g0 + tp) * NS + i] : 0.0;
+                nbz[PD - 1][i] = tp >= 0 ? Bz[(g0 + tp) * NS + i] : 0.0;
             }
         }
         if (lane == seed) {
