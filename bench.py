@@ -394,13 +394,13 @@ def run_gpu(args):
     achieved = alg_bytes / (filt_ms / 1000.0) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of this stage from
-                # the ncu --set full capture of this command (profiles/README.md, state e):
-                # sweep 1 1.18 GB + sweep 2 5.42 + head 0.26 GB + head marks / threshold / count /
-                # emit 0.47 GB
-                "traffic": 7.33e9 if WORKLOAD == "c2" else None,   # captured for the headline workload only
-                "traffic_unit": "bytes per launch (ncu, profiles/r01_ncu_g_chain_kernels_final.txt "
-                                "+ r01_ncu_f_chain_kernels.txt for the bookkeeping kernels)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of this stage from an ncu
+                # pass over one step of this command in the final state of the round
+                # (profiles/r01_traffic_final_state.csv): sweep 1 1.18 GB + tile scan 0.02 + sweep 2
+                # 5.57 (plain head part 0.04) + threshold / head marks 0.15 + boundary marks 0.14 +
+                # count / emit 0.14 GB
+                "traffic": 7.24e9 if WORKLOAD == "c2" else None,   # captured for the headline workload only
+                "traffic_unit": "bytes per launch (ncu, profiles/r01_traffic_final_state.csv)",
                 "kernel": "ss_filtfilt_detect_sos + ss_detect_emit = filter (summary, tilescan, "
                           "apply with fused crossing marks) + auto threshold + count/scan/emit: "
                           "the filter, threshold and detect stages of the chain",
