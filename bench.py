@@ -221,8 +221,23 @@ def run_gpu(args):
         if world > 1:
             return ssdist.run_chain_sharded(x, FS, flt, SP_WIN, edge='falling', align_type='min',
                                             ncomps=2, chunksize=CHUNK)
-        return pipeline.run_chain(x, FS, filt=flt, sp_win=SP_WIN, edge='falling',
-                                  align_type='min', ncomps=2, chunksize=CHUNK)
+        # lazy: the chain of this step is queued before the previous step's counts are read
+        # (ChainResult.finalize: the one host sync per step), so the GPU does not idle while the
+        # host gets from that synchronisation to the next step's first launch
+        r = pipeline.run_chain(x, FS, filt=flt, sp_win=SP_WIN, edge='falling',
+                               align_type='min', ncomps=2, chunksize=CHUNK, lazy=True)
+        prev, pending["res"] = pending["res"], r
+        if prev is not None:
+            prev.finalize()
+        return r
+
+    pending = {"res": None}
+
+    def finish_last():
+        # inside the timed region: the last step's counts are read (and its arrays trimmed) too
+        if pending["res"] is not None:
+            pending["res"].finalize()
+            pending["res"] = None
 
     def barrier():
         if world > 1:
@@ -232,6 +247,7 @@ def run_gpu(args):
     res = None
     for _ in range(args.warmup):
         res = step()
+    finish_last()
     barrier()
 
     # filter-stage events (the dominant kernels) + whole-step events, all on the
@@ -288,6 +304,7 @@ def run_gpu(args):
     ev0.record()
     for _ in range(args.steps):
         res = step()
+    finish_last()
     ev1.record()
     barrier()
     launches = int(_lib.load().ss_launch_count() - launches0)

@@ -38,9 +38,27 @@ class ChainResult(object):
         self.evecs = None           # float64 (n_contacts, n_win, n_win): leading ncomps columns, rest zero
         self.scores = None          # float64 (n_spk, ncomps)
         self.time = None            # host float64 (n_win,)
+        self._pending = None        # run_chain(lazy=True): (capacity, exact rerun, hint key)
+
+    def finalize(self):
+        """A result of run_chain(lazy=True) holds capacity-sized arrays whose true lengths are
+        still on the device.  finalize() is the one host synchronisation of the chain: it reads
+        the two counts, trims the arrays to views of their true length and, if the capacity
+        was too small, replaces the result by the exact rerun.  Idempotent; returns self."""
+        if self._pending is None:
+            return self
+        cap, rerun, key = self._pending
+        self._pending = None
+        n_det, _ = _trim_to_counts(self, cap)
+        if n_det > cap:
+            exact, n_det, _ = rerun()
+            self.__dict__.update(exact.__dict__)
+        _CAPACITY_HINTS[key] = n_det
+        return self
 
     def per_contact(self, c):
         """Host copies shaped like the reference's per-contact results."""
+        self.finalize()
         off = self.offsets.cpu().numpy()
         offd = self.offsets_detected.cpu().numpy()
         lo, hi = int(off[c]), int(off[c + 1])
@@ -63,7 +81,7 @@ _CAPACITY_HINTS = {}
 
 def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
               thresh='auto', ncomps=2, chunksize=1E6, pca=True, thr_override=None, fused=True,
-              speculate=True, resample=1):
+              speculate=True, resample=1, lazy=False):
     """x: CUDA tensor (n_contacts, n_samples), int16/float32/float64.
     filt: a spikesort_b200.filters filter object or None.
     thresh: 'auto' / numeric string (multiple of the std of the first 10 s) or a number.
@@ -77,20 +95,24 @@ def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='
     are sized by that call's count + 25 % instead, every kernel bounds its work by the
     device-side offsets, and the counts are read once at the end; if the capacity turns out
     too small the chain is simply run again with exact sizes.  Results are identical.
+    lazy: with a capacity-sized chain, do not even read the counts: the result comes back
+    with everything queued and ChainResult.finalize() (called by per_contact(), or by the
+    caller once the NEXT recording's chain has been queued) does the one synchronisation.
+    Back-to-back calls then keep the GPU busy across calls - otherwise it idles ~0.1 ms per
+    call while the host gets from the synchronisation to the first launch of the next one.
     resample: align on the cubic-spline upsampled window (align_spikes(resample=...),
     extract.py:245-258; the tutorial uses 10); waveforms are extracted at the original rate."""
     key = (tuple(x.shape), x.dtype, float(FS), tuple(sp_win), edge, align_type, str(thresh),
            id(type(filt)), int(chunksize), bool(fused), int(resample))
+    args = (x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize, pca, thr_override,
+            fused)
     hint = _CAPACITY_HINTS.get(key) if speculate else None
     if hint is not None:
         cap = int(hint * 1.25) + 1024
-        res, n_det, n_kept = _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps,
-                                        chunksize, pca, thr_override, fused, cap, resample)
-        if n_det <= cap:
-            _CAPACITY_HINTS[key] = n_det
-            return res
-    res, n_det, n_kept = _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
-                                    pca, thr_override, fused, None, resample)
+        res = _run_chain(*args, cap, resample, defer=True)
+        res._pending = (cap, lambda: _run_chain(*args, None, resample), key)
+        return res if lazy else res.finalize()
+    res, n_det, n_kept = _run_chain(*args, None, resample)
     if speculate:
         if len(_CAPACITY_HINTS) > 64:
             _CAPACITY_HINTS.clear()
@@ -98,10 +120,28 @@ def run_chain(x, FS, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='
     return res
 
 
+def _trim_to_counts(res, cap):
+    """The one host sync of the capacity-sized chain: both counts at once, then trim (views).
+    Returns (n_detected, n_kept); nothing is trimmed when the capacity was exceeded."""
+    t = _lib.torch()
+    n_det, n_kept = (int(v) for v in t.stack((res.offsets_detected[-1], res.offsets[-1])).tolist())
+    if n_det <= cap:
+        res.spt_detected = res.spt_detected[:n_det]
+        res.spt, res.valid = res.spt[:n_kept], res.valid[:n_kept]
+        res.waves = res.waves[:, :n_kept, :]
+        if res.scores is not None:
+            if n_kept == 0:
+                res.scores = res.evals = res.evecs = None
+            else:
+                res.scores = res.scores[:n_kept]
+    return n_det, n_kept
+
+
 def _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize, pca, thr_override,
-               fused, cap, resample=1):
+               fused, cap, resample=1, defer=False):
     """The chain; cap=None: exact sizes (two host syncs), else capacity-sized arrays and one
-    sync at the end.  Returns (ChainResult, n_detected, n_kept)."""
+    sync at the end.  Returns (ChainResult, n_detected, n_kept) - or, with defer, only the
+    ChainResult with everything queued and nothing read back (_trim_to_counts finishes it)."""
     t = _lib.require_cuda()
     res = ChainResult()
     sp_win = list(sp_win)
@@ -153,17 +193,9 @@ def _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
         res.scores = _ops.pca_project(waves, res.evals, res.evecs, ncomps, offsets=offsets)
     if cap is None:
         return res, int(res.spt_detected.numel()), int(res.spt.numel())
-    # the one host sync of the speculative chain: both counts at once, then trim (views)
-    n_det, n_kept = (int(v) for v in t.stack((res.offsets_detected[-1], res.offsets[-1])).tolist())
-    if n_det <= cap:
-        res.spt_detected = res.spt_detected[:n_det]
-        res.spt, res.valid = res.spt[:n_kept], res.valid[:n_kept]
-        res.waves = res.waves[:, :n_kept, :]
-        if res.scores is not None:
-            if n_kept == 0:
-                res.scores = res.evals = res.evecs = None
-            else:
-                res.scores = res.scores[:n_kept]
+    if defer:
+        return res
+    n_det, n_kept = _trim_to_counts(res, cap)
     return res, n_det, n_kept
 
 

@@ -496,6 +496,22 @@ def test_speculative_chain_equals_exact_chain(env):
         a, b = spec.per_contact(c), exact.per_contact(c)
         for k in a:
             assert np.array_equal(a[k], b[k]), k
+    # lazy results: two chains queued back to back, finalised afterwards (in any order), and a
+    # lazy result whose capacity was too small
+    l1 = pipeline.run_chain(x, FS, lazy=True, **kw)
+    l2 = pipeline.run_chain(x, FS, lazy=True, **kw)
+    assert l1._pending is not None and l2._pending is not None
+    assert l1.spt.numel() > exact.spt.numel()                 # still capacity-sized
+    l2.finalize()
+    l1.finalize()
+    pipeline._CAPACITY_HINTS[key] = 10
+    l3 = pipeline.run_chain(x, FS, lazy=True, **kw)
+    assert l3.finalize() is l3 and l3.finalize() is l3        # idempotent
+    assert pipeline._CAPACITY_HINTS[key] == exact.spt_detected.numel()
+    for r in (l1, l2, l3):
+        for name in ('thresh', 'spt_detected', 'offsets_detected', 'spt', 'offsets', 'valid',
+                     'evals', 'evecs', 'scores', 'waves'):
+            assert torch.equal(getattr(r, name), getattr(exact, name)), name
     # unfused path too
     pipeline._CAPACITY_HINTS.clear()
     u1 = pipeline.run_chain(x, FS, fused=False, **kw)
