@@ -745,3 +745,30 @@ def test_pca_eig_top_special_matrices(env):
             assert np.abs(Z.T @ Z - np.eye(k)).max() < 1e-10, (g, k)
             res = np.abs(A[g] @ Z - Z * wv[:k]).max()
             assert res <= 1e-10 * scale + 1e-290, (g, k, res)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_filter_geometry_int16_high_order(env, oracle, seed):
+    """The int16 path of orders >= 3 (tile-per-lane summary sweep with cp.async staging and
+    funnel-shift realignment, section-by-section second sweep) on random chunk geometry: chunks
+    barely longer than the padding (every tile touches the odd extension), chunks of a few
+    tiles, short last chunks, row-strided views starting on odd and even samples."""
+    rng = np.random.default_rng(900 + seed)
+    name = ['lp3', 'bp4', 'bp8', 'ellip10', 'butter12'][seed % 5]
+    b, a = DESIGNS[name]()
+    from spikesort_b200._design import tf2sos_exact
+    sos, padlen = tf2sos_exact(b, a)
+    n_c = int(rng.integers(1, 4))
+    cs = int(rng.integers(padlen + 2, 400 if seed % 2 else 5000))
+    n_chunks = int(rng.integers(1, 5))
+    last = int(rng.integers(padlen + 1, cs + 1))
+    n = (n_chunks - 1) * cs + last
+    off = int(rng.integers(0, 4))
+    parent = np.round(rng.standard_normal((n_c, n + off + 3)) * 250.0 + 20.0).astype(np.int16)
+    view = _dev(env, parent)[:, off:off + n]
+    got = env['ops'].filtfilt_sos(view, sos, padlen, cs).cpu().numpy()
+    x = parent[:, off:off + n]
+    ref = np.stack([np.concatenate([oracle.filtfilt(b, a, x[c, lo:min(lo + cs, n)])
+                                    for lo in range(0, n, cs)]) for c in range(n_c)])
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) < TIGHT[name] * 10, (name, n_c, cs, n_chunks, last, off)
