@@ -73,6 +73,22 @@ def _run_sharded_fabric(torch, dist_mod, x_full, S, FS, flt, sp_win, chunksize, 
 @pytest.mark.parametrize("transport", ["collective", "fabric", "fabric-capacity"])
 @pytest.mark.parametrize("S,chunksize", [(2, 20000), (3, 10000), (4, 30000)])
 def test_sharded_chain_equals_whole(cuda, S, chunksize, transport):
+    from spikesort_b200 import filters
+    _check_sharded(cuda, S, chunksize, transport, filters.Filter(300., 40.))
+
+
+@pytest.mark.parametrize("transport", ["collective", "fabric-capacity"])
+def test_sharded_chain_equals_whole_band_pass(cuda, transport):
+    """The same with a higher-order band-pass: the int16 shards go through the tile-per-lane
+    summary sweep (separate prepare call) and the section-by-section second sweep."""
+    import numpy as np
+    from spikesort_b200 import filters
+    flt = filters.Filter(np.array([150., 900.]), np.array([60., 1200.]))
+    assert flt.sections(3000)[0].shape[0] >= 2
+    _check_sharded(cuda, 3, 10000, transport, flt)
+
+
+def _check_sharded(cuda, S, chunksize, transport, flt):
     import torch
     from spikesort_b200 import dist as ssd, filters, pipeline, synth
     FS, n_c = 3000, 5
@@ -87,7 +103,6 @@ def test_sharded_chain_equals_whole(cuda, S, chunksize, transport):
         for c, d in enumerate((-7, -3, -1, 0, 2)):
             x[c, r * n + d:r * n + d + 10] += tpl
         x[1, r * n + 1:r * n + 11] += tpl                              # a double near the edge
-    flt = filters.Filter(300., 40.)
     sp_win = [-1.0, 2.0]                                               # 3 + 6 samples at 3 kHz
     whole = pipeline.run_chain(x, FS, filt=flt, sp_win=sp_win, edge='falling', align_type='min',
                                thresh='4', ncomps=2, chunksize=chunksize)
