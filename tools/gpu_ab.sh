@@ -2,6 +2,7 @@
 # A/B of library builds on one box: bench lines of bench.py --workload $W for every lib in build/lib_v*.so
 mkdir -p gpurun_out
 W=${W:-c2-bp8}
+shopt -s nullglob
 for lib in default spikesort_b200/build/lib_v*.so; do
   [ "$lib" = default ] && unset SPIKESORT_B200_LIB || export SPIKESORT_B200_LIB=$PWD/$lib
   timeout 300 python bench.py --workload $W --steps 10 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "
