@@ -42,6 +42,7 @@ extern "C" {
 #define SS_VERSION 100            /* 0.1.0 */
 
 typedef enum { SS_I16 = 0, SS_F32 = 1, SS_F64 = 2 } ss_dtype;
+typedef enum { SS_GRAM_AUTO = 0, SS_GRAM_F64 = 1, SS_GRAM_TC = 2 } ss_gram_mode;
 
 typedef enum {
     SS_OK = 0,
@@ -158,6 +159,13 @@ int ss_detect_emit(int64_t n_rows, int64_t n_samples, double FS, int64_t index_o
  *                  shards' filtered samples), readable by windows that cross the edge.
  * t_min / t_max passed to align / extract are then those of the WHOLE recording.
  * All three are 0 for an unsharded recording.
+ *   d_halo_miss : optional device int32 counter (NULL: none).  A window sample that lies
+ *                  inside the recording but beyond the stored neighbour samples (an
+ *                  alignment walk longer than the halo) cannot be read; the kernels use 0
+ *                  for it and ADD the number of affected spikes (resampled alignment:
+ *                  samples) here.  The counter is never reset by the library; a non-zero
+ *                  value means the shard's result differs from the unsharded one and the
+ *                  call must be repeated with a wider halo.
  */
 
 /* ------------------------------------------------------------------- align
@@ -174,7 +182,7 @@ int ss_align(const void *d_x, int dtype, int64_t n_samples, int64_t ld, double F
              double sp_win0, int win0, int win1, double t_min, double t_max,
              double lo, double hi, int use_min, double *d_spt, int64_t n_spk,
              int max_iter, int64_t index_offset, int64_t halo_before, int64_t halo_after,
-             void *stream);
+             int32_t *d_halo_miss, void *stream);
 
 /* Replaces remove_doubles (extract.py:277-288) per row: keeps the first time
  * of each row and every time with (int64)((t[k]-t[k-1])/tol) > 1.
@@ -209,11 +217,15 @@ int ss_extract(const void *d_x, int dtype, int64_t n_samples, int64_t ld, double
                int win0, int win1, double t_min, double t_max,
                const double *d_spt, int64_t n_spk,
                float *d_waves, uint8_t *d_valid, int32_t *d_n_invalid,
-               int64_t index_offset, int64_t halo_before, int64_t halo_after, void *stream);
+               int64_t index_offset, int64_t halo_before, int64_t halo_after,
+               int32_t *d_halo_miss, void *stream);
 
 /* --------------------------------------------------------------------- PCA
- * Replaces PCA / fetPCA (features.py:224-231, 326-344) on a float32 waveform
- * block (n_win, n_spk, n_c).  A "group" is one PCA problem:
+ * Replaces PCA / fetPCA (features.py:224-231, 326-344) on a waveform block
+ * (n_win, n_spk, n_c) of element type `dtype` (ss_dtype): float32 from extract_spikes,
+ * float64 from resample_spikes / extract_spikes(resample != 1), int16 exact - the reference
+ * promotes every dtype to float64 (features.py:224) and so do the kernels.
+ * A "group" is one PCA problem:
  *   d_offsets == NULL : n_groups = n_c, group g = contact g over all spikes
  *                       (fetPCA's loop, features.py:335-336);
  *   d_offsets != NULL : n_c must be 1, group g = spikes [d_offsets[g], d_offsets[g+1]).
@@ -223,7 +235,13 @@ int ss_extract(const void *d_x, int dtype, int64_t n_samples, int64_t ld, double
  *                  spike of the group); it only conditions the arithmetic, the
  *                  covariance does not depend on it.  Partial Grams of time shards
  *                  computed with the same ref add up: this is what the multi-GPU
- *                  path all-reduces.
+ *                  path all-reduces.  `mode` (ss_gram_mode) picks the arithmetic:
+ *                  SS_GRAM_F64 exact float64 products on the CUDA cores; SS_GRAM_TC
+ *                  3xTF32 on the tensor cores (tcgen05; float32 blocks with n_win <= 31
+ *                  and <= 4 contacts, ~1e-7 relative on the covariance; silently
+ *                  SS_GRAM_F64 when the block is not eligible); SS_GRAM_AUTO = TC from
+ *                  65536 spikes per group on.  The choice depends on the call's shape
+ *                  only, never on the data.
  * ss_pca_eig     : covariance (ddof=1) from gram/sum/count, symmetric Jacobi
  *                  eigensolve, eigenvalues |.| sorted descending, eigenvectors
  *                  in columns (features.py:225-229).  d_counts[g] = spikes per group.
@@ -237,9 +255,9 @@ int ss_extract(const void *d_x, int dtype, int64_t n_samples, int64_t ld, double
  *                  float64 when d_offsets == NULL, else (n_spk, ncomps).
  */
 size_t ss_pca_workspace_bytes(int n_win, int64_t n_groups);
-int ss_pca_gram(const float *d_waves, int n_win, int64_t n_spk, int n_c,
+int ss_pca_gram(const void *d_waves, int dtype, int n_win, int64_t n_spk, int n_c,
                 const int64_t *d_offsets, int64_t n_groups, const double *d_ref,
-                double *d_gram, double *d_sum,
+                double *d_gram, double *d_sum, int mode,
                 void *d_ws, size_t ws_bytes, void *stream);
 int ss_pca_eig(const double *d_gram, const double *d_sum,
                const int64_t *d_counts, int n_win, int64_t n_groups,
@@ -247,20 +265,20 @@ int ss_pca_eig(const double *d_gram, const double *d_sum,
 int ss_pca_eig_top(const double *d_gram, const double *d_sum,
                    const int64_t *d_counts, int n_win, int64_t n_groups, int ncomps,
                    double *d_evals, double *d_evecs, void *stream);
-int ss_pca_project(const float *d_waves, int n_win, int64_t n_spk, int n_c,
+int ss_pca_project(const void *d_waves, int dtype, int n_win, int64_t n_spk, int n_c,
                    const int64_t *d_offsets, int64_t n_groups,
                    const double *d_evals, const double *d_evecs, int ncomps,
                    double *d_scores, void *stream);
 
 /* ------------------------------------------------------- cheap features (8f)
- * Replaces fetP2P / fetMin (features.py:473-474, 483-484) on a float32 waveform block
- * (n_win, n_spk, n_c): d_min[s, c] = min_w, d_p2p[s, c] = max_w - min_w (float32, as
- * np.ptp on float32).  Either output may be NULL.
+ * Replaces fetP2P / fetMin (features.py:473-474, 483-484) on a float32 or float64
+ * waveform block (n_win, n_spk, n_c): d_min[s, c] = min_w, d_p2p[s, c] = max_w - min_w, in
+ * the block's own dtype (as np.min / np.ptp).  Either output may be NULL.
  * ss_normalize_columns replaces normalize (features.py:191-193) on a row-major float64
  * (n_rows, n_cols) matrix, in place: (x - colmin) / (colmax - colmin).  Both bit-exact.
  */
-int ss_wave_minmax(const float *d_waves, int n_win, int64_t n_spk, int n_c,
-                   float *d_min, float *d_p2p, void *stream);
+int ss_wave_minmax(const void *d_waves, int dtype, int n_win, int64_t n_spk, int n_c,
+                   void *d_min, void *d_p2p, void *stream);
 size_t ss_normalize_workspace_bytes(int n_cols);
 int ss_normalize_columns(double *d_x, int64_t n_rows, int n_cols, void *d_ws, size_t ws_bytes,
                          void *stream);
@@ -290,7 +308,7 @@ int ss_align_resampled(const void *d_x, int dtype, int64_t n_samples, int64_t ld
                        int use_min, const double *d_plan_f64, const int32_t *d_plan_i32,
                        int n_out, const double *d_rtime, double *d_spt, int64_t n_spk,
                        int max_iter, int64_t index_offset, int64_t halo_before,
-                       int64_t halo_after, void *stream);
+                       int64_t halo_after, int32_t *d_halo_miss, void *stream);
 
 /* ------------------------------------------------------- zero-phase FIR (8f)
  * Replaces FilterFir.__call__ = scipy.signal.filtfilt(b, [1], x) (filters.py:41-74) for
@@ -343,13 +361,19 @@ int ss_filtfilt_detect_sos_peer(const void *d_x, int dtype, int64_t n_contacts, 
  *                            -> slot `rank` of every arena;
  *   ss_shard_gram_reduce   : sum of the slots in rank order (bit-identical on every rank),
  *                            per-contact counts of every rank in d_all_counts (world, n_c).
- *                            A status word (*d_status, may be NULL = 0) travels with every
- *                            partial; *d_status_max is its maximum over the ranks - how all
- *                            ranks learn that one of them overflowed a capacity-sized list.
+ *                            A status word travels with every partial: SS_SHARD_OVERFLOW (1)
+ *                            when *d_status (may be NULL) is non-zero - a capacity-sized list
+ *                            overflowed - and SS_SHARD_HALO_MISS (2) when *d_halo_miss (may
+ *                            be NULL; the counter of ss_align / ss_extract) is non-zero - a
+ *                            window left the halo.  *d_status_max is the maximum over the
+ *                            ranks: how all ranks learn that the step must be repeated
+ *                            (exact sizes / a wider halo).
  * Kernels that take (d_spt, n_spk, d_offsets) ignore entries at or beyond
  * d_offsets[n_rows], so a list with spare capacity can be passed without a host sync.
  */
 #define SS_MAX_PEERS 16
+#define SS_SHARD_OVERFLOW 1
+#define SS_SHARD_HALO_MISS 2
 size_t ss_shard_arena_bytes(int n_c, int H, int n_win, int world);
 int ss_shard_arena_offsets(int n_c, int H, int n_win, int world, size_t *out7);
 int ss_peer_barrier(void *const *arenas, int rank, int world, uint64_t epoch, double timeout_s,
@@ -368,7 +392,8 @@ int ss_shard_put_last(const double *d_spt, const int64_t *d_offsets, int n_c, in
                       void *const *arenas, int rank, int world, void *stream);
 int ss_shard_gram_put(const double *d_gram, const double *d_sum, const double *d_ref,
                       const int64_t *d_offsets, int n_c, int H, int n_win, void *const *arenas,
-                      int rank, int world, const int64_t *d_status, void *stream);
+                      int rank, int world, const int64_t *d_status, const int32_t *d_halo_miss,
+                      void *stream);
 int ss_shard_gram_reduce(const void *arena, int n_c, int H, int n_win, int world, double *d_gram,
                          double *d_sum, int64_t *d_counts, int64_t *d_all_counts,
                          int64_t *d_status_max, void *stream);
@@ -382,7 +407,7 @@ int ss_merge_shard(const double *d_spt, const uint8_t *d_valid, const double *d_
                    const int64_t *d_block_base, const int64_t *d_n_tot, double *d_spt_out,
                    uint8_t *d_valid_out, double *d_scores_out, float *d_waves_out, void *stream);
 /* reference waveform for the Gram shift of ss_pca_gram: the first spike of every group */
-int ss_pca_first_wave(const float *d_waves, int n_win, int64_t n_spk, int n_c,
+int ss_pca_first_wave(const void *d_waves, int dtype, int n_win, int64_t n_spk, int n_c,
                       const int64_t *d_offsets, int64_t n_groups, double *d_ref, void *stream);
 
 #ifdef __cplusplus

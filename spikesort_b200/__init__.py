@@ -18,7 +18,7 @@ __all__ = ["filters", "extract", "features", "DeviceSignal", "to_device", "insta
            "sort_frontend"]
 
 _HOT_PATH = {
-    "filters": ("Filter", "ZeroPhaseFilter", "filter_proxy", "fltLinearIIR", "clean_after_exit"),
+    "filters": ("Filter", "ZeroPhaseFilter", "FilterFir", "filter_proxy", "fltLinearIIR", "clean_after_exit"),
     "extract": ("detect_spikes", "filter_spt", "extract_spikes", "resample_spikes",
                 "align_spikes", "remove_doubles"),
     "features": ("PCA", "fetPCA", "add_mask", "fetP2P", "fetMin", "fetSpIdx", "fetSpTime",

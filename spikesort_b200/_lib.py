@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SPIKESORT_B200_LIB") or os.path.join(_HERE, "libspikesort_b200.so")
 
 SS_I16, SS_F32, SS_F64 = 0, 1, 2
+SS_GRAM_AUTO, SS_GRAM_F64, SS_GRAM_TC = 0, 1, 2
 SS_ERR_PADLEN = -3
 SS_ERR_UNSUPPORTED = -5
 
@@ -48,18 +49,18 @@ SIGNATURES = {
     "ss_detect_mark": (_int, [_vp, _int, _i64, _i64, _i64, _vp, _int, _vp, _sz, _vp, _vp]),
     "ss_detect_emit": (_int, [_i64, _i64, _dbl, _i64, _vp, _sz, _vp, _i64, _vp]),
     "ss_align": (_int, [_vp, _int, _i64, _i64, _dbl, _vp, _i64, _vp, _dbl, _int, _int, _dbl,
-                        _dbl, _dbl, _dbl, _int, _vp, _i64, _int, _i64, _i64, _i64, _vp]),
+                        _dbl, _dbl, _dbl, _int, _vp, _i64, _int, _i64, _i64, _i64, _vp, _vp]),
     "ss_remove_doubles_workspace_bytes": (_sz, [_i64]),
     "ss_remove_doubles_mark": (_int, [_vp, _i64, _vp, _i64, _dbl, _vp, _vp, _sz, _vp, _vp]),
     "ss_remove_doubles_emit": (_int, [_vp, _i64, _vp, _sz, _vp, _i64, _vp]),
     "ss_extract": (_int, [_vp, _int, _i64, _i64, _dbl, _vp, _int, _vp, _i64, _vp, _int, _int,
-                          _dbl, _dbl, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+                          _dbl, _dbl, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "ss_pca_workspace_bytes": (_sz, [_int, _i64]),
-    "ss_pca_gram": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ss_pca_gram": (_int, [_vp, _int, _int, _i64, _int, _vp, _i64, _vp, _vp, _vp, _int, _vp, _sz, _vp]),
     "ss_pca_eig": (_int, [_vp, _vp, _vp, _int, _i64, _vp, _vp, _vp]),
     "ss_pca_eig_top": (_int, [_vp, _vp, _vp, _int, _i64, _int, _vp, _vp, _vp]),
-    "ss_pca_project": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp, _int, _vp, _vp]),
-    "ss_wave_minmax": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp]),
+    "ss_pca_project": (_int, [_vp, _int, _int, _i64, _int, _vp, _i64, _vp, _vp, _int, _vp, _vp]),
+    "ss_wave_minmax": (_int, [_vp, _int, _int, _i64, _int, _vp, _vp, _vp]),
     "ss_normalize_workspace_bytes": (_sz, [_int]),
     "ss_normalize_columns": (_int, [_vp, _i64, _int, _vp, _sz, _vp]),
     "ss_copy_2d_async": (_int, [_vp, _sz, _vp, _sz, _sz, _sz, _int, _vp]),
@@ -73,11 +74,11 @@ SIGNATURES = {
                                       _vp, _vp]),
     "ss_shard_append_boundary": (_int, [_vp, _vp, _int, _i64, _vp, _dbl, _vp, _vp, _vp]),
     "ss_shard_put_last": (_int, [_vp, _vp, _int, _int, _int, _vp, _int, _int, _vp]),
-    "ss_shard_gram_put": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _vp, _int, _int, _vp, _vp]),
+    "ss_shard_gram_put": (_int, [_vp, _vp, _vp, _vp, _int, _int, _int, _vp, _int, _int, _vp, _vp, _vp]),
     "ss_shard_gram_reduce": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ss_merge_shard": (_int, [_vp, _vp, _vp, _int, _vp, _int, _i64, _i64, _vp, _int, _vp, _vp, _vp, _vp, _vp,
                               _vp, _vp, _vp]),
-    "ss_pca_first_wave": (_int, [_vp, _int, _i64, _int, _vp, _i64, _vp, _vp]),
+    "ss_pca_first_wave": (_int, [_vp, _int, _int, _i64, _int, _vp, _i64, _vp, _vp]),
     "ss_resample": (_int, [_vp, _int, _int, _i64, _int, _vp, _vp, _int, _vp, _vp]),
     "ss_align_resampled": (_int, [_vp, _int, _i64, _i64, _dbl, _vp, _i64, _vp, _int, _int, _dbl,
                                   _dbl, _dbl, _dbl, _int, _vp, _vp, _int, _vp, _vp, _i64, _int,

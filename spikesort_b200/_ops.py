@@ -230,9 +230,10 @@ def detect(x, thr, falling, FS, shard=_WHOLE, cap=None):
 
 
 # ---------------------------------------------------------------------- align
-def align(x, spt, offsets, rows, FS, sp_win, use_min, shard=_WHOLE):
+def align(x, spt, offsets, rows, FS, sp_win, use_min, shard=_WHOLE, halo_miss=None):
     """In-place alignment of CUDA float64 times `spt`.  offsets: CUDA int64
-    [n_rows+1] or None (single row); rows: CUDA int32 row ids or None."""
+    [n_rows+1] or None (single row); rows: CUDA int32 row ids or None.
+    halo_miss: CUDA int32[1] counter of spikes whose window left the shard's halo."""
     lib = _lib.load()
     n = x.shape[1]
     win0, win1, _ = window_params(sp_win, FS)
@@ -244,7 +245,7 @@ def align(x, spt, offsets, rows, FS, sp_win, use_min, shard=_WHOLE):
                       _lib.ptr(rows), n_rows, _lib.ptr(offsets), float(sp_win[0]), win0, win1,
                       t_min, t_max, float(lo), float(hi), int(bool(use_min)), _lib.ptr(spt),
                       spt.numel(), MAX_ALIGN_ITER, shard.index_offset, shard.halo_before,
-                      shard.halo_after, _lib.stream_ptr())
+                      shard.halo_after, _lib.ptr(halo_miss), _lib.stream_ptr())
     _lib.check(rc, "ss_align")
     _launched(1 if spt.numel() > 0 else 0)
     return spt
@@ -285,7 +286,8 @@ def remove_doubles(spt, offsets, tol, prev_last=None, also=None, cap=None):
 
 
 # -------------------------------------------------------------------- extract
-def extract(x, spt, FS, sp_win, contacts=None, offsets=None, rows=None, shard=_WHOLE):
+def extract(x, spt, FS, sp_win, contacts=None, offsets=None, rows=None, shard=_WHOLE,
+            halo_miss=None):
     """Returns (waves float32 (n_win, n_spk, n_c), valid uint8[n_spk], n_invalid int32[1])
     as CUDA tensors.  contacts: CUDA int32 list (reference mode) or None (row mode)."""
     lib = _lib.load()
@@ -303,7 +305,8 @@ def extract(x, spt, FS, sp_win, contacts=None, offsets=None, rows=None, shard=_W
                         _lib.ptr(contacts), n_c, _lib.ptr(rows), n_rows, _lib.ptr(offsets),
                         win0, win1, t_min, t_max, _lib.ptr(spt), n_spk, _lib.ptr(waves),
                         _lib.ptr(valid), _lib.ptr(n_invalid), shard.index_offset,
-                        shard.halo_before, shard.halo_after, _lib.stream_ptr())
+                        shard.halo_before, shard.halo_after, _lib.ptr(halo_miss),
+                        _lib.stream_ptr())
     _lib.check(rc, "ss_extract")
     _launched(1 if n_spk > 0 else 0)
     return waves, valid, n_invalid
@@ -318,16 +321,22 @@ def pca_first_wave(waves, offsets=None):
     n_win, n_spk, n_c = waves.shape
     n_groups = n_c if offsets is None else offsets.numel() - 1
     ref = t.empty((n_groups, n_win), dtype=t.float64, device=waves.device)
-    rc = lib.ss_pca_first_wave(_lib.ptr(waves), n_win, n_spk, n_c, _lib.ptr(offsets), n_groups,
+    rc = lib.ss_pca_first_wave(_lib.ptr(waves), _lib.ss_dtype_of(waves), n_win, n_spk, n_c,
+                               _lib.ptr(offsets), n_groups,
                                _lib.ptr(ref), _lib.stream_ptr())
     _lib.check(rc, "ss_pca_first_wave")
     _launched(1)
     return ref
 
 
-def pca_gram(waves, offsets=None, ref=None):
-    """Gram / sums of CUDA float32 waves (n_win, n_spk, n_c) per group.
-    Returns (gram (G, n_win, n_win), sum (G, n_win), ref (G, n_win), counts (G,))."""
+GRAM_MODES = {"auto": _lib.SS_GRAM_AUTO, "f64": _lib.SS_GRAM_F64, "tc": _lib.SS_GRAM_TC}
+
+
+def pca_gram(waves, offsets=None, ref=None, mode="auto"):
+    """Gram / sums of CUDA waves (n_win, n_spk, n_c) (float32 / float64 / int16) per group.
+    Returns (gram (G, n_win, n_win), sum (G, n_win), ref (G, n_win), counts (G,)).
+    mode: 'f64' exact float64 products, 'tc' 3xTF32 tensor cores (eligible float32 blocks),
+    'auto' = 'tc' from 65536 spikes per group on - a function of the call's shape only."""
     lib = _lib.load()
     t = _lib.torch()
     n_win, n_spk, n_c = waves.shape
@@ -342,9 +351,9 @@ def pca_gram(waves, offsets=None, ref=None):
     gram = t.empty((n_groups, n_win, n_win), dtype=t.float64, device=waves.device)
     ssum = t.empty((n_groups, n_win), dtype=t.float64, device=waves.device)
     ws = _lib.workspace(lib.ss_pca_workspace_bytes(n_win, n_groups))
-    rc = lib.ss_pca_gram(_lib.ptr(waves), n_win, n_spk, n_c, _lib.ptr(offsets), n_groups,
-                         _lib.ptr(ref), _lib.ptr(gram), _lib.ptr(ssum), _lib.ptr(ws), ws.numel(),
-                         _lib.stream_ptr())
+    rc = lib.ss_pca_gram(_lib.ptr(waves), _lib.ss_dtype_of(waves), n_win, n_spk, n_c,
+                         _lib.ptr(offsets), n_groups, _lib.ptr(ref), _lib.ptr(gram), _lib.ptr(ssum),
+                         GRAM_MODES[mode], _lib.ptr(ws), ws.numel(), _lib.stream_ptr())
     _lib.check(rc, "ss_pca_gram")
     _launched(2)          # partial Grams, ordered reduction
     return gram, ssum, ref, counts
@@ -378,7 +387,8 @@ def pca_project(waves, evals, evecs, ncomps, offsets=None):
     n_groups = evals.shape[0]
     width = ncomps * (n_c if offsets is None else 1)
     scores = t.empty((n_spk, width), dtype=t.float64, device=waves.device)
-    rc = lib.ss_pca_project(_lib.ptr(waves), n_win, n_spk, n_c, _lib.ptr(offsets), n_groups,
+    rc = lib.ss_pca_project(_lib.ptr(waves), _lib.ss_dtype_of(waves), n_win, n_spk, n_c,
+                            _lib.ptr(offsets), n_groups,
                             _lib.ptr(evals), _lib.ptr(evecs), int(ncomps), _lib.ptr(scores),
                             _lib.stream_ptr())
     _lib.check(rc, "ss_pca_project")
@@ -388,15 +398,15 @@ def pca_project(waves, evals, evecs, ncomps, offsets=None):
 
 # ------------------------------------------------------------- cheap features
 def wave_minmax(waves, want_min=True, want_p2p=True):
-    """(min, max - min) over the time axis of CUDA float32 waves (n_win, n_spk, n_c);
-    each (n_spk, n_c) float32 or None."""
+    """(min, max - min) over the time axis of CUDA float32 / float64 waves
+    (n_win, n_spk, n_c); each (n_spk, n_c) in the waves' dtype or None."""
     lib = _lib.load()
     t = _lib.torch()
     n_win, n_spk, n_c = waves.shape
-    mn = t.empty((n_spk, n_c), dtype=t.float32, device=waves.device) if want_min else None
-    pp = t.empty((n_spk, n_c), dtype=t.float32, device=waves.device) if want_p2p else None
-    rc = lib.ss_wave_minmax(_lib.ptr(waves), n_win, n_spk, n_c, _lib.ptr(mn), _lib.ptr(pp),
-                            _lib.stream_ptr())
+    mn = t.empty((n_spk, n_c), dtype=waves.dtype, device=waves.device) if want_min else None
+    pp = t.empty((n_spk, n_c), dtype=waves.dtype, device=waves.device) if want_p2p else None
+    rc = lib.ss_wave_minmax(_lib.ptr(waves), _lib.ss_dtype_of(waves), n_win, n_spk, n_c,
+                            _lib.ptr(mn), _lib.ptr(pp), _lib.stream_ptr())
     _lib.check(rc, "ss_wave_minmax")
     _launched(1 if n_spk > 0 else 0)
     return mn, pp
@@ -442,7 +452,8 @@ def resample(waves, plan):
     return out
 
 
-def align_resampled(x, spt, offsets, rows, FS, sp_win, use_min, resample_factor, shard=_WHOLE):
+def align_resampled(x, spt, offsets, rows, FS, sp_win, use_min, resample_factor, shard=_WHOLE,
+                    halo_miss=None):
     """align() with the extremum searched on the spline-upsampled window
     (extract.py:245-258 with resample != 1)."""
     from ._spline import spline_plan
@@ -460,7 +471,7 @@ def align_resampled(x, spt, offsets, rows, FS, sp_win, use_min, resample_factor,
                                 float(lo), float(hi), int(bool(use_min)), _lib.ptr(pf), _lib.ptr(pi),
                                 plan.n_out, _lib.ptr(rt), _lib.ptr(spt), spt.numel(), MAX_ALIGN_ITER,
                                 shard.index_offset, shard.halo_before, shard.halo_after,
-                                _lib.stream_ptr())
+                                _lib.ptr(halo_miss), _lib.stream_ptr())
     _lib.check(rc, "ss_align_resampled")
     _launched(1 if spt.numel() > 0 else 0)
     return spt

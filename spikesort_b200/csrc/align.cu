@@ -42,7 +42,8 @@ align_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t l
              const int32_t *__restrict__ rows, int64_t n_rows, const int64_t *__restrict__ offsets,
              double sp_win0, int win0, int win1, double t_min, double t_max, double lo, double hi,
              int use_min, double *__restrict__ spt, int64_t n_spk, int max_iter,
-             int64_t index_offset, int64_t halo_before, int64_t halo_after)
+             int64_t index_offset, int64_t halo_before, int64_t halo_after,
+             int32_t *__restrict__ halo_miss)
 {
     const int64_t s = (int64_t)blockIdx.x * (32 * AL_WARPS) + threadIdx.x;
     if (s >= n_spk || (offsets && s >= __ldg(offsets + n_rows))) return;   // spare capacity
@@ -51,7 +52,7 @@ align_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t l
     const int64_t row0 = r * ld;
     const int n_win = win1 - win0;
     double t = spt[s];
-    bool moved = false;
+    bool moved = false, missed = false;
     for (int it = 0; it < max_iter; ++it) {
         if (!(t >= t_min && t <= t_max)) break;                 // filter_spt, extract.py:108-110
         const int centre = __double2int_rz(__dmul_rn(__ddiv_rn(t, 1000.0), FS));   // :150
@@ -80,6 +81,7 @@ align_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t l
                 const int64_t i = first + k;
                 float v = 0.f;
                 if (i >= -halo_before && i < n_samples + halo_after) v = ss_load_f32(x, dtype, row0 + i);
+                else missed = missed || ss_beyond_halo(i, n_samples, halo_before, halo_after);
                 if (use_min) v = -v;
                 if (k == 0 || v > best) { best = v; best_k = k; }
             }
@@ -91,6 +93,7 @@ align_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t l
         if (!(shift < lo || shift > hi)) break;                 // :263-264
     }
     if (moved) spt[s] = t;
+    if (missed && halo_miss) atomicAdd(halo_miss, 1);
 }
 
 // keep[k] = first of its row, or (int64)((t[k]-t[k-1])/tol) > 1
@@ -196,6 +199,7 @@ extern "C" int ss_align(const void *d_x, int dtype, int64_t n_samples, int64_t l
                         double sp_win0, int win0, int win1, double t_min, double t_max, double lo,
                         double hi, int use_min, double *d_spt, int64_t n_spk, int max_iter,
                         int64_t index_offset, int64_t halo_before, int64_t halo_after,
+                        int32_t *d_halo_miss,
                         void *stream)
 {
     if (n_spk == 0) return SS_OK;
@@ -211,7 +215,8 @@ extern "C" int ss_align(const void *d_x, int dtype, int64_t n_samples, int64_t l
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     align_kernel<<<(unsigned)ss_cdiv(n_spk, 32 * AL_WARPS), 32 * AL_WARPS, 0, st>>>(
         d_x, dtype, n_samples, ld, FS, d_rows, n_rows, d_offsets, sp_win0, win0, win1, t_min,
-        t_max, lo, hi, use_min, d_spt, n_spk, max_iter, index_offset, halo_before, halo_after);
+        t_max, lo, hi, use_min, d_spt, n_spk, max_iter, index_offset, halo_before, halo_after,
+        d_halo_miss);
     SS_LAUNCH_CHECK("align_kernel");
     return SS_OK;
 }

@@ -83,4 +83,14 @@ __device__ __forceinline__ double ss_to_f64(int16_t v)
 __device__ __forceinline__ double ss_to_f64(float v) { return (double)v; }
 __device__ __forceinline__ double ss_to_f64(double v) { return v; }
 
+// Time shards: a window sample at local index i that lies beyond the neighbour samples stored
+// around the shard (but inside the recording: a side without a neighbour has halo 0) cannot be
+// read; the kernels substitute 0 and count the event so that the host can redo the call
+// with a wider halo (the reference, one process, would simply read the sample).
+__device__ __forceinline__ bool ss_beyond_halo(int64_t i, int64_t n_samples, int64_t halo_before,
+                                               int64_t halo_after)
+{
+    return (halo_before > 0 && i < -halo_before) || (halo_after > 0 && i >= n_samples + halo_after);
+}
+
 static inline int ss_elem_size(int dtype) { return dtype == SS_I16 ? 2 : dtype == SS_F32 ? 4 : 8; }

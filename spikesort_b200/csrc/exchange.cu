@@ -190,11 +190,15 @@ __global__ void put_last_kernel(const double *__restrict__ spt, const int64_t *_
 __global__ void __launch_bounds__(XC_THREADS)
 gram_put_kernel(const double *__restrict__ gram, const double *__restrict__ ssum,
                 const double *__restrict__ ref, const int64_t *__restrict__ offsets, int n_c,
-                int n_win, PeerPtrs slots, int world, const int64_t *__restrict__ status)
+                int n_win, PeerPtrs slots, int world, const int64_t *__restrict__ status,
+                const int32_t *__restrict__ halo_miss)
 {
     const int64_t c = blockIdx.x;
     if (c == 0 && threadIdx.x == 0) {
-        const double st = status ? (double)*status : 0.0;
+        // status word of the step: 1 = a capacity-sized list overflowed, 2 = a window left the
+        // halo (SS_SHARD_OVERFLOW / SS_SHARD_HALO_MISS); every rank sees the maximum
+        double st = (status && *status) ? 1.0 : 0.0;
+        if (halo_miss && *halo_miss) st = 2.0;
         const size_t at = (size_t)n_c * (n_win * n_win + n_win + 1);
         for (int p = 0; p < world; ++p) reinterpret_cast<double *>(slots.p[p])[at] = st;
     }
@@ -248,7 +252,8 @@ gram_reduce_kernel(const double *__restrict__ slots, size_t slot_stride_f64, int
 }
 
 // reference waveform of every group for the Gram shift: the group's first spike
-__global__ void first_wave_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, int n_c,
+template <typename T>
+__global__ void first_wave_kernel(const T *__restrict__ waves, int n_win, int64_t n_spk, int n_c,
                                   const int64_t *__restrict__ offsets, int64_t n_groups,
                                   double *__restrict__ ref)
 {
@@ -402,14 +407,14 @@ extern "C" int ss_shard_put_last(const double *d_spt, const int64_t *d_offsets, 
 extern "C" int ss_shard_gram_put(const double *d_gram, const double *d_sum, const double *d_ref,
                                  const int64_t *d_offsets, int n_c, int H, int n_win,
                                  void *const *arenas, int rank, int world,
-                                 const int64_t *d_status, void *stream)
+                                 const int64_t *d_status, const int32_t *d_halo_miss, void *stream)
 {
     SS_REQUIRE(d_gram && d_sum && d_ref && d_offsets && arenas && rank >= 0 && rank < world &&
                world <= SS_MAX_PEERS, SS_ERR_ARG, "gram_put: bad argument");
     const ArenaLayout L = arena_layout(n_c, H, n_win, world);
     gram_put_kernel<<<n_c, XC_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         d_gram, d_sum, d_ref, d_offsets, n_c, n_win,
-        peer_ptrs(arenas, world, L.slots + L.slot_stride * (size_t)rank), world, d_status);
+        peer_ptrs(arenas, world, L.slots + L.slot_stride * (size_t)rank), world, d_status, d_halo_miss);
     SS_LAUNCH_CHECK("gram_put_kernel");
     return SS_OK;
 }
@@ -429,13 +434,20 @@ extern "C" int ss_shard_gram_reduce(const void *arena, int n_c, int H, int n_win
     return SS_OK;
 }
 
-extern "C" int ss_pca_first_wave(const float *d_waves, int n_win, int64_t n_spk, int n_c,
+extern "C" int ss_pca_first_wave(const void *d_waves, int dtype, int n_win, int64_t n_spk, int n_c,
                                  const int64_t *d_offsets, int64_t n_groups, double *d_ref,
                                  void *stream)
 {
     SS_REQUIRE(d_ref && (d_waves || n_spk == 0) && n_groups >= 1 && n_win >= 1, SS_ERR_ARG, "first_wave: bad argument");
-    first_wave_kernel<<<(unsigned)ss_cdiv(n_groups * n_win, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        d_waves, n_win, n_spk, n_c, d_offsets, n_groups, d_ref);
+    SS_REQUIRE(dtype >= SS_I16 && dtype <= SS_F64, SS_ERR_ARG, "first_wave: bad dtype %d", dtype);
+    const unsigned blocks = (unsigned)ss_cdiv(n_groups * n_win, 256);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == SS_F32)
+        first_wave_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float *>(d_waves), n_win, n_spk, n_c, d_offsets, n_groups, d_ref);
+    else if (dtype == SS_F64)
+        first_wave_kernel<double><<<blocks, 256, 0, st>>>(reinterpret_cast<const double *>(d_waves), n_win, n_spk, n_c, d_offsets, n_groups, d_ref);
+    else
+        first_wave_kernel<int16_t><<<blocks, 256, 0, st>>>(reinterpret_cast<const int16_t *>(d_waves), n_win, n_spk, n_c, d_offsets, n_groups, d_ref);
     SS_LAUNCH_CHECK("first_wave_kernel");
     return SS_OK;
 }

@@ -39,7 +39,8 @@ extract_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t
                int win0, int n_win, double t_min, double t_max,
                const double *__restrict__ spt, int64_t n_spk,
                float *__restrict__ waves, uint8_t *__restrict__ valid, int32_t *__restrict__ n_invalid,
-               int64_t index_offset, int64_t halo_before, int64_t halo_after)
+               int64_t index_offset, int64_t halo_before, int64_t halo_after,
+               int32_t *__restrict__ halo_miss)
 {
     extern __shared__ float tile[];                 // [n_win][EX_PAIRS + 1]
     __shared__ int64_t s_first[EX_PAIRS];           // first sample of the window, per local spike
@@ -90,6 +91,8 @@ extract_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, int64_t
             float v = 0.f;
             if (live && i >= -halo_before && i < n_samples + halo_after)
                 v = ss_load_f32(x, dtype, base + i);
+            else if (live && halo_miss && ss_beyond_halo(i, n_samples, halo_before, halo_after))
+                atomicAdd(halo_miss, 1);
             tile[w * (EX_PAIRS + 1) + p] = v;
         }
     }
@@ -116,7 +119,8 @@ extract_rows_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, in
                     int win0, int n_win, double t_min, double t_max,
                     const double *__restrict__ spt, int64_t n_spk,
                     float *__restrict__ waves, uint8_t *__restrict__ valid, int32_t *__restrict__ n_invalid,
-                    int64_t index_offset, int64_t halo_before, int64_t halo_after)
+                    int64_t index_offset, int64_t halo_before, int64_t halo_after,
+                    int32_t *__restrict__ halo_miss)
 {
     const int64_t s = (int64_t)blockIdx.x * 256 + threadIdx.x;
     if (s >= n_spk) return;
@@ -145,12 +149,15 @@ extract_rows_kernel(const void *__restrict__ x, int dtype, int64_t n_samples, in
             for (int w = 0; w < n_win; ++w) dst[(int64_t)w * n_spk] = ss_load_f32(x, dtype, base + w);
         }
     } else {
+        bool missed = false;
         for (int w = 0; w < n_win; ++w) {
             const int64_t i = first + w;
             float v = 0.f;
             if (i >= -halo_before && i < n_samples + halo_after) v = ss_load_f32(x, dtype, row0 + i);
+            else missed = missed || ss_beyond_halo(i, n_samples, halo_before, halo_after);
             dst[(int64_t)w * n_spk] = v;
         }
+        if (missed && halo_miss) atomicAdd(halo_miss, 1);
     }
 }
 
@@ -163,7 +170,7 @@ extern "C" int ss_extract(const void *d_x, int dtype, int64_t n_samples, int64_t
                           const int64_t *d_offsets, int win0, int win1, double t_min, double t_max,
                           const double *d_spt, int64_t n_spk, float *d_waves, uint8_t *d_valid,
                           int32_t *d_n_invalid, int64_t index_offset, int64_t halo_before,
-                          int64_t halo_after, void *stream)
+                          int64_t halo_after, int32_t *d_halo_miss, void *stream)
 {
     SS_REQUIRE(d_n_invalid, SS_ERR_ARG, "extract: null d_n_invalid");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -184,7 +191,8 @@ extern "C" int ss_extract(const void *d_x, int dtype, int64_t n_samples, int64_t
     if (!d_contacts) {
         extract_rows_kernel<<<(unsigned)ss_cdiv(n_spk, 256), 256, 0, st>>>(
             d_x, dtype, n_samples, ld, FS, d_rows, n_rows, d_offsets, win0, n_win, t_min, t_max,
-            d_spt, n_spk, d_waves, d_valid, d_n_invalid, index_offset, halo_before, halo_after);
+            d_spt, n_spk, d_waves, d_valid, d_n_invalid, index_offset, halo_before, halo_after,
+            d_halo_miss);
         SS_LAUNCH_CHECK("extract_rows_kernel");
         return SS_OK;
     }
@@ -198,7 +206,7 @@ extern "C" int ss_extract(const void *d_x, int dtype, int64_t n_samples, int64_t
     extract_kernel<<<grid, EX_PAIRS, smem, st>>>(d_x, dtype, n_samples, ld, FS, d_contacts, n_c, CB,
                                                 d_rows, n_rows, d_offsets, win0, n_win, t_min, t_max,
                                                 d_spt, n_spk, d_waves, d_valid, d_n_invalid,
-                                                index_offset, halo_before, halo_after);
+                                                index_offset, halo_before, halo_after, d_halo_miss);
     SS_LAUNCH_CHECK("extract_kernel");
     return SS_OK;
 }

@@ -14,21 +14,27 @@ namespace {
 constexpr int NM_THREADS = 256;
 constexpr int NM_PARTS = 592;           // row ranges (4 per SM)
 
-// one thread per (spike, contact): waves is (n_win, n_spk, n_c), outputs (n_spk, n_c)
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
+// one thread per (spike, contact): waves is (n_win, n_spk, n_c), outputs (n_spk, n_c) in the
+// waveforms' own dtype (np.ptp / np.min keep it: float32 from extract_spikes, float64 from
+// resample_spikes)
+template <typename T>
 __global__ void __launch_bounds__(256)
-wave_minmax_kernel(const float *__restrict__ waves, int n_win, int64_t n_pairs,
-                   float *__restrict__ mn_out, float *__restrict__ p2p_out)
+wave_minmax_kernel(const T *__restrict__ waves, int n_win, int64_t n_pairs,
+                   T *__restrict__ mn_out, T *__restrict__ p2p_out)
 {
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_pairs) return;
-    float mn = __ldg(waves + idx), mx = mn;
+    T mn = __ldg(waves + idx), mx = mn;
     for (int w = 1; w < n_win; ++w) {
-        const float v = __ldg(waves + (int64_t)w * n_pairs + idx);
+        const T v = __ldg(waves + (int64_t)w * n_pairs + idx);
         mn = v < mn ? v : mn;
         mx = v > mx ? v : mx;
     }
     if (mn_out) mn_out[idx] = mn;
-    if (p2p_out) p2p_out[idx] = __fsub_rn(mx, mn);
+    if (p2p_out) p2p_out[idx] = sub_rn(mx, mn);
 }
 
 // partial column min/max of a row-major (n_rows, n_cols) float64 matrix: block b takes a
@@ -93,15 +99,23 @@ normalize_apply_kernel(double *__restrict__ x, int64_t n_elems, int n_cols,
 
 }  // namespace
 
-extern "C" int ss_wave_minmax(const float *d_waves, int n_win, int64_t n_spk, int n_c,
-                              float *d_min, float *d_p2p, void *stream)
+extern "C" int ss_wave_minmax(const void *d_waves, int dtype, int n_win, int64_t n_spk, int n_c,
+                              void *d_min, void *d_p2p, void *stream)
 {
     if (n_spk == 0) return SS_OK;
     SS_REQUIRE(d_waves && (d_min || d_p2p), SS_ERR_ARG, "wave_minmax: null pointer");
     SS_REQUIRE(n_win >= 1 && n_spk > 0 && n_c >= 1, SS_ERR_ARG, "wave_minmax: bad shape");
+    SS_REQUIRE(dtype == SS_F32 || dtype == SS_F64, SS_ERR_UNSUPPORTED,
+               "wave_minmax: waveforms must be float32 or float64 (dtype %d)", dtype);
     const int64_t n_pairs = n_spk * n_c;
-    wave_minmax_kernel<<<(unsigned)ss_cdiv(n_pairs, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        d_waves, n_win, n_pairs, d_min, d_p2p);
+    const unsigned blocks = (unsigned)ss_cdiv(n_pairs, 256);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (dtype == SS_F32)
+        wave_minmax_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float *>(d_waves), n_win, n_pairs,
+                                                         reinterpret_cast<float *>(d_min), reinterpret_cast<float *>(d_p2p));
+    else
+        wave_minmax_kernel<double><<<blocks, 256, 0, st>>>(reinterpret_cast<const double *>(d_waves), n_win, n_pairs,
+                                                          reinterpret_cast<double *>(d_min), reinterpret_cast<double *>(d_p2p));
     SS_LAUNCH_CHECK("wave_minmax_kernel");
     return SS_OK;
 }

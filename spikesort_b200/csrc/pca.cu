@@ -36,9 +36,11 @@ static int pc_parts(int64_t n_groups)
     return (int)p;
 }
 
-// grid (parts, n_groups)
+// grid (parts, n_groups); T = element type of the waveform block (the reference promotes any
+// dtype to float64, features.py:224: float32 from extract_spikes, float64 from resample_spikes)
+template <typename T>
 __global__ void __launch_bounds__(PC_THREADS)
-pca_gram_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, int n_c,
+pca_gram_kernel(const T *__restrict__ waves, int n_win, int64_t n_spk, int n_c,
                 const int64_t *__restrict__ offsets, const double *__restrict__ ref,
                 double *__restrict__ ws_gram, double *__restrict__ ws_sum)
 {
@@ -90,7 +92,7 @@ pca_gram_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, int n
             const int w = idx / PC_SC, sl = idx - w * PC_SC;
             double v = 0.0;
             if (sl < ns && w < n_win)
-                v = (double)__ldg(waves + ((int64_t)w * n_spk + base + sl) * n_c + c) - s_ref[w];
+                v = ss_to_f64(__ldg(waves + ((int64_t)w * n_spk + base + sl) * n_c + c)) - s_ref[w];
             sh[sl * RS + w] = v;
         }
         __syncthreads();
@@ -643,8 +645,9 @@ pca_eig_top_kernel(const double *__restrict__ gram, const double *__restrict__ s
     }
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256)
-pca_project_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, int n_c,
+pca_project_kernel(const T *__restrict__ waves, int n_win, int64_t n_spk, int n_c,
                    const int64_t *__restrict__ offsets, int64_t n_groups,
                    const double *__restrict__ evals, const double *__restrict__ evecs, int ncomps,
                    double *__restrict__ scores)
@@ -669,7 +672,7 @@ pca_project_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
     const double *V = evecs + g * n_win * n_win;
     const int64_t step = n_spk * (int64_t)n_c;
     for (int w = 0; w < n_win; ++w) {
-        const double xv = (double)__ldg(waves + (int64_t)w * step + idx);
+        const double xv = ss_to_f64(__ldg(waves + (int64_t)w * step + idx));
 #pragma unroll
         for (int j = 0; j < PC_MAX_COMPS; ++j)
             if (j < ncomps) acc[j] += __ldg(V + w * n_win + j) * xv;
@@ -691,11 +694,14 @@ extern "C" size_t ss_pca_workspace_bytes(int n_win, int64_t n_groups)
     return (size_t)n_groups * pc_parts(n_groups) * ((size_t)nwp * nwp + nwp) * sizeof(double);
 }
 
-extern "C" int ss_pca_gram(const float *d_waves, int n_win, int64_t n_spk, int n_c,
+extern "C" int ss_pca_gram(const void *d_waves, int dtype, int n_win, int64_t n_spk, int n_c,
                            const int64_t *d_offsets, int64_t n_groups, const double *d_ref,
-                           double *d_gram, double *d_sum, void *d_ws, size_t ws_bytes, void *stream)
+                           double *d_gram, double *d_sum, int mode, void *d_ws, size_t ws_bytes,
+                           void *stream)
 {
     SS_REQUIRE((d_waves || n_spk == 0) && d_ref && d_gram && d_sum && d_ws, SS_ERR_ARG, "pca_gram: null pointer");
+    SS_REQUIRE(dtype >= SS_I16 && dtype <= SS_F64, SS_ERR_ARG, "pca_gram: bad dtype %d", dtype);
+    SS_REQUIRE(mode >= SS_GRAM_AUTO && mode <= SS_GRAM_TC, SS_ERR_ARG, "pca_gram: bad mode %d", mode);
     SS_REQUIRE(n_win >= 1 && n_win <= PC_MAX_WIN, SS_ERR_UNSUPPORTED, "pca_gram: n_win %d outside [1, %d]", n_win, PC_MAX_WIN);
     SS_REQUIRE(n_spk >= 0 && n_c >= 1 && n_groups >= 1 && n_groups <= 65535, SS_ERR_ARG, "pca_gram: bad shape");
     SS_REQUIRE(d_offsets ? n_c == 1 : n_groups == n_c, SS_ERR_ARG, "pca_gram: group layout mismatch");
@@ -705,27 +711,39 @@ extern "C" int ss_pca_gram(const float *d_waves, int n_win, int64_t n_spk, int n
     double *ws_gram = reinterpret_cast<double *>(d_ws);
     double *ws_sum = ws_gram + (size_t)n_groups * parts * nwp * nwp;
     const size_t smem = (size_t)PC_SC * (nwp + 2) * sizeof(double);
-    SS_CUDA_CHECK(cudaFuncSetAttribute(pca_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)((size_t)PC_SC * (PC_MAX_WIN + 2) * sizeof(double))));
-    // Large problems go to the tensor cores (3xTF32, ~1e-7 relative on the covariance);
-    // small ones stay on the float64 CUDA-core kernel (exact products, ~1e-15).
-    // SS_PCA_TC=0 / 1 forces the choice.
+    const int smem_max = (int)((size_t)PC_SC * (PC_MAX_WIN + 2) * sizeof(double));
+    SS_CUDA_CHECK(cudaFuncSetAttribute(pca_gram_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    SS_CUDA_CHECK(cudaFuncSetAttribute(pca_gram_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    SS_CUDA_CHECK(cudaFuncSetAttribute(pca_gram_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    // Large float32 problems go to the tensor cores (3xTF32 with short float32 accumulation
+    // chunks, ~1e-7 relative on the covariance); small ones and float64 / int16 blocks stay on
+    // the float64 CUDA-core kernel (exact products, ~1e-15).  The choice depends on the SHAPE
+    // of the call only (n_spk is the capacity in the speculative chain), so ss_pca_gram_mode
+    // lets the caller pin it: the chain pins the float64 kernel unless told otherwise.
+    // SS_PCA_TC=0 / 1 forces the choice for A/B runs.
     const char *force = getenv("SS_PCA_TC");
     const int64_t per_group = d_offsets ? n_spk / (n_groups > 0 ? n_groups : 1) : n_spk;
-    bool use_tc = ssi::pca_gram_tc_eligible(n_win, n_spk, n_c, d_offsets != nullptr) &&
-                  (reinterpret_cast<uintptr_t>(d_waves) % 16 == 0) && per_group >= 65536;
+    const bool tc_ok = dtype == SS_F32 && ssi::pca_gram_tc_eligible(n_win, n_spk, n_c, d_offsets != nullptr) &&
+                       (reinterpret_cast<uintptr_t>(d_waves) % 16 == 0);
+    bool use_tc = tc_ok && (mode == SS_GRAM_TC || (mode == SS_GRAM_AUTO && per_group >= 65536));
     if (force && force[0] == '0') use_tc = false;
-    if (force && force[0] == '1')
-        use_tc = ssi::pca_gram_tc_eligible(n_win, n_spk, n_c, d_offsets != nullptr) &&
-                 (reinterpret_cast<uintptr_t>(d_waves) % 16 == 0);
+    if (force && force[0] == '1') use_tc = tc_ok;
     if (use_tc) {
-        const int rc = ssi::pca_gram_tc(d_waves, n_win, n_spk, n_c, d_offsets, n_groups, d_ref,
-                                        ws_gram, ws_sum, parts, nwp, st);
+        const int rc = ssi::pca_gram_tc(reinterpret_cast<const float *>(d_waves), n_win, n_spk, n_c,
+                                        d_offsets, n_groups, d_ref, ws_gram, ws_sum, parts, nwp, st);
         if (rc) return rc;
     } else {
         // unused upper-triangle tiles of partials are never read; no memset needed
-        pca_gram_kernel<<<dim3(parts, (unsigned)n_groups), PC_THREADS, smem, st>>>(
-            d_waves, n_win, n_spk, n_c, d_offsets, d_ref, ws_gram, ws_sum);
+        const dim3 grid(parts, (unsigned)n_groups);
+        if (dtype == SS_F32)
+            pca_gram_kernel<float><<<grid, PC_THREADS, smem, st>>>(
+                reinterpret_cast<const float *>(d_waves), n_win, n_spk, n_c, d_offsets, d_ref, ws_gram, ws_sum);
+        else if (dtype == SS_F64)
+            pca_gram_kernel<double><<<grid, PC_THREADS, smem, st>>>(
+                reinterpret_cast<const double *>(d_waves), n_win, n_spk, n_c, d_offsets, d_ref, ws_gram, ws_sum);
+        else
+            pca_gram_kernel<int16_t><<<grid, PC_THREADS, smem, st>>>(
+                reinterpret_cast<const int16_t *>(d_waves), n_win, n_spk, n_c, d_offsets, d_ref, ws_gram, ws_sum);
         SS_LAUNCH_CHECK("pca_gram_kernel");
     }
     pca_gram_reduce_kernel<<<(unsigned)n_groups, PC_THREADS, 0, st>>>(ws_gram, ws_sum, n_win, parts, d_gram, d_sum);
@@ -769,7 +787,7 @@ extern "C" int ss_pca_eig_top(const double *d_gram, const double *d_sum, const i
     return SS_OK;
 }
 
-extern "C" int ss_pca_project(const float *d_waves, int n_win, int64_t n_spk, int n_c,
+extern "C" int ss_pca_project(const void *d_waves, int dtype, int n_win, int64_t n_spk, int n_c,
                               const int64_t *d_offsets, int64_t n_groups, const double *d_evals,
                               const double *d_evecs, int ncomps, double *d_scores, void *stream)
 {
@@ -780,7 +798,14 @@ extern "C" int ss_pca_project(const float *d_waves, int n_win, int64_t n_spk, in
     SS_REQUIRE(d_offsets ? n_c == 1 : n_groups == n_c, SS_ERR_ARG, "pca_project: group layout mismatch");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int64_t total = n_spk * n_c;
-    pca_project_kernel<<<(unsigned)ss_cdiv(total, 256), 256, 0, st>>>(d_waves, n_win, n_spk, n_c, d_offsets, n_groups, d_evals, d_evecs, ncomps, d_scores);
+    SS_REQUIRE(dtype >= SS_I16 && dtype <= SS_F64, SS_ERR_ARG, "pca_project: bad dtype %d", dtype);
+    const unsigned blocks = (unsigned)ss_cdiv(total, 256);
+    if (dtype == SS_F32)
+        pca_project_kernel<float><<<blocks, 256, 0, st>>>(reinterpret_cast<const float *>(d_waves), n_win, n_spk, n_c, d_offsets, n_groups, d_evals, d_evecs, ncomps, d_scores);
+    else if (dtype == SS_F64)
+        pca_project_kernel<double><<<blocks, 256, 0, st>>>(reinterpret_cast<const double *>(d_waves), n_win, n_spk, n_c, d_offsets, n_groups, d_evals, d_evecs, ncomps, d_scores);
+    else
+        pca_project_kernel<int16_t><<<blocks, 256, 0, st>>>(reinterpret_cast<const int16_t *>(d_waves), n_win, n_spk, n_c, d_offsets, n_groups, d_evals, d_evecs, ncomps, d_scores);
     SS_LAUNCH_CHECK("pca_project_kernel");
     return SS_OK;
 }

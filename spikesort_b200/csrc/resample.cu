@@ -130,7 +130,8 @@ align_resampled_kernel(const void *__restrict__ x, int dtype, int64_t n_samples,
                        const double *__restrict__ plan_f64, const int32_t *__restrict__ plan_i32,
                        int n_out, const double *__restrict__ rtime,
                        double *__restrict__ spt, int64_t n_spk, int max_iter,
-                       int64_t index_offset, int64_t halo_before, int64_t halo_after)
+                       int64_t index_offset, int64_t halo_before, int64_t halo_after,
+                       int32_t *__restrict__ halo_miss)
 {
     extern __shared__ __align__(16) char smem[];
     double *zs = reinterpret_cast<double *>(smem);                      // [n_win][RA_BLOCK]
@@ -163,9 +164,10 @@ align_resampled_kernel(const void *__restrict__ x, int dtype, int64_t n_samples,
             const int64_t base = __shfl_sync(SS_FULL, row0, src);
             for (int k = lane; k < n_win; k += 32) {
                 const int64_t i = f + k;
-                zs[k * RA_BLOCK + warp0 + src] =
-                    (i >= -halo_before && i < n_samples + halo_after)
-                        ? (double)ss_load_f32(x, dtype, base + i) : 0.0;
+                const bool stored = i >= -halo_before && i < n_samples + halo_after;
+                zs[k * RA_BLOCK + warp0 + src] = stored ? (double)ss_load_f32(x, dtype, base + i) : 0.0;
+                if (!stored && halo_miss && ss_beyond_halo(i, n_samples, halo_before, halo_after))
+                    atomicAdd(halo_miss, 1);
             }
         }
         __syncwarp();
@@ -222,7 +224,7 @@ extern "C" int ss_align_resampled(const void *d_x, int dtype, int64_t n_samples,
                                   int use_min, const double *d_plan_f64, const int32_t *d_plan_i32,
                                   int n_out, const double *d_rtime, double *d_spt, int64_t n_spk,
                                   int max_iter, int64_t index_offset, int64_t halo_before,
-                                  int64_t halo_after, void *stream)
+                                  int64_t halo_after, int32_t *d_halo_miss, void *stream)
 {
     if (n_spk == 0) return SS_OK;
     SS_REQUIRE(d_x && d_spt && d_plan_f64 && d_plan_i32 && d_rtime, SS_ERR_ARG, "align_resampled: null pointer");
@@ -238,7 +240,7 @@ extern "C" int ss_align_resampled(const void *d_x, int dtype, int64_t n_samples,
     align_resampled_kernel<<<(unsigned)ss_cdiv(n_spk, RA_BLOCK), RA_BLOCK, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
         d_x, dtype, n_samples, ld, FS, d_rows, n_rows, d_offsets, win0, n_win, t_min, t_max, lo, hi,
         use_min, d_plan_f64, d_plan_i32, n_out, d_rtime, d_spt, n_spk, max_iter, index_offset,
-        halo_before, halo_after);
+        halo_before, halo_after, d_halo_miss);
     SS_LAUNCH_CHECK("align_resampled_kernel");
     return SS_OK;
 }

@@ -275,6 +275,11 @@ class PeerFabric(_Fabric):
 
 _FABRICS = {}
 _CAPACITY_HINTS = {}
+SHARD_OVERFLOW, SHARD_HALO_MISS = 1, 2          # status word of a sharded step (header)
+
+
+class HaloError(RuntimeError):
+    """An alignment walk left even the widest halo a shard can hold of its neighbour."""
 
 
 def peer_fabric(n_c, H, n_win):
@@ -309,6 +314,8 @@ class ShardedChain(object):
                                 self.H if rank > 0 else 0, self.H if rank < n_ranks - 1 else 0)
         self.sos, self.padlen = filt.sections(FS)
         self.res = ChainResult()
+        # spikes whose alignment / extraction window left the H neighbour samples (device counter)
+        self.halo_miss = t.zeros(1, dtype=t.int32, device=x.device)
         # filtered signal with room for the neighbours' samples on both sides
         self.buf = t.empty((self.n_c, self.n + 2 * self.H), dtype=t.float64, device=x.device)
         self.sig = self.buf[:, self.H:self.H + self.n]
@@ -320,10 +327,11 @@ class ShardedChain(object):
     def _align(self, spt):
         if self.resample != 1:
             _ops.align_resampled(self.sig, spt, self._offsets, None, self.FS, self.sp_win,
-                                 self.use_min, self.resample, shard=self.shard)
+                                 self.use_min, self.resample, shard=self.shard,
+                                 halo_miss=self.halo_miss)
         else:
             _ops.align(self.sig, spt, self._offsets, None, self.FS, self.sp_win, self.use_min,
-                       shard=self.shard)
+                       shard=self.shard, halo_miss=self.halo_miss)
 
     # 1. sweep 1 of the filter (needs nothing from other ranks)
     def prepare(self):
@@ -386,7 +394,8 @@ class ShardedChain(object):
                                            prev_last=prev_last)
         r.spt, r.offsets = spt, offsets
         waves, valid, n_invalid = _ops.extract(self.sig, spt, self.FS, self.sp_win, contacts=None,
-                                               offsets=offsets, shard=self.shard)
+                                               offsets=offsets, shard=self.shard,
+                                               halo_miss=self.halo_miss)
         r.waves, r.valid, r.n_invalid, r.time = waves, valid, n_invalid, self.time
         counts = (offsets[1:] - offsets[:-1]).contiguous()
         if spt.numel() > 0:
@@ -402,7 +411,7 @@ class ShardedChain(object):
     #    and no reference has to be agreed on between ranks
     def gram(self, ref):
         t = self.t
-        gram, ssum, _, counts = _ops.pca_gram(self.res.waves, offsets=self.res.offsets, ref=ref)
+        gram, ssum, _, counts = _ops.pca_gram(self.res.waves, offsets=self.res.offsets, ref=ref, mode="f64")
         n = counts.to(t.float64)
         sr = ssum[:, :, None] * ref[:, None, :]
         gram0 = gram + sr + sr.transpose(1, 2) + n[:, None, None] * ref[:, :, None] * ref[:, None, :]
@@ -505,12 +514,14 @@ class ShardedChain(object):
                                                prev_last=prev_last)
         r.spt, r.offsets = spt, offsets
         waves, valid, n_invalid = _ops.extract(self.sig, spt, self.FS, self.sp_win, contacts=None,
-                                               offsets=offsets, shard=self.shard)
+                                               offsets=offsets, shard=self.shard,
+                                               halo_miss=self.halo_miss)
         r.waves, r.valid, r.n_invalid, r.time = waves, valid, n_invalid, self.time
-        gram, ssum, ref, _ = _ops.pca_gram(waves, offsets=offsets)
+        gram, ssum, ref, _ = _ops.pca_gram(waves, offsets=offsets, mode="f64")
         rc = lib.ss_shard_gram_put(_lib.ptr(gram), _lib.ptr(ssum), _lib.ptr(ref), _lib.ptr(offsets),
                                    n_c, H, n_win, ptrs, self.rank, self.n_ranks,
-                                   _lib.ptr(self._overflow), _lib.stream_ptr())
+                                   _lib.ptr(self._overflow), _lib.ptr(self.halo_miss),
+                                   _lib.stream_ptr())
         _lib.check(rc, "ss_shard_gram_put")
         _ops._launched(1)
 
@@ -540,6 +551,7 @@ class ShardedChain(object):
         t, r = self.t, self.res
         n_det, n_kept, bad = (int(v) for v in t.stack(
             (r.offsets_detected[-1], r.offsets[-1], self._status[0])).tolist())
+        self.status = bad                       # 0, SHARD_OVERFLOW or SHARD_HALO_MISS (any rank)
         if bad:
             return False, n_det
         r.spt_detected = r.spt_detected[:n_det]
@@ -550,16 +562,43 @@ class ShardedChain(object):
         return True, n_det
 
 
+class PendingShard(object):
+    """run_chain_sharded(lazy=True): this rank's step is queued, nothing has been read back.
+    finalize() is the step's one host synchronisation (true list lengths + the status word
+    every rank received with the Gram partials); if any rank overflowed its capacity or lost a
+    window beyond the halo, ALL ranks see it and redo the step together."""
+
+    def __init__(self, chain, redo, remember):
+        self._chain, self._redo, self._remember = chain, redo, remember
+        self._res = None
+
+    def finalize(self):
+        if self._res is None:
+            ok, n_det = self._chain.finalize()
+            self._res = self._chain.res if ok else self._redo(self._chain.status)
+            if ok:
+                self._remember(n_det)
+            self._chain = None
+        return self._res
+
+
 def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
                       thresh='auto', ncomps=2, chunksize=1E6, index_offset=None, n_total=None,
-                      transport=None, speculate=True):
+                      transport=None, speculate=True, halo=None, lazy=False):
     """The chain on this rank's time shard `x` (CUDA tensor, every rank the same number
     of samples unless index_offset/n_total say otherwise), with the exchange steps of
     the module docstring.  Spike times are global; `all_counts` gives the layout of the
     concatenated list.  transport: 'peer' (NVLink peer memory, default) or 'nccl'
     (torch.distributed collectives); SS_TRANSPORT overrides the default.  speculate: as
     pipeline.run_chain - capacity-sized lists from the previous call's count, one host sync
-    at the end, exact rerun (agreed on by all ranks) if any shard overflowed."""
+    at the end, exact rerun (agreed on by all ranks) if any shard overflowed.
+    halo: neighbour samples kept on each side of the shard (default 4 windows).  A spike
+    whose alignment walk leaves them is COUNTED on the device (ss_align / ss_extract
+    `d_halo_miss`), every rank learns of it through the status word, and the step is redone
+    with a halo four times as wide (up to the whole neighbour shard; beyond that HaloError) -
+    the result always equals the unsharded chain's.
+    lazy: (peer transport, a capacity hint from an earlier call) return a PendingShard with
+    the step queued and no host synchronisation; its finalize() gives the result."""
     import os
     t = _lib.require_cuda()
     rank, n_ranks = world()
@@ -572,10 +611,10 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
         transport = os.environ.get("SS_TRANSPORT", "peer")
     if transport not in ("peer", "nccl"):
         raise ValueError("transport must be 'peer' or 'nccl'")
-    fabric = None
-    if transport == "peer" and n_ranks > 1:
-        win0, win1, _ = _ops.window_params(list(sp_win), FS)
-        fabric = peer_fabric(x.shape[0], min(4 * (win1 - win0), n), win1 - win0)
+    win0, win1, _ = _ops.window_params(list(sp_win), FS)
+    n_win = win1 - win0
+    H0 = min(4 * n_win if halo is None else int(halo), n)
+    use_fabric = transport == "peer" and n_ranks > 1
     prof = os.environ.get("SS_DIST_PROFILE") and rank == 0
     marks = []
 
@@ -585,12 +624,14 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
             t.cuda.synchronize()
             marks.append((name, time.perf_counter()))
 
-    def new_chain():
+    def new_chain(H, fabric):
         return ShardedChain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize, rank,
-                            n_ranks, index_offset, n_total, fabric=fabric)
+                            n_ranks, index_offset, n_total, halo=H, fabric=fabric)
 
-    def fabric_pass(cap):
-        ch = new_chain()
+    def fabric_queue(H, cap):
+        """Queue the whole step on the stream; returns the chain (nothing read back)."""
+        fabric = peer_fabric(x.shape[0], H, n_win)
+        ch = new_chain(H, fabric)
         mark("start")
         ch.prepare()
         mark("prepare")
@@ -610,30 +651,12 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
         ch.fab_extract_gram()
         fabric.barrier(rank)
         mark("extract+gram put")
-        res = ch.fab_project()
+        ch.fab_project()
         mark("reduce+project")
-        if cap is None:
-            return True, res, int(res.spt_detected.numel())
-        ok, n_det = ch.finalize()
-        return ok, res, n_det
+        return ch
 
-    if fabric is not None:
-        # all ranks decide alike: the hint exists on every rank or on none (same call
-        # history), an overflow on any rank is seen by all (status word of the Gram slots)
-        key = (tuple(x.shape), x.dtype, float(FS), tuple(sp_win), edge, align_type, str(thresh),
-               id(type(filt)), int(chunksize), n_ranks, rank)
-        hint = _CAPACITY_HINTS.get(key) if speculate else None
-        cap = None if hint is None else int(hint * 1.25) + 1024 + x.shape[0]
-        ok, res, n_det = fabric_pass(cap)
-        if not ok:
-            marks[:] = []
-            ok, res, n_det = fabric_pass(None)
-        if speculate:
-            if len(_CAPACITY_HINTS) > 64:
-                _CAPACITY_HINTS.clear()
-            _CAPACITY_HINTS[key] = n_det
-    else:
-        ch = new_chain()
+    def collective_pass(H):
+        ch = new_chain(H, None)
         mark("start")
         ch.prepare()
         mark("prepare")
@@ -657,11 +680,72 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
         res = ch.project(gram, ssum, counts)
         res.all_counts = all_counts
         mark("project")
+        missed = ch.halo_miss.to(t.float64)
+        if n_ranks > 1:
+            _dist().all_reduce(missed, op=_dist().ReduceOp.MAX)
+        return res, (SHARD_HALO_MISS if float(missed.item()) > 0 else 0)
+
+    key = (tuple(x.shape), x.dtype, float(FS), tuple(sp_win), edge, align_type, str(thresh),
+           id(type(filt)), int(chunksize), n_ranks, rank, H0)
+
+    def remember(n_det):
+        if speculate:
+            if len(_CAPACITY_HINTS) > 64:
+                _CAPACITY_HINTS.clear()
+            _CAPACITY_HINTS[key] = n_det
+
+    def exact_until_clean(H, status):
+        """Exact-size passes, the halo widened after every miss; all ranks take the same
+        branches (the status word is the same on every rank)."""
+        while True:
+            if status >= SHARD_HALO_MISS:
+                if H >= n:
+                    raise HaloError("an alignment walk crossed a whole neighbour shard (%d "
+                                    "samples): shard the recording into longer pieces" % n)
+                H = min(4 * H, n)
+            marks[:] = []
+            if use_fabric:
+                ch = fabric_queue(H, None)
+                status = int(ch._status.item())
+                res, n_det = ch.res, int(ch.res.spt_detected.numel())
+            else:
+                res, status = collective_pass(H)
+                n_det = int(res.spt_detected.numel())
+            if status == 0:
+                remember(n_det)
+                return res
+
+    if use_fabric:
+        # all ranks decide alike: the hint exists on every rank or on none (same call
+        # history); an overflow or a halo miss on any rank is seen by all (status word)
+        hint = _CAPACITY_HINTS.get(key) if speculate else None
+        if hint is None:
+            res = exact_until_clean(H0, 0)
+        else:
+            cap = int(hint * 1.25) + 1024 + x.shape[0]
+            ch = fabric_queue(H0, cap)
+            pending = PendingShard(ch, lambda status: exact_until_clean(H0, status), remember)
+            if lazy:
+                return pending
+            res = pending.finalize()
+    else:
+        res = exact_until_clean(H0, 0)
     if prof:
         print("dist profile (ms): " + ", ".join(
             "%s %.3f" % (marks[i][0], 1000 * (marks[i][1] - marks[i - 1][1]))
             for i in range(1, len(marks))), flush=True)
-    return res
+    return PendingShard_done(res) if lazy else res
+
+
+class PendingShard_done(object):
+    """A finished step behind the PendingShard interface (first call of a shape, or the
+    collective transport: nothing was deferred)."""
+
+    def __init__(self, res):
+        self._res = res
+
+    def finalize(self):
+        return self._res
 
 
 def sort_frontend_sharded(spike_data, filt, sp_win=(-0.2, 0.8), edge='falling', align_type='min',

@@ -15,105 +15,125 @@ from ._design import tf2sos_exact
 from ._signal import DeviceSignal
 
 
-class _IIRBase(object):
-    """Coefficients on the host with SciPy (as the reference), application on the GPU."""
+class _ZeroPhaseOnDevice(object):
+    """A zero-phase (forward-backward) filter whose taps come from a host-side design
+    routine and whose arithmetic runs on the GPU.
 
-    def _design_filter(self, FS):                      # pragma: no cover - abstract
+    Subclasses say what to design (`_spec`); this class memoises the taps per sampling
+    rate (the reference's classes do the same, one design per FS), turns them into what
+    the kernels take - exact second-order sections for a recursive filter, the plain taps
+    for an FIR one - and applies them to a whole recording or to one 1-D signal."""
+
+    def _spec(self, FS):                               # pragma: no cover - abstract
+        """(b, a) for sampling rate FS."""
         raise NotImplementedError
 
+    def _memo(self, name):
+        return self.__dict__.setdefault(name, {})
+
+    def _design_filter(self, FS):
+        """(b, a), the pair the reference classes return from the method of this name."""
+        taps = self._memo('_coefs_cache')
+        if FS not in taps:
+            taps[FS] = self._spec(FS)
+        return taps[FS]
+
+    def is_recursive(self, FS):
+        """False for an FIR design (a == [1]): that one runs as a stencil, not as a scan."""
+        return np.size(self._design_filter(FS)[1]) > 1
+
     def sections(self, FS):
-        """(sos, padlen) of the filter the reference would apply at this FS."""
-        if FS not in self._sos_cache:
-            b, a = self._design_filter(FS)
-            self._sos_cache[FS] = tf2sos_exact(b, a)
-        return self._sos_cache[FS]
+        """(sos, padlen) of the recursive filter the reference would apply at this FS."""
+        plans = self._memo('_sos_cache')
+        if FS not in plans:
+            plans[FS] = tf2sos_exact(*self._design_filter(FS))
+        return plans[FS]
 
     def apply(self, x, FS, chunksize):
         """CUDA recording (n_contacts, n_samples) -> CUDA float64, chunk by chunk."""
+        b, a = self._design_filter(FS)
+        if not self.is_recursive(FS):                  # FIR: no recurrence, a stencil
+            return _ops.filtfilt_fir(x, np.asarray(b, dtype=np.float64) / np.ravel(a)[0], chunksize)
         sos, padlen = self.sections(FS)
         return _ops.filtfilt_sos(x, sos, padlen, chunksize)
 
     def __call__(self, x, FS):
-        """filtfilt of one 1-D signal; returns a float64 ndarray (``filters.py:99-101``)."""
-        arr = np.asarray(x)
-        if arr.ndim != 1:
+        """filtfilt of one 1-D signal -> float64 ndarray (``filters.py:36-38,72-74,99-101``)."""
+        signal_1d = np.asarray(x)
+        if signal_1d.ndim != 1:
             raise ValueError("expected a 1-D signal")
-        dev = _lib.to_device_2d(arr)
+        dev = _lib.to_device_2d(signal_1d)
         return self.apply(dev, FS, max(dev.shape[1], 1))[0].cpu().numpy()
 
 
-class Filter(_IIRBase):
-    """``filters.py:77-101``: IIR design from pass/stop edges in Hz."""
+class Filter(_ZeroPhaseOnDevice):
+    """``filters.py:77-101``: IIR design from pass / stop edges in Hz."""
 
     def __init__(self, fpass, fstop, gpass=1, gstop=10, ftype='butter'):
-        self.ftype = ftype
-        self.fp = np.asarray(fpass)
-        self.fs = np.asarray(fstop)
-        self._coefs_cache = {}
-        self._sos_cache = {}
-        self.gstop = gstop
-        self.gpass = gpass
+        self.fp, self.fs = np.asarray(fpass), np.asarray(fstop)
+        self.gpass, self.gstop, self.ftype = gpass, gstop, ftype
 
-    def _design_filter(self, FS):
-        if FS not in self._coefs_cache:
-            from scipy import signal
-            wp, ws = self.fp * 2 / FS, self.fs * 2 / FS
-            self._coefs_cache[FS] = signal.iirdesign(wp=wp, ws=ws, gstop=self.gstop,
-                                                     gpass=self.gpass, ftype=self.ftype)
-        return self._coefs_cache[FS]
+    def _spec(self, FS):
+        # the reference scales the edges as `f * 2 / FS` (filters.py:88); the same
+        # expression here, so that the designed taps are the same bits
+        return _scaled_iirdesign(self.fp * 2 / FS, self.fs * 2 / FS, self)
 
 
-class ZeroPhaseFilter(_IIRBase):
-    """``filters.py:10-38``: band given as ``fband`` with transition width ``tw``."""
+class ZeroPhaseFilter(_ZeroPhaseOnDevice):
+    """``filters.py:10-38``: pass band `fband` (Hz) with transition width `tw` on both sides."""
 
     def __init__(self, ftype, fband, tw=200., stop=20):
-        self.gstop = stop
-        self.gpass = 1
-        self.fband = fband
-        self.tw = tw
-        self.ftype = ftype
-        self._coefs_cache = {}
-        self._sos_cache = {}
+        self.ftype, self.fband, self.tw = ftype, fband, tw
+        self.gpass, self.gstop = 1, stop
 
-    def _design_filter(self, FS):
-        if FS not in self._coefs_cache:
-            from scipy import signal
-            wp = np.array(self.fband)
-            ws = wp + np.array([-self.tw, self.tw])
-            wp, ws = wp * 2.0 / FS, ws * 2.0 / FS
-            self._coefs_cache[FS] = signal.iirdesign(wp=wp, ws=ws, gstop=self.gstop,
-                                                     gpass=self.gpass, ftype=self.ftype)
-        return self._coefs_cache[FS]
+    def _spec(self, FS):
+        inner = np.array(self.fband)
+        outer = inner + np.array([-self.tw, self.tw])
+        return _scaled_iirdesign(inner * 2.0 / FS, outer * 2.0 / FS, self)
 
 
-class FilterFir(object):
-    """``filters.py:41-74``: remez FIR of `order` taps, applied forwards and backwards.
-    (The reference passes the rate to remez as ``Hz=FS``; SciPy now calls it ``fs``.)"""
+def _scaled_iirdesign(wp, ws, owner):
+    from scipy import signal
+    return signal.iirdesign(wp=wp, ws=ws, gpass=owner.gpass, gstop=owner.gstop, ftype=owner.ftype)
+
+
+class FilterFir(_ZeroPhaseOnDevice):
+    """``filters.py:41-74``: `order`-tap remez FIR between f_pass and f_stop (Hz), applied
+    forwards and backwards.  (The reference hands the rate to remez as ``Hz=FS``; SciPy now
+    calls that keyword ``fs``.)"""
 
     def __init__(self, f_pass, f_stop, order):
-        self._coefs_cache = {}
-        self.fp = f_pass
-        self.fs = f_stop
-        self.order = order
+        self.fp, self.fs, self.order = f_pass, f_stop, order
 
-    def _design_filter(self, FS):
-        if FS not in self._coefs_cache:
-            from scipy import signal
-            bands = [0, min(self.fs, self.fp), max(self.fs, self.fp), FS / 2]
-            gains = [int(self.fp < self.fs), int(self.fp > self.fs)]
-            self._coefs_cache[FS] = (signal.remez(self.order, bands, gains, fs=FS), [1])
-        return self._coefs_cache[FS]
+    def _spec(self, FS):
+        from scipy import signal
+        lo, hi = sorted((self.fs, self.fp))
+        lowpass = self.fp < self.fs
+        taps = signal.remez(self.order, [0, lo, hi, FS / 2], [int(lowpass), int(self.fp > self.fs)],
+                            fs=FS)
+        return taps, [1]
 
-    def apply(self, x, FS, chunksize):
-        b, _ = self._design_filter(FS)
-        return _ops.filtfilt_fir(x, b, chunksize)
 
-    def __call__(self, x, FS):
-        arr = np.asarray(x)
-        if arr.ndim != 1:
-            raise ValueError("expected a 1-D signal")
-        dev = _lib.to_device_2d(arr)
-        return self.apply(dev, FS, max(dev.shape[1], 1))[0].cpu().numpy()
+class _AdoptedFilter(_ZeroPhaseOnDevice):
+    """A filter object of the REFERENCE package (anything with its `_design_filter(FS)` ->
+    (b, a) method, e.g. an instance created before install()): its taps, our arithmetic."""
+
+    def __init__(self, foreign):
+        self._foreign = foreign
+
+    def _spec(self, FS):
+        return self._foreign._design_filter(FS)
+
+
+def _on_device(filter_obj):
+    if hasattr(filter_obj, "apply"):
+        return filter_obj
+    if hasattr(filter_obj, "_design_filter"):
+        return _AdoptedFilter(filter_obj)
+    raise TypeError("filter_proxy on the CUDA path needs a filter that exposes its taps "
+                    "(Filter / ZeroPhaseFilter / FilterFir, or any object with "
+                    "_design_filter(FS) -> (b, a)); an arbitrary Python callable cannot run "
+                    "on the GPU and there is no CPU fallback")
 
 
 def filter_proxy(spikes, filter_obj, chunksize=1E6):
@@ -121,13 +141,10 @@ def filter_proxy(spikes, filter_obj, chunksize=1E6):
     float64 filtered recording, resident on the GPU."""
     if filter_obj is None:
         return spikes
-    if not hasattr(filter_obj, "apply"):
-        raise TypeError("filter_proxy on the CUDA path needs a spikesort_b200 filter object "
-                        "(Filter / ZeroPhaseFilter / FilterFir); arbitrary Python callables "
-                        "cannot run on the GPU and there is no CPU fallback")
+    runner = _on_device(filter_obj)
     sp_dict = spikes.copy()
     x = _lib.to_device_2d(spikes['data'])
-    out = filter_obj.apply(x, sp_dict['FS'], int(chunksize))
+    out = runner.apply(x, sp_dict['FS'], int(chunksize))
     sp_dict['data'] = DeviceSignal(out)
     return sp_dict
 

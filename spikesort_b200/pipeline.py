@@ -137,6 +137,12 @@ def _trim_to_counts(res, cap):
     return n_det, n_kept
 
 
+def _scan_filter(filt, FS):
+    """True when `filt` runs through the fused recursive-filter kernels (an IIR design)."""
+    probe = getattr(filt, "is_recursive", None)
+    return bool(probe and probe(FS))
+
+
 def _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize, pca, thr_override,
                fused, cap, resample=1, defer=False):
     """The chain; cap=None: exact sizes (two host syncs), else capacity-sized arrays and one
@@ -148,7 +154,7 @@ def _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
     falling = edge in _FALLING
     auto = thr_override is None and isinstance(thresh, str)
     frac = (8.0 if thresh == 'auto' else float(thresh)) if auto else None
-    if filt is not None and fused and hasattr(filt, "sections"):
+    if filt is not None and fused and _scan_filter(filt, FS):
         # filter with the threshold and the crossing marks produced in the same sweep
         sos, padlen = filt.sections(FS)
         if auto:
@@ -188,7 +194,7 @@ def _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
     res.waves, res.valid, res.n_invalid = waves, valid, n_invalid
     res.time = _ops.window_params(sp_win, FS)[2]
     if pca and (cap is not None or spt.numel() > 0):
-        gram, ssum, _, counts = _ops.pca_gram(waves, offsets=offsets)
+        gram, ssum, _, counts = _ops.pca_gram(waves, offsets=offsets, mode="f64")
         res.evals, res.evecs = _ops.pca_eig(gram, ssum, counts, top=ncomps)   # leading pairs only
         res.scores = _ops.pca_project(waves, res.evals, res.evecs, ncomps, offsets=offsets)
     if cap is None:
@@ -200,7 +206,8 @@ def _run_chain(x, FS, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
 
 
 def sort_frontend(spike_data, filt=None, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
-                  thresh='auto', ncomps=2, chunksize=1E6, contacts=None, slabs='auto', resample=1):
+                  thresh='auto', ncomps=2, chunksize=1E6, contacts=None, slabs='auto', resample=1,
+                  halo=None):
     """The whole front end for a multi-contact recording in ONE call, host in / host out.
 
     spike_data: the reference's raw-recording dict {'data', 'FS', 'n_contacts'}; 'data' may
@@ -220,12 +227,15 @@ def sort_frontend(spike_data, filt=None, sp_win=(-0.2, 0.8), edge='falling', ali
     upload overlaps the chain on the previous slab ('auto': up to 6 slabs; 1: one upload, one
     chain).  Slabs are time shards on one GPU (dist.ShardedChain over a LocalFabric): spike
     times and waveforms are identical to the unsliced chain, PCA scores to round-off.
+    halo: samples a slab keeps of each neighbour (default 4 windows).  A spike whose alignment
+    walk needs more is counted on the device; the call then reruns unsliced, so the result
+    never depends on the slicing.
     """
     t = _lib.require_cuda()
     FS = spike_data['FS']
     if contacts is None and slabs != 1:
         piped = _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, ncomps,
-                                     chunksize, slabs, resample)
+                                     chunksize, slabs, resample, halo)
         if piped is not None:
             return piped
     x = _lib.to_device_2d(spike_data['data'])            # one H2D copy (pinned: ~55 GB/s)
@@ -238,7 +248,7 @@ def sort_frontend(spike_data, filt=None, sp_win=(-0.2, 0.8), edge='falling', ali
     return results_to_host(res, ids, FS, ncomps)
 
 
-def _merge_and_fetch(results, ids, FS, ncomps, time):
+def _merge_and_fetch(results, ids, FS, ncomps, time, status=None):
     """ChainResults of one or more time slabs/shards (in time order) -> the reference's
     per-contact dicts on the host.  The device first brings everything into the host's
     layout (ss_merge_shard: lists contact-major across slabs, one contiguous waveform block
@@ -285,7 +295,8 @@ def _merge_and_fetch(results, ids, FS, ncomps, time):
         _lib.check(rc, "ss_merge_shard")
         _ops._launched((1 if r.spt.numel() else 0) + (1 if r.spt_detected.numel() else 0))
     dev_arrays = {'thresh': r0.thresh, 'det': det_all, 'spt': spt_all, 'valid': val_all,
-                  'scores': sc_all, 'waves': wav_all, 'ends_k': ends_k, 'ends_d': ends_d}
+                  'scores': sc_all, 'waves': wav_all, 'ends_k': ends_k, 'ends_d': ends_d,
+                  'status': status}               # status word of a sharded step (dist.py)
     # One pinned host block per call, leased from a pool and handed out as the result arrays
     # themselves (views): no second host copy, no page faults on fresh memory.  A block
     # returns to the pool when the caller has dropped every array that points into it.
@@ -307,6 +318,8 @@ def _merge_and_fetch(results, ids, FS, ncomps, time):
     t.cuda.current_stream().synchronize()
     out = {'FS': FS, 'n_contacts': n_c, 'contacts': ids, 'spt': [None] * n_c,
            'spt_aligned': [None] * n_c, 'sp_waves': [None] * n_c, 'features': [None] * n_c}
+    if h['status'] is not None:
+        out['_status'] = int(h['status'][0])
     names = ["Ch0:PC%d" % j for j in range(ncomps)]
     ok, od = h['ends_k'], h['ends_d']
     valid_all = h['valid'].view(np.bool_)                 # uint8 0/1 -> bool, same bytes
@@ -328,31 +341,46 @@ def _merge_and_fetch(results, ids, FS, ncomps, time):
     return out
 
 
-_HOST_BLOCKS = []                  # [(pinned uint8 tensor, its ndarray)]
+_HOST_BLOCKS = []                  # [[pinned uint8 tensor, its ndarray, leased?]]
 _MAX_HOST_BLOCKS = 6
 
 
+class _Lease(object):
+    """Exports a pooled pinned block through the array interface.  Every result array handed
+    to the caller is a view whose base chain ends in the ndarray made from this object, so the
+    object lives exactly as long as somebody can still see the block's bytes; its finalizer
+    hands the block back to the pool."""
+
+    def __init__(self, arr):
+        self.__array_interface__ = dict(arr.__array_interface__)
+
+
+def _release(entry):
+    entry[2] = False
+
+
 def _lease_host_block(nbytes):
-    """(pinned uint8 tensor, ndarray over the same memory) of at least nbytes.  A pooled block
-    is free when nothing but the pool refers to its ndarray (result arrays are views of it,
-    so they keep it busy for as long as the caller holds them)."""
-    import sys
+    """(pinned uint8 tensor, ndarray over the same memory) of at least nbytes.  Leases are
+    tracked explicitly (weakref.finalize on the lease object), not by reference counts."""
+    import weakref
     t = _lib.torch()
-    for i, (ten, arr) in enumerate(_HOST_BLOCKS):
-        if arr.nbytes >= nbytes and sys.getrefcount(arr) <= 3:     # pool tuple, loop variable, argument
-            return ten, arr
-    for i, (ten, arr) in enumerate(_HOST_BLOCKS):                  # free but too small: replace
-        if sys.getrefcount(arr) <= 3:
-            del _HOST_BLOCKS[i]
-            break
-    if len(_HOST_BLOCKS) >= _MAX_HOST_BLOCKS:
-        # the caller keeps many results alive: plain (pageable) memory, owned by the arrays
-        arr = np.empty(nbytes, dtype=np.uint8)
-        return t.from_numpy(arr), arr
-    ten = t.empty(int(nbytes * 1.25) + 4096, dtype=t.uint8).pin_memory()
-    arr = ten.numpy()
-    _HOST_BLOCKS.append((ten, arr))
-    return ten, arr
+    entry = next((e for e in _HOST_BLOCKS if not e[2] and e[1].nbytes >= nbytes), None)
+    if entry is None:
+        for i, e in enumerate(_HOST_BLOCKS):                       # free but too small: replace
+            if not e[2]:
+                del _HOST_BLOCKS[i]
+                break
+        if len(_HOST_BLOCKS) >= _MAX_HOST_BLOCKS:
+            # the caller keeps many results alive: plain (pageable) memory, owned by the arrays
+            arr = np.empty(nbytes, dtype=np.uint8)
+            return t.from_numpy(arr), arr
+        ten = t.empty(int(nbytes * 1.25) + 4096, dtype=t.uint8).pin_memory()
+        entry = [ten, ten.numpy(), False]
+        _HOST_BLOCKS.append(entry)
+    entry[2] = True
+    lease = _Lease(entry[1])
+    weakref.finalize(lease, _release, entry)
+    return entry[0], np.asarray(lease)
 
 
 def results_to_host(res, ids, FS, ncomps):
@@ -384,12 +412,12 @@ def _slab_bounds(n, chunksize, n0, want):
 
 
 def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, ncomps, chunksize,
-                         slabs, resample=1):
+                         slabs, resample=1, halo=None):
     """sort_frontend with the upload of slab s+1 overlapping the chain on slab s.  Returns
     None when the input does not qualify (device-resident, FIR / no filter, too short)."""
     t = _lib.torch()
     data = spike_data['data']
-    if hasattr(data, "device_tensor") or filt is None or not hasattr(filt, "sections"):
+    if hasattr(data, "device_tensor") or filt is None or not _scan_filter(filt, spike_data['FS']):
         return None
     lazy = hasattr(data, "read_slab")                     # io.LazyRecording: slabs come from files
     if lazy:
@@ -416,7 +444,7 @@ def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, nco
     n_c, n = shape
     win0, win1, time = _ops.window_params(list(sp_win), FS)
     n_win = win1 - win0
-    H = 4 * n_win
+    H = 4 * n_win if halo is None else int(halo)
     bounds = _slab_bounds(n, chunksize, int(10 * FS) if isinstance(thresh, str) else 0,
                           6 if slabs == 'auto' else slabs)
     if bounds is None or min(b - a for a, b in bounds) < max(H, 1):
@@ -465,8 +493,8 @@ def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, nco
         _SLAB_FABRICS[key] = ssd.LocalFabric(n_c, H, n_win, S, dev)
     fab = _SLAB_FABRICS[key]
     chains = [ssd.ShardedChain(xdev[:, a:b], FS, filt, sp_win, edge, align_type, thresh, ncomps,
-                               chunksize, rank=k, n_ranks=S, index_offset=a, n_total=n, fabric=fab,
-                               resample=resample)
+                               chunksize, rank=k, n_ranks=S, index_offset=a, n_total=n, halo=H,
+                               fabric=fab, resample=resample)
               for k, (a, b) in enumerate(bounds)]
 
     def finish(k):
@@ -498,10 +526,19 @@ def _sort_frontend_slabs(spike_data, filt, sp_win, edge, align_type, thresh, nco
         r = chains[k].res
         r.scores = _ops.pca_project(r.waves, res0.evals, res0.evecs, ncomps, offsets=r.offsets)
     mark("project queued")
-    out = _merge_and_fetch([c.res for c in chains], list(range(n_c)), FS, ncomps, time)
+    out = _merge_and_fetch([c.res for c in chains], list(range(n_c)), FS, ncomps, time,
+                           status=chains[0]._status)
     if feeder is not None:
         feeder.close()
     mark("merged, fetched, assembled")
+    if out.pop('_status', 0) >= ssd.SHARD_HALO_MISS:
+        # a spike's alignment walk (or its window afterwards) left the H samples a slab keeps
+        # of its neighbours: the slab result differs from the reference's.  The recording is on
+        # the device in one piece by now - run it unsliced, where every sample is readable.
+        res = run_chain(xdev, FS, filt=filt, sp_win=sp_win, edge=edge, align_type=align_type,
+                        thresh=thresh, ncomps=ncomps, chunksize=chunksize, resample=resample)
+        out = results_to_host(res, list(range(n_c)), FS, ncomps)
+        mark("halo miss: unsliced rerun")
     if prof is not None:
         print("e2e profile (ms): " + ", ".join("%s %.2f" % (prof[i][0], 1e3 * (prof[i][1] - prof[i - 1][1]))
                                                for i in range(1, len(prof))), flush=True)

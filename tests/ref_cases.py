@@ -142,52 +142,111 @@ def check_linear_iir_detect(flt, ex):                   # test_core.py:33-43
     assert len(spt['data']) == c.n_spikes
 
 
-def check_pca_whitening(fet):                           # test_features.py:38-51
+class FeatureCase(object):
+    """tests/test_features.py:9-23 (`setup`): two template "cells" of 100 points, integer
+    valued, as a (n_pts, 2, 1) waveform block.  (`np.int` is `int` in today's NumPy.)"""
+
+    def __init__(self):
+        self.gain = 1000
+        n_pts = 100
+        FS = 5E3
+        time = np.arange(n_pts, dtype=np.float32) / n_pts - 0.5
+        cells = self.gain * np.vstack((np.sin(time * 2 * np.pi) / 2.0, np.abs(time) * 2 - 1))
+        self.cells = cells.astype(int)
+        self.spikes_dict = {"data": self.cells.T[:, :, np.newaxis], "time": time, "FS": FS}
+
+
+def check_fetP2P(fet):                                  # test_features.py:25-36
+    c = FeatureCase()
+    spikes_dict = c.spikes_dict.copy()
+    n_spikes = 200
+    amps = np.random.RandomState(7).randint(1, 100, n_spikes)[:, np.newaxis]
+    spikes = amps * c.cells[0, :]                       # int64 waveforms, as in the reference
+    spikes_dict['data'] = spikes.T[:, :, np.newaxis]
+    p2p = fet.fetP2P(spikes_dict)
+    assert (p2p['data'] == amps * c.gain).all()
+
+
+def check_pca_whitening(fet):                           # test_features.py:38-51 (float64 input)
     rng = np.random.RandomState(1221)
-    n_dim, n_obs = 2, 2000
-    A = np.array([[2.0, 1.0], [1.0, 3.0]])
-    data = np.dot(A, rng.randn(n_dim, n_obs)).astype(np.float32)
-    evals, evecs, score = fet.PCA(data, n_dim)
-    assert ((np.cov(score) - np.eye(n_dim)) ** 2).mean() < 0.01
+    n_dim, n_obs = 2, 100
+    raw_data = rng.randn(n_dim, n_obs)
+    mixing = np.array([[-1, 1], [1, 1]])
+    mix_data = np.dot(mixing, raw_data)
+    mix_data = mix_data - mix_data.mean(1)[:, np.newaxis]
+    evals, evecs, score = fet.PCA(mix_data, n_dim)
+    proj_cov = np.cov(score)
+    assert np.mean((proj_cov - np.eye(n_dim)) ** 2) < 0.01
 
 
 def check_fetpca_separates(fet):                        # test_features.py:53-70
+    c = FeatureCase()
     rng = np.random.RandomState(3)
-    n_pts, n_spk = 30, 200
-    tt = np.linspace(0, 1, n_pts)
-    t1, t2 = np.sin(2 * np.pi * tt), np.sin(4 * np.pi * tt)
-    labels = rng.rand(n_spk) > 0.5
-    waves = np.where(labels[None, :], t1[:, None], t2[:, None]) + 0.01 * rng.randn(n_pts, n_spk)
-    sp = {'data': waves[:, :, None].astype(np.float32), 'time': tt, 'FS': 1}
-    f = fet.fetPCA(sp, ncomps=1)
-    pc = f['data'][:, 0]
-    a, b = pc[labels], pc[~labels]
-    assert abs(a.mean() - b.mean()) > 5 * max(a.std(), b.std())
-    assert f['names'] == ['Ch0:PC0']
+    spikes_dict = c.spikes_dict.copy()
+    n_spikes = 200
+    amp_var_fact = 0.4
+    amp_var = 1 + amp_var_fact * rng.rand(n_spikes, 1)
+    _amps = rng.rand(n_spikes) > 0.5
+    amps = amp_var * np.vstack((_amps >= 0.5, _amps < 0.5)).T
+    spikes = np.dot(amps, c.cells).T
+    spikes = spikes.astype(np.float32)                  # the reference's own cast
+    spikes_dict['data'] = spikes[:, :, np.newaxis]
+    pcs = fet.fetPCA(spikes_dict, ncomps=1)['data']
+    compare = ~np.logical_xor(pcs[:, 0].astype(int) + 1, _amps)
+    # the sign of a principal axis is arbitrary (LAPACK's too): the reference's check holds
+    # for one orientation, its mirror image for the other
+    mirrored = ~np.logical_xor((-pcs[:, 0]).astype(int) + 1, _amps)
+    assert n_spikes in (np.sum(compare), np.sum(mirrored))
 
 
-def check_fetpca_multichannel_labels(fet):              # test_features.py:72-100
+def check_fetpca_multichannel_labels(fet):              # test_features.py:72-100 (float64 block)
+    c = FeatureCase()
+    spike1, spike2 = c.cells
+    ch0_spikes = np.vstack((spike1, spike2, spike1 + spike2)).T
+    ch1_spikes = np.vstack((spike1 * 2, spike2 / 2., spike1 * 2 - spike2 / 2.)).T
+    spikes = np.empty((ch0_spikes.shape[0], ch0_spikes.shape[1], 2))
+    spikes[:, :, 0] = ch0_spikes
+    spikes[:, :, 1] = ch1_spikes
+    features = fet.fetPCA({'data': spikes}, ncomps=3)
+    names = features['names']
+    ch0_feats = np.empty((3, 3))
+    ch1_feats = np.empty((3, 3))
+    for fidx in range(3):
+        i0 = names.index('Ch%d:PC%d' % (0, fidx))
+        i1 = names.index('Ch%d:PC%d' % (1, fidx))
+        ch0_feats[fidx, :] = features['data'][:, i0]
+        ch1_feats[fidx, :] = features['data'][:, i1]
+    np.testing.assert_array_almost_equal(ch0_feats[:, 2], ch0_feats[:, 0] + ch0_feats[:, 1])
+    np.testing.assert_array_almost_equal(ch1_feats[:, 2], ch1_feats[:, 0] - ch1_feats[:, 1])
+
+
+def check_fetpca_mask_and_subset(fet):                  # features.py:172-181,298-307 via fetPCA
     rng = np.random.RandomState(5)
     n_pts, n_spk, n_c = 20, 300, 3
-    base = rng.randn(n_pts, n_spk).astype(np.float32)
-    data = np.stack([base * (k + 1) for k in range(n_c)], axis=2)
+    base = rng.randn(n_pts, n_spk)
+    data = np.stack([base * (k + 1) for k in range(n_c)], axis=2)       # float64
     sp = {'data': data, 'time': np.arange(n_pts, dtype=float), 'FS': 1,
           'is_valid': rng.rand(n_spk) > 0.1}
     f = fet.fetPCA(sp, ncomps=2)
     assert f['names'] == ['Ch0:PC0', 'Ch0:PC1', 'Ch1:PC0', 'Ch1:PC1', 'Ch2:PC0', 'Ch2:PC1']
     assert f['data'].shape == (n_spk, 6)
-    # scaling a channel does not change whitened scores (up to sign)
-    for k in range(1, n_c):
+    for k in range(1, n_c):                             # scaling a channel: same whitened scores
         for j in range(2):
-            r = f['data'][:, 2 * k + j]
-            q = f['data'][:, j]
+            r, q = f['data'][:, 2 * k + j], f['data'][:, j]
             assert min(np.abs(r - q).max(), np.abs(r + q).max()) < 1e-6 * np.abs(q).max()
-    assert np.array_equal(f['is_valid'], sp['is_valid'])          # add_mask, :209-217
+    assert np.array_equal(f['is_valid'], sp['is_valid'])
     sub = fet.fetPCA(sp, ncomps=1, contacts=[2])
     assert sub['data'].shape == (n_spk, 1)
+    try:
+        fet.fetPCA(sp, contacts=[7])
+    except IndexError:
+        pass
+    else:
+        raise AssertionError("contacts=[7] on 3 contacts must raise IndexError")
 
 
 EXTRACT_CASES = [check_detect, check_align, check_align_short_win, check_align_edge,
                  check_align_double_spikes, check_remove_doubles_roundoff, check_extract,
                  check_extract_and_resample, check_mask_of_truncated_spikes, check_filter_spt]
-FEATURE_CASES = [check_pca_whitening, check_fetpca_separates, check_fetpca_multichannel_labels]
+FEATURE_CASES = [check_fetP2P, check_pca_whitening, check_fetpca_separates,
+                 check_fetpca_multichannel_labels, check_fetpca_mask_and_subset]

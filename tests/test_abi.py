@@ -65,7 +65,7 @@ def test_argument_errors_without_gpu(lib):
     rc = lib.ss_filtfilt_sos(one, 0, 1, 500, 500, sos, 1, 6, 1000, one, 500, one, 8, None)
     assert rc == -4                                # workspace too small
     rc = lib.ss_align(one, 7, 100, 100, 25000.0, None, 1, None, -0.2, -5, 20, 0.2, 3.0, -0.1, 0.7,
-                      0, one, 3, 10, 0, 0, 0, None)
+                      0, one, 3, 10, 0, 0, 0, None, None)
     assert rc == -1
 
 

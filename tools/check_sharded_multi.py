@@ -33,10 +33,22 @@ sp_win = [-0.2, 0.8]
 whole = pipeline.run_chain(x, FS, filt=flt, sp_win=sp_win, edge='falling', align_type='min',
                            thresh='auto', ncomps=2, chunksize=chunk)
 ok = True
-for transport in ("peer", "nccl", "peer"):
-    res = ssd.run_chain_sharded(x[:, rank * n:(rank + 1) * n].contiguous(), FS, flt, sp_win,
-                                edge='falling', align_type='min', thresh='auto', ncomps=2,
-                                chunksize=chunk, transport=transport)
+mine_x = x[:, rank * n:(rank + 1) * n].contiguous()
+# (transport, halo, lazy): the plain runs (the second 'peer' one capacity-sized), a halo too
+# narrow for the spikes on the shard boundaries - every rank must learn of the miss and all of
+# them redo the step with a wider halo - and the pipelined (lazy) form of the peer transport
+cases = [("peer", None, False), ("nccl", None, False), ("peer", None, False), ("peer", 2, False),
+         ("peer", 2, False), ("nccl", 2, False), ("peer", None, True)]
+for transport, halo, lazy in cases:
+    res = ssd.run_chain_sharded(mine_x, FS, flt, sp_win, edge='falling', align_type='min',
+                                thresh='auto', ncomps=2, chunksize=chunk, transport=transport,
+                                halo=halo, lazy=lazy)
+    if lazy:
+        nxt = ssd.run_chain_sharded(mine_x, FS, flt, sp_win, edge='falling', align_type='min',
+                                    thresh='auto', ncomps=2, chunksize=chunk, transport=transport,
+                                    halo=halo, lazy=True)      # queued behind the first step
+        res = res.finalize()
+        nxt.finalize()
     torch.cuda.synchronize()
     lo_t, hi_t = rank * n * 1000.0 / FS, (rank + 1) * n * 1000.0 / FS
     good = torch.equal(res.thresh, whole.thresh)
@@ -60,8 +72,8 @@ for transport in ("peer", "nccl", "peer"):
     flag = torch.tensor([int(good)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("transport %-4s world %d: %s (%d spikes on rank 0)" %
-              (transport, world, "OK" if int(flag) else "MISMATCH", n_mine), flush=True)
+        print("transport %-4s halo %-4s lazy %d world %d: %s (%d spikes on rank 0)" %
+              (transport, halo, lazy, world, "OK" if int(flag) else "MISMATCH", n_mine), flush=True)
     ok &= bool(int(flag))
 dist.barrier()
 dist.destroy_process_group()
