@@ -13,42 +13,44 @@ pytestmark = pytest.mark.gpu
 
 
 def _ramp_recording(torch, cuda, n, at, length):
-    """float64 row: flat noise-free baseline with one long descending ramp starting at `at`."""
+    """float64 row: flat baseline with one long ASCENDING ramp of negative values starting at
+    `at` (its minimum); aligning on the minimum walks down it to the left, 3 samples per pass
+    (with sp_win = [-1, 2] ms at 3 kHz only the window's first sample re-queues a spike)."""
     x = torch.zeros((1, n), dtype=torch.float64, device=cuda)
-    x[0, at:at + length] = -torch.arange(1, length + 1, dtype=torch.float64, device=cuda)
-    x[0, at + length:at + length + 4] = torch.tensor([-30.0, -10.0, -2.0, 0.0], device=cuda)
+    x[0, at:at + length] = -torch.arange(length, 0, -1, dtype=torch.float64, device=cuda)
     return x
 
 
 def test_align_counts_windows_beyond_the_halo(cuda):
     import torch
     from spikesort_b200 import _ops
-    FS, sp_win = 3000.0, [-1.0, 2.0]                       # window = 9 samples, walk <= 6 per pass
-    n, split, length = 4000, 2000, 120
-    x = _ramp_recording(torch, cuda, n, split - 10, length)
-    t0 = (split - 9) * 1000.0 / FS
+    FS, sp_win = 3000.0, [-1.0, 2.0]                       # window = 9 samples
+    n, split, length = 4000, 2000, 140
+    at = split - 110
+    x = _ramp_recording(torch, cuda, n, at, length)
+    t0 = (split + 9) * 1000.0 / FS                         # in the right shard, on the ramp
     whole = torch.tensor([t0], dtype=torch.float64, device=cuda)
     _ops.align(x, whole, None, None, FS, sp_win, True)
-    assert float(whole[0]) > (split + 100) * 1000.0 / FS   # walked down the whole ramp
+    assert float(whole[0]) < (split - 100) * 1000.0 / FS   # walked down the whole ramp
 
     def shard_align(H):
-        # left shard = samples [0, split) with H samples of the right neighbour behind it
-        buf = x[:, :split + H].contiguous()
-        sh = _ops.Shard(index_offset=0, n_total=n, halo_before=0, halo_after=H)
+        # right shard = samples [split, n) with H samples of the left neighbour before it
+        buf = x[:, split - H:].contiguous()
+        sh = _ops.Shard(index_offset=split, n_total=n, halo_before=H, halo_after=0)
         spt = torch.tensor([t0], dtype=torch.float64, device=cuda)
         miss = torch.zeros(1, dtype=torch.int32, device=cuda)
-        _ops.align(buf[:, :split], spt, None, None, FS, sp_win, True, shard=sh, halo_miss=miss)
+        _ops.align(buf[:, H:], spt, None, None, FS, sp_win, True, shard=sh, halo_miss=miss)
         return float(spt[0]), int(miss[0])
 
     t_short, miss_short = shard_align(36)                  # the default 4 windows: not enough
     assert miss_short == 1 and t_short != float(whole[0])
     t_wide, miss_wide = shard_align(144)
     assert miss_wide == 0 and t_wide == float(whole[0])
-    # without a neighbour on that side (halo 0 = end of the recording) nothing is counted
-    sh = _ops.Shard(index_offset=0, n_total=split, halo_before=0, halo_after=0)
-    spt = torch.tensor([t0], dtype=torch.float64, device=cuda)
+    # without a neighbour on that side (halo 0 = start of the recording) nothing is counted
+    sh = _ops.Shard(index_offset=0, n_total=n - split, halo_before=0, halo_after=0)
+    spt = torch.tensor([9 * 1000.0 / FS], dtype=torch.float64, device=cuda)
     miss = torch.zeros(1, dtype=torch.int32, device=cuda)
-    _ops.align(x[:, :split].contiguous(), spt, None, None, FS, sp_win, True, shard=sh, halo_miss=miss)
+    _ops.align(x[:, split:].contiguous(), spt, None, None, FS, sp_win, True, shard=sh, halo_miss=miss)
     assert int(miss[0]) == 0
 
 
