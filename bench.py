@@ -101,8 +101,30 @@ def cpu_chain(x, pool=None, keep=None):
     return dt, sum(o[1] for o in out)
 
 
+def _shim_chain_one(args):
+    """One contact through the UNMODIFIED reference files (oracle/ref_shim.py loads them from
+    /root/reference with the py3 shims): filter_proxy -> detect -> align -> extract -> fetPCA."""
+    import warnings
+    from oracle import ref_shim
+    x, c = args
+    flt, ext, fet = ref_shim.filters(), ref_shim.load("extract"), ref_shim.load("features")
+    raw = {'data': x, 'FS': FS, 'n_contacts': 1}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        f = flt.filter_proxy(raw, flt.Filter(*FILTER_ARGS), CHUNK)
+        spt = ext.detect_spikes(f, thresh='auto', edge='falling', contact=0)
+        spa = ext.align_spikes(f, spt, SP_WIN, type='min', contact=0)
+        wv = ext.extract_spikes(f, spa, SP_WIN, contacts=0)
+        ft = fet.fetPCA(wv, ncomps=2) if len(spa['data']) > 1 else None
+    return c, len(spa['data']), spa['data'], ft['data'] if ft else None
+
+
 def run_reference(args):
-    """--impl reference: the CPU oracle port, all host cores, bounded sample per step."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores.
+    kind "port": oracle/port.py (C filtfilt + NumPy), a process pool over contacts, every step
+    the WHOLE configured recording (the config printed is the config run).  kind "shim"
+    (--ref-kind shim, only where /root/reference exists, i.e. not on the GPU box): the
+    unmodified reference files themselves on a stated, bounded part of the recording."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return
@@ -111,28 +133,42 @@ def run_reference(args):
     from spikesort_b200 import synth
     port.build()
     cores = os.cpu_count() or 1
-    n_sample = 3000000                                   # 32 contacts x 100 s per step
-    x = synth.make_recording(N_CONTACTS, n_sample, FS, seed=SEED, rate_hz=RATE_HZ,
-                             noise=10.0).numpy()
+    shim = args.ref_kind == "shim"
+    if shim and not os.path.isdir("/root/reference"):
+        print(json.dumps({"impl": "reference", "unavailable": "kind=shim needs /root/reference "
+                          "(absent on the GPU box); the default kind=port runs everywhere"}))
+        return
+    n_sample = 3000000 if shim else N_SAMPLES
+    x = synth.make_recording(N_CONTACTS, N_SAMPLES, FS, seed=SEED, rate_hz=RATE_HZ,
+                             noise=10.0).numpy()[:, :n_sample]
+    worker = _shim_chain_one if shim else _cpu_chain_one
     ctx = mp.get_context("fork")
-    with ctx.Pool(min(cores, N_CONTACTS)) as pool:
+    n_proc = min(cores, N_CONTACTS)
+    with ctx.Pool(n_proc) as pool:
         for _ in range(max(args.warmup, 1)):
-            cpu_chain(x[:, :300000], pool)
+            list(pool.map(worker, [(x[c:c + 1, :300000], c) for c in range(N_CONTACTS)]))
         times = []
         for _ in range(args.steps):
-            dt, _ = cpu_chain(x, pool)
-            times.append(dt)
+            t0 = time.perf_counter()
+            list(pool.map(worker, [(x[c:c + 1], c) for c in range(N_CONTACTS)]))
+            times.append(time.perf_counter() - t0)
     total = sum(times)
     value = N_CONTACTS * n_sample * args.steps / total
-    sample = ("%d contacts x %d samples (100 s of the 600 s recording) per step, process pool "
-              "over contacts" % (N_CONTACTS, n_sample))
+    if shim:
+        sample = ("UNMODIFIED reference files (oracle/ref_shim.py): %d contacts x the first %d of the "
+                  "%d samples per step, process pool over contacts" % (N_CONTACTS, n_sample, N_SAMPLES))
+    else:
+        sample = ("all %d samples of all %d contacts per step (the whole configured recording), "
+                  "oracle/port.py chain, process pool over contacts" % (n_sample, N_CONTACTS))
+    config = dict(CONFIG) if not shim else dict(CONFIG, n_samples=n_sample,
+                                                note="kind=shim runs a part of the recording")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1000.0 * total / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": CONFIG,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(cores, N_CONTACTS),
-                         "kind": "port", "sample": sample},
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_proc,
+                         "kind": "shim" if shim else "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -555,8 +591,16 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c2-bp8"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c2-bp8", "c1", "c4", "c5"])
+    ap.add_argument("--ref-kind", default="port", choices=["port", "shim"],
+                    help="--impl reference: the oracle port (default, runs anywhere) or the "
+                         "unmodified reference files through oracle/ref_shim.py")
     args = ap.parse_args()
+    if args.workload in ("c1", "c4", "c5"):
+        # the configs that are not the driver's bench line: tools/bench_extra.py
+        from tools import bench_extra
+        bench_extra.main(args.workload, args)
+        return
     select_workload(args.workload)
     if args.workload == "c3":
         args.no_e2e = args.no_cpu_baseline = True

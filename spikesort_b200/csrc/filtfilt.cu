@@ -868,27 +868,33 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
 }
 
 // ---------------------------------------------------------------- single-pass span kernel
-// For filters whose state decays to round-off within a tile or two (|A^T| ~ 1e-19 for the
+// For filters whose state decays to round-off within one tile (|A^T| ~ 1e-19 for the
 // first-order high-pass of fltLinearIIR) a tile's start state depends - to float64 accuracy -
-// only on the K tiles before it (forward) / after it (backward).  A CTA then filters a SPAN of
-// consecutive tiles of one unit on its own: one warp per tile, W = SP_WARPS - 2K owned tiles
-// plus K warm-up tiles on either side (computed, not stored).  No summary sweep, no tile scan,
-// no second read of x from DRAM (the warm-up tiles are the neighbour CTAs' owned tiles: L2 hits):
+// only on the ONE tile before it (forward) / after it (backward).  A CTA then filters a SPAN of
+// SP_WARPS consecutive tiles of one unit on its own, one warp per tile.  No summary sweep, no
+// tile scan, no second read of x from DRAM:
 //   forward : every warp runs the cascade over its tile from a zero start state (the unit's
-//             first tile from zi*ext[0]; the first warm-up tile from the steady state of its
-//             first sample, which removes the DC part of what the truncation drops), publishes
-//             the tile's end state; after a CTA barrier warp w folds the end states of warps
-//             < w with A^T (Horner) into its true start state z and corrects its outputs by
-//             (C A^(16 lane + i)) z = hrowF[i] . (A^(16 lane) z);
+//             first tile from zi*ext[0]) and publishes the tile's end state; after a CTA
+//             barrier warp w takes the end state of warp w-1 as its start state z and corrects
+//             its outputs by (C A^(16 lane + i)) z.  The first warp of the span has no warp
+//             before it: its start state is the zero-state end state of the tile in front of the
+//             span, a LINEAR functional of that tile's 512 samples - one dot product with the
+//             summary weights of the two-sweep path (F row of the table; + A^T zi x[first]
+//             for what a DC offset leaves of the tile before that);
 //   backward: the same over the forward outputs in reverse (the unit's last tile from
-//             zi*y[-1]; samples of the right padding are y[-1], the steady-state input);
-//   epilogue: crossing marks from the registers, then the 16 samples of a lane go to global
-//             memory as 128-bit stores through an XOR-swizzled shared tile (conflict-free
-//             both ways; 512 contiguous bytes per store instruction).
+//             zi*y[-1]; samples of the right padding are y[-1], the steady-state input).  The
+//             last warp's start state comes from the tile behind the span: Bz . x (zero-state
+//             backward end state of that tile's zero-state forward output) + M e (response to
+//             that tile's forward start state e = this warp's forward end state);
+//   epilogue: crossing marks from the registers (an integer test of the high words first:
+//             only tiles holding a sample beyond the threshold pay for the float64
+//             comparisons), then the 16 samples of a lane go to global memory as 128-bit
+//             stores through an XOR-swizzled shared tile (conflict-free both ways; 512
+//             contiguous bytes per store instruction).
 // Interior tiles read their samples straight into registers with 128-bit loads (lane l owns
 // samples [16 l, 16 l + 16): 32 contiguous bytes of int16) - no transposition on the way in.
-// The host picks this kernel when the truncation bound (build_tables: span_err) is below
-// 1e-17 of the input scale for K <= 2; everything else takes the exact two-sweep scan.
+// The host picks this kernel when the truncation bound (build_tables: span_err, one tile of
+// history) is below 1e-17 of the input scale; everything else takes the exact two-sweep scan.
 constexpr int SP_WARPS = 16;
 constexpr int SP_MAX_NS = 4;
 constexpr double SP_ERR_BOUND = 1e-17;   // truncation per unit of input scale (float64 eps: 1.1e-16)
@@ -897,76 +903,131 @@ template <int NS>
 struct SpanParams {
     double hrowF[FS_S][NS];       // C A^i of the whole cascade, i < S
     double AT[NS][NS];            // A^T, T = 512
+    double M[NS][NS];             // backward end state per unit of forward start state (one tile)
     double zi[NS];                // steady state for a unit step
     const double *apow;           // device table [NS][NS][32]: A^(16 lane)
-    int K;                        // warm-up tiles on either side
+    const double *dot;            // device table [2 NS + 1][512]: F rows, Bz rows, ylast row
+    // state update with the output substituted (one dependent FMA per sample instead of two):
+    // z0' = z1 + al[s][0] x - a1 z0,  z1' = al[s][1] x - a2 z0,  al = (b1 - a1 b0, b2 - a2 b0)
+    double al[(NS + 1) / 2][2];
 };
 
-// section_pass that also hands back the lane's inclusive state after the warp scan
+// Owned tiles of span s of a launch over tiles [t_lo, t_end) of a unit with nt tiles:
+// boundaries every SP_WARPS tiles; a boundary that would fall on the unit's LAST tile moves one
+// tile down, so that the tile behind a span is never the last one (whose right padding and
+// y[-1] substitution the Bz functional does not describe).  The host never ends a launch
+// range on nt - 1 (head_cut).
+__host__ __device__ inline int span_bound(int s, int t_lo, int t_end, int nt)
+{
+    int b = t_lo + SP_WARPS * s;
+    if (b > t_end) b = t_end;
+    if (b == nt - 1 && b > t_lo && b < t_end) b = nt - 2;
+    return b;
+}
+
+// z <- z + P * shfl(z): one inclusive-scan step with the multiply-add predicated on the
+// shuffle's own in-range flag (no select, no lane comparison)
+template <bool REV>
+__device__ __forceinline__ void scan_step1(double &z, double P, int d)
+{
+    if (REV)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, olo, ohi;\n\t.reg .f64 o;\n\t"
+                     "mov.b64 {lo, hi}, %0;\n\t"
+                     "shfl.sync.down.b32 olo|p, lo, %2, 0x1f, 0xffffffff;\n\t"
+                     "shfl.sync.down.b32 ohi|p, hi, %2, 0x1f, 0xffffffff;\n\t"
+                     "mov.b64 o, {olo, ohi};\n\t"
+                     "@p fma.rn.f64 %0, %1, o, %0;\n\t}"
+                     : "+d"(z) : "d"(P), "r"(d));
+    else
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, olo, ohi;\n\t.reg .f64 o;\n\t"
+                     "mov.b64 {lo, hi}, %0;\n\t"
+                     "shfl.sync.up.b32 olo|p, lo, %2, 0x0, 0xffffffff;\n\t"
+                     "shfl.sync.up.b32 ohi|p, hi, %2, 0x0, 0xffffffff;\n\t"
+                     "mov.b64 o, {olo, ohi};\n\t"
+                     "@p fma.rn.f64 %0, %1, o, %0;\n\t}"
+                     : "+d"(z) : "d"(P), "r"(d));
+}
+
+// value of the neighbouring lane in processing order, 0 for the first lane
+template <bool REV>
+__device__ __forceinline__ double prev_lane_or_zero(double z)
+{
+    double r;
+    if (REV)
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, olo, ohi;\n\t"
+                     "mov.b64 {lo, hi}, %1;\n\t"
+                     "shfl.sync.down.b32 olo|p, lo, 1, 0x1f, 0xffffffff;\n\t"
+                     "shfl.sync.down.b32 ohi|p, hi, 1, 0x1f, 0xffffffff;\n\t"
+                     "@!p mov.b32 olo, 0;\n\t@!p mov.b32 ohi, 0;\n\t"
+                     "mov.b64 %0, {olo, ohi};\n\t}"
+                     : "=d"(r) : "d"(z));
+    else
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, olo, ohi;\n\t"
+                     "mov.b64 {lo, hi}, %1;\n\t"
+                     "shfl.sync.up.b32 olo|p, lo, 1, 0x0, 0xffffffff;\n\t"
+                     "shfl.sync.up.b32 ohi|p, hi, 1, 0x0, 0xffffffff;\n\t"
+                     "@!p mov.b32 olo, 0;\n\t@!p mov.b32 ohi, 0;\n\t"
+                     "mov.b64 %0, {olo, ohi};\n\t}"
+                     : "=d"(r) : "d"(z));
+    return r;
+}
+
+// One section over the warp's tile: lane-local pass from (z0, z1) - zero except in the seeded
+// lane -, inclusive lane scan with A_s^(S 2^k).  Returns the state at the START of the lane's
+// segment (p0, p1: zero for the seeded lane, whose local pass began from the true state) and
+// the inclusive end state (e0, e1).  The correction y[i] += (C_s A_s^i) . p is the caller's.
 template <bool SO, bool REV>
-__device__ __forceinline__ void section_pass_e(const double (&c)[5], const double (&h)[FS_S][2],
-                                               const double (&Pm)[5][2][2], double (&v)[FS_S],
-                                               double z0, double z1, int lane, double &e0, double &e1)
+__device__ __forceinline__ void span_section(const double (&c)[5], const double (&al)[2],
+                                             const double (&Pm)[5][2][2], double (&v)[FS_S],
+                                             double z0, double z1, int lane, double &p0, double &p1,
+                                             double &e0, double &e1)
 {
 #pragma unroll
     for (int ii = 0; ii < FS_S; ++ii) {
         const int i = REV ? FS_S - 1 - ii : ii;
         const double x = v[i];
-        const double y = z0 + c[0] * x;
+        v[i] = fma(c[0], x, z0);
         if (SO) {
-            z0 = z1 + c[1] * x - c[3] * y;
-            z1 = c[2] * x - c[4] * y;
+            const double n0 = fma(-c[3], z0, fma(al[0], x, z1));
+            z1 = fma(-c[4], z0, al[1] * x);
+            z0 = n0;
         } else {
-            z0 = c[1] * x - c[3] * y;
+            z0 = fma(-c[3], z0, al[0] * x);
         }
-        v[i] = y;
     }
+    if (SO) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        const int d = 1 << k;
-        const bool act = REV ? (lane + d < 32) : (lane >= d);
-        const double o0 = REV ? ss_shfl_down(z0, d) : ss_shfl_up(z0, d);
-        if (SO) {
+        for (int k = 0; k < 5; ++k) {
+            const int d = 1 << k;
+            const bool act = REV ? (lane + d < 32) : (lane >= d);
+            const double o0 = REV ? ss_shfl_down(z0, d) : ss_shfl_up(z0, d);
             const double o1 = REV ? ss_shfl_down(z1, d) : ss_shfl_up(z1, d);
             if (act) {
                 z0 = z0 + Pm[k][0][0] * o0 + Pm[k][0][1] * o1;
                 z1 = z1 + Pm[k][1][0] * o0 + Pm[k][1][1] * o1;
             }
-        } else if (act) {
-            z0 = z0 + Pm[k][0][0] * o0;
         }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) scan_step1<REV>(z0, Pm[k][0][0], 1 << k);
     }
     e0 = z0;
     e1 = z1;
-    const bool seeded = REV ? lane == 31 : lane == 0;
-    const double t0 = REV ? ss_shfl_down(z0, 1) : ss_shfl_up(z0, 1);
-    const double p0 = seeded ? 0.0 : t0;
-    double p1 = 0.0;
-    if (SO) {
-        const double t1 = REV ? ss_shfl_down(z1, 1) : ss_shfl_up(z1, 1);
-        p1 = seeded ? 0.0 : t1;
-    }
+    p0 = prev_lane_or_zero<REV>(z0);
+    p1 = SO ? prev_lane_or_zero<REV>(z1) : 0.0;
+}
+
+template <bool SO, bool REV>
+__device__ __forceinline__ void span_correct(const double (&h)[FS_S][2], double (&v)[FS_S], double p0,
+                                             double p1)
+{
 #pragma unroll
     for (int ii = 0; ii < FS_S; ++ii) {
         const int i = REV ? FS_S - 1 - ii : ii;
-        double acc = v[i] + h[ii][0] * p0;
-        if (SO) acc += h[ii][1] * p1;
+        double acc = fma(h[ii][0], p0, v[i]);
+        if (SO) acc = fma(h[ii][1], p1, acc);
         v[i] = acc;
     }
-}
-
-template <int NB, bool FO, bool REV>
-__device__ __forceinline__ void cascade_pass_e(const FiltParams<NB, FO> &P, double (&v)[FS_S],
-                                               const double (&zt)[FiltParams<NB, FO>::NS], int lane,
-                                               double (&e)[FiltParams<NB, FO>::NS])
-{
-    double dummy;
-#pragma unroll
-    for (int s = 0; s < NB; ++s)
-        section_pass_e<true, REV>(P.sec[s], P.hrow[s], P.P[s], v, zt[2 * s], zt[2 * s + 1], lane,
-                                  e[2 * s], e[2 * s + 1]);
-    if (FO) section_pass_e<false, REV>(P.sec[NB], P.hrow[NB], P.P[NB], v, zt[2 * NB], 0.0, lane,
-                                       e[2 * NB], dummy);
 }
 
 // 16 consecutive samples of a lane, straight from global memory (16-byte aligned address)
@@ -977,10 +1038,17 @@ __device__ __forceinline__ void span_load16(const int16_t *p, double (&v)[FS_S])
     const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
+#ifdef SS_SPAN_XOR_CVT
         // two int16 -> float64, exact: offset binary in the low mantissa word of 2^52
         const unsigned ob = w[k] ^ 0x80008000u;
         v[2 * k] = __hiloint2double(0x43300000, (int)(ob & 0xffffu)) - 4503599627403264.0;
         v[2 * k + 1] = __hiloint2double(0x43300000, (int)(ob >> 16)) - 4503599627403264.0;
+#else
+        // I2F.F64.S16 on the low half, shift + I2F.F64 on the high half: 3 instructions per pair
+        // (the 2^52 trick costs 7: this kernel is bound by issue slots, not by the convert pipe)
+        v[2 * k] = (double)(short)(w[k] & 0xffffu);
+        v[2 * k + 1] = (double)((int)w[k] >> 16);
+#endif
     }
 }
 __device__ __forceinline__ void span_load16(const float *p, double (&v)[FS_S])
@@ -1000,6 +1068,77 @@ __device__ __forceinline__ void span_load16(const double *p, double (&v)[FS_S])
     }
 }
 
+// The 16 samples [16 lane, 16 lane + 16) of tile t of the unit as float64: interior tiles with
+// a 16-byte aligned address straight into registers, everything else through the warp's
+// shared tile.  r0 = chunk-relative index of the tile's first sample.
+__device__ __forceinline__ void span_load_tile(const void *__restrict__ x, const FiltGeom &g,
+                                               const TileInfo &ti, int t, double *tile_s, int lane,
+                                               double (&v)[FS_S])
+{
+    const int64_t row0 = ti.c * g.ld_in;
+    const int64_t e0 = (int64_t)t * FS_T - ti.pad;
+    const int64_t r0 = e0 - g.edge;
+    const bool interior = r0 >= 0 && r0 + FS_T <= ti.L;
+    const int64_t base = row0 + ti.cs0 + r0;
+    const int esz = g.dtype == SS_I16 ? 2 : (g.dtype == SS_F32 ? 4 : 8);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) + (uintptr_t)base * esz) & 15u) == 0;
+    if (interior && aligned) {
+        if (g.dtype == SS_I16) span_load16(reinterpret_cast<const int16_t *>(x) + base + FS_S * lane, v);
+        else if (g.dtype == SS_F32) span_load16(reinterpret_cast<const float *>(x) + base + FS_S * lane, v);
+        else span_load16(reinterpret_cast<const double *>(x) + base + FS_S * lane, v);
+        return;
+    }
+    if (interior) {
+        // unaligned view: coalesced element loads
+        if (g.dtype == SS_I16) {
+            const int16_t *p = reinterpret_cast<const int16_t *>(x) + base;
+#pragma unroll
+            for (int k = 0; k < FS_S; ++k) tile_s[32 * k + lane] = ss_to_f64(__ldg(p + 32 * k + lane));
+        } else if (g.dtype == SS_F32) {
+            const float *p = reinterpret_cast<const float *>(x) + base;
+#pragma unroll
+            for (int k = 0; k < FS_S; ++k) tile_s[32 * k + lane] = (double)__ldg(p + 32 * k + lane);
+        } else {
+            const double *p = reinterpret_cast<const double *>(x) + base;
+#pragma unroll
+            for (int k = 0; k < FS_S; ++k) tile_s[32 * k + lane] = __ldg(p + 32 * k + lane);
+        }
+    } else {
+        TileInfo tj = ti;
+        tj.t = t;
+#pragma unroll 1
+        for (int k = 0; k < FS_S; ++k)
+            tile_s[32 * k + lane] = ext_value(x, g.dtype, row0, tj, g.edge, e0 + 32 * k + lane);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < FS_S; ++i) v[i] = tile_s[lane * FS_S + i];
+    __syncwarp();
+}
+
+// NS dot products of the lane's 16 samples with rows q0 .. q0 + NS of the summary-weight
+// table, summed over the warp (every lane gets the totals)
+template <int NS>
+__device__ __forceinline__ void span_dot(const double *__restrict__ dot, int q0, const double (&xv)[FS_S],
+                                         int lane, double (&z)[NS])
+{
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+        const double2 *w = reinterpret_cast<const double2 *>(dot + (size_t)(q0 + q) * FS_T + FS_S * lane);
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < FS_S / 2; ++k) {
+            const double2 ww = __ldg(w + k);
+            a0 = fma(ww.x, xv[2 * k], a0);
+            a1 = fma(ww.y, xv[2 * k + 1], a1);
+        }
+        double acc = a0 + a1;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(SS_FULL, acc, d);
+        z[q] = acc;
+    }
+}
+
 template <int NB, bool FO, bool MARK>
 __global__ void __launch_bounds__(32 * SP_WARPS, 2)
 filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
@@ -1008,126 +1147,136 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
                  double *__restrict__ out, const MarkParams mk)
 {
     constexpr int NS = FiltParams<NB, FO>::NS;
-    extern __shared__ __align__(1024) double sp_smem[];          // [SP_WARPS][512] tiles, then states
+    constexpr int NSEC = FiltParams<NB, FO>::NSEC;
+    constexpr bool SINGLE = NSEC == 1;                             // one section: its in-warp
+    constexpr bool SO1 = NB == 1;                                  // correction folds into the tile-level one
+    extern __shared__ __align__(1024) double sp_smem[];            // [SP_WARPS][512] tiles, then states
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *tile_s = sp_smem + warp * FS_T;
-    double *ends = sp_smem + SP_WARPS * FS_T;                     // [SP_WARPS][NS]
-    const int K = SP.K, W = SP_WARPS - 2 * K;
+    double *ends_f = sp_smem + SP_WARPS * FS_T, *ends_b = ends_f + SP_WARPS * NS;
 
     TileInfo ti = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
-    const int64_t own_lo = g.t_lo + (int64_t)blockIdx.x * W;
-    int64_t own_hi = own_lo + W;
-    if (own_hi > ti.nt) own_hi = ti.nt;
-    if (own_hi > g.t_hi) own_hi = g.t_hi;
+    const int nt = (int)ti.nt;
+    const int t_lo = (int)g.t_lo, t_end = g.t_hi < ti.nt ? (int)g.t_hi : nt;
+    const int own_lo = span_bound((int)blockIdx.x, t_lo, t_end, nt);
+    const int own_hi = span_bound((int)blockIdx.x + 1, t_lo, t_end, nt);
     if (own_hi <= own_lo) return;                                  // block-uniform
-    const int64_t act_lo = own_lo - K > 0 ? own_lo - K : 0;
-    const int64_t act_hi = own_hi + K < ti.nt ? own_hi + K : ti.nt;
-    const int64_t t_base = own_lo - K;                             // tile of warp 0 (may be < 0)
-    ti.t = t_base + warp;
-    const bool active = ti.t >= act_lo && ti.t < act_hi;
-    const bool owned = ti.t >= own_lo && ti.t < own_hi;
-    const int w_lo = (int)(act_lo - t_base), w_hi = (int)(act_hi - t_base);   // active warps [w_lo, w_hi)
-
-    const int64_t row0 = ti.c * g.ld_in;
-    const int64_t e0 = ti.t * FS_T - ti.pad;                       // ext index of the tile's first sample
+    const int n_own = own_hi - own_lo;                             // <= SP_WARPS + 1: see below
+    // (a moved boundary makes one span SP_WARPS - 1 and never longer than SP_WARPS tiles)
+    const int t = own_lo + warp;
+    const bool owned = warp < n_own;
+    ti.t = t;
+    const int64_t e0 = (int64_t)t * FS_T - ti.pad;                 // ext index of the tile's first sample
     const int64_t r0 = e0 - g.edge;                                // chunk-relative index
     const int64_t ext_len = ti.L + 2 * (int64_t)g.edge;
-    const bool interior = active && r0 >= 0 && r0 + FS_T <= ti.L;
+    const bool interior = owned && r0 >= 0 && r0 + FS_T <= ti.L;
+
+    // ---- start states that come from outside the span (first / last owned warp)
+    double zt[NS];                                                 // seed of the forward pass
+#pragma unroll
+    for (int i = 0; i < NS; ++i) zt[i] = 0.0;
+    double bz[NS];                                                 // Bz . x of the tile behind the span
+#pragma unroll
+    for (int i = 0; i < NS; ++i) bz[i] = 0.0;
     double v[FS_S];
-    if (active) {
-        const int64_t base = row0 + ti.cs0 + r0;
-        const int esz = g.dtype == SS_I16 ? 2 : (g.dtype == SS_F32 ? 4 : 8);
-        const bool aligned = ((reinterpret_cast<uintptr_t>(x) + (uintptr_t)base * esz) & 15u) == 0;
-        if (interior && aligned) {
-            if (g.dtype == SS_I16) span_load16(reinterpret_cast<const int16_t *>(x) + base + FS_S * lane, v);
-            else if (g.dtype == SS_F32) span_load16(reinterpret_cast<const float *>(x) + base + FS_S * lane, v);
-            else span_load16(reinterpret_cast<const double *>(x) + base + FS_S * lane, v);
-        } else if (interior) {
-            // unaligned view: coalesced element loads through the warp's shared tile
-            if (g.dtype == SS_I16) {
-                const int16_t *p = reinterpret_cast<const int16_t *>(x) + base;
+    if (warp == 0 && own_lo > 0) {
+        span_load_tile(x, g, ti, own_lo - 1, tile_s, lane, v);
+        double f[NS];
+        span_dot<NS>(SP.dot, 0, v, lane, f);
+        const double x_first = ss_shfl(v[0], 0);
 #pragma unroll
-                for (int k = 0; k < FS_S; ++k) tile_s[32 * k + lane] = ss_to_f64(__ldg(p + 32 * k + lane));
-            } else if (g.dtype == SS_F32) {
-                const float *p = reinterpret_cast<const float *>(x) + base;
+        for (int r = 0; r < NS; ++r) {
+            double acc = f[r];
 #pragma unroll
-                for (int k = 0; k < FS_S; ++k) tile_s[32 * k + lane] = (double)__ldg(p + 32 * k + lane);
-            } else {
-                const double *p = reinterpret_cast<const double *>(x) + base;
-#pragma unroll
-                for (int k = 0; k < FS_S; ++k) tile_s[32 * k + lane] = __ldg(p + 32 * k + lane);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < FS_S; ++i) v[i] = tile_s[lane * FS_S + i];
-            __syncwarp();
-        } else {
-#pragma unroll 1
-            for (int k = 0; k < FS_S; ++k)
-                tile_s[32 * k + lane] = ext_value(x, g.dtype, row0, ti, g.edge, e0 + 32 * k + lane);
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < FS_S; ++i) v[i] = tile_s[lane * FS_S + i];
-            __syncwarp();
+            for (int q = 0; q < NS; ++q) acc = fma(SP.AT[r][q], SP.zi[q] * x_first, acc);
+            zt[r] = lane == 0 ? acc : 0.0;
         }
+    }
+    if (warp == n_own - 1 && own_hi < nt) {
+        span_load_tile(x, g, ti, own_hi, tile_s, lane, v);
+        span_dot<NS>(SP.dot, NS, v, lane, bz);
+    }
+    if (owned) {
+        span_load_tile(x, g, ti, t, tile_s, lane, v);
     } else {
 #pragma unroll
         for (int i = 0; i < FS_S; ++i) v[i] = 0.0;
     }
+    if (owned && t == 0) {
+        const double x_first = ss_shfl(v[0], 0);                   // ext[0] (left padding)
+#pragma unroll
+        for (int i = 0; i < NS; ++i) zt[i] = lane == 0 ? SP.zi[i] * x_first : 0.0;
+    }
 
-    // ---- forward
-    double zt[NS], en[NS];
+    // -------- forward
+    double en[NS];
     {
-        // start state of the seeded lane: exact for the unit's first tile, the steady state of
-        // the first sample for the CTA's first warm-up tile, zero (fixed after the barrier) else
-        const double x_first = ss_shfl(v[0], 0);
-        const bool warm = active && (ti.t == 0 || warp == w_lo);
+        double p0 = 0.0, p1 = 0.0;
+        if constexpr (SINGLE) {
+            double e1 = 0.0;
+            span_section<SO1, false>(P.sec[0], SP.al[0], P.P[0], v, zt[0], SO1 ? zt[NS - 1] : 0.0, lane,
+                                     p0, p1, en[0], e1);
+            if (SO1) en[NS - 1] = e1;
+        } else {
 #pragma unroll
-        for (int i = 0; i < NS; ++i) zt[i] = (lane == 0 && warm) ? SP.zi[i] * x_first : 0.0;
-    }
-    cascade_pass_e<NB, FO, false>(P, v, zt, lane, en);
-    if (lane == 31) {
+            for (int sct = 0; sct < NB; ++sct) {
+                double q0, q1;
+                span_section<true, false>(P.sec[sct], SP.al[sct], P.P[sct], v, zt[2 * sct], zt[2 * sct + 1],
+                                          lane, q0, q1, en[2 * sct], en[2 * sct + 1]);
+                span_correct<true, false>(P.hrow[sct], v, q0, q1);
+            }
+            if (FO) {
+                double q0, q1, e1;
+                span_section<false, false>(P.sec[NB], SP.al[NB], P.P[NB], v, zt[2 * NB], 0.0, lane, q0, q1,
+                                           en[2 * NB], e1);
+                span_correct<false, false>(P.hrow[NB], v, q0, q1);
+            }
+        }
+        if (lane == 31) {
 #pragma unroll
-        for (int i = 0; i < NS; ++i) ends[warp * NS + i] = active ? en[i] : 0.0;
-    }
-    __syncthreads();
-    if (active && warp > w_lo) {
+            for (int i = 0; i < NS; ++i) ends_f[warp * NS + i] = en[i];
+        }
+        __syncthreads();
+        const bool have = owned && warp > 0;                       // start state = end state of warp - 1
         double z[NS];
 #pragma unroll
-        for (int i = 0; i < NS; ++i) z[i] = 0.0;
-        for (int sidx = w_lo; sidx < warp; ++sidx) {               // z <- A^T z + e_s
-            double nz[NS];
+        for (int r = 0; r < NS; ++r) z[r] = have ? ends_f[(warp - 1) * NS + r] : 0.0;
+        if constexpr (SINGLE) {
+            // p <- p + A^(16 lane) z, then the one correction
+            const double a00 = __ldg(SP.apow + lane);
+            if (SO1) {
+                const double a01 = __ldg(SP.apow + 32 + lane), a10 = __ldg(SP.apow + 64 + lane);
+                const double a11 = __ldg(SP.apow + 96 + lane);
+                p0 = fma(a00, z[0], fma(a01, z[NS - 1], p0));
+                p1 = fma(a10, z[0], fma(a11, z[NS - 1], p1));
+            } else {
+                p0 = fma(a00, z[0], p0);
+            }
+            span_correct<SO1, false>(P.hrow[0], v, p0, p1);
+        } else if (have) {
+            double pz[NS];                                         // A^(16 lane) z
 #pragma unroll
             for (int r = 0; r < NS; ++r) {
-                double acc = ends[sidx * NS + r];
+                double acc = 0.0;
 #pragma unroll
-                for (int q = 0; q < NS; ++q) acc += SP.AT[r][q] * z[q];
-                nz[r] = acc;
+                for (int q = 0; q < NS; ++q) acc = fma(__ldg(SP.apow + (r * NS + q) * 32 + lane), z[q], acc);
+                pz[r] = acc;
             }
 #pragma unroll
-            for (int r = 0; r < NS; ++r) z[r] = nz[r];
-        }
-        double pz[NS];                                             // A^(16 lane) z
+            for (int i = 0; i < FS_S; ++i) {
+                double acc = v[i];
 #pragma unroll
-        for (int r = 0; r < NS; ++r) {
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < NS; ++q) acc += __ldg(SP.apow + (r * NS + q) * 32 + lane) * z[q];
-            pz[r] = acc;
-        }
-#pragma unroll
-        for (int i = 0; i < FS_S; ++i) {
-            double acc = v[i];
-#pragma unroll
-            for (int q = 0; q < NS; ++q) acc += SP.hrowF[i][q] * pz[q];
-            v[i] = acc;
+                for (int q = 0; q < NS; ++q) acc = fma(SP.hrowF[i][q], pz[q], acc);
+                v[i] = acc;
+            }
         }
     }
 
-    // ---- backward over the forward output
+    // -------- backward over the forward output
     {
-        double seed = ss_shfl(v[FS_S - 1], 31);                    // last forward output of the tile
-        if (active && ti.t == ti.nt - 1) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) zt[i] = 0.0;
+        if (owned && t == nt - 1) {
             // the unit's last tile: y[-1] sits at offset o; the right padding behind it is the
             // steady-state input y[-1]
             const int o = (int)(ext_len - 1 - e0);
@@ -1139,78 +1288,125 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
 #pragma unroll
             for (int i = 0; i < FS_S; ++i)
                 if (FS_S * lane + i > o) v[i] = yl;
-            seed = yl;
-        }
-        const bool warm = active && (ti.t == ti.nt - 1 || warp == w_hi - 1);
 #pragma unroll
-        for (int i = 0; i < NS; ++i) zt[i] = (lane == 31 && warm) ? SP.zi[i] * seed : 0.0;
-    }
-    __syncthreads();                                               // `ends` is reused below
-    cascade_pass_e<NB, FO, true>(P, v, zt, lane, en);
-    if (lane == 0) {
-#pragma unroll
-        for (int i = 0; i < NS; ++i) ends[warp * NS + i] = active ? en[i] : 0.0;
-    }
-    __syncthreads();
-    if (!owned) return;                                            // warm-up tiles are done
-    if (warp < w_hi - 1) {
-        double z[NS];
-#pragma unroll
-        for (int i = 0; i < NS; ++i) z[i] = 0.0;
-        for (int sidx = w_hi - 1; sidx > warp; --sidx) {
-            double nz[NS];
+            for (int i = 0; i < NS; ++i) zt[i] = lane == 31 ? SP.zi[i] * yl : 0.0;
+        } else if (warp == n_own - 1) {
+            // start state from the tile behind the span: Bz . x + M e, e = forward start state
+            // of that tile = the zero-start end state of this one (one tile of history)
 #pragma unroll
             for (int r = 0; r < NS; ++r) {
-                double acc = ends[sidx * NS + r];
+                double acc = bz[r];
 #pragma unroll
-                for (int q = 0; q < NS; ++q) acc += SP.AT[r][q] * z[q];
-                nz[r] = acc;
+                for (int q = 0; q < NS; ++q) acc = fma(SP.M[r][q], ss_shfl(en[q], 31), acc);
+                zt[r] = lane == 31 ? acc : 0.0;
+            }
+        }
+        double p0 = 0.0, p1 = 0.0;
+        if constexpr (SINGLE) {
+            double e1 = 0.0;
+            span_section<SO1, true>(P.sec[0], SP.al[0], P.P[0], v, zt[0], SO1 ? zt[NS - 1] : 0.0, lane,
+                                    p0, p1, en[0], e1);
+            if (SO1) en[NS - 1] = e1;
+        } else {
+#pragma unroll
+            for (int sct = 0; sct < NB; ++sct) {
+                double q0, q1;
+                span_section<true, true>(P.sec[sct], SP.al[sct], P.P[sct], v, zt[2 * sct], zt[2 * sct + 1],
+                                         lane, q0, q1, en[2 * sct], en[2 * sct + 1]);
+                span_correct<true, true>(P.hrow[sct], v, q0, q1);
+            }
+            if (FO) {
+                double q0, q1, e1;
+                span_section<false, true>(P.sec[NB], SP.al[NB], P.P[NB], v, zt[2 * NB], 0.0, lane, q0, q1,
+                                          en[2 * NB], e1);
+                span_correct<false, true>(P.hrow[NB], v, q0, q1);
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) ends_b[warp * NS + i] = en[i];
+        }
+        __syncthreads();
+        if (!owned) return;
+        const bool have = warp + 1 < n_own;
+        double z[NS];
+#pragma unroll
+        for (int r = 0; r < NS; ++r) z[r] = have ? ends_b[(warp + 1) * NS + r] : 0.0;
+        if constexpr (SINGLE) {
+            const double a00 = __ldg(SP.apow + (31 - lane));
+            if (SO1) {
+                const double a01 = __ldg(SP.apow + 32 + (31 - lane)), a10 = __ldg(SP.apow + 64 + (31 - lane));
+                const double a11 = __ldg(SP.apow + 96 + (31 - lane));
+                p0 = fma(a00, z[0], fma(a01, z[NS - 1], p0));
+                p1 = fma(a10, z[0], fma(a11, z[NS - 1], p1));
+            } else {
+                p0 = fma(a00, z[0], p0);
+            }
+            span_correct<SO1, true>(P.hrow[0], v, p0, p1);
+        } else if (have) {
+            double pz[NS];                                         // A^(16 (31 - lane)) z
+#pragma unroll
+            for (int r = 0; r < NS; ++r) {
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < NS; ++q)
+                    acc = fma(__ldg(SP.apow + (r * NS + q) * 32 + (31 - lane)), z[q], acc);
+                pz[r] = acc;
             }
 #pragma unroll
-            for (int r = 0; r < NS; ++r) z[r] = nz[r];
-        }
-        double pz[NS];                                             // A^(16 (31 - lane)) z
+            for (int i = 0; i < FS_S; ++i) {
+                double acc = v[i];
 #pragma unroll
-        for (int r = 0; r < NS; ++r) {
-            double acc = 0.0;
-#pragma unroll
-            for (int q = 0; q < NS; ++q) acc += __ldg(SP.apow + (r * NS + q) * 32 + (31 - lane)) * z[q];
-            pz[r] = acc;
-        }
-#pragma unroll
-        for (int i = 0; i < FS_S; ++i) {
-            double acc = v[i];
-#pragma unroll
-            for (int q = 0; q < NS; ++q) acc += SP.hrowF[FS_S - 1 - i][q] * pz[q];
-            v[i] = acc;
+                for (int q = 0; q < NS; ++q) acc = fma(SP.hrowF[FS_S - 1 - i][q], pz[q], acc);
+                v[i] = acc;
+            }
         }
     }
 
     // ---- epilogue: marks, stores
     if (MARK) {
         const double th = __ldg(mk.thr + ti.c);
-        const double nx = ss_shfl_down(v[0], 1);
-        uint32_t bits = 0;
+        // Cheap necessary condition first: a crossing needs a sample beyond the threshold.  With
+        // the usual signs (falling: th < 0, rising: th > 0) "beyond" is an integer comparison of
+        // the HIGH words; only tiles that hold such a sample (a few per cent) pay for the exact
+        // float64 comparisons.  Other sign combinations always take the exact path.
+        bool maybe = true;
+        const int hth = __double2hiint(th);
+        if (mk.falling && th < 0.0) {
+            unsigned m = 0;
 #pragma unroll
-        for (int i = 0; i < FS_S - 1; ++i)
-            bits |= (uint32_t)ssi::crossing(v[i], v[i + 1], th, mk.falling) << i;
-        if (lane < 31) bits |= (uint32_t)ssi::crossing(v[FS_S - 1], nx, th, mk.falling) << (FS_S - 1);
-        const int64_t rl = r0 + FS_S * lane;                  // chunk-relative index of bit 0
-        if (!interior) {
-            const int64_t lo = rl < 0 ? -rl : 0, hi = ti.L - 1 - rl;
-            uint32_t keep = 0;
-            if (lo < FS_S && hi > 0) {
-                const int h = hi < FS_S ? (int)hi : FS_S;
-                keep = ((h >= 32 ? 0xffffffffu : ((1u << h) - 1u))) & ~((1u << (int)lo) - 1u);
-            }
-            bits &= keep;
+            for (int i = 0; i < FS_S; ++i) m = max(m, (unsigned)__double2hiint(v[i]));
+            maybe = m >= (unsigned)hth;
+        } else if (!mk.falling && th > 0.0) {
+            int m = (int)0x80000000;
+#pragma unroll
+            for (int i = 0; i < FS_S; ++i) m = max(m, __double2hiint(v[i]));
+            maybe = m >= hth;
         }
-        if (bits) {
-            const int64_t s = ti.cs0 + rl;
-            uint32_t *mrow = mk.mask + ti.c * mk.words_per_row;
-            const uint64_t w = (uint64_t)bits << (int)(s & 31);
-            if ((uint32_t)w) atomicOr(mrow + (s >> 5), (uint32_t)w);
-            if (w >> 32) atomicOr(mrow + (s >> 5) + 1, (uint32_t)(w >> 32));
+        if (__any_sync(SS_FULL, maybe)) {
+            const double nx = ss_shfl_down(v[0], 1);
+            uint32_t bits = 0;
+#pragma unroll
+            for (int i = 0; i < FS_S - 1; ++i)
+                bits |= (uint32_t)ssi::crossing(v[i], v[i + 1], th, mk.falling) << i;
+            if (lane < 31) bits |= (uint32_t)ssi::crossing(v[FS_S - 1], nx, th, mk.falling) << (FS_S - 1);
+            const int64_t rl = r0 + FS_S * lane;              // chunk-relative index of bit 0
+            if (!interior) {
+                const int64_t lo = rl < 0 ? -rl : 0, hi = ti.L - 1 - rl;
+                uint32_t keep = 0;
+                if (lo < FS_S && hi > 0) {
+                    const int h = hi < FS_S ? (int)hi : FS_S;
+                    keep = ((h >= 32 ? 0xffffffffu : ((1u << h) - 1u))) & ~((1u << (int)lo) - 1u);
+                }
+                bits &= keep;
+            }
+            if (bits) {
+                const int64_t s = ti.cs0 + rl;
+                uint32_t *mrow = mk.mask + ti.c * mk.words_per_row;
+                const uint64_t w = (uint64_t)bits << (int)(s & 31);
+                if ((uint32_t)w) atomicOr(mrow + (s >> 5), (uint32_t)w);
+                if (w >> 32) atomicOr(mrow + (s >> 5) + 1, (uint32_t)(w >> 32));
+            }
         }
     }
     double *orow = out + ti.c * g.ld_out + ti.cs0;
@@ -1863,10 +2059,18 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
             const double *d_tab_s = nullptr;
             { const int rc_tab = device_table(T, tab_bytes_s, &d_tab_s); if (rc_tab) return rc_tab; }
             SPn.apow = d_tab_s + (size_t)(2 * NS + 1) * FS_T;
-            SPn.K = span_warmup;
-            const int W = SP_WARPS - 2 * SPn.K;
-            const dim3 grid((unsigned)ss_cdiv(nt_hi_s - t_lo, W), (unsigned)j_count, (unsigned)g.n_contacts);
-            const size_t smem = ((size_t)SP_WARPS * FS_T + (size_t)SP_WARPS * NS) * sizeof(double);
+            for (int sct = 0; sct < NSEC; ++sct) {
+                const q_t b0 = sos[sct * 6 + 0], b1 = sos[sct * 6 + 1], b2 = sos[sct * 6 + 2];
+                const q_t a1 = sos[sct * 6 + 4], a2 = sos[sct * 6 + 5];
+                SPn.al[sct][0] = (double)(b1 - a1 * b0);
+                SPn.al[sct][1] = (double)(b2 - a2 * b0);
+            }
+            SPn.dot = d_tab_s;
+            for (int i = 0; i < NS; ++i)
+                for (int j = 0; j < NS; ++j) SPn.M[i][j] = T.M[i][j];
+            (void)span_warmup;
+            const dim3 grid((unsigned)ss_cdiv(nt_hi_s - t_lo, SP_WARPS), (unsigned)j_count, (unsigned)g.n_contacts);
+            const size_t smem = ((size_t)SP_WARPS * FS_T + (size_t)2 * SP_WARPS * NS) * sizeof(double);
             MarkParams mkp;
             if (mk) mkp = *mk;
             else mkp = MarkParams{nullptr, nullptr, 0, 0, 0, nullptr, nullptr, 0, 0};
@@ -2006,8 +2210,7 @@ static int make_plan(FiltPlan &pl, int dtype, int64_t n_contacts, int64_t n_samp
         const char *force = getenv("SS_FILT_SPAN");
         const bool allowed = !(force && force[0] == '0');
         if (allowed && S.ns <= SP_MAX_NS) {
-            if (pl.T.span_err[0] <= SP_ERR_BOUND) pl.span_warmup = 1;
-            else if (pl.T.span_err[1] <= SP_ERR_BOUND) pl.span_warmup = 2;
+            if (pl.T.span_err[0] <= SP_ERR_BOUND) pl.span_warmup = 1;     // one tile of history
         }
     }
     if (pl.span_warmup) {
@@ -2071,6 +2274,7 @@ static void head_cut(const FiltGeom &g, int64_t n0, int64_t &jh, int64_t &t_cut,
     const int64_t cs0 = jh * g.chunksize, r_need = n0 - cs0;
     t_cut = ss_cdiv(r_need + pad + g.edge, FS_T);          // first tile with r0 >= r_need
     int64_t r_end = t_cut * FS_T - pad - g.edge;
+    if (g.span && t_cut == nt_jh - 1) t_cut = nt_jh;       // span kernel: no range ends on the last tile
     if (t_cut >= nt_jh || r_end >= L) {                    // the whole chunk
         t_cut = nt_jh;
         r_end = L;

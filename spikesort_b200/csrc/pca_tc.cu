@@ -1,51 +1,57 @@
 // K6 on the 5th-generation tensor cores: per-contact Gram matrices of spike waveforms
-// in 3xTF32 (tcgen05.mma.kind::tf32, accumulators in TMEM, float64 across chunks).
+// in split-TF32 (tcgen05.mma.kind::tf32, accumulators in TMEM, float64 across blocks).
 //
 // Replaces the contraction inside np.cov, reference src/spike_sort/core/features.py:225
 // (K = np.cov(data), data = (n_win, n_spikes) per contact).
 //
 // Shape of the problem: M = N = n_win (25..31) is tiny, K = n_spikes is huge, so the
-// kernel is HBM-bound; the tensor cores are used to keep the arithmetic off the critical
-// path (the float64 CUDA-core kernel in pca.cu is FP64-pipe bound on 10^7 spikes).
+// kernel should be HBM-bound; the tensor cores keep the arithmetic off the critical path
+// (the float64 CUDA-core kernel in pca.cu is FP64-pipe bound on 10^7 spikes).
 //
 //  * up to 4 contacts share one 128 x 128 tile: contact p owns rows/columns
-//    [32p, 32p + n_win) and row 32p + n_win is a row of ones, so column 32p + n_win of
-//    the product holds the row sums needed for the mean (the off-diagonal blocks are
-//    cross-contact products nobody reads);
-//  * raw float32 rows (one (time step, K-block) = 32 spikes x n_c contacts, contiguous in
-//    the reference's (n_win, n_spk, n_c) layout) arrive in shared memory by 1-D bulk
-//    async copies (cp.async.bulk + mbarrier complete_tx), 128 spikes per copy, 2 stages;
-//  * all threads convert a raw stage into the canonical K-major SWIZZLE_128B UMMA layout:
-//    d = x - ref, hi = tf32(d), lo = d - hi;
-//  * one thread issues, per 8 spikes, hi.hi^T + hi.lo^T + lo.hi^T as three
-//    128x128x8 tcgen05.mma into the same TMEM accumulator and commits to the mbarrier
-//    that frees the canonical stage (2 stages: conversion of block b+1 overlaps the
-//    MMAs of block b);
-//  * every 256 spikes the float32 accumulators are read back (tcgen05.ld 32x32b.x32,
-//    warp p reads contact p's diagonal block) and added to float64 registers.
+//    [32p, 32p + n_win) and row 32p + n_win is a row of ones, so that column of the product
+//    holds the row sums needed for the mean (the off-diagonal blocks are cross-contact
+//    products nobody reads; with P < 4 contacts the MMA's N shrinks to 32 P);
+//  * d = x - ref is split as d = H + L, H = tf32(d) (round to nearest), L = d - H (exact in
+//    float32).  With T = sum H (H + 2L)^T the Gram is G = (T + T^T) / 2 up to the L L^T
+//    term (2^-22 relative): TWO MMAs per 8 spikes (H.H^T and H.(2L)^T into the same TMEM
+//    accumulator) instead of the three of the classical 3xTF32, and the symmetrisation makes
+//    the ones-row trick deliver sum(H + L) as well;
+//  * the float32 TMEM accumulation truncates, a systematic shrink of ~2e-8 per accumulation:
+//    the accumulator is read back every 32 spikes (8 accumulations, two TMEM buffers
+//    alternate) into float64 registers - measured Gram error ~2e-7 (256-spike chunks: 2e-6);
+//  * warp-specialised, mbarrier-synchronised, no block-wide barrier in the loop:
+//      warp 8      producer: 1-D bulk async copies (cp.async.bulk + complete_tx) of the raw
+//                  float32 rows, 64 spikes x n_c contacts per copy, TC_R stages;
+//      warps 0-3   converters: raw stage -> canonical K-major SWIZZLE_128B tiles of H and 2L
+//                  (TC_C stages), 128-bit shared-memory reads and writes;
+//      warp 9      one thread issues the MMAs and commits to the barriers that free the
+//                  canonical stage and publish the accumulator;
+//      warps 4-7   epilogue: warp p reads contact p's 32 x 32 diagonal block from TMEM
+//                  (tcgen05.ld 32x32b.x32) and adds it to float64 registers.
 // Every mbarrier wait is bounded: a protocol error traps instead of hanging the GPU.
 #include "common.cuh"
 #include "internal.cuh"
 
 namespace {
 
-constexpr int TC_KB = 32;                  // spikes per K-block
+constexpr int TC_KB = 32;                  // spikes per K-block (= one accumulation chunk)
 constexpr int TC_RW = 32;                  // rows per contact in the tile (n_win + 1 <= 32)
-constexpr int TC_R = 2;                    // raw stages
-constexpr int TC_RB = 4;                   // K-blocks per raw stage: one bulk copy moves a row of
-                                           // 128 spikes (2 KB at 4 contacts); 512-byte copies cost
-                                           // ~10 % more (copy-engine overhead per request)
-constexpr int TC_C = 2;                    // canonical (hi/lo) stages
-constexpr int TC_CHUNK = 8;                // K-blocks per float32 accumulation chunk (256 spikes:
-                                           // the TMEM accumulation truncates, so chunks stay short)
-constexpr int TC_THREADS = 256;
+constexpr int TC_R = 4;                    // raw stages
+constexpr int TC_RB = 2;                   // K-blocks per raw stage: one bulk copy moves a row of
+                                           // 64 spikes (1 KB at 4 contacts)
+constexpr int TC_C = 3;                    // canonical (H / 2L) stages
+constexpr int TC_NCONV = 4;                // converter warps (0..3)
+constexpr int TC_EPI0 = 4;                 // epilogue warps 4..7 (warp % 4 = TMEM lane quadrant)
+constexpr int TC_PRODUCER = 8, TC_ISSUER = 9;
+constexpr int TC_THREADS = 320;
 constexpr int TC_CANON_BYTES = (TC_KB / 4) * 16 * 128;   // one 128-row x 32-spike matrix: 16 KB
 // canonical K-major SWIZZLE_128B layout: one tile row = 32 spikes = 128 B, 8-row groups of
 // 1024 B, the 16-byte chunk c of row r stored at chunk c ^ (r % 8).  (The no-swizzle
 // "interleave" layout ran the MMAs at ~1/4 rate: 86 % tensor-pipe-active cycles at 18 % of
 // peak in ncu - operand fetch bank conflicts.)
 constexpr uint32_t TC_SBO = 1024;          // M-direction stride between 8-row groups (bytes)
-constexpr int TC_TMEM_COLS = 256;          // two 128-column accumulators (chunks alternate)
+constexpr int TC_TMEM_COLS = 256;          // two 128-column accumulators (blocks alternate)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -105,6 +111,11 @@ __device__ __forceinline__ float tf32_round(float v)
     return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // grid (parts, n_packs): contact mode n_packs == 1 and the CTA holds all n_c <= 4
 // contacts; offsets mode (n_c == 1) one group per blockIdx.y.
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -121,14 +132,17 @@ pca_gram_tc_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
     const int64_t g0 = offsets ? blockIdx.y : 0;           // first group of this CTA
     const int raw_row = TC_RB * TC_KB * n_c * 4 + 16;      // bytes, 16 B pad: conflict-free reads
 
-    unsigned char *canon_hi = smem;                                    // [C][16 KB]
-    unsigned char *canon_lo = canon_hi + TC_C * TC_CANON_BYTES;        // [C][16 KB]
-    unsigned char *raw = canon_lo + TC_C * TC_CANON_BYTES;             // [R][n_win][raw_row]
+    unsigned char *canon_h = smem;                                     // [C][16 KB]  H
+    unsigned char *canon_l = canon_h + TC_C * TC_CANON_BYTES;          // [C][16 KB]  2L
+    unsigned char *raw = canon_l + TC_C * TC_CANON_BYTES;              // [R][n_win][raw_row]
     const int raw_stage = ((n_win * raw_row) + 127) & ~127;
     uint64_t *bars = reinterpret_cast<uint64_t *>(raw + TC_R * raw_stage);
-    uint64_t *raw_full = bars, *canon_empty = bars + TC_R, *accum_full = bars + TC_R + TC_C;   // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + TC_R + TC_C + 2);
+    uint64_t *raw_full = bars, *raw_empty = raw_full + TC_R, *canon_full = raw_empty + TC_R,
+             *canon_empty = canon_full + TC_C, *accum_full = canon_empty + TC_C,
+             *accum_empty = accum_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(accum_empty + 2);
     float *ref_s = reinterpret_cast<float *>(tmem_slot + 4);           // [P][TC_RW]
+    double *sym_s = reinterpret_cast<double *>(canon_h);               // epilogue scratch (tiles are dead)
 
     // spike range of this CTA
     int64_t lo_all, hi_all;
@@ -139,6 +153,7 @@ pca_gram_tc_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
     const int64_t lo = min(lo_all + (int64_t)part * per, hi_all), hi = min(lo + per, hi_all);
     const int64_t b0 = lo & ~(int64_t)3;                   // 16-byte aligned block origin
     const int nblk = (int)((hi - b0 + TC_KB - 1) / TC_KB);
+    const int nsb = (nblk + TC_RB - 1) / TC_RB;
 
     // ---- one-time setup
     for (int i = tid; i < 2 * TC_C * TC_CANON_BYTES / 16; i += TC_THREADS)
@@ -148,10 +163,9 @@ pca_gram_tc_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
         ref_s[i] = w < n_win ? (float)ref[(g0 + p) * n_win + w] : 0.f;
     }
     if (tid == 0) {
-        for (int i = 0; i < TC_R; ++i) mbar_init(raw_full + i, 1);
-        for (int i = 0; i < TC_C; ++i) mbar_init(canon_empty + i, 1);
-        mbar_init(accum_full, 1);
-        mbar_init(accum_full + 1, 1);
+        for (int i = 0; i < TC_R; ++i) { mbar_init(raw_full + i, 1); mbar_init(raw_empty + i, TC_NCONV); }
+        for (int i = 0; i < TC_C; ++i) { mbar_init(canon_full + i, TC_NCONV); mbar_init(canon_empty + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(accum_full + i, 1); mbar_init(accum_empty + i, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -159,184 +173,197 @@ pca_gram_tc_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
                      ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
+    // the zero fill above was written by the generic proxy; the MMAs read through the async one
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
-    // instruction descriptor: D f32, A/B tf32, both K-major, N = 128, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-
     double acc[TC_RW];
 #pragma unroll
     for (int j = 0; j < TC_RW; ++j) acc[j] = 0.0;
 
-    // warp 7 issues the bulk copies of a block: lane 0 arms the barrier with the byte count,
-    // lane w copies row w (one elected thread issuing all rows serialises ~25 copies per block)
-    auto issue_load = [&](int sb) {                        // super-block = TC_RB K-blocks
-        const int st = sb % TC_R;
-        const int64_t s0 = b0 + (int64_t)sb * (TC_RB * TC_KB);
-        const int64_t nsp = min((int64_t)(TC_RB * TC_KB), n_spk - s0);
-        const uint32_t bytes = (uint32_t)(nsp * n_c * 4);
-        const uint32_t bar = smem_u32(raw_full + st);
-        if (lane == 0)
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                         ::"r"(bar), "r"(bytes * (uint32_t)n_win)
-                         : "memory");
-        __syncwarp();
-        if (lane < n_win) {
-            const float *src = waves + ((int64_t)lane * n_spk + s0) * n_c;
-            const uint32_t dst = smem_u32(raw + st * raw_stage + lane * raw_row);
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
-                         "[%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
-                         : "memory");
-        }
-    };
-
-    const int nsb = (nblk + TC_RB - 1) / TC_RB;
-    if (warp == TC_THREADS / 32 - 1)
-        for (int sb = 0; sb < TC_R - 1 && sb < nsb; ++sb) issue_load(sb);
-
-    // every thread converts the same <= 4 (row, 4-spike group) items of every block: decode once
-    const int WG = (n_win + 1 + 7) / 8;                    // 8-row groups per contact (incl. ones row)
-    const int n_items = 8 * P * WG * (TC_KB / 4);          // <= 1024
-    constexpr int TC_IT = 4;
-    int it_raw[TC_IT], it_can[TC_IT], it_kind[TC_IT], it_s[TC_IT];     // kind 0 skip, 1 data, 2 ones
-    float it_ref[TC_IT];
-#pragma unroll
-    for (int k = 0; k < TC_IT; ++k) {
-        const int id = tid + k * TC_THREADS;
-        it_kind[k] = 0; it_raw[k] = 0; it_can[k] = 0; it_s[k] = 0; it_ref[k] = 0.f;
-        if (id < n_items) {
-            const int i0 = id & 7;
-            int rest = id >> 3;
-            const int p = rest % P;
-            rest /= P;
-            const int wq = rest % WG, kc = rest / WG;
-            const int w = wq * 8 + i0;
-            if (w <= n_win) {
-                const int r = p * TC_RW + w;
-                it_kind[k] = w < n_win ? 1 : 2;
-                it_raw[k] = w * raw_row + (4 * kc * n_c + p) * 4;
-                it_can[k] = (r >> 3) * (int)TC_SBO + (r & 7) * 128 + ((kc ^ (r & 7)) << 4);
-                it_s[k] = 4 * kc;
-                it_ref[k] = ref_s[p * TC_RW + w];
+    if (warp == TC_PRODUCER) {
+        // ---- raw float32 rows -> shared memory: lane 0 arms the barrier with the byte count,
+        // lane w copies row w (one elected thread issuing all rows serialises ~25 copies)
+        for (int sb = 0; sb < nsb; ++sb) {
+            const int st = sb % TC_R;
+            mbar_wait(raw_empty + st, (uint32_t)(((sb / TC_R) & 1) ^ 1));
+            const int64_t s0 = b0 + (int64_t)sb * (TC_RB * TC_KB);
+            const int64_t nsp = min((int64_t)(TC_RB * TC_KB), n_spk - s0);
+            const uint32_t bytes = (uint32_t)(nsp * n_c * 4);
+            const uint32_t bar = smem_u32(raw_full + st);
+            if (lane == 0)
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                             ::"r"(bar), "r"(bytes * (uint32_t)n_win)
+                             : "memory");
+            __syncwarp();
+            if (lane < n_win) {
+                const float *src = waves + ((int64_t)lane * n_spk + s0) * n_c;
+                const uint32_t dst = smem_u32(raw + st * raw_stage + lane * raw_row);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+                             "[%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+                             : "memory");
             }
         }
-    }
-    const int cstride = n_c * 4;                           // bytes between consecutive spikes of a row
-    for (int b = 0; b < nblk; ++b) {
-        const int sb = b / TC_RB;
-        if (warp == TC_THREADS / 32 - 1 && b % TC_RB == 0 && sb + TC_R - 1 < nsb)
-            issue_load(sb + TC_R - 1);
-        mbar_wait(raw_full + sb % TC_R, (uint32_t)((sb / TC_R) & 1));
-        if (b >= TC_C) mbar_wait(canon_empty + b % TC_C, (uint32_t)(((b / TC_C) - 1) & 1));
-
-        // ---- raw float32 -> canonical hi / lo tf32 tiles
-        const unsigned char *rs = raw + (sb % TC_R) * raw_stage + (b % TC_RB) * (TC_KB * n_c * 4);
-        unsigned char *ch = canon_hi + (b % TC_C) * TC_CANON_BYTES;
-        unsigned char *cl = canon_lo + (b % TC_C) * TC_CANON_BYTES;
-        const int64_t s0 = b0 + (int64_t)b * TC_KB;
-        const bool whole = s0 >= lo && s0 + TC_KB <= hi;   // no masking needed
-        if (n_c == 4 && !offsets) {
-            // 4-contact fast path: thread (w = tid%32, kc = tid/32) converts 4 spikes of row w
-            // for all 4 contacts: four 128-bit raw reads, eight 128-bit canonical stores
-            const int w = tid & 31, kc = tid >> 5;
-            if (w <= n_win) {
-                float d[4][4];                             // [spike j][contact p]
+    } else if (warp < TC_NCONV) {
+        // ---- raw float32 -> canonical H / 2L tiles
+        const int ctid = tid;                              // 0 .. 128 * TC_NCONV / 4 - 1
+        constexpr int CT = 32 * TC_NCONV;
+        // generic path: every thread converts the same (row, 4-spike group) items of every block
+        const int WG = (n_win + 1 + 7) / 8;                // 8-row groups per contact (incl. ones row)
+        const int n_items = 8 * P * WG * (TC_KB / 4);      // <= 1024
+        constexpr int TC_IT = 1024 / CT;
+        int it_raw[TC_IT], it_can[TC_IT], it_kind[TC_IT], it_s[TC_IT];     // kind 0 skip, 1 data, 2 ones
+        float it_ref[TC_IT];
+        const bool fast4 = n_c == 4 && !offsets;
+        if (!fast4) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (w < n_win) {
-                        const float4 q = *reinterpret_cast<const float4 *>(rs + w * raw_row + (4 * kc + j) * 16);
-                        d[j][0] = q.x - ref_s[0 * TC_RW + w];
-                        d[j][1] = q.y - ref_s[1 * TC_RW + w];
-                        d[j][2] = q.z - ref_s[2 * TC_RW + w];
-                        d[j][3] = q.w - ref_s[3 * TC_RW + w];
-                    } else {
-                        d[j][0] = d[j][1] = d[j][2] = d[j][3] = 1.0f;
-                    }
-                    if (!whole) {
-                        const int64_t sp = s0 + 4 * kc + j;
-                        if (sp < lo || sp >= hi) d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.f;
+            for (int k = 0; k < TC_IT; ++k) {
+                const int id = ctid + k * CT;
+                it_kind[k] = 0; it_raw[k] = 0; it_can[k] = 0; it_s[k] = 0; it_ref[k] = 0.f;
+                if (id < n_items) {
+                    const int i0 = id & 7;
+                    int rest = id >> 3;
+                    const int p = rest % P;
+                    rest /= P;
+                    const int wq = rest % WG, kc = rest / WG;
+                    const int w = wq * 8 + i0;
+                    if (w <= n_win) {
+                        const int r = p * TC_RW + w;
+                        it_kind[k] = w < n_win ? 1 : 2;
+                        it_raw[k] = w * raw_row + (4 * kc * n_c + p) * 4;
+                        it_can[k] = (r >> 3) * (int)TC_SBO + (r & 7) * 128 + ((kc ^ (r & 7)) << 4);
+                        it_s[k] = 4 * kc;
+                        it_ref[k] = ref_s[p * TC_RW + w];
                     }
                 }
+            }
+        }
+        const int cstride = n_c * 4;                       // bytes between consecutive spikes of a row
+        for (int b = 0; b < nblk; ++b) {
+            const int sb = b / TC_RB, st = sb % TC_R, cs = b % TC_C;
+            if (b % TC_RB == 0) mbar_wait(raw_full + st, (uint32_t)((sb / TC_R) & 1));
+            mbar_wait(canon_empty + cs, (uint32_t)(((b / TC_C) & 1) ^ 1));
+            const unsigned char *rs = raw + st * raw_stage + (b % TC_RB) * (TC_KB * n_c * 4);
+            unsigned char *ch = canon_h + cs * TC_CANON_BYTES;
+            unsigned char *cl = canon_l + cs * TC_CANON_BYTES;
+            const int64_t s0 = b0 + (int64_t)b * TC_KB;
+            const bool whole = s0 >= lo && s0 + TC_KB <= hi;   // no masking needed
+            if (fast4) {
+                // thread (w = lane, kc) converts 4 spikes of row w for all 4 contacts: four
+                // 128-bit raw reads, eight 128-bit canonical stores; TC_NCONV warps x 2 passes
+                const int w = lane;
+                if (w <= n_win) {
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
+                    for (int half = 0; half < 8 / TC_NCONV; ++half) {
+                        const int kc = warp + half * TC_NCONV;
+                        float d[4][4];                         // [spike j][contact p]
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (w < n_win) {
+                                const float4 q = *reinterpret_cast<const float4 *>(rs + w * raw_row + (4 * kc + j) * 16);
+                                d[j][0] = q.x - ref_s[0 * TC_RW + w];
+                                d[j][1] = q.y - ref_s[1 * TC_RW + w];
+                                d[j][2] = q.z - ref_s[2 * TC_RW + w];
+                                d[j][3] = q.w - ref_s[3 * TC_RW + w];
+                            } else {
+                                d[j][0] = d[j][1] = d[j][2] = d[j][3] = 1.0f;
+                            }
+                            if (!whole) {
+                                const int64_t sp = s0 + 4 * kc + j;
+                                if (sp < lo || sp >= hi) d[j][0] = d[j][1] = d[j][2] = d[j][3] = 0.f;
+                            }
+                        }
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            float h[4], l[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                h[j] = tf32_round(d[j][p]);
+                                l[j] = 2.0f * (d[j][p] - h[j]);    // exact; the MMA truncates to tf32
+                            }
+                            const int r = p * TC_RW + w;
+                            const int off = (r >> 3) * (int)TC_SBO + (r & 7) * 128 + ((kc ^ (r & 7)) << 4);
+                            *reinterpret_cast<float4 *>(ch + off) = make_float4(h[0], h[1], h[2], h[3]);
+                            *reinterpret_cast<float4 *>(cl + off) = make_float4(l[0], l[1], l[2], l[3]);
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < TC_IT; ++k) {
+                    if (it_kind[k] == 0) continue;
+                    float d[4];
+                    if (it_kind[k] == 1) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            d[j] = *reinterpret_cast<const float *>(rs + it_raw[k] + j * cstride) - it_ref[k];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) d[j] = 1.0f;
+                    }
+                    if (!whole) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int64_t sp = s0 + it_s[k] + j;
+                            if (sp < lo || sp >= hi) d[j] = 0.f;
+                        }
+                    }
                     float h[4], l[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        h[j] = tf32_round(d[j][p]);
-                        l[j] = d[j][p] - h[j];          // the MMA truncates to tf32 itself
+                        h[j] = tf32_round(d[j]);
+                        l[j] = 2.0f * (d[j] - h[j]);
                     }
-                    const int r = p * TC_RW + w;
-                    const int off = (r >> 3) * (int)TC_SBO + (r & 7) * 128 + ((kc ^ (r & 7)) << 4);
-                    *reinterpret_cast<float4 *>(ch + off) = make_float4(h[0], h[1], h[2], h[3]);
-                    *reinterpret_cast<float4 *>(cl + off) = make_float4(l[0], l[1], l[2], l[3]);
+                    *reinterpret_cast<float4 *>(ch + it_can[k]) = make_float4(h[0], h[1], h[2], h[3]);
+                    *reinterpret_cast<float4 *>(cl + it_can[k]) = make_float4(l[0], l[1], l[2], l[3]);
                 }
             }
-        } else
-#pragma unroll
-        for (int k = 0; k < TC_IT; ++k) {
-            if (it_kind[k] == 0) continue;
-            float d[4];
-            if (it_kind[k] == 1) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    d[j] = *reinterpret_cast<const float *>(rs + it_raw[k] + j * cstride) - it_ref[k];
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) d[j] = 1.0f;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(canon_full + cs);
+                if (b % TC_RB == TC_RB - 1 || b == nblk - 1) mbar_arrive(raw_empty + st);
             }
-            if (!whole) {
+        }
+    } else if (warp == TC_ISSUER) {
+        // ---- one thread issues all MMAs
+        if (lane == 0) {
+            // instruction descriptor: D f32, A/B tf32, both K-major, N = 32 P, M = 128
+            const uint32_t Ncols = 32u * (uint32_t)P;
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((Ncols >> 3) << 17) | ((128u >> 4) << 24);
+            for (int b = 0; b < nblk; ++b) {
+                const int cs = b % TC_C, ab = b & 1;
+                mbar_wait(canon_full + cs, (uint32_t)((b / TC_C) & 1));
+                mbar_wait(accum_empty + ab, (uint32_t)(((b >> 1) & 1) ^ 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t ah = smem_u32(canon_h + cs * TC_CANON_BYTES);
+                const uint32_t al = smem_u32(canon_l + cs * TC_CANON_BYTES);
+                const uint32_t td = tmem_base + (uint32_t)(ab * 128);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t sp = s0 + it_s[k] + j;
-                    if (sp < lo || sp >= hi) d[j] = 0.f;
+                for (int k = 0; k < TC_KB / 8; ++k) {
+                    const uint64_t dh = umma_desc(ah + k * 32), dl = umma_desc(al + k * 32);
+                    umma_tf32(td, dh, dh, idesc, k == 0 ? 0u : 1u);     // H H^T
+                    umma_tf32(td, dh, dl, idesc, 1u);                   // H (2L)^T
                 }
+                umma_commit(canon_empty + cs);
+                umma_commit(accum_full + ab);
             }
-            float h[4], l[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                h[j] = tf32_round(d[j]);
-                l[j] = d[j] - h[j];                 // the MMA truncates to tf32 itself
-            }
-            *reinterpret_cast<float4 *>(ch + it_can[k]) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4 *>(cl + it_can[k]) = make_float4(l[0], l[1], l[2], l[3]);
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-
-        const bool chunk_end = (b % TC_CHUNK == TC_CHUNK - 1) || b == nblk - 1;
-        const int ci = b / TC_CHUNK;                       // chunk index; accumulator ci & 1
-        if (tid == 0) {
+    } else if (warp >= TC_EPI0 && warp < TC_EPI0 + 4) {
+        // ---- accumulators -> float64: warp p reads contact p's diagonal block
+        const int p = warp - TC_EPI0;
+        for (int b = 0; b < nblk; ++b) {
+            const int ab = b & 1;
+            mbar_wait(accum_full + ab, (uint32_t)((b >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t ah = smem_u32(ch), al = smem_u32(cl);
-            const uint32_t td = tmem_base + (uint32_t)((ci & 1) * 128);
-#pragma unroll
-            for (int k = 0; k < TC_KB / 8; ++k) {
-                const uint64_t dh = umma_desc(ah + k * 32), dl = umma_desc(al + k * 32);
-                const uint32_t first = (b % TC_CHUNK == 0 && k == 0) ? 0u : 1u;
-                umma_tf32(td, dh, dh, idesc, first);
-                umma_tf32(td, dh, dl, idesc, 1u);
-                umma_tf32(td, dl, dh, idesc, 1u);
-            }
-            umma_commit(canon_empty + b % TC_C);
-            if (chunk_end) umma_commit(accum_full + (ci & 1));
-        }
-        // the epilogue of a chunk runs one block LATER (or at the very end): its MMAs have
-        // drained by then, and the next chunk accumulates in the other TMEM buffer meanwhile
-        const bool last = b == nblk - 1;
-        for (int pass = 0; pass < 2; ++pass) {
-            int ce;                                        // chunk whose accumulator is read now
-            if (pass == 0) { if (!(b % TC_CHUNK == 0 && b > 0)) continue; ce = ci - 1; }
-            else { if (!last) continue; ce = ci; }
-            mbar_wait(accum_full + (ce & 1), (uint32_t)((ce >> 1) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (warp < P) {
+            if (p < P) {
                 uint32_t v[TC_RW];
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) +
-                                       (uint32_t)((ce & 1) * 128 + warp * TC_RW);
+                const uint32_t taddr = tmem_base + ((uint32_t)(p * 32) << 16) +
+                                       (uint32_t)(ab * 128 + p * TC_RW);
                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -349,27 +376,36 @@ pca_gram_tc_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
                              : "r"(taddr)
                              : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(accum_empty + ab);      // the MMAs may overwrite it now
 #pragma unroll
                 for (int j = 0; j < TC_RW; ++j) acc[j] += (double)__uint_as_float(v[j]);
+            } else {
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(accum_empty + ab);
             }
-            // the buffer is overwritten (accumulate = 0) by chunk ce + 2, whose first MMAs
-            // are issued after at least one more __syncthreads: order the reads before it
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         }
     }
 
-    // ---- partial results of this (group, part): row `lane` of contact `warp`
-    if (warp < P && lane < n_win) {
-        const int64_t slot = (g0 + warp) * parts + part;
-        double *og = ws_gram + slot * nwp * nwp + (int64_t)lane * nwp;
+    // ---- partial results of this (group, part): G = (T + T^T) / 2 per contact, through shared
+    // memory (the tiles are dead once every MMA has been committed and read back)
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp >= TC_EPI0 && warp < TC_EPI0 + 4 && warp - TC_EPI0 < P) {
+        const int p = warp - TC_EPI0;
+        double *T = sym_s + p * (TC_RW * (TC_RW + 1));                // [32][33]
 #pragma unroll
-        for (int j = 0; j < TC_RW; ++j)
-            if (j < n_win) og[j] = acc[j];
-        double sv = 0.0;
-#pragma unroll
-        for (int j = 0; j < TC_RW; ++j)
-            if (j == n_win) sv = acc[j];
-        ws_sum[slot * nwp + lane] = sv;
+        for (int j = 0; j < TC_RW; ++j) T[lane * (TC_RW + 1) + j] = acc[j];
+        __syncwarp();
+        if (lane < n_win) {
+            const int64_t slot = (g0 + p) * parts + part;
+            double *og = ws_gram + slot * nwp * nwp + (int64_t)lane * nwp;
+            for (int j = 0; j < n_win; ++j)
+                og[j] = 0.5 * (T[lane * (TC_RW + 1) + j] + T[j * (TC_RW + 1) + lane]);
+            ws_sum[slot * nwp + lane] = 0.5 * (T[lane * (TC_RW + 1) + n_win] + T[n_win * (TC_RW + 1) + lane]);
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -395,7 +431,8 @@ int ssi::pca_gram_tc(const float *d_waves, int n_win, int64_t n_spk, int n_c,
     const int raw_row = TC_RB * TC_KB * n_c * 4 + 16;
     const int raw_stage = ((n_win * raw_row) + 127) & ~127;
     const size_t smem = (size_t)2 * TC_C * TC_CANON_BYTES + (size_t)TC_R * raw_stage +
-                        (TC_R + TC_C + 2) * 8 + 16 + (size_t)4 * TC_RW * 4 + 64 + 1024;
+                        (2 * TC_R + 2 * TC_C + 4) * 8 + 16 + (size_t)4 * TC_RW * 4 + 64 + 1024;
+    SS_REQUIRE(smem <= 232448, SS_ERR_UNSUPPORTED, "pca_gram_tc: %zu bytes of shared memory", smem);
     SS_CUDA_CHECK(cudaFuncSetAttribute(pca_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     const dim3 grid((unsigned)parts, (unsigned)(d_offsets ? n_groups : 1));

@@ -60,7 +60,8 @@ SPAN_DESIGNS = {
 
 
 @pytest.mark.parametrize("name", sorted(SPAN_DESIGNS))
-@pytest.mark.parametrize("n,W,K", [(9000, 14, 1), (3000, 3, 1), (5000, 4, 2), (700, 14, 1)])
+@pytest.mark.parametrize("n,W,K", [(9000, 16, 1), (3000, 3, 1), (512 * 4 + 300, 4, 1), (700, 16, 1),
+                                   (512 * 17 - 12 - 40, 16, 1)])
 def test_span_formulation_is_the_filter(name, n, W, K):
     """Fast-decaying filters: spans with K warm-up tiles reproduce filtfilt to round-off, with
     a large DC offset in the data (the steady-state warm start removes it from what the

@@ -1,8 +1,8 @@
 """Prototype (NumPy, CPU) of the single-pass span kernel of K1 (filt_span_kernel,
 spikesort_b200/csrc/filtfilt.cu): fixed left padding with pad + edge = 0 (mod 16), right
-padding to whole tiles, spans of W owned tiles with K warm-up tiles on either side, tile-local
-passes from zero / steady-state seeds, Horner fold of the tile end states with A^T inside the
-span, correction by C A^j, the y[-1] override of the right padding.  Also the host-side
+padding to whole tiles, spans of W owned tiles, tile-local passes from zero seeds, start state of a tile = end state of
+the tile before it (one tile of history; further back is below the truncation bound), the
+span's edge states from dot products with the neighbour tiles' samples (F / Bz weights + M), correction by C A^j, the y[-1] override of the right padding.  Also the host-side
 truncation bound that decides whether a filter may take this kernel (build_tables: span_err).
 Not product code and not the oracle; checked against scipy.signal.filtfilt in
 tests/test_proto_filtfilt.py."""
@@ -82,7 +82,16 @@ def span_error_bound(sos, K):
     return float((np.abs(R) * zmax).sum(1).max() * gain)
 
 
-def filtfilt_span(sos, padlen, x, W=14, K=1):
+def span_bound(s, t_lo, t_end, nt, W):
+    """Owned-tile boundaries of the kernel (span_bound in filtfilt.cu)."""
+    b = min(t_lo + W * s, t_end)
+    if b == nt - 1 and b > t_lo and b < t_end:
+        b = nt - 2
+    return b
+
+
+def filtfilt_span(sos, padlen, x, W=16, K=1):
+    """K is kept for the bound only: the kernel uses one tile of history."""
     secs, ns = _sections(sos)
     A, B, C, D = _state_space(secs, ns)
     zi = np.linalg.solve(np.eye(ns) - A, B)
@@ -92,6 +101,23 @@ def filtfilt_span(sos, padlen, x, W=14, K=1):
     for j in range(T):
         rows[j] = r
         r = r @ A
+    # summary weights of one tile (build_tables): F = sum_i u_{T-1-i} x_i, Bz = sum_i x_i G_i
+    u = np.empty((T, ns))
+    cur = B.copy()
+    for m in range(T):
+        u[m] = cur
+        cur = A @ cur
+    h = np.empty(T)
+    h[0] = D
+    h[1:] = u[:-1] @ C
+    Fw = u[::-1]                                               # (T, ns): weight of x_i
+    Gw = np.empty((T, ns))
+    for i in range(T):
+        Gw[i] = (u[i:] * h[:T - i, None]).sum(0)
+    M = np.empty((ns, ns))
+    for k in range(ns):
+        _, M[:, k] = _run(secs, np.zeros(ns), rows[::-1, k])
+
     x = np.asarray(x, np.float64)
     L = len(x)
     ext = np.concatenate((2 * x[0] - x[padlen:0:-1], x, 2 * x[-1] - x[-2:-padlen - 2:-1]))
@@ -101,41 +127,42 @@ def filtfilt_span(sos, padlen, x, W=14, K=1):
     q = nt * T - p - ext_len
     sig = np.concatenate((np.full(p, ext[0]), ext, np.zeros(q)))
     out = np.full(nt * T, np.nan)
-    for own_lo in range(0, nt, W):
-        own_hi = min(own_lo + W, nt)
-        act_lo, act_hi = max(0, own_lo - K), min(nt, own_hi + K)
-        tiles = list(range(act_lo, act_hi))
-        v = {}
-        ends = {}
+    n_spans = -(-nt // W)
+    for sp in range(n_spans):
+        own_lo, own_hi = span_bound(sp, 0, nt, nt, W), span_bound(sp + 1, 0, nt, nt, W)
+        if own_hi <= own_lo:
+            continue
+        tiles = list(range(own_lo, own_hi))
+        v, ends = {}, {}
         for t in tiles:                                        # forward, tile-local
             xt = sig[t * T:(t + 1) * T]
-            seed = zi * xt[0] if (t == 0 or t == act_lo) else np.zeros(ns)
+            seed = np.zeros(ns)
+            if t == 0:
+                seed = zi * xt[0]
+            elif t == own_lo:                                  # from the tile in front of the span
+                xp = sig[(t - 1) * T:t * T]
+                seed = xp @ Fw + AT @ (zi * xp[0])
             v[t], ends[t] = _run(secs, seed, xt)
-        for t in tiles:                                        # Horner + correction
-            z = np.zeros(ns)
-            for s in range(act_lo, t):
-                z = AT @ z + ends[s]
-            if t > act_lo:
-                v[t] = v[t] + rows @ z
+        for t in tiles[1:]:
+            v[t] = v[t] + rows @ ends[t - 1]
         endb = {}
         for t in tiles:                                        # backward, tile-local
             y = v[t]
-            seedv = y[-1]
+            seed = np.zeros(ns)
             if t == nt - 1:
                 o = ext_len - 1 - (t * T - p)
                 yl = y[o]
                 y = y.copy()
                 y[o + 1:] = yl
-                seedv = yl
-            seed = zi * seedv if (t == nt - 1 or t == act_hi - 1) else np.zeros(ns)
+                seed = zi * yl
+            elif t == own_hi - 1:                              # from the tile behind the span
+                xn = sig[(t + 1) * T:(t + 2) * T]
+                seed = xn @ Gw + M @ ends[t]
             yb, endb[t] = _run(secs, seed, y[::-1])
             v[t] = yb[::-1]
-        for t in range(own_lo, own_hi):
-            z = np.zeros(ns)
-            for s in range(act_hi - 1, t, -1):
-                z = AT @ z + endb[s]
+        for t in tiles:
             res = v[t]
-            if t < act_hi - 1:
-                res = res + (rows @ z)[::-1]
+            if t < own_hi - 1:
+                res = res + (rows @ endb[t + 1])[::-1]
             out[t * T:(t + 1) * T] = res
     return out[p + padlen:p + padlen + L]
