@@ -253,18 +253,21 @@ def run_gpu(args):
                              rate_hz=RATE_HZ, noise=10.0)
     torch.cuda.synchronize()
 
+    last = {"res": None}
+
     def step():
-        if world > 1:
-            return ssdist.run_chain_sharded(x, FS, flt, SP_WIN, edge='falling', align_type='min',
-                                            ncomps=2, chunksize=CHUNK)
         # lazy: the chain of this step is queued before the previous step's counts are read
-        # (ChainResult.finalize: the one host sync per step), so the GPU does not idle while the
-        # host gets from that synchronisation to the next step's first launch
-        r = pipeline.run_chain(x, FS, filt=flt, sp_win=SP_WIN, edge='falling',
-                               align_type='min', ncomps=2, chunksize=CHUNK, lazy=True)
+        # (finalize(): the one host sync per step), so the GPU does not idle while the host gets
+        # from that synchronisation to the next step's first launch - single GPU and sharded alike
+        if world > 1:
+            r = ssdist.run_chain_sharded(x, FS, flt, SP_WIN, edge='falling', align_type='min',
+                                         ncomps=2, chunksize=CHUNK, lazy=True)
+        else:
+            r = pipeline.run_chain(x, FS, filt=flt, sp_win=SP_WIN, edge='falling',
+                                   align_type='min', ncomps=2, chunksize=CHUNK, lazy=True)
         prev, pending["res"] = pending["res"], r
         if prev is not None:
-            prev.finalize()
+            last["res"] = prev.finalize()
         return r
 
     pending = {"res": None}
@@ -272,7 +275,7 @@ def run_gpu(args):
     def finish_last():
         # inside the timed region: the last step's counts are read (and its arrays trimmed) too
         if pending["res"] is not None:
-            pending["res"].finalize()
+            last["res"] = pending["res"].finalize()
             pending["res"] = None
 
     def barrier():
@@ -350,6 +353,7 @@ def run_gpu(args):
     ms_pca = [a.elapsed_time(b) for a, b in p_ev[:pidx["i"]]]
     ms_total = ev0.elapsed_time(ev1)
     ms_filter = [a.elapsed_time(b) for a, b in f_ev[:idx["i"]]]
+    res = last["res"]
     n_spk = int(res.spt.numel())
     n_det = int(res.spt_detected.numel())
 
@@ -493,6 +497,16 @@ def run_gpu(args):
             "ms": ms_step - pca_ms, "algorithmic_bytes": chain_bytes - pca_bytes,
             "frac": (chain_bytes - pca_bytes) / ((ms_step - pca_ms) / 1000.0) / 1e9 / peak}
 
+    # ---- N > 1: every rank's results of a few contacts to rank 0 (outside the timed region)
+    PAR_C = 4                                             # contacts compared at N > 1
+    gathered = None
+    if world > 1 and not args.no_cpu_baseline:
+        mine = []
+        for c in range(PAR_C):
+            g = res.per_contact(c)
+            mine.append((g['spt'], g.get('scores')))
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object(mine, gathered, dst=0)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -507,28 +521,54 @@ def run_gpu(args):
         xs = x[:, :n_sample].cpu().numpy()
         oracle_out = {}
         dt, _ = cpu_chain(xs, None, keep=oracle_out)
+        cpu = {"value": N_CONTACTS * n_sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "all %d samples (600 s) of all %d contacts of rank 0's recording, "
+                         "oracle/port.py chain (C filtfilt + NumPy), 1 core as the reference "
+                         "runs, %.1f s" % (n_sample, N_CONTACTS, dt)}
         # north_star: end-to-end spike-time mismatches are counted and reported - the GPU
         # chain (own filter) against the CPU oracle chain on the same recording
         mism, total, worst = 0, 0, 0.0
-        for c in range(N_CONTACTS):
-            g = res.per_contact(c)
-            o_spt, o_sc = oracle_out[c]
-            total += len(o_spt)
-            if len(o_spt) == len(g['spt']) and np.array_equal(o_spt, g['spt']):
-                # (with N > 1 the PCA basis comes from ALL shards, the oracle here sees rank 0's)
-                if world == 1 and o_sc is not None and 'scores' in g:
-                    sgn = np.sign(np.sum(g['scores'] * o_sc, axis=0))
-                    worst = max(worst, float(np.abs(g['scores'] * sgn - o_sc).max() /
-                                             np.abs(o_sc).max()))
-            else:
-                mism += len(np.setxor1d(o_spt, g['spt']))
+        if world == 1:
+            for c in range(N_CONTACTS):
+                g = res.per_contact(c)
+                o_spt, o_sc = oracle_out[c]
+                total += len(o_spt)
+                if len(o_spt) == len(g['spt']) and np.array_equal(o_spt, g['spt']):
+                    if o_sc is not None and 'scores' in g:
+                        sgn = np.sign(np.sum(g['scores'] * o_sc, axis=0))
+                        worst = max(worst, float(np.abs(g['scores'] * sgn - o_sc).max() /
+                                                 np.abs(o_sc).max()))
+                else:
+                    mism += len(np.setxor1d(o_spt, g['spt']))
+            against = "oracle/port.py chain on the whole recording, every contact"
+        else:
+            # the WHOLE sharded recording (all ranks' shards in time order, regenerated here from
+            # their seeds) through the oracle for the first PAR_C contacts; every rank's spike
+            # times and the scores in the merged PCA basis against it
+            whole = np.concatenate(
+                [synth.make_recording(N_CONTACTS, N_SAMPLES, FS, seed=SEED + r, device=dev,
+                                      rate_hz=RATE_HZ, noise=10.0)[:PAR_C].cpu().numpy()
+                 for r in range(world)], axis=1)
+            o_all = {}
+            cpu_chain(whole, None, keep=o_all)
+            for c in range(PAR_C):
+                g_spt = np.concatenate([gathered[r][c][0] for r in range(world)])
+                parts = [gathered[r][c][1] for r in range(world) if gathered[r][c][1] is not None and
+                         len(gathered[r][c][0])]
+                g_sc = np.concatenate(parts, axis=0) if parts else None
+                o_spt, o_sc = o_all[c]
+                total += len(o_spt)
+                if len(o_spt) == len(g_spt) and np.array_equal(o_spt, g_spt):
+                    if o_sc is not None and g_sc is not None:
+                        sgn = np.sign(np.sum(g_sc * o_sc, axis=0))
+                        worst = max(worst, float(np.abs(g_sc * sgn - o_sc).max() / np.abs(o_sc).max()))
+                else:
+                    mism += len(np.setxor1d(o_spt, g_spt))
+            against = ("oracle/port.py chain on the whole %d-shard recording (%d x %d samples), "
+                       "contacts 0..%d, all ranks' spike times and merged-basis scores"
+                       % (world, PAR_C, world * N_SAMPLES, PAR_C - 1))
         parity = {"spike_times_compared": total, "spike_time_mismatches": mism,
-                  "pca_score_max_rel_err": worst if world == 1 else None,
-                  "against": "oracle/port.py chain on the whole recording, every contact"}
-        cpu = {"value": N_CONTACTS * n_sample / dt, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": "all %d samples (600 s) of all %d contacts of the same recording, "
-                         "oracle/port.py chain (C filtfilt + NumPy), 1 core as the reference "
-                         "runs, %.1f s" % (n_sample, N_CONTACTS, dt)}
+                  "pca_score_max_rel_err": worst, "against": against}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -92,10 +92,25 @@ def _clean_conjugates(r):
     return np.array(out, dtype=np.complex128)
 
 
+_FACTORED = {}      # (b bytes, a bytes) -> (sos, padlen): the factorisation costs milliseconds
+
+
 def tf2sos_exact(b, a):
     """Return (sos, padlen): float64 array (n_sections, 6) in SciPy's layout with
     a0 == 1, a possible first-order section last; padlen = 3*max(len(a), len(b))
-    as scipy.signal.filtfilt computes it for the ORIGINAL coefficient vectors."""
+    as scipy.signal.filtfilt computes it for the ORIGINAL coefficient vectors.
+    Results are memoised per coefficient vectors (fltLinearIIR builds a fresh Filter
+    object on every call)."""
+    key = (np.asarray(b, dtype=np.float64).tobytes(), np.asarray(a, dtype=np.float64).tobytes())
+    hit = _FACTORED.get(key)
+    if hit is None:
+        if len(_FACTORED) > 256:
+            _FACTORED.clear()
+        hit = _FACTORED[key] = _tf2sos_exact(b, a)
+    return hit[0].copy(), hit[1]
+
+
+def _tf2sos_exact(b, a):
     from scipy import signal
     if mp is None:
         raise RuntimeError("mpmath is required to factor the filter")

@@ -37,6 +37,7 @@
 #include <cstring>
 #include <mutex>
 #include <map>
+#include <type_traits>
 #include <cstdlib>
 
 namespace {
@@ -895,7 +896,9 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
 // samples [16 l, 16 l + 16): 32 contiguous bytes of int16) - no transposition on the way in.
 // The host picks this kernel when the truncation bound (build_tables: span_err, one tile of
 // history) is below 1e-17 of the input scale; everything else takes the exact two-sweep scan.
-constexpr int SP_WARPS = 16;
+constexpr int SP_WARPS = 16;             // warps per CTA: SP_OWN tile owners + 2 helpers
+constexpr int SP_OWN = 14;               // tiles per span
+constexpr int SP_HELP_F = SP_OWN, SP_HELP_B = SP_OWN + 1;   // helper warps (= their state slots)
 constexpr int SP_MAX_NS = 4;
 constexpr double SP_ERR_BOUND = 1e-17;   // truncation per unit of input scale (float64 eps: 1.1e-16)
 
@@ -912,17 +915,24 @@ struct SpanParams {
     double al[(NS + 1) / 2][2];
 };
 
-// Owned tiles of span s of a launch over tiles [t_lo, t_end) of a unit with nt tiles:
-// boundaries every SP_WARPS tiles; a boundary that would fall on the unit's LAST tile moves one
-// tile down, so that the tile behind a span is never the last one (whose right padding and
-// y[-1] substitution the Bz functional does not describe).  The host never ends a launch
-// range on nt - 1 (head_cut).
-__host__ __device__ inline int span_bound(int s, int t_lo, int t_end, int nt)
+// Tiles of span s of a unit with nt tiles: boundaries every SP_OWN tiles from the unit's first
+// tile - independent of which tiles a launch stores, so that a tile is computed by the same
+// arithmetic whatever range it is launched in.  A boundary that would fall on the unit's LAST
+// tile moves one tile down: the tile behind a span is then never the last one (whose right
+// padding and y[-1] substitution the Bz functional does not describe).
+__host__ __device__ inline int span_bound(int s, int nt)
 {
-    int b = t_lo + SP_WARPS * s;
-    if (b > t_end) b = t_end;
-    if (b == nt - 1 && b > t_lo && b < t_end) b = nt - 2;
+    int b = SP_OWN * s;
+    if (b > nt) b = nt;
+    if (b == nt - 1 && s > 0) b = nt - 2;
     return b;
+}
+// span that holds tile t
+__host__ __device__ inline int span_of(int t, int nt)
+{
+    int s = t / SP_OWN;
+    if (span_bound(s + 1, nt) <= t) ++s;
+    return s;
 }
 
 // z <- z + P * shfl(z): one inclusive-scan step with the multiply-add predicated on the
@@ -1158,11 +1168,11 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
     TileInfo ti = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
     const int nt = (int)ti.nt;
     const int t_lo = (int)g.t_lo, t_end = g.t_hi < ti.nt ? (int)g.t_hi : nt;
-    const int own_lo = span_bound((int)blockIdx.x, t_lo, t_end, nt);
-    const int own_hi = span_bound((int)blockIdx.x + 1, t_lo, t_end, nt);
-    if (own_hi <= own_lo) return;                                  // block-uniform
-    const int n_own = own_hi - own_lo;                             // <= SP_WARPS + 1: see below
-    // (a moved boundary makes one span SP_WARPS - 1 and never longer than SP_WARPS tiles)
+    if (t_end <= t_lo) return;
+    const int span = span_of(t_lo, nt) + (int)blockIdx.x;
+    const int own_lo = span_bound(span, nt), own_hi = span_bound(span + 1, nt);
+    if (own_hi <= own_lo || own_lo >= t_end) return;               // block-uniform
+    const int n_own = own_hi - own_lo;                             // <= SP_OWN
     const int t = own_lo + warp;
     const bool owned = warp < n_own;
     ti.t = t;
@@ -1170,42 +1180,86 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
     const int64_t r0 = e0 - g.edge;                                // chunk-relative index
     const int64_t ext_len = ti.L + 2 * (int64_t)g.edge;
     const bool interior = owned && r0 >= 0 && r0 + FS_T <= ti.L;
+    const bool stored = owned && t >= t_lo && t < t_end;
 
-    // ---- start states that come from outside the span (first / last owned warp)
+    double v[FS_S];
+    double bz[NS];                                                 // helper B: Bz . x of the tile behind
+#pragma unroll
+    for (int i = 0; i < NS; ++i) bz[i] = 0.0;
+    if (warp >= SP_OWN) {
+        // ---- helpers: the states that come from outside the span, off the owners' critical path
+        double f[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) f[i] = 0.0;
+        if (warp == SP_HELP_F && own_lo > 0) {
+            span_load_tile(x, g, ti, own_lo - 1, tile_s, lane, v);
+            span_dot<NS>(SP.dot, 0, v, lane, f);
+            const double x_first = ss_shfl(v[0], 0);
+#pragma unroll
+            for (int r = 0; r < NS; ++r)
+#pragma unroll
+                for (int q = 0; q < NS; ++q) f[r] = fma(SP.AT[r][q], SP.zi[q] * x_first, f[r]);
+        }
+        if (warp == SP_HELP_B && own_hi < nt) {
+            span_load_tile(x, g, ti, own_hi, tile_s, lane, v);
+            span_dot<NS>(SP.dot, NS, v, lane, bz);
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) ends_f[warp * NS + i] = f[i];
+        }
+        __syncthreads();                                           // forward end states published
+        if (lane == 0) {
+            // helper B: backward start state of the span's last tile = Bz . x + M e, e = forward
+            // start state of the tile behind = zero-start end state of the last owned tile
+#pragma unroll
+            for (int r = 0; r < NS; ++r) {
+                double acc = bz[r];
+                if (warp == SP_HELP_B && own_hi < nt) {
+#pragma unroll
+                    for (int q = 0; q < NS; ++q) acc = fma(SP.M[r][q], ends_f[(n_own - 1) * NS + q], acc);
+                }
+                ends_b[warp * NS + r] = acc;
+            }
+        }
+        __syncthreads();
+        return;
+    }
+    // The owners' code exists twice: FAST for spans whose SP_OWN tiles are all interior int16
+    // tiles with 16-byte aligned input and output, all stored (no seeds, no padding, no
+    // clipping: straight-line code without the joins that cost ~100 register moves per tile),
+    // and the general one.  The choice is CTA-uniform, both run the same two barriers.
+    const int64_t r_first = (int64_t)own_lo * FS_T - ti.pad - g.edge;
+#ifdef SS_SPAN_NOFAST
+    const bool fast = false && g.dtype == SS_I16 && n_own == SP_OWN && own_lo > 0 && own_hi < nt &&
+                      own_lo >= t_lo && own_hi <= t_end && r_first >= 0 &&
+                      r_first + (int64_t)SP_OWN * FS_T <= ti.L &&
+                      ((reinterpret_cast<uintptr_t>(x) + 2 * (uintptr_t)(ti.c * g.ld_in + ti.cs0 + r_first)) & 15u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(out + ti.c * g.ld_out + ti.cs0 + r_first) & 15u) == 0;
+#else
+    const bool fast = g.dtype == SS_I16 && n_own == SP_OWN && own_lo > 0 && own_hi < nt &&
+                      own_lo >= t_lo && own_hi <= t_end && r_first >= 0 &&
+                      r_first + (int64_t)SP_OWN * FS_T <= ti.L &&
+                      ((reinterpret_cast<uintptr_t>(x) + 2 * (uintptr_t)(ti.c * g.ld_in + ti.cs0 + r_first)) & 15u) == 0 &&
+                      (reinterpret_cast<uintptr_t>(out + ti.c * g.ld_out + ti.cs0 + r_first) & 15u) == 0;
+#endif
+    auto owners = [&](auto fast_c) {
+    constexpr bool FAST = decltype(fast_c)::value;
     double zt[NS];                                                 // seed of the forward pass
 #pragma unroll
     for (int i = 0; i < NS; ++i) zt[i] = 0.0;
-    double bz[NS];                                                 // Bz . x of the tile behind the span
-#pragma unroll
-    for (int i = 0; i < NS; ++i) bz[i] = 0.0;
-    double v[FS_S];
-    if (warp == 0 && own_lo > 0) {
-        span_load_tile(x, g, ti, own_lo - 1, tile_s, lane, v);
-        double f[NS];
-        span_dot<NS>(SP.dot, 0, v, lane, f);
-        const double x_first = ss_shfl(v[0], 0);
-#pragma unroll
-        for (int r = 0; r < NS; ++r) {
-            double acc = f[r];
-#pragma unroll
-            for (int q = 0; q < NS; ++q) acc = fma(SP.AT[r][q], SP.zi[q] * x_first, acc);
-            zt[r] = lane == 0 ? acc : 0.0;
-        }
-    }
-    if (warp == n_own - 1 && own_hi < nt) {
-        span_load_tile(x, g, ti, own_hi, tile_s, lane, v);
-        span_dot<NS>(SP.dot, NS, v, lane, bz);
-    }
-    if (owned) {
-        span_load_tile(x, g, ti, t, tile_s, lane, v);
+    if constexpr (FAST) {
+        span_load16(reinterpret_cast<const int16_t *>(x) + (ti.c * g.ld_in + ti.cs0 + r0) + FS_S * lane, v);
     } else {
+        if (owned) {
+            span_load_tile(x, g, ti, t, tile_s, lane, v);
+        } else {
 #pragma unroll
-        for (int i = 0; i < FS_S; ++i) v[i] = 0.0;
-    }
-    if (owned && t == 0) {
-        const double x_first = ss_shfl(v[0], 0);                   // ext[0] (left padding)
+            for (int i = 0; i < FS_S; ++i) v[i] = 0.0;
+        }
+        const double x_first = ss_shfl(v[0], 0);                   // tile 0: ext[0] (left padding)
 #pragma unroll
-        for (int i = 0; i < NS; ++i) zt[i] = lane == 0 ? SP.zi[i] * x_first : 0.0;
+        for (int i = 0; i < NS; ++i) zt[i] = (owned && t == 0 && lane == 0) ? SP.zi[i] * x_first : 0.0;
     }
 
     // -------- forward
@@ -1237,10 +1291,12 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
             for (int i = 0; i < NS; ++i) ends_f[warp * NS + i] = en[i];
         }
         __syncthreads();
-        const bool have = owned && warp > 0;                       // start state = end state of warp - 1
+        // start state = zero-start end state of the tile before (helper F for the first warp)
+        const bool have = FAST || owned;
+        const int src = warp > 0 ? warp - 1 : SP_HELP_F;
         double z[NS];
 #pragma unroll
-        for (int r = 0; r < NS; ++r) z[r] = have ? ends_f[(warp - 1) * NS + r] : 0.0;
+        for (int r = 0; r < NS; ++r) z[r] = have ? ends_f[src * NS + r] : 0.0;
         if constexpr (SINGLE) {
             // p <- p + A^(16 lane) z, then the one correction
             const double a00 = __ldg(SP.apow + lane);
@@ -1276,7 +1332,7 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
     {
 #pragma unroll
         for (int i = 0; i < NS; ++i) zt[i] = 0.0;
-        if (owned && t == nt - 1) {
+        if (!FAST && owned && t == nt - 1) {
             // the unit's last tile: y[-1] sits at offset o; the right padding behind it is the
             // steady-state input y[-1]
             const int o = (int)(ext_len - 1 - e0);
@@ -1290,16 +1346,6 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
                 if (FS_S * lane + i > o) v[i] = yl;
 #pragma unroll
             for (int i = 0; i < NS; ++i) zt[i] = lane == 31 ? SP.zi[i] * yl : 0.0;
-        } else if (warp == n_own - 1) {
-            // start state from the tile behind the span: Bz . x + M e, e = forward start state
-            // of that tile = the zero-start end state of this one (one tile of history)
-#pragma unroll
-            for (int r = 0; r < NS; ++r) {
-                double acc = bz[r];
-#pragma unroll
-                for (int q = 0; q < NS; ++q) acc = fma(SP.M[r][q], ss_shfl(en[q], 31), acc);
-                zt[r] = lane == 31 ? acc : 0.0;
-            }
         }
         double p0 = 0.0, p1 = 0.0;
         if constexpr (SINGLE) {
@@ -1327,11 +1373,14 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
             for (int i = 0; i < NS; ++i) ends_b[warp * NS + i] = en[i];
         }
         __syncthreads();
-        if (!owned) return;
-        const bool have = warp + 1 < n_own;
+        if (!FAST && !stored) return;
+        // start state = zero-start end state of the tile behind (helper B for the last warp; it
+        // wrote zeros when the span ends with the unit, whose last tile was seeded above)
+        const bool have = true;
+        const int src = warp + 1 < n_own ? warp + 1 : SP_HELP_B;
         double z[NS];
 #pragma unroll
-        for (int r = 0; r < NS; ++r) z[r] = have ? ends_b[(warp + 1) * NS + r] : 0.0;
+        for (int r = 0; r < NS; ++r) z[r] = ends_b[src * NS + r];
         if constexpr (SINGLE) {
             const double a00 = __ldg(SP.apow + (31 - lane));
             if (SO1) {
@@ -1391,7 +1440,7 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
                 bits |= (uint32_t)ssi::crossing(v[i], v[i + 1], th, mk.falling) << i;
             if (lane < 31) bits |= (uint32_t)ssi::crossing(v[FS_S - 1], nx, th, mk.falling) << (FS_S - 1);
             const int64_t rl = r0 + FS_S * lane;              // chunk-relative index of bit 0
-            if (!interior) {
+            if (!FAST && !interior) {
                 const int64_t lo = rl < 0 ? -rl : 0, hi = ti.L - 1 - rl;
                 uint32_t keep = 0;
                 if (lo < FS_S && hi > 0) {
@@ -1410,8 +1459,8 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
         }
     }
     double *orow = out + ti.c * g.ld_out + ti.cs0;
-    const bool out_aligned = (reinterpret_cast<uintptr_t>(orow + r0) & 15u) == 0;
-    if (interior && out_aligned) {
+    const bool out_aligned = FAST || (reinterpret_cast<uintptr_t>(orow + r0) & 15u) == 0;
+    if (FAST || (interior && out_aligned)) {
         // lane's row of 8 16-byte chunks, chunk k at position k ^ (lane & 7): conflict-free
         // 128-bit writes; read back so that one store instruction covers 512 contiguous bytes
         double2 *t2 = reinterpret_cast<double2 *>(tile_s);
@@ -1446,6 +1495,9 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
             }
         }
     }
+    };
+    if (fast) owners(std::true_type{});
+    else owners(std::false_type{});
 }
 
 // One thread per tile: the crossing whose first sample is the last chunk sample of the
@@ -2069,7 +2121,9 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
             for (int i = 0; i < NS; ++i)
                 for (int j = 0; j < NS; ++j) SPn.M[i][j] = T.M[i][j];
             (void)span_warmup;
-            const dim3 grid((unsigned)ss_cdiv(nt_hi_s - t_lo, SP_WARPS), (unsigned)j_count, (unsigned)g.n_contacts);
+            // spans are unit-aligned; the launch covers those holding tiles [t_lo, nt_hi_s)
+            const int s_first = span_of((int)t_lo, (int)nt_max_s), s_last = span_of((int)nt_hi_s - 1, (int)nt_max_s);
+            const dim3 grid((unsigned)(s_last - s_first + 2), (unsigned)j_count, (unsigned)g.n_contacts);
             const size_t smem = ((size_t)SP_WARPS * FS_T + (size_t)2 * SP_WARPS * NS) * sizeof(double);
             MarkParams mkp;
             if (mk) mkp = *mk;

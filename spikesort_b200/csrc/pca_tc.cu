@@ -21,13 +21,13 @@
 //    the accumulator is read back every 32 spikes (8 accumulations, two TMEM buffers
 //    alternate) into float64 registers - measured Gram error ~2e-7 (256-spike chunks: 2e-6);
 //  * warp-specialised, mbarrier-synchronised, no block-wide barrier in the loop:
-//      warp 8      producer: 1-D bulk async copies (cp.async.bulk + complete_tx) of the raw
+//      warp 12     producer: 1-D bulk async copies (cp.async.bulk + complete_tx) of the raw
 //                  float32 rows, 64 spikes x n_c contacts per copy, TC_R stages;
-//      warps 0-3   converters: raw stage -> canonical K-major SWIZZLE_128B tiles of H and 2L
+//      warps 0-7   converters: raw stage -> canonical K-major SWIZZLE_128B tiles of H and 2L
 //                  (TC_C stages), 128-bit shared-memory reads and writes;
-//      warp 9      one thread issues the MMAs and commits to the barriers that free the
+//      warp 13     one thread issues the MMAs and commits to the barriers that free the
 //                  canonical stage and publish the accumulator;
-//      warps 4-7   epilogue: warp p reads contact p's 32 x 32 diagonal block from TMEM
+//      warps 8-11  epilogue: warp p reads contact p's 32 x 32 diagonal block from TMEM
 //                  (tcgen05.ld 32x32b.x32) and adds it to float64 registers.
 // Every mbarrier wait is bounded: a protocol error traps instead of hanging the GPU.
 #include "common.cuh"
@@ -37,14 +37,24 @@ namespace {
 
 constexpr int TC_KB = 32;                  // spikes per K-block (= one accumulation chunk)
 constexpr int TC_RW = 32;                  // rows per contact in the tile (n_win + 1 <= 32)
-constexpr int TC_R = 4;                    // raw stages
+#ifndef TC_R_STAGES
+#define TC_R_STAGES 4
+#define TC_C_STAGES 3
+#endif
+constexpr int TC_R = TC_R_STAGES;          // raw stages
 constexpr int TC_RB = 2;                   // K-blocks per raw stage: one bulk copy moves a row of
                                            // 64 spikes (1 KB at 4 contacts)
-constexpr int TC_C = 3;                    // canonical (H / 2L) stages
-constexpr int TC_NCONV = 4;                // converter warps (0..3)
-constexpr int TC_EPI0 = 4;                 // epilogue warps 4..7 (warp % 4 = TMEM lane quadrant)
-constexpr int TC_PRODUCER = 8, TC_ISSUER = 9;
-constexpr int TC_THREADS = 320;
+#ifndef TC_PF_STAGES
+#define TC_PF_STAGES 0                     // L2 prefetch distance of the producer in raw stages; measured
+#endif                                     // SLOWER with 12 (2.07 vs 1.64 ms on 10^7 spikes): off
+constexpr int TC_PF = TC_PF_STAGES;
+constexpr int TC_C = TC_C_STAGES;          // canonical (H / 2L) stages
+constexpr int TC_NCONV = 8;                // converter warps (0..7): ~400 instructions per 32-spike block
+                                           // and warp - with four of them (one per scheduler, nothing to
+                                           // hide their latencies behind) they were the critical path
+constexpr int TC_EPI0 = 8;                 // epilogue warps 8..11 (warp % 4 = TMEM lane quadrant)
+constexpr int TC_PRODUCER = 12, TC_ISSUER = 13;
+constexpr int TC_THREADS = 448;
 constexpr int TC_CANON_BYTES = (TC_KB / 4) * 16 * 128;   // one 128-row x 32-spike matrix: 16 KB
 // canonical K-major SWIZZLE_128B layout: one tile row = 32 spikes = 128 B, 8-row groups of
 // 1024 B, the 16-byte chunk c of row r stored at chunk c ^ (r % 8).  (The no-swizzle
@@ -187,8 +197,23 @@ pca_gram_tc_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
     if (warp == TC_PRODUCER) {
         // ---- raw float32 rows -> shared memory: lane 0 arms the barrier with the byte count,
         // lane w copies row w (one elected thread issuing all rows serialises ~25 copies)
+        // The shared-memory stages hold ~100 KB of copies in flight per SM - not enough to cover
+        // the DRAM latency of 25 row streams that lie 160 MB apart.  L2 prefetches TC_PF
+        // super-blocks ahead (no shared memory needed) turn the staged copies into L2 hits.
+        auto prefetch = [&](int sb) {
+            const int64_t s0 = b0 + (int64_t)sb * (TC_RB * TC_KB);
+            const int64_t nsp = min((int64_t)(TC_RB * TC_KB), n_spk - s0);
+            if (lane < n_win && nsp > 0) {
+                const float *src = waves + ((int64_t)lane * n_spk + s0) * n_c;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+                             ::"l"(src), "r"((uint32_t)(nsp * n_c * 4)) : "memory");
+            }
+        };
+        if (TC_PF > 0)
+            for (int sb = 0; sb < TC_PF && sb < nsb; ++sb) prefetch(sb);
         for (int sb = 0; sb < nsb; ++sb) {
             const int st = sb % TC_R;
+            if (TC_PF > 0 && sb + TC_PF < nsb) prefetch(sb + TC_PF);
             mbar_wait(raw_empty + st, (uint32_t)(((sb / TC_R) & 1) ^ 1));
             const int64_t s0 = b0 + (int64_t)sb * (TC_RB * TC_KB);
             const int64_t nsp = min((int64_t)(TC_RB * TC_KB), n_spk - s0);
@@ -243,6 +268,21 @@ pca_gram_tc_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
             }
         }
         const int cstride = n_c * 4;                       // bytes between consecutive spikes of a row
+        // 4-contact fast path: row w = lane, K-groups kc = warp + TC_NCONV * half
+        int f4_raw[8 / TC_NCONV], f4_can[8 / TC_NCONV][4];
+        float f4_ref[4];
+#pragma unroll
+        for (int half = 0; half < 8 / TC_NCONV; ++half) {
+            const int kc = warp + half * TC_NCONV;
+            f4_raw[half] = lane * raw_row + 4 * kc * 16;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int r = p * TC_RW + lane;
+                f4_can[half][p] = (r >> 3) * (int)TC_SBO + (r & 7) * 128 + ((kc ^ (r & 7)) << 4);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) f4_ref[p] = (fast4 && lane < n_win) ? ref_s[p * TC_RW + lane] : 0.f;
         for (int b = 0; b < nblk; ++b) {
             const int sb = b / TC_RB, st = sb % TC_R, cs = b % TC_C;
             if (b % TC_RB == 0) mbar_wait(raw_full + st, (uint32_t)((sb / TC_R) & 1));
@@ -252,7 +292,40 @@ pca_gram_tc_kernel(const float *__restrict__ waves, int n_win, int64_t n_spk, in
             unsigned char *cl = canon_l + cs * TC_CANON_BYTES;
             const int64_t s0 = b0 + (int64_t)b * TC_KB;
             const bool whole = s0 >= lo && s0 + TC_KB <= hi;   // no masking needed
-            if (fast4) {
+            if (fast4 && whole) {
+                // the common block: no masking, offsets and references hoisted out of the loop.
+                // thread (w = lane, kc) converts 4 spikes of row w for all 4 contacts: four
+                // 128-bit raw reads, eight 128-bit canonical stores; TC_NCONV warps x 2 passes
+                if (lane < n_win) {
+#pragma unroll
+                    for (int half = 0; half < 8 / TC_NCONV; ++half) {
+                        const float4 *src = reinterpret_cast<const float4 *>(rs + f4_raw[half]);
+                        const float4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+                        const float dd[4][4] = {{q0.x, q1.x, q2.x, q3.x}, {q0.y, q1.y, q2.y, q3.y},
+                                                {q0.z, q1.z, q2.z, q3.z}, {q0.w, q1.w, q2.w, q3.w}};
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            float h[4], l[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float d = dd[p][j] - f4_ref[p];
+                                h[j] = tf32_round(d);
+                                l[j] = 2.0f * (d - h[j]);          // exact; the MMA truncates to tf32
+                            }
+                            *reinterpret_cast<float4 *>(ch + f4_can[half][p]) = make_float4(h[0], h[1], h[2], h[3]);
+                            *reinterpret_cast<float4 *>(cl + f4_can[half][p]) = make_float4(l[0], l[1], l[2], l[3]);
+                        }
+                    }
+                } else if (lane == n_win) {
+#pragma unroll
+                    for (int half = 0; half < 8 / TC_NCONV; ++half)
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) {
+                            *reinterpret_cast<float4 *>(ch + f4_can[half][p]) = make_float4(1.f, 1.f, 1.f, 1.f);
+                            *reinterpret_cast<float4 *>(cl + f4_can[half][p]) = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                }
+            } else if (fast4) {
                 // thread (w = lane, kc) converts 4 spikes of row w for all 4 contacts: four
                 // 128-bit raw reads, eight 128-bit canonical stores; TC_NCONV warps x 2 passes
                 const int w = lane;

@@ -92,9 +92,19 @@ class ZeroPhaseFilter(_ZeroPhaseOnDevice):
         return _scaled_iirdesign(inner * 2.0 / FS, outer * 2.0 / FS, self)
 
 
+_DESIGNED = {}      # design arguments -> (b, a): fltLinearIIR designs the same filter on every call
+
+
 def _scaled_iirdesign(wp, ws, owner):
     from scipy import signal
-    return signal.iirdesign(wp=wp, ws=ws, gpass=owner.gpass, gstop=owner.gstop, ftype=owner.ftype)
+    key = (np.asarray(wp, dtype=np.float64).tobytes(), np.asarray(ws, dtype=np.float64).tobytes(),
+           np.ndim(wp), float(owner.gpass), float(owner.gstop), str(owner.ftype))
+    if key not in _DESIGNED:
+        if len(_DESIGNED) > 256:
+            _DESIGNED.clear()
+        _DESIGNED[key] = signal.iirdesign(wp=wp, ws=ws, gpass=owner.gpass, gstop=owner.gstop,
+                                          ftype=owner.ftype)
+    return _DESIGNED[key]
 
 
 class FilterFir(_ZeroPhaseOnDevice):

@@ -90,7 +90,7 @@ def span_bound(s, t_lo, t_end, nt, W):
     return b
 
 
-def filtfilt_span(sos, padlen, x, W=16, K=1):
+def filtfilt_span(sos, padlen, x, W=14, K=1):
     """K is kept for the bound only: the kernel uses one tile of history."""
     secs, ns = _sections(sos)
     A, B, C, D = _state_space(secs, ns)
