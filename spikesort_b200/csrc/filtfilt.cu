@@ -2254,6 +2254,14 @@ static int make_plan(FiltPlan &pl, int dtype, int64_t n_contacts, int64_t n_samp
                nb, MAX_NB);
     int rc = make_geom(pl.g, dtype, n_contacts, n_samples, ld_in, ld_out, chunksize, padlen);
     if (rc) return rc;                                  // (argument checks before the tables)
+    {
+        // the caller sizes the workspace with ss_filtfilt_workspace_bytes whatever algorithm the
+        // filter ends up with (the single-pass kernel does not touch it)
+        const size_t need = (size_t)pl.g.total_tiles * (size_t)(4 * S.ns + 1) * sizeof(double) +
+                            (size_t)(2 * S.ns + 1) * FS_T * sizeof(double);
+        SS_REQUIRE(ws_bytes >= need, SS_ERR_WORKSPACE, "filtfilt: workspace %zu < %zu bytes", ws_bytes,
+                   need);
+    }
     rc = get_tables(sos, n_sections, fo, S, pl.T);
     SS_REQUIRE(rc == SS_OK, rc, "filtfilt: filter has a pole at z = 1 (no steady state)");
     // Which algorithm: a property of the FILTER only (never of the data, the addresses or the
@@ -2270,11 +2278,6 @@ static int make_plan(FiltPlan &pl, int dtype, int64_t n_contacts, int64_t n_samp
     if (pl.span_warmup) {
         rc = make_geom(pl.g, dtype, n_contacts, n_samples, ld_in, ld_out, chunksize, padlen, true);
         if (rc) return rc;
-    } else {
-        const size_t need = (size_t)pl.g.total_tiles * (size_t)(4 * S.ns + 1) * sizeof(double) +
-                            (size_t)(2 * S.ns + 1) * FS_T * sizeof(double);
-        SS_REQUIRE(ws_bytes >= need, SS_ERR_WORKSPACE, "filtfilt: workspace %zu < %zu bytes", ws_bytes,
-                   need);
     }
     SS_REQUIRE(pl.g.units_per_contact <= 65535 && pl.g.n_contacts <= 65535, SS_ERR_ARG,
                "filtfilt: more than 65535 chunks per contact or contacts (%lld, %lld)",
