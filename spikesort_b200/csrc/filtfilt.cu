@@ -775,6 +775,11 @@ filt_summary_wide_kernel(const int16_t *__restrict__ x, const FiltGeom g, const 
     }
 }
 
+// (Tried in round 2 and dropped, both SLOWER on B200 than the coalesced element loads / stores
+//  through padded shared memory below: reading a lane's 32 contiguous int16 bytes with two or
+//  three 128-bit loads, +0.06 ms per configs[1] stage; storing through an XOR-swizzled tile with
+//  128-bit shared and global accesses, no gain.  The kernel is bound by the L1 / shared pipe
+//  either way; what the 128-bit forms save in instructions they lose in sector efficiency.)
 template <int NB, bool FO, bool MARK>
 __global__ void __launch_bounds__(32 * FS_WPB, (NB + (FO ? 1 : 0) >= 2) ? APPLY_MIN_CTAS : 0)
 filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
@@ -899,7 +904,13 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
 constexpr int SP_WARPS = 16;             // warps per CTA: SP_OWN tile owners + 2 helpers
 constexpr int SP_OWN = 14;               // tiles per span
 constexpr int SP_HELP_F = SP_OWN, SP_HELP_B = SP_OWN + 1;   // helper warps (= their state slots)
+#ifndef SP_PER_CTA
+#define SP_PER_CTA 1                     // consecutive spans of a unit per CTA (with the next span's
+                                         // samples prefetched by cp.async; measured SLOWER for 2, 4, 8: 1.93,
+                                         // 1.84, 1.85 ms against 1.76 ms per configs[1] stage)
+#endif
 constexpr int SP_MAX_NS = 4;
+constexpr int SP_TILE = FS_PADT + 8;     // doubles per warp tile in shared memory (16-byte multiple)
 constexpr double SP_ERR_BOUND = 1e-17;   // truncation per unit of input scale (float64 eps: 1.1e-16)
 
 template <int NS>
@@ -1040,11 +1051,9 @@ __device__ __forceinline__ void span_correct(const double (&h)[FS_S][2], double 
     }
 }
 
-// 16 consecutive samples of a lane, straight from global memory (16-byte aligned address)
-__device__ __forceinline__ void span_load16(const int16_t *p, double (&v)[FS_S])
+// 16 int16 samples (two 128-bit words) -> float64
+__device__ __forceinline__ void span_convert16(const uint4 a, const uint4 b, double (&v)[FS_S])
 {
-    const uint4 a = __ldg(reinterpret_cast<const uint4 *>(p));
-    const uint4 b = __ldg(reinterpret_cast<const uint4 *>(p) + 1);
     const unsigned w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -1060,6 +1069,20 @@ __device__ __forceinline__ void span_load16(const int16_t *p, double (&v)[FS_S])
         v[2 * k + 1] = (double)((int)w[k] >> 16);
 #endif
     }
+}
+// 16 consecutive samples of a lane, straight from global memory (16-byte aligned address)
+__device__ __forceinline__ void span_load16(const int16_t *p, double (&v)[FS_S])
+{
+    span_convert16(__ldg(reinterpret_cast<const uint4 *>(p)), __ldg(reinterpret_cast<const uint4 *>(p) + 1), v);
+}
+// the lane's 32 bytes of a tile into its private slot of the prefetch buffer (read back by the
+// same lane after cp.async.wait_group: no barrier involved)
+__device__ __forceinline__ void span_prefetch32(void *smem_dst, const void *gmem_src)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                 ::"r"(d + 16), "l"(reinterpret_cast<const char *>(gmem_src) + 16) : "memory");
 }
 __device__ __forceinline__ void span_load16(const float *p, double (&v)[FS_S])
 {
@@ -1162,14 +1185,40 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
     constexpr bool SO1 = NB == 1;                                  // correction folds into the tile-level one
     extern __shared__ __align__(1024) double sp_smem[];            // [SP_WARPS][512] tiles, then states
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *tile_s = sp_smem + warp * FS_T;
-    double *ends_f = sp_smem + SP_WARPS * FS_T, *ends_b = ends_f + SP_WARPS * NS;
+    double *tile_s = sp_smem + warp * SP_TILE;
+    double *ends_f = sp_smem + SP_WARPS * SP_TILE, *ends_b = ends_f + SP_WARPS * NS;
 
-    TileInfo ti = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
-    const int nt = (int)ti.nt;
-    const int t_lo = (int)g.t_lo, t_end = g.t_hi < ti.nt ? (int)g.t_hi : nt;
+    const TileInfo unit = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
+    const int nt = (int)unit.nt;
+    const int t_lo = (int)g.t_lo, t_end = g.t_hi < unit.nt ? (int)g.t_hi : nt;
     if (t_end <= t_lo) return;
-    const int span = span_of(t_lo, nt) + (int)blockIdx.x;
+    unsigned char *raw_s = reinterpret_cast<unsigned char *>(ends_b + SP_WARPS * NS);   // [2][SP_WARPS][1 KB]
+    // FAST spans: SP_OWN interior int16 tiles, 16-byte aligned input and output, all stored, and
+    // neighbour tiles (the helpers') interior too
+    auto span_fast = [&](int sp) {
+#ifdef SS_SPAN_NOFAST
+        return false;
+#else
+        const int lo = span_bound(sp, nt), hi = span_bound(sp + 1, nt);
+        const int64_t rf = (int64_t)lo * FS_T - unit.pad - g.edge;
+        return g.dtype == SS_I16 && hi - lo == SP_OWN && lo > 0 && hi < nt && lo >= t_lo && hi <= t_end &&
+               rf - FS_T >= 0 && rf + (int64_t)(SP_OWN + 1) * FS_T <= unit.L &&
+               ((reinterpret_cast<uintptr_t>(x) + 2 * (uintptr_t)(unit.c * g.ld_in + unit.cs0 + rf)) & 15u) == 0 &&
+               (reinterpret_cast<uintptr_t>(out + unit.c * g.ld_out + unit.cs0 + rf) & 15u) == 0;
+#endif
+    };
+    // A CTA takes SP_PER_CTA consecutive spans of the unit; while it works on one, the raw
+    // samples of the next are already on their way into shared memory (cp.async, every lane
+    // fetches exactly the 32 bytes it will read itself).
+    const int span0 = span_of(t_lo, nt) + SP_PER_CTA * (int)blockIdx.x;
+    bool have_pref = false;
+    for (int it = 0; it < SP_PER_CTA; ++it) {
+        const int span = span0 + it;
+        const int buf = it & 1;
+        const bool pref = it + 1 < SP_PER_CTA && span_fast(span) && span_fast(span + 1);
+        const bool had = have_pref;
+        auto one_span = [&](bool have_pref) {
+    TileInfo ti = unit;
     const int own_lo = span_bound(span, nt), own_hi = span_bound(span + 1, nt);
     if (own_hi <= own_lo || own_lo >= t_end) return;               // block-uniform
     const int n_own = own_hi - own_lo;                             // <= SP_OWN
@@ -1191,8 +1240,23 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
         double f[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) f[i] = 0.0;
+        if (pref) {
+            // the next span's neighbour tiles into this helper's slot of the other buffer
+            const int nlo = span_bound(span + 1, nt), nhi = span_bound(span + 2, nt);
+            const int tn = warp == SP_HELP_F ? nlo - 1 : nhi;
+            const int64_t rn = (int64_t)tn * FS_T - ti.pad - g.edge;
+            span_prefetch32(raw_s + ((buf ^ 1) * SP_WARPS + warp) * 1024 + 32 * lane,
+                            reinterpret_cast<const int16_t *>(x) + (ti.c * g.ld_in + ti.cs0 + rn) + FS_S * lane);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
         if (warp == SP_HELP_F && own_lo > 0) {
-            span_load_tile(x, g, ti, own_lo - 1, tile_s, lane, v);
+            if (have_pref) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(1) : "memory");
+                const uint4 *rp = reinterpret_cast<const uint4 *>(raw_s + (buf * SP_WARPS + warp) * 1024 + 32 * lane);
+                span_convert16(rp[0], rp[1], v);
+            } else {
+                span_load_tile(x, g, ti, own_lo - 1, tile_s, lane, v);
+            }
             span_dot<NS>(SP.dot, 0, v, lane, f);
             const double x_first = ss_shfl(v[0], 0);
 #pragma unroll
@@ -1201,7 +1265,13 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
                 for (int q = 0; q < NS; ++q) f[r] = fma(SP.AT[r][q], SP.zi[q] * x_first, f[r]);
         }
         if (warp == SP_HELP_B && own_hi < nt) {
-            span_load_tile(x, g, ti, own_hi, tile_s, lane, v);
+            if (have_pref) {
+                asm volatile("cp.async.wait_group %0;" ::"n"(1) : "memory");
+                const uint4 *rp = reinterpret_cast<const uint4 *>(raw_s + (buf * SP_WARPS + warp) * 1024 + 32 * lane);
+                span_convert16(rp[0], rp[1], v);
+            } else {
+                span_load_tile(x, g, ti, own_hi, tile_s, lane, v);
+            }
             span_dot<NS>(SP.dot, NS, v, lane, bz);
         }
         if (lane == 0) {
@@ -1230,26 +1300,35 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
     // clipping: straight-line code without the joins that cost ~100 register moves per tile),
     // and the general one.  The choice is CTA-uniform, both run the same two barriers.
     const int64_t r_first = (int64_t)own_lo * FS_T - ti.pad - g.edge;
-#ifdef SS_SPAN_NOFAST
-    const bool fast = false && g.dtype == SS_I16 && n_own == SP_OWN && own_lo > 0 && own_hi < nt &&
-                      own_lo >= t_lo && own_hi <= t_end && r_first >= 0 &&
-                      r_first + (int64_t)SP_OWN * FS_T <= ti.L &&
-                      ((reinterpret_cast<uintptr_t>(x) + 2 * (uintptr_t)(ti.c * g.ld_in + ti.cs0 + r_first)) & 15u) == 0 &&
-                      (reinterpret_cast<uintptr_t>(out + ti.c * g.ld_out + ti.cs0 + r_first) & 15u) == 0;
-#else
-    const bool fast = g.dtype == SS_I16 && n_own == SP_OWN && own_lo > 0 && own_hi < nt &&
-                      own_lo >= t_lo && own_hi <= t_end && r_first >= 0 &&
-                      r_first + (int64_t)SP_OWN * FS_T <= ti.L &&
-                      ((reinterpret_cast<uintptr_t>(x) + 2 * (uintptr_t)(ti.c * g.ld_in + ti.cs0 + r_first)) & 15u) == 0 &&
-                      (reinterpret_cast<uintptr_t>(out + ti.c * g.ld_out + ti.cs0 + r_first) & 15u) == 0;
-#endif
+    const bool fast = span_fast(span);
     auto owners = [&](auto fast_c) {
     constexpr bool FAST = decltype(fast_c)::value;
     double zt[NS];                                                 // seed of the forward pass
 #pragma unroll
     for (int i = 0; i < NS; ++i) zt[i] = 0.0;
     if constexpr (FAST) {
-        span_load16(reinterpret_cast<const int16_t *>(x) + (ti.c * g.ld_in + ti.cs0 + r0) + FS_S * lane, v);
+        if (pref) {
+            // this warp's tile of the NEXT span into the other prefetch buffer: its DRAM latency
+            // passes behind this span's arithmetic
+            const int64_t rn = (int64_t)(span_bound(span + 1, nt) + warp) * FS_T - ti.pad - g.edge;
+            span_prefetch32(raw_s + ((buf ^ 1) * SP_WARPS + warp) * 1024 + 32 * lane,
+                            reinterpret_cast<const int16_t *>(x) + (ti.c * g.ld_in + ti.cs0 + rn) + FS_S * lane);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        uint4 ra, rb;
+        if (have_pref) {
+            if (pref) asm volatile("cp.async.wait_group %0;" ::"n"(1) : "memory");
+            else asm volatile("cp.async.wait_group %0;" ::"n"(0) : "memory");
+            const uint4 *rp = reinterpret_cast<const uint4 *>(raw_s + (buf * SP_WARPS + warp) * 1024 + 32 * lane);
+            ra = rp[0];
+            rb = rp[1];
+        } else {
+            const uint4 *gp = reinterpret_cast<const uint4 *>(
+                reinterpret_cast<const int16_t *>(x) + (ti.c * g.ld_in + ti.cs0 + r0) + FS_S * lane);
+            ra = __ldg(gp);
+            rb = __ldg(gp + 1);
+        }
+        span_convert16(ra, rb, v);
     } else {
         if (owned) {
             span_load_tile(x, g, ti, t, tile_s, lane, v);
@@ -1498,6 +1577,10 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
     };
     if (fast) owners(std::true_type{});
     else owners(std::false_type{});
+        };
+        one_span(had);
+        have_pref = pref;
+    }
 }
 
 // One thread per tile: the crossing whose first sample is the last chunk sample of the
@@ -2123,8 +2206,10 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
             (void)span_warmup;
             // spans are unit-aligned; the launch covers those holding tiles [t_lo, nt_hi_s)
             const int s_first = span_of((int)t_lo, (int)nt_max_s), s_last = span_of((int)nt_hi_s - 1, (int)nt_max_s);
-            const dim3 grid((unsigned)(s_last - s_first + 2), (unsigned)j_count, (unsigned)g.n_contacts);
-            const size_t smem = ((size_t)SP_WARPS * FS_T + (size_t)2 * SP_WARPS * NS) * sizeof(double);
+            const dim3 grid((unsigned)ss_cdiv(s_last - s_first + 2, SP_PER_CTA), (unsigned)j_count,
+                            (unsigned)g.n_contacts);
+            const size_t smem = ((size_t)SP_WARPS * SP_TILE + (size_t)2 * SP_WARPS * NS) * sizeof(double) +
+                                (size_t)2 * SP_WARPS * 1024;
             MarkParams mkp;
             if (mk) mkp = *mk;
             else mkp = MarkParams{nullptr, nullptr, 0, 0, 0, nullptr, nullptr, 0, 0};
@@ -2266,14 +2351,14 @@ static int make_plan(FiltPlan &pl, int dtype, int64_t n_contacts, int64_t n_samp
     SS_REQUIRE(rc == SS_OK, rc, "filtfilt: filter has a pole at z = 1 (no steady state)");
     // Which algorithm: a property of the FILTER only (never of the data, the addresses or the
     // sharding), so that a unit is filtered by the same arithmetic wherever it is processed.
-    // SS_FILT_SPAN=0 pins the two-sweep scan (A/B runs).
+    // The single-pass span kernel moves 15 % fewer DRAM bytes (x is read once) but is bound by
+    // issue slots and measured 3 % SLOWER than the two-sweep scan on B200 (configs[1] stage 1.76
+    // against 1.71 ms, profiles/README.md): it is opt-in, SS_FILT_SPAN=1.
     pl.span_warmup = 0;
     {
-        const char *force = getenv("SS_FILT_SPAN");
-        const bool allowed = !(force && force[0] == '0');
-        if (allowed && S.ns <= SP_MAX_NS) {
-            if (pl.T.span_err[0] <= SP_ERR_BOUND) pl.span_warmup = 1;     // one tile of history
-        }
+        const char *want = getenv("SS_FILT_SPAN");
+        if (want && want[0] == '1' && S.ns <= SP_MAX_NS && pl.T.span_err[0] <= SP_ERR_BOUND)
+            pl.span_warmup = 1;                         // one tile of history
     }
     if (pl.span_warmup) {
         rc = make_geom(pl.g, dtype, n_contacts, n_samples, ld_in, ld_out, chunksize, padlen, true);
