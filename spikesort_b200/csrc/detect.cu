@@ -258,6 +258,30 @@ int ssi::mark_head(const void *d_x, int dtype, int64_t n_rows, int64_t n_valid, 
                        reinterpret_cast<char *>(d_ws), st);
 }
 
+namespace {
+// exclusive scan of the block counts (row-major) + row offsets
+int scan_blocks(const DetLayout &L, int64_t n_rows, char *ws, int64_t *d_offsets, cudaStream_t st)
+{
+    const int32_t *counts = reinterpret_cast<const int32_t *>(ws + L.off_counts);
+    int64_t *offsets = reinterpret_cast<int64_t *>(ws + L.off_offsets);
+    if (n_rows >= 2 && L.blocks_per_row >= 256) {
+        // one CTA per row (the scratch area behind the offsets holds the row totals: the
+        // threshold partial sums that also live there are dead by now)
+        int64_t *row_tot = reinterpret_cast<int64_t *>(ws + L.off_scratch);
+        ssb::scan_row_totals_kernel<<<(unsigned)n_rows, ssb::SCAN_THREADS, 0, st>>>(counts, L.blocks_per_row, row_tot);
+        SS_LAUNCH_CHECK("scan_row_totals_kernel");
+        ssb::scan_rows_kernel<<<(unsigned)n_rows, ssb::SCAN_THREADS, 0, st>>>(counts, L.blocks_per_row, n_rows,
+                                                                          row_tot, offsets, d_offsets);
+        SS_LAUNCH_CHECK("scan_rows_kernel");
+        return SS_OK;
+    }
+    ssb::scan_counts_kernel<<<1, ssb::SCAN_THREADS, 0, st>>>(counts, L.n_blocks, offsets, L.blocks_per_row,
+                                                         n_rows, d_offsets);
+    SS_LAUNCH_CHECK("scan_counts_kernel");
+    return SS_OK;
+}
+}  // namespace
+
 int ssi::count_and_scan(int64_t n_rows, int64_t n_samples, void *d_ws, int64_t *d_offsets,
                         cudaStream_t st)
 {
@@ -267,11 +291,7 @@ int ssi::count_and_scan(int64_t n_rows, int64_t n_samples, void *d_ws, int64_t *
     detect_count_kernel<<<(unsigned)ss_cdiv(L.n_blocks, DT_WARPS), 32 * DT_WARPS, 0, st>>>(
         reinterpret_cast<const uint32_t *>(ws + L.off_mask), counts, L.n_blocks);
     SS_LAUNCH_CHECK("detect_count_kernel");
-    ssb::scan_counts_kernel<<<1, ssb::SCAN_THREADS, 0, st>>>(
-        counts, L.n_blocks, reinterpret_cast<int64_t *>(ws + L.off_offsets), L.blocks_per_row,
-        n_rows, d_offsets);
-    SS_LAUNCH_CHECK("scan_counts_kernel");
-    return SS_OK;
+    return scan_blocks(L, n_rows, ws, d_offsets, st);
 }
 
 extern "C" int ss_detect_mark(const void *d_x, int dtype, int64_t n_rows, int64_t n_samples,
@@ -287,11 +307,7 @@ extern "C" int ss_detect_mark(const void *d_x, int dtype, int64_t n_rows, int64_
     char *ws = reinterpret_cast<char *>(d_ws);
     const int rc = launch_mark(d_x, dtype, n_rows, n_samples, ld, d_thr, falling, L, ws, st);
     if (rc) return rc;
-    ssb::scan_counts_kernel<<<1, ssb::SCAN_THREADS, 0, st>>>(
-        reinterpret_cast<int32_t *>(ws + L.off_counts), L.n_blocks,
-        reinterpret_cast<int64_t *>(ws + L.off_offsets), L.blocks_per_row, n_rows, d_offsets);
-    SS_LAUNCH_CHECK("scan_counts_kernel");
-    return SS_OK;
+    return scan_blocks(L, n_rows, ws, d_offsets, st);
 }
 
 extern "C" int ss_detect_emit(int64_t n_rows, int64_t n_samples, double FS, int64_t index_offset,

@@ -84,6 +84,10 @@ struct MarkParams {
     double *peer_right;          // right neighbour's from_left  [n_contacts][halo_H], or null
     int halo_H;
     int64_t shard_n;             // samples per contact of this shard
+    // two-sweep path: first / last output sample of every tile, written by the apply kernel
+    // (dense, 8 B per tile) so that the tile-end pairs are tested from two coalesced arrays
+    // instead of two scattered 8-byte reads of the stored signal per tile (or null)
+    double *first_s, *last_s;
 };
 
 struct PeerHalo { double *left, *right; int H; };
@@ -810,6 +814,10 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
     if (MARK) {
         // crossings (i, i+1) with both samples in this tile and this chunk; the pair that
         // ends a tile or a chunk is marked by filt_boundary_mark_kernel afterwards
+        if (mk.first_s) {
+            if (lane == 0) mk.first_s[tile] = v[0];
+            if (lane == 31) mk.last_s[tile] = v[FS_S - 1];
+        }
         const double th = __ldg(mk.thr + ti.c);
         const double nx = ss_shfl_down(v[0], 1);
         uint32_t bits = 0;
@@ -1599,8 +1607,19 @@ filt_boundary_mark_kernel(const double *__restrict__ y, const FiltGeom g, const 
     if (r < 0) return;
     const int64_t s = ti.cs0 + r;
     if (s + 1 >= mk.n_samples) return;
-    const double *row = y + ti.c * g.ld_out;
-    if (ssi::crossing(row[s], row[s + 1], __ldg(mk.thr + ti.c), mk.falling))
+    double a, b;
+    const int64_t t_end = g.t_hi < ti.nt ? g.t_hi : ti.nt;
+    if (mk.first_s && t >= g.t_lo && t + 1 < t_end && r0 + FS_T - 1 <= ti.L - 2) {
+        // both samples were produced by the launch this kernel follows: the tile's last and
+        // the next tile's first sample, from the dense per-tile arrays
+        a = mk.last_s[ti.g0 + t];
+        b = mk.first_s[ti.g0 + t + 1];
+    } else {
+        const double *row = y + ti.c * g.ld_out;
+        a = row[s];
+        b = row[s + 1];
+    }
+    if (ssi::crossing(a, b, __ldg(mk.thr + ti.c), mk.falling))
         atomicOr(mk.mask + ti.c * mk.words_per_row + (s >> 5), 1u << (int)(s & 31));
 }
 
@@ -2212,7 +2231,8 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
                                 (size_t)2 * SP_WARPS * 1024;
             MarkParams mkp;
             if (mk) mkp = *mk;
-            else mkp = MarkParams{nullptr, nullptr, 0, 0, 0, nullptr, nullptr, 0, 0};
+            else mkp = MarkParams{nullptr, nullptr, 0, 0, 0, nullptr, nullptr, 0, 0, nullptr, nullptr};
+            mkp.first_s = mkp.last_s = nullptr;
             mkp.peer_left = g_peer_halo.left;
             mkp.peer_right = g_peer_halo.right;
             mkp.halo_H = g_peer_halo.H;
@@ -2289,14 +2309,16 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
         mkp.peer_right = g_peer_halo.right;
         mkp.halo_H = g_peer_halo.H;
         mkp.shard_n = g.n_samples;
+        mkp.first_s = F;                       // F / Bz are dead once the tile scan has run
+        mkp.last_s = Bz;
         filt_apply_kernel<NB, FO, true><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, mkp);
         SS_LAUNCH_CHECK("filt_apply_kernel<mark>");
         const dim3 bgrid((unsigned)ss_cdiv(nt_max, 256), (unsigned)j_count, (unsigned)g.n_contacts);
-        filt_boundary_mark_kernel<<<bgrid, 256, 0, st>>>(d_out, g, *mk);
+        filt_boundary_mark_kernel<<<bgrid, 256, 0, st>>>(d_out, g, mkp);
         SS_LAUNCH_CHECK("filt_boundary_mark_kernel");
     } else {
         MarkParams none = {nullptr, nullptr, 0, 0, 0, g_peer_halo.left, g_peer_halo.right,
-                           g_peer_halo.H, g.n_samples};
+                           g_peer_halo.H, g.n_samples, nullptr, nullptr};
         filt_apply_kernel<NB, FO, false><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, none);
         SS_LAUNCH_CHECK("filt_apply_kernel");
     }
@@ -2484,6 +2506,7 @@ extern "C" int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_cont
     mk.peer_left = mk.peer_right = nullptr;
     mk.halo_H = 0;
     mk.shard_n = n_samples;
+    mk.first_s = mk.last_s = nullptr;
     SS_CUDA_CHECK(cudaMemsetAsync(mk.mask, 0, (size_t)L.words_per_row * n_contacts * 4, st));
     const int64_t units = pl.g.units_per_contact;
     if (!auto_thr) {

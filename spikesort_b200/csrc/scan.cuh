@@ -62,4 +62,84 @@ scan_counts_kernel(const int32_t *__restrict__ counts, int64_t n, int64_t *__res
     }
 }
 
+// The same for counts laid out [n_rows][per_row] with MANY rows of blocks (detection: 32-384
+// contacts x thousands of 8192-sample blocks): one CTA per row, two launches - row totals, then
+// every row scans its own counts from the sum of the rows before it.  (The single CTA above
+// took 36 us for the 70 k counts of configs[1].)
+static __global__ void __launch_bounds__(SCAN_THREADS)
+scan_row_totals_kernel(const int32_t *__restrict__ counts, int64_t per_row, int64_t *__restrict__ row_tot)
+{
+    __shared__ int64_t wsum[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t *c = counts + (int64_t)blockIdx.x * per_row;
+    int64_t s = 0;
+    for (int64_t i = tid; i < per_row; i += SCAN_THREADS) s += c[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(SS_FULL, s, d);
+    if (lane == 0) wsum[warp] = s;
+    __syncthreads();
+    if (warp == 0) {
+        s = wsum[lane];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(SS_FULL, s, d);
+        if (lane == 0) row_tot[blockIdx.x] = s;
+    }
+}
+
+static __global__ void __launch_bounds__(SCAN_THREADS)
+scan_rows_kernel(const int32_t *__restrict__ counts, int64_t per_row, int64_t n_rows,
+                 const int64_t *__restrict__ row_tot, int64_t *__restrict__ offsets,
+                 int64_t *__restrict__ row_offsets)
+{
+    __shared__ int64_t warp_base[32];
+    __shared__ int64_t s_base, s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t r = blockIdx.x;
+    if (warp == 0) {                                      // rows before this one, in row order
+        int64_t b = 0;
+        for (int64_t k = lane; k < r; k += 32) b += row_tot[k];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) b += __shfl_xor_sync(SS_FULL, b, d);
+        if (lane == 0) { s_base = b; s_carry = b; }
+    }
+    __syncthreads();
+    const int32_t *c = counts + r * per_row;
+    int64_t *o = offsets + r * per_row;
+    for (int64_t i0 = 0; i0 < per_row; i0 += SCAN_THREADS) {
+        const int64_t i = i0 + tid;
+        const int64_t v = i < per_row ? (int64_t)c[i] : 0;
+        int64_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int64_t up = __shfl_up_sync(SS_FULL, inc, d);
+            if (lane >= d) inc += up;
+        }
+        if (lane == 31) warp_base[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const int64_t w = warp_base[lane];
+            int64_t winc = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int64_t up = __shfl_up_sync(SS_FULL, winc, d);
+                if (lane >= d) winc += up;
+            }
+            warp_base[lane] = winc - w;
+        }
+        __syncthreads();
+        const int64_t carry = s_carry;
+        if (i < per_row) o[i] = carry + warp_base[warp] + inc - v;
+        __syncthreads();
+        if (tid == SCAN_THREADS - 1) s_carry = carry + warp_base[warp] + inc;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        row_offsets[r] = s_base;
+        if (r == n_rows - 1) {
+            row_offsets[n_rows] = s_carry;
+            offsets[n_rows * per_row] = s_carry;
+        }
+    }
+}
+
 }  // namespace ssb
