@@ -53,6 +53,8 @@ SEED = 2
 RATE_HZ = 10.0
 SM_COUNT = 148                      # B200
 WORKLOAD = "c2"
+TRAFFIC_SCAN_C2 = 7.13e9            # two-sweep scan (default): x read twice + float64 written once
+TRAFFIC_SPAN_C2 = 6.20e9            # SS_FILT_SPAN=1: x read once
 FILTER_ARGS = (800., 100.)          # fltLinearIIR(800, 100): order-1 Butterworth high-pass
 CONFIG = {
     "workload": "configs[1]: 32-channel 30 kHz 10-minute synthetic int16 recording "
@@ -449,20 +451,26 @@ def run_gpu(args):
     alg_bytes = N_CONTACTS * N_SAMPLES * (2 + 8) + N_CONTACTS * min(N_SAMPLES, 10 * FS) * 8 + \
         N_CONTACTS * N_SAMPLES * 8 + n_det * 8
     achieved = alg_bytes / (filt_ms / 1000.0) / 1e9
+    # bytes the kernels of this stage really move: dram__bytes_read.sum + dram__bytes_write.sum
+    # summed over the stage's launches of one step, from the ncu launch list of this command in
+    # the final state of the round (profiles/r02_launches_c2*.csv; captured for configs[1] only)
+    span = os.environ.get("SS_FILT_SPAN", "0")[:1] == "1"
+    traffic = {False: TRAFFIC_SCAN_C2, True: TRAFFIC_SPAN_C2}[span] if WORKLOAD == "c2" else None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of the kernels of this stage from an ncu
-                # pass over one step of this command in the final state of the round
-                # (profiles/r01_traffic_final_state.csv): sweep 1 1.18 GB + tile scan 0.02 + sweep 2
-                # 5.57 (plain head part 0.04) + threshold / head marks 0.15 + boundary marks 0.14 +
-                # count / emit 0.14 GB
-                "traffic": 7.24e9 if WORKLOAD == "c2" else None,   # captured for the headline workload only
-                "traffic_unit": "bytes per launch (ncu, profiles/r01_traffic_final_state.csv)",
-                "kernel": "ss_filtfilt_detect_sos + ss_detect_emit = filter (summary, tilescan, "
-                          "apply with fused crossing marks) + auto threshold + count/scan/emit: "
-                          "the filter, threshold and detect stages of the chain",
+                "traffic": traffic,
+                "traffic_unit": "bytes per launch (ncu launch list, profiles/r02_launches_c2%s.csv)"
+                                % ("_span" if span else ""),
+                "frac_moved": (traffic / (filt_ms / 1000.0) / 1e9 / peak) if traffic else None,
+                "kernel": ("ss_filtfilt_detect_sos + ss_detect_emit = filter (%s, crossing marks fused) + "
+                           "auto threshold + count/scan/emit: the filter, threshold and detect stages "
+                           "of the chain" % ("single-pass span kernel" if span else
+                                             "summary sweep, tile scan, apply sweep")),
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": filt_ms,
-                "share_of_step": filt_ms / ms_step, "peak_source": peak_src}
+                "share_of_step": filt_ms / ms_step, "peak_source": peak_src,
+                "note": "frac counts SURVEY 8(d)'s algorithmic bytes (incl. the detect pass over the "
+                        "filtered signal, which the fused marks never make: it may exceed the bytes "
+                        "moved); frac_moved counts the DRAM bytes ncu measured for the same launches"}
     # FP64 side of the same stage: FMAs per sample of the two sweeps - per
     # second-order section and direction 5 (recurrence) + 2 (correction) + 20/16 (lane scan),
     # first-order 3 + 1 + 5/16, plus the 2*NS+1 dot products of sweep 1.  Order 1 is far from
