@@ -84,10 +84,6 @@ struct MarkParams {
     double *peer_right;          // right neighbour's from_left  [n_contacts][halo_H], or null
     int halo_H;
     int64_t shard_n;             // samples per contact of this shard
-    // two-sweep path: first / last output sample of every tile, written by the apply kernel
-    // (dense, 8 B per tile) so that the tile-end pairs are tested from two coalesced arrays
-    // instead of two scattered 8-byte reads of the stored signal per tile (or null)
-    double *first_s, *last_s;
 };
 
 struct PeerHalo { double *left, *right; int H; };
@@ -98,6 +94,7 @@ struct TileInfo {
                                          // tile in unit, left padding, first tile of unit
 };
 
+template <bool MAYBE_SPAN = true>
 __device__ __forceinline__ TileInfo decode_unit(const FiltGeom &g, int64_t c, int64_t j)
 {
     TileInfo ti;
@@ -107,7 +104,9 @@ __device__ __forceinline__ TileInfo decode_unit(const FiltGeom &g, int64_t c, in
     ti.L = last ? g.len_last : g.chunksize;
     ti.nt = last ? g.nt_last : g.nt_full;
     ti.t = 0;
-    ti.pad = g.span ? (int64_t)g.pad_l : ti.nt * FS_T - (ti.L + 2 * (int64_t)g.edge);
+    // (the two-sweep kernels are instantiated without the span branch: the sweep-2 kernels of
+    //  the higher orders sit at their register cap and spilled for it)
+    ti.pad = (MAYBE_SPAN && g.span) ? (int64_t)g.pad_l : ti.nt * FS_T - (ti.L + 2 * (int64_t)g.edge);
     ti.g0 = c * g.tiles_per_contact + j * g.nt_full;
     return ti;
 }
@@ -118,7 +117,7 @@ __device__ __forceinline__ TileInfo decode_unit(const FiltGeom &g, int64_t c, in
 __device__ __forceinline__ bool decode_tile(const FiltGeom &g, int warp, TileInfo &ti,
                                             int64_t &tile)
 {
-    ti = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
+    ti = decode_unit<false>(g, blockIdx.z, g.j_begin + blockIdx.y);
     ti.t = g.t_lo + (int64_t)blockIdx.x * FS_WPB + warp;
     tile = ti.g0 + ti.t;
     return ti.t < ti.nt && ti.t < g.t_hi;
@@ -814,9 +813,12 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
     if (MARK) {
         // crossings (i, i+1) with both samples in this tile and this chunk; the pair that
         // ends a tile or a chunk is marked by filt_boundary_mark_kernel afterwards
-        if (mk.first_s) {
-            if (lane == 0) mk.first_s[tile] = v[0];
-            if (lane == 31) mk.last_s[tile] = v[FS_S - 1];
+        // first / last output sample of the tile into the (dead) F / Bz arrays in front of Zf:
+        // the tile-end pairs are then tested from two dense arrays (filt_boundary_mark_kernel)
+        {
+            double *first_s = const_cast<double *>(Zf) - 2 * g.total_tiles * NS;
+            if (lane == 0) first_s[tile] = v[0];
+            if (lane == 31) first_s[g.total_tiles * NS + tile] = v[FS_S - 1];
         }
         const double th = __ldg(mk.thr + ti.c);
         const double nx = ss_shfl_down(v[0], 1);
@@ -1595,7 +1597,8 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
 // tile (its partner lives in the next tile or the next chunk).  Runs after the apply
 // kernel, reads the stored float64 output.
 __global__ void __launch_bounds__(256)
-filt_boundary_mark_kernel(const double *__restrict__ y, const FiltGeom g, const MarkParams mk)
+filt_boundary_mark_kernel(const double *__restrict__ y, const FiltGeom g, const MarkParams mk,
+                          const double *__restrict__ first_s, const double *__restrict__ last_s)
 {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const TileInfo ti = decode_unit(g, blockIdx.z, g.j_begin + blockIdx.y);
@@ -1609,11 +1612,11 @@ filt_boundary_mark_kernel(const double *__restrict__ y, const FiltGeom g, const 
     if (s + 1 >= mk.n_samples) return;
     double a, b;
     const int64_t t_end = g.t_hi < ti.nt ? g.t_hi : ti.nt;
-    if (mk.first_s && t >= g.t_lo && t + 1 < t_end && r0 + FS_T - 1 <= ti.L - 2) {
+    if (first_s && t >= g.t_lo && t + 1 < t_end && r0 + FS_T - 1 <= ti.L - 2) {
         // both samples were produced by the launch this kernel follows: the tile's last and
         // the next tile's first sample, from the dense per-tile arrays
-        a = mk.last_s[ti.g0 + t];
-        b = mk.first_s[ti.g0 + t + 1];
+        a = last_s[ti.g0 + t];
+        b = first_s[ti.g0 + t + 1];
     } else {
         const double *row = y + ti.c * g.ld_out;
         a = row[s];
@@ -2231,8 +2234,7 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
                                 (size_t)2 * SP_WARPS * 1024;
             MarkParams mkp;
             if (mk) mkp = *mk;
-            else mkp = MarkParams{nullptr, nullptr, 0, 0, 0, nullptr, nullptr, 0, 0, nullptr, nullptr};
-            mkp.first_s = mkp.last_s = nullptr;
+            else mkp = MarkParams{nullptr, nullptr, 0, 0, 0, nullptr, nullptr, 0, 0};
             mkp.peer_left = g_peer_halo.left;
             mkp.peer_right = g_peer_halo.right;
             mkp.halo_H = g_peer_halo.H;
@@ -2243,7 +2245,7 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
                 filt_span_kernel<NB, FO, true><<<grid, 32 * SP_WARPS, smem, st>>>(d_x, g, P, SPn, d_out, mkp);
                 SS_LAUNCH_CHECK("filt_span_kernel<mark>");
                 const dim3 bgrid((unsigned)ss_cdiv(nt_max_s, 256), (unsigned)j_count, (unsigned)g.n_contacts);
-                filt_boundary_mark_kernel<<<bgrid, 256, 0, st>>>(d_out, g, *mk);
+                filt_boundary_mark_kernel<<<bgrid, 256, 0, st>>>(d_out, g, *mk, nullptr, nullptr);
                 SS_LAUNCH_CHECK("filt_boundary_mark_kernel");
             } else {
                 SS_CUDA_CHECK(cudaFuncSetAttribute(filt_span_kernel<NB, FO, false>,
@@ -2309,16 +2311,16 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
         mkp.peer_right = g_peer_halo.right;
         mkp.halo_H = g_peer_halo.H;
         mkp.shard_n = g.n_samples;
-        mkp.first_s = F;                       // F / Bz are dead once the tile scan has run
-        mkp.last_s = Bz;
         filt_apply_kernel<NB, FO, true><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, mkp);
         SS_LAUNCH_CHECK("filt_apply_kernel<mark>");
         const dim3 bgrid((unsigned)ss_cdiv(nt_max, 256), (unsigned)j_count, (unsigned)g.n_contacts);
-        filt_boundary_mark_kernel<<<bgrid, 256, 0, st>>>(d_out, g, mkp);
+        // (F / Bz are dead once the tile scan has run: the apply kernel left the tiles' first /
+        //  last samples there)
+        filt_boundary_mark_kernel<<<bgrid, 256, 0, st>>>(d_out, g, mkp, F, Bz);
         SS_LAUNCH_CHECK("filt_boundary_mark_kernel");
     } else {
         MarkParams none = {nullptr, nullptr, 0, 0, 0, g_peer_halo.left, g_peer_halo.right,
-                           g_peer_halo.H, g.n_samples, nullptr, nullptr};
+                           g_peer_halo.H, g.n_samples};
         filt_apply_kernel<NB, FO, false><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, none);
         SS_LAUNCH_CHECK("filt_apply_kernel");
     }
@@ -2506,7 +2508,6 @@ extern "C" int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_cont
     mk.peer_left = mk.peer_right = nullptr;
     mk.halo_H = 0;
     mk.shard_n = n_samples;
-    mk.first_s = mk.last_s = nullptr;
     SS_CUDA_CHECK(cudaMemsetAsync(mk.mask, 0, (size_t)L.words_per_row * n_contacts * 4, st));
     const int64_t units = pl.g.units_per_contact;
     if (!auto_thr) {
@@ -2553,7 +2554,7 @@ extern "C" int ss_filtfilt_detect_sos(const void *d_x, int dtype, int64_t n_cont
         g.j_begin = jh;
         g.j_count = 1;
         const int64_t nt = g.nt_full;
-        filt_boundary_mark_kernel<<<dim3((unsigned)ss_cdiv(nt, 256), 1, (unsigned)n_contacts), 256, 0, st>>>(d_out, g, mk);
+        filt_boundary_mark_kernel<<<dim3((unsigned)ss_cdiv(nt, 256), 1, (unsigned)n_contacts), 256, 0, st>>>(d_out, g, mk, nullptr, nullptr);
         SS_LAUNCH_CHECK("filt_boundary_mark_kernel");
     }
     return ssi::count_and_scan(n_contacts, n_samples, d_det_ws, d_offsets, st);
