@@ -53,8 +53,8 @@ SEED = 2
 RATE_HZ = 10.0
 SM_COUNT = 148                      # B200
 WORKLOAD = "c2"
-TRAFFIC_SCAN_C2 = 7.13e9            # two-sweep scan (default): x read twice + float64 written once
-TRAFFIC_SPAN_C2 = 6.20e9            # SS_FILT_SPAN=1: x read once
+TRAFFIC_SCAN_C2 = 7.135e9            # two-sweep scan (default): x read twice + float64 written once
+TRAFFIC_SPAN_C2 = 6.18e9            # SS_FILT_SPAN=1: x read once
 FILTER_ARGS = (800., 100.)          # fltLinearIIR(800, 100): order-1 Butterworth high-pass
 CONFIG = {
     "workload": "configs[1]: 32-channel 30 kHz 10-minute synthetic int16 recording "

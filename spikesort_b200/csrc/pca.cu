@@ -75,18 +75,12 @@ pca_gram_kernel(const T *__restrict__ waves, int n_win, int64_t n_spk, int n_c,
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[t][i][j] = 0.0;
     double sacc = 0.0;
-    // Few tiles (n_win ~ 30: 36 of them): one tile per thread would leave 220 of the 256 threads
-    // idle.  The staged spikes are then split S ways - thread (tile, sub) takes spikes sub, sub +
-    // S, ... - and the S partial tiles are added in a fixed order at the end (62 -> 20 us for
-    // the 164 k spikes of configs[1]).
-    const int S = n_tiles <= PC_THREADS / 2 ? PC_THREADS / n_tiles : 1;
     int my_ti[PC_MAX_TILES], my_tj[PC_MAX_TILES];
     bool my_ok[PC_MAX_TILES];
-    const int sub = S > 1 ? tid / n_tiles : 0;
 #pragma unroll
     for (int t = 0; t < PC_MAX_TILES; ++t) {
-        const int k = S > 1 ? tid - sub * n_tiles : tid + t * PC_THREADS;
-        my_ok[t] = S > 1 ? (t == 0 && sub < S) : k < n_tiles;
+        const int k = tid + t * PC_THREADS;
+        my_ok[t] = k < n_tiles;
         my_ti[t] = my_ok[t] ? s_ti[k] : 0;
         my_tj[t] = my_ok[t] ? s_tj[k] : 0;
     }
@@ -107,7 +101,7 @@ pca_gram_kernel(const T *__restrict__ waves, int n_win, int64_t n_spk, int n_c,
             if (my_ok[t]) {
                 const double *pa = sh + 4 * my_ti[t], *pb = sh + 4 * my_tj[t];
 #pragma unroll 4
-                for (int s = sub; s < ns; s += S) {
+                for (int s = 0; s < ns; ++s) {
                     const double2 a01 = *reinterpret_cast<const double2 *>(pa + s * RS);
                     const double2 a23 = *reinterpret_cast<const double2 *>(pa + s * RS + 2);
                     const double2 b01 = *reinterpret_cast<const double2 *>(pb + s * RS);
@@ -127,37 +121,14 @@ pca_gram_kernel(const T *__restrict__ waves, int n_win, int64_t n_spk, int n_c,
     }
 
     double *og = ws_gram + ((int64_t)g * parts + part) * nwp * nwp;
-    if (S > 1) {
-        // partial tiles of the S sub-ranges through shared memory, summed in sub order
-        double *red = sh;                                  // [S][n_tiles][16] <= 32 KB (host sizes it)
-        if (my_ok[0]) {
-            double *mine = red + ((size_t)sub * n_tiles + (tid - sub * n_tiles)) * 16;
+#pragma unroll
+    for (int t = 0; t < PC_MAX_TILES; ++t)
+        if (my_ok[t])
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) mine[4 * i + j] = acc[0][i][j];
-        }
-        __syncthreads();
-        if (tid < n_tiles) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    double tot = 0.0;
-                    for (int u = 0; u < S; ++u) tot += red[((size_t)u * n_tiles + tid) * 16 + 4 * i + j];
-                    og[(4 * my_ti[0] + i) * nwp + 4 * my_tj[0] + j] = tot;
-                }
-        }
-    } else {
-#pragma unroll
-        for (int t = 0; t < PC_MAX_TILES; ++t)
-            if (my_ok[t])
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        og[(4 * my_ti[t] + i) * nwp + 4 * my_tj[t] + j] = acc[t][i][j];
-    }
+                for (int j = 0; j < 4; ++j)
+                    og[(4 * my_ti[t] + i) * nwp + 4 * my_tj[t] + j] = acc[t][i][j];
     if (tid < nwp) ws_sum[((int64_t)g * parts + part) * nwp + tid] = sacc;
 }
 
@@ -798,14 +769,7 @@ extern "C" int ss_pca_gram(const void *d_waves, int dtype, int n_win, int64_t n_
     const int parts = pc_parts(n_groups), nwp = pc_pad4(n_win);
     double *ws_gram = reinterpret_cast<double *>(d_ws);
     double *ws_sum = ws_gram + (size_t)n_groups * parts * nwp * nwp;
-    size_t smem = (size_t)PC_SC * (nwp + 2) * sizeof(double);
-    {
-        const int ntile = nwp / 4, n_tiles = ntile * (ntile + 1) / 2;
-        if (n_tiles <= PC_THREADS / 2) {               // the kernel's split mode: room for the partial tiles
-            const size_t red = (size_t)(PC_THREADS / n_tiles) * n_tiles * 16 * sizeof(double);
-            if (red > smem) smem = red;
-        }
-    }
+    const size_t smem = (size_t)PC_SC * (nwp + 2) * sizeof(double);
     const int smem_max = (int)((size_t)PC_SC * (PC_MAX_WIN + 2) * sizeof(double));
     SS_CUDA_CHECK(cudaFuncSetAttribute(pca_gram_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     SS_CUDA_CHECK(cudaFuncSetAttribute(pca_gram_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));

@@ -32,6 +32,18 @@ for i, h in enumerate(hdr):
                 print("   pipe %-60s %.1f" % (h.split('.')[0], float(r[i])))
         except ValueError:
             pass
+tens = []
+for i, h in enumerate(hdr):
+    if ('tensor' in h or 'tmem' in h) and not h.startswith('device__'):
+        try:
+            if float(r[i]) != 0.0 and ('.avg' in h or '.sum' in h) and 'peak_sustained_elapsed.per_second' not in h \
+                    and not h.endswith('peak_sustained') and '.max' not in h and '.min' not in h:
+                tens.append("   %-88s %s %s" % (h, r[i], units[i]))
+        except ValueError:
+            pass
+if tens:
+    print("tensor / TMEM counters (non-zero):")
+    print("\n".join(tens[:24]))
 items = []
 for i, h in enumerate(hdr):
     if 'issue_stalled' in h and h.endswith('per_issue_active.ratio') and 'not_issued' not in h:
