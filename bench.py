@@ -261,24 +261,54 @@ def run_gpu(args):
         # lazy: the chain of this step is queued before the previous step's counts are read
         # (finalize(): the one host sync per step), so the GPU does not idle while the host gets
         # from that synchronisation to the next step's first launch - single GPU and sharded alike
+        # Consecutive (independent) steps alternate between two streams (SS_BENCH_STREAMS=1: one),
+        # so that the latency-bound tail of one step (align ... PCA, ~0.3 ms of small kernels)
+        # runs under the next step's filter; sharded steps also alternate between two arena sets
+        slot = nstep["i"] % len(streams) if streams else 0
+        st = streams[slot] if streams else None
+        nstep["i"] += 1
         if world > 1:
-            r = ssdist.run_chain_sharded(x, FS, flt, SP_WIN, edge='falling', align_type='min',
-                                         ncomps=2, chunksize=CHUNK, lazy=True)
+            if st is not None:
+                with torch.cuda.stream(st):
+                    r = ssdist.run_chain_sharded(x, FS, flt, SP_WIN, edge='falling', align_type='min',
+                                                 ncomps=2, chunksize=CHUNK, lazy=True, slot=slot)
+                r._bench_stream = st
+            else:
+                r = ssdist.run_chain_sharded(x, FS, flt, SP_WIN, edge='falling', align_type='min',
+                                             ncomps=2, chunksize=CHUNK, lazy=True)
         else:
-            r = pipeline.run_chain(x, FS, filt=flt, sp_win=SP_WIN, edge='falling',
-                                   align_type='min', ncomps=2, chunksize=CHUNK, lazy=True)
+            if st is not None:
+                with torch.cuda.stream(st):
+                    r = pipeline.run_chain(x, FS, filt=flt, sp_win=SP_WIN, edge='falling',
+                                           align_type='min', ncomps=2, chunksize=CHUNK, lazy=True)
+                r._bench_stream = st
+            else:
+                r = pipeline.run_chain(x, FS, filt=flt, sp_win=SP_WIN, edge='falling',
+                                       align_type='min', ncomps=2, chunksize=CHUNK, lazy=True)
         prev, pending["res"] = pending["res"], r
         if prev is not None:
-            last["res"] = prev.finalize()
+            last["res"] = finalize(prev)
         return r
 
+    def finalize(r):
+        st = getattr(r, "_bench_stream", None)
+        if st is None:
+            return r.finalize()
+        with torch.cuda.stream(st):
+            return r.finalize()
+
     pending = {"res": None}
+    nstep = {"i": 0}
+    n_streams = env_int("SS_BENCH_STREAMS", 2)
+    streams = [torch.cuda.Stream() for _ in range(n_streams)] if n_streams > 1 else []
 
     def finish_last():
         # inside the timed region: the last step's counts are read (and its arrays trimmed) too
         if pending["res"] is not None:
-            last["res"] = pending["res"].finalize()
+            last["res"] = finalize(pending["res"])
             pending["res"] = None
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
 
     def barrier():
         if world > 1:
@@ -286,6 +316,9 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     res = None
+    # every stream needs its own warm-up (the caching allocator keeps one pool per stream: the
+    # first steps on a stream allocate their 5 GB of buffers with cudaMalloc)
+    args.warmup = max(args.warmup, 5 * max(len(streams), 1))
     for _ in range(args.warmup):
         res = step()
     finish_last()
@@ -343,6 +376,8 @@ def run_gpu(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
+    for st in streams:
+        st.wait_event(ev0)
     for _ in range(args.steps):
         res = step()
     finish_last()
@@ -350,11 +385,37 @@ def run_gpu(args):
     barrier()
     launches = int(_lib.load().ss_launch_count() - launches0)
     clocks = sampler.stop()
-    _ops.filtfilt_detect, _ops.filtfilt_prepare = orig_filtfilt, orig_prepare
-    _ops.pca_gram, _ops.pca_project = orig_gram, orig_project
     ms_pca = [a.elapsed_time(b) for a, b in p_ev[:pidx["i"]]]
     ms_total = ev0.elapsed_time(ev1)
     ms_filter = [a.elapsed_time(b) for a, b in f_ev[:idx["i"]]]
+    # the same stage with nothing else on the GPU: a few more steps on ONE stream, after the timed
+    # region (in the timed region the other stream's align ... PCA kernels run under the filter)
+    ms_filter_alone, ms_step_alone = [], None
+    if streams:
+        n_iso = 10                                         # the first 4 re-warm the stream
+        f_ev[:] = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                   for _ in range(n_iso)]
+        idx["i"], idx["open"] = 0, False
+        p_ev[:] = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                   for _ in range(n_iso)]
+        pidx["i"] = 0
+        saved, streams[:] = list(streams), streams[:1]     # (its allocator pool is warm)
+        iso0, iso1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for k in range(n_iso):
+            if k == 4:
+                with torch.cuda.stream(streams[0]):
+                    iso0.record()
+            step()
+        finish_last()
+        with torch.cuda.stream(streams[0]):
+            iso1.record()
+        barrier()
+        streams[:] = saved
+        ms_filter_alone = [a.elapsed_time(b) for a, b in f_ev[:idx["i"]]][4:]
+        ms_step_alone = iso0.elapsed_time(iso1) / (n_iso - 4)
+        ms_pca = [a.elapsed_time(b) for a, b in p_ev[:pidx["i"]]][4:]     # (un-overlapped)
+    _ops.filtfilt_detect, _ops.filtfilt_prepare = orig_filtfilt, orig_prepare
+    _ops.pca_gram, _ops.pca_project = orig_gram, orig_project
     res = last["res"]
     n_spk = int(res.spt.numel())
     n_det = int(res.spt_detected.numel())
@@ -450,6 +511,16 @@ def run_gpu(args):
     # detect N*8 + n_spk*8 per contact (the fused call covers all three stages)
     alg_bytes = N_CONTACTS * N_SAMPLES * (2 + 8) + N_CONTACTS * min(N_SAMPLES, 10 * FS) * 8 + \
         N_CONTACTS * N_SAMPLES * 8 + n_det * 8
+    # The stage is timed twice with CUDA events on the launching stream: inside the timed region
+    # (where consecutive steps alternate between two streams and the OTHER step's align / extract /
+    # PCA kernels run under the filter: the interval is longer than the kernels need and adds up
+    # to more than the step), and - `roofline` proper - on one stream right after it, same
+    # buffers, same launches, nothing else on the GPU: the number that can be compared with the
+    # serialised ncu launch list (profiles/r02_launches_c2.txt).
+    region_ms = filt_ms
+    if ms_filter_alone:
+        filt_ms = statistics.mean(ms_filter_alone)
+    step_alone = ms_step_alone if ms_filter_alone else ms_step
     achieved = alg_bytes / (filt_ms / 1000.0) / 1e9
     # bytes the kernels of this stage really move: dram__bytes_read.sum + dram__bytes_write.sum
     # summed over the stage's launches of one step, from the ncu launch list of this command in
@@ -467,7 +538,16 @@ def run_gpu(args):
                            "of the chain" % ("single-pass span kernel" if span else
                                              "summary sweep, tile scan, apply sweep")),
                 "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": filt_ms,
-                "share_of_step": filt_ms / ms_step, "peak_source": peak_src,
+                "share_of_step": filt_ms / step_alone, "peak_source": peak_src,
+                "measured": ("CUDA events around the stage's launches on ONE stream, %d steps right "
+                             "after the timed region (single-stream step: single_stream_ms_per_step); "
+                             "in_timed_region = the same events inside the timed region, where two "
+                             "streams overlap consecutive steps" % len(ms_filter_alone))
+                if ms_filter_alone else "CUDA events around the stage's launches inside the timed region",
+                "in_timed_region": {"ms_per_launch": region_ms, "streams": max(len(streams), 1),
+                                    "frac": alg_bytes / (region_ms / 1000.0) / 1e9 / peak,
+                                    "share_of_step": region_ms / ms_step},
+                "single_stream_ms_per_step": step_alone,
                 "note": "frac counts SURVEY 8(d)'s algorithmic bytes (incl. the detect pass over the "
                         "filtered signal, which the fused marks never make: it may exceed the bytes "
                         "moved); frac_moved counts the DRAM bytes ncu measured for the same launches"}
@@ -497,13 +577,16 @@ def run_gpu(args):
              "achieved_GBs": chain_bytes / (ms_step / 1000.0) / 1e9,
              "frac": chain_bytes / (ms_step / 1000.0) / 1e9 / peak}
     if ms_pca:
-        # north_star's target is stated on the filter -> detect -> extract chain
+        # north_star's target is stated on the filter -> detect -> extract chain; with two
+        # streams the PCA of one step runs under the next step's filter, so the split is taken
+        # from the single-stream steps measured right after the timed region
         pca_ms = statistics.mean(ms_pca)
         pca_bytes = n_spk * (n_win * 8 + 16)
         chain["pca_ms"] = pca_ms
+        chain["single_stream_ms_per_step"] = step_alone
         chain["filter_detect_extract"] = {
-            "ms": ms_step - pca_ms, "algorithmic_bytes": chain_bytes - pca_bytes,
-            "frac": (chain_bytes - pca_bytes) / ((ms_step - pca_ms) / 1000.0) / 1e9 / peak}
+            "ms": step_alone - pca_ms, "algorithmic_bytes": chain_bytes - pca_bytes,
+            "frac": (chain_bytes - pca_bytes) / ((step_alone - pca_ms) / 1000.0) / 1e9 / peak}
 
     # ---- N > 1: every rank's results of a few contacts to rank 0 (outside the timed region)
     PAR_C = 4                                             # contacts compared at N > 1
@@ -634,8 +717,8 @@ def select_workload(name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="profiling runs only")

@@ -282,9 +282,11 @@ class HaloError(RuntimeError):
     """An alignment walk left even the widest halo a shard can hold of its neighbour."""
 
 
-def peer_fabric(n_c, H, n_win):
-    """Cached PeerFabric of the default process group (the rendezvous costs milliseconds)."""
-    key = (int(n_c), int(H), int(n_win), world()[1], int(_lib.torch().cuda.current_device()))
+def peer_fabric(n_c, H, n_win, slot=0):
+    """Cached PeerFabric of the default process group (the rendezvous costs milliseconds).
+    slot: independent arena sets for steps that are in flight at the same time on different
+    streams (every rank must use the same slot for the same step)."""
+    key = (int(n_c), int(H), int(n_win), world()[1], int(_lib.torch().cuda.current_device()), int(slot))
     if key not in _FABRICS:
         _FABRICS[key] = PeerFabric(n_c, H, n_win)
     return _FABRICS[key]
@@ -584,7 +586,7 @@ class PendingShard(object):
 
 def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_type='min',
                       thresh='auto', ncomps=2, chunksize=1E6, index_offset=None, n_total=None,
-                      transport=None, speculate=True, halo=None, lazy=False):
+                      transport=None, speculate=True, halo=None, lazy=False, slot=0):
     """The chain on this rank's time shard `x` (CUDA tensor, every rank the same number
     of samples unless index_offset/n_total say otherwise), with the exchange steps of
     the module docstring.  Spike times are global; `all_counts` gives the layout of the
@@ -598,7 +600,10 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
     with a halo four times as wide (up to the whole neighbour shard; beyond that HaloError) -
     the result always equals the unsharded chain's.
     lazy: (peer transport, a capacity hint from an earlier call) return a PendingShard with
-    the step queued and no host synchronisation; its finalize() gives the result."""
+    the step queued and no host synchronisation; its finalize() gives the result.
+    slot: arena set of the step (peer transport).  Steps queued on DIFFERENT CUDA streams must
+    use different slots - their exchange kernels then run independently of each other; all
+    ranks pass the same slot for the same step."""
     import os
     t = _lib.require_cuda()
     rank, n_ranks = world()
@@ -630,7 +635,7 @@ def run_chain_sharded(x, FS, filt, sp_win=(-0.2, 0.8), edge='falling', align_typ
 
     def fabric_queue(H, cap):
         """Queue the whole step on the stream; returns the chain (nothing read back)."""
-        fabric = peer_fabric(x.shape[0], H, n_win)
+        fabric = peer_fabric(x.shape[0], H, n_win, slot)
         ch = new_chain(H, fabric)
         mark("start")
         ch.prepare()

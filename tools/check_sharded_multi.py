@@ -38,12 +38,32 @@ mine_x = x[:, rank * n:(rank + 1) * n].contiguous()
 # narrow for the spikes on the shard boundaries - every rank must learn of the miss and all of
 # them redo the step with a wider halo - and the pipelined (lazy) form of the peer transport
 cases = [("peer", None, False), ("nccl", None, False), ("peer", None, False), ("peer", 2, False),
-         ("peer", 2, False), ("nccl", 2, False), ("peer", None, True)]
+         ("peer", 2, False), ("nccl", 2, False), ("peer", None, True), ("peer", None, "streams")]
+side = [torch.cuda.Stream(), torch.cuda.Stream()]
 for transport, halo, lazy in cases:
-    res = ssd.run_chain_sharded(mine_x, FS, flt, sp_win, edge='falling', align_type='min',
-                                thresh='auto', ncomps=2, chunksize=chunk, transport=transport,
-                                halo=halo, lazy=lazy)
-    if lazy:
+    if lazy == "streams":
+        # two steps in flight on two streams, each with its own arena set (slot)
+        for st in side:
+            st.wait_stream(torch.cuda.current_stream())
+        pend = []
+        for rep in range(4):
+            with torch.cuda.stream(side[rep % 2]):
+                pend.append(ssd.run_chain_sharded(mine_x, FS, flt, sp_win, edge='falling',
+                                                  align_type='min', thresh='auto', ncomps=2,
+                                                  chunksize=chunk, transport=transport, lazy=True,
+                                                  slot=rep % 2))
+            if rep >= 1:
+                with torch.cuda.stream(side[(rep - 1) % 2]):
+                    res = pend[rep - 1].finalize()
+        with torch.cuda.stream(side[1]):
+            res = pend[3].finalize()
+        torch.cuda.synchronize()
+        lazy = 2
+    else:
+        res = ssd.run_chain_sharded(mine_x, FS, flt, sp_win, edge='falling', align_type='min',
+                                    thresh='auto', ncomps=2, chunksize=chunk, transport=transport,
+                                    halo=halo, lazy=lazy)
+    if lazy is True:
         nxt = ssd.run_chain_sharded(mine_x, FS, flt, sp_win, edge='falling', align_type='min',
                                     thresh='auto', ncomps=2, chunksize=chunk, transport=transport,
                                     halo=halo, lazy=True)      # queued behind the first step
