@@ -33,6 +33,7 @@
 // summaries per sample).  All tables are computed on the host in binary128.
 #include "common.cuh"
 #include "internal.cuh"
+#include <cuda.h>                   // CUtensorMap (encoded through the runtime's driver entry point)
 #include <vector>
 #include <cstring>
 #include <mutex>
@@ -778,11 +779,96 @@ filt_summary_wide_kernel(const int16_t *__restrict__ x, const FiltGeom g, const 
     }
 }
 
+// crossing marks of a finished tile from the registers: pairs (i, i+1) with both samples in this
+// tile and this chunk; the pair that ends a tile or a chunk is marked by
+// filt_boundary_mark_kernel afterwards, from the tile's first / last output sample left in the
+// (dead) F / Bz arrays in front of Zf
+template <int NS>
+__device__ __forceinline__ void mark_tile(const FiltGeom &g, const TileInfo &ti, int64_t tile, int64_t r0,
+                                          const double (&v)[FS_S], const double *Zf,
+                                          const MarkParams &mk, int lane)
+{
+    {
+        double *first_s = const_cast<double *>(Zf) - 2 * g.total_tiles * NS;
+        if (lane == 0) first_s[tile] = v[0];
+        if (lane == 31) first_s[g.total_tiles * NS + tile] = v[FS_S - 1];
+    }
+    const double th = __ldg(mk.thr + ti.c);
+    const double nx = ss_shfl_down(v[0], 1);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int i = 0; i < FS_S - 1; ++i)
+        bits |= (uint32_t)ssi::crossing(v[i], v[i + 1], th, mk.falling) << i;
+    if (lane < 31) bits |= (uint32_t)ssi::crossing(v[FS_S - 1], nx, th, mk.falling) << (FS_S - 1);
+    const int64_t rl = r0 + FS_S * lane;                  // chunk-relative index of bit 0
+    if (!(r0 >= 0 && r0 + FS_T <= ti.L)) {
+        // keep bits i with 0 <= rl + i and rl + i + 1 < L
+        const int64_t lo = rl < 0 ? -rl : 0, hi = ti.L - 1 - rl;
+        uint32_t keep = 0;
+        if (lo < FS_S && hi > 0) {
+            const int h = hi < FS_S ? (int)hi : FS_S;
+            keep = ((h >= 32 ? 0xffffffffu : ((1u << h) - 1u))) & ~((1u << (int)lo) - 1u);
+        }
+        bits &= keep;
+    }
+    if (bits) {
+        const int64_t s = ti.cs0 + rl;                    // sample index of bit 0 in the row
+        uint32_t *mrow = mk.mask + ti.c * mk.words_per_row;
+        // a lane that straddles the start of the row has s < 0: its kept bits all land in
+        // word (s >> 5) + 1 = 0, and word -1 must not be touched at all (an atomicOr of
+        // zero there faulted when the mask was the first allocation of its segment)
+        const uint64_t w = (uint64_t)bits << (int)(s & 31);
+        if ((uint32_t)w) atomicOr(mrow + (s >> 5), (uint32_t)w);
+        if (w >> 32) atomicOr(mrow + (s >> 5) + 1, (uint32_t)(w >> 32));
+    }
+}
+
+// the lanes' segments -> padded shared memory -> coalesced float64 stores of the chunk part;
+// tiles holding one of the shard's first / last halo_H samples also store them into the
+// neighbour ranks' arenas
+__device__ __forceinline__ void store_tile(const FiltGeom &g, const TileInfo &ti, int64_t r0,
+                                           const double (&v)[FS_S], double *sm, double *out,
+                                           const MarkParams &mk, int lane)
+{
+#pragma unroll
+    for (int i = 0; i < FS_S; ++i) sm[lane * (FS_S + 1) + i] = v[i];
+    __syncwarp();
+    double *orow = out + ti.c * g.ld_out + ti.cs0;
+    const int base = lane + (lane >> 4);
+    if (r0 >= 0 && r0 + FS_T <= ti.L) {
+        double *o = orow + r0 + lane;
+#pragma unroll
+        for (int k = 0; k < FS_S; ++k) __stcs(o + 32 * k, sm[34 * k + base]);
+    } else {
+#pragma unroll 1
+        for (int k = 0; k < FS_S; ++k) {
+            const int64_t r = r0 + 32 * k + lane;
+            if (r >= 0 && r < ti.L) __stcs(orow + r, sm[34 * k + base]);
+        }
+    }
+    if (mk.peer_left || mk.peer_right) {
+        // (warp-uniform test)
+        const int64_t s_lo = ti.cs0 + r0, H = mk.halo_H, n = mk.shard_n;
+        if (s_lo < H || s_lo + FS_T > n - H) {
+#pragma unroll 1
+            for (int k = 0; k < FS_S; ++k) {
+                const int64_t r = r0 + 32 * k + lane;
+                if (r < 0 || r >= ti.L) continue;
+                const int64_t sidx = ti.cs0 + r;
+                const double val = sm[34 * k + base];
+                if (mk.peer_left && sidx < H) mk.peer_left[ti.c * H + sidx] = val;
+                if (mk.peer_right && sidx >= n - H) mk.peer_right[ti.c * H + (sidx - (n - H))] = val;
+            }
+        }
+    }
+}
+
 // (Tried in round 2 and dropped, both SLOWER on B200 than the coalesced element loads / stores
 //  through padded shared memory below: reading a lane's 32 contiguous int16 bytes with two or
 //  three 128-bit loads, +0.06 ms per configs[1] stage; storing through an XOR-swizzled tile with
 //  128-bit shared and global accesses, no gain.  The kernel is bound by the L1 / shared pipe
-//  either way; what the 128-bit forms save in instructions they lose in sector efficiency.)
+//  either way; what the 128-bit forms save in instructions they lose in sector efficiency.
+//  filt_apply_tma_kernel below takes both transpositions off the LSU instead.)
 template <int NB, bool FO, bool MARK>
 __global__ void __launch_bounds__(32 * FS_WPB, (NB + (FO ? 1 : 0) >= 2) ? APPLY_MIN_CTAS : 0)
 filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
@@ -881,6 +967,157 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
             }
         }
     }
+}
+
+// ------------------------------------------------ sweep 2 through the async-copy engine (TMA)
+// The two transpositions of filt_apply_kernel (coalesced elements <-> a lane's 16 consecutive
+// samples) are 96 LSU instructions per lane and tile and keep the L1 / shared pipe 85 % busy at
+// 79 % of the copy bandwidth (profiles/r01_ncu_g_chain_kernels_final.txt).  For int16 recordings
+// this kernel hands both to the copy engine:
+//   in : ONE bulk copy (cp.async.bulk global -> shared, mbarrier complete_tx) of the 16-byte
+//        aligned 1040-byte window that holds the tile's 512 int16 samples; a lane then reads its
+//        own 32 + 16 bytes with three 128-bit shared loads and realigns them with funnel shifts
+//        (the misalignment - 0..7 samples - is uniform over the warp);
+//   out: the lane's 16 float64 are the 128-byte ROW `lane` of a 32 x 128 B shared tile in the
+//        SWIZZLE_128B pattern (16-byte chunk j of row l at chunk j ^ (l & 7): eight conflict-free
+//        128-bit shared stores), and ONE tensor store (cp.async.bulk.tensor.2d shared -> global)
+//        through a tensor map that describes the output as rows of 16 float64 writes the 4 KB.
+// Tiles that touch the padding / odd extension / chunk end, whose first output sample is not a
+// whole number of 128-byte rows from the tensor map's base (odd chunk geometries, the shorter
+// last chunk) or that feed a neighbour shard's halo take the element path of filt_apply_kernel.
+constexpr int TM_SLAB = 5120;              // per warp: 4 KB tile (1024-aligned) + mbarrier, and
+                                           // room for the padded tile of the element path
+constexpr int TM_IN_BYTES = FS_T * 2 + 16;
+
+__device__ __forceinline__ uint32_t fa_smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// bounded wait: a protocol error traps instead of hanging the device
+__device__ __forceinline__ void fa_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    for (long long spin = 0; spin < (1LL << 26); ++spin) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\t"
+                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                     "selp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(bar), "r"(parity)
+                     : "memory");
+        if (ok) return;
+    }
+    __trap();
+}
+
+// values sh .. sh + 15 of the 24 int16 in W (sh = 2 K0 + odd), exact float64
+template <int K0>
+__device__ __forceinline__ void realign_convert(const uint32_t (&W)[12], int bsh, double (&v)[FS_S])
+{
+#pragma unroll
+    for (int m = 0; m < FS_S / 2; ++m) {
+        const uint32_t pr = __funnelshift_r(W[m + K0], W[m + K0 + 1], bsh);
+        // two int16 -> float64: offset binary in the low mantissa word of 2^52 (one XOR for both)
+        const uint32_t ob = pr ^ 0x80008000u;
+        v[2 * m] = __hiloint2double(0x43300000, (int)(ob & 0xffffu)) - 4503599627403264.0;
+        v[2 * m + 1] = __hiloint2double(0x43300000, (int)(ob >> 16)) - 4503599627403264.0;
+    }
+}
+
+#ifndef TM_MIN_CTAS
+#define TM_MIN_CTAS 8
+#endif
+// tma_e0: the tensor map describes the output as rows of 16 float64 starting at element tma_e0
+// of `out`
+template <int NB, bool FO, bool MARK>
+__global__ void __launch_bounds__(32 * FS_WPB, TM_MIN_CTAS)
+filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
+                      const __grid_constant__ FiltParams<NB, FO> P,
+                      const double *__restrict__ Zf, const double *__restrict__ Zb,
+                      double *__restrict__ out, const MarkParams mk,
+                      const __grid_constant__ CUtensorMap tmap, const int tma_e0)
+{
+    constexpr int NS = FiltParams<NB, FO>::NS;
+    __shared__ __align__(1024) unsigned char slab_all[FS_WPB][TM_SLAB];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    TileInfo ti;
+    int64_t tile;
+    if (!decode_tile(g, warp, ti, tile)) return;
+    unsigned char *slab = slab_all[warp];
+    const int64_t r0 = ti.t * FS_T - ti.pad - g.edge;
+    const int64_t E = ti.c * g.ld_out + ti.cs0 + r0;       // first output element of the tile
+    bool fast = r0 >= 0 && r0 + FS_T <= ti.L && E >= tma_e0 && ((E - tma_e0) & 15) == 0;
+    if (mk.peer_left || mk.peer_right) {
+        const int64_t s_lo = ti.cs0 + r0;
+        if (s_lo < mk.halo_H || s_lo + FS_T > mk.shard_n - mk.halo_H) fast = false;
+    }
+    double v[FS_S];
+    if (!fast) {
+        load_tile(x, g, ti, reinterpret_cast<double *>(slab), lane, v);
+    } else {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(x + ti.c * g.ld_in + ti.cs0 + r0);
+        const uintptr_t a0 = a & ~(uintptr_t)15;
+        const int sh = (int)(a - a0) >> 1;                  // 0..7 samples, warp-uniform
+        const uint32_t bar = fa_smem_u32(slab + FS_T * 8), dst = fa_smem_u32(slab);
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                         ::"r"(bar), "r"((uint32_t)TM_IN_BYTES) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+                         "[%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(a0), "r"((uint32_t)TM_IN_BYTES), "r"(bar)
+                         : "memory");
+        }
+        __syncwarp();
+        fa_mbar_wait(bar, 0);
+        uint32_t W[12];
+        {
+            const uint4 *q = reinterpret_cast<const uint4 *>(slab + 32 * lane);
+            const uint4 c0 = q[0], c1 = q[1], c2 = q[2];
+            W[0] = c0.x; W[1] = c0.y; W[2] = c0.z; W[3] = c0.w;
+            W[4] = c1.x; W[5] = c1.y; W[6] = c1.z; W[7] = c1.w;
+            W[8] = c2.x; W[9] = c2.y; W[10] = c2.z; W[11] = c2.w;
+        }
+        const int bsh = (sh & 1) * 16;
+        switch (sh >> 1) {
+        case 0: realign_convert<0>(W, bsh, v); break;
+        case 1: realign_convert<1>(W, bsh, v); break;
+        case 2: realign_convert<2>(W, bsh, v); break;
+        default: realign_convert<3>(W, bsh, v); break;
+        }
+        __syncwarp();                                       // the tile buffer is reused for the output
+    }
+
+    // forward from the true tile state, then backward over the forward output
+    double zt[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) zt[i] = (lane == 0) ? Zf[tile * NS + i] : 0.0;
+    cascade_pass<NB, FO, false>(P, v, zt, lane);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) zt[i] = (lane == 31) ? Zb[tile * NS + i] : 0.0;
+    cascade_pass<NB, FO, true>(P, v, zt, lane);
+
+    if (MARK) mark_tile<NS>(g, ti, tile, r0, v, Zf, mk, lane);
+    if (!fast) {
+        store_tile(g, ti, r0, v, reinterpret_cast<double *>(slab), out, mk, lane);
+        return;
+    }
+    double2 *row = reinterpret_cast<double2 *>(slab + 128 * lane);
+#pragma unroll
+    for (int j = 0; j < FS_S / 2; ++j) row[j ^ (lane & 7)] = make_double2(v[2 * j], v[2 * j + 1]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+        const int32_t r = (int32_t)((E - tma_e0) >> 4);
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                     ::"l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"(r), "r"(fa_smem_u32(slab))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        // the shared tile must outlive the copy engine's read of it
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------- single-pass span kernel
@@ -2154,6 +2391,54 @@ static int make_geom(FiltGeom &g, int dtype, int64_t n_contacts, int64_t n_sampl
 
 enum { PH_SUMMARY = 1, PH_APPLY = 2, PH_ALL = 3 };
 
+// Tensor map of the filtered signal for filt_apply_tma_kernel: rows of 16 float64 (128 B, the
+// SWIZZLE_128B span) starting at element e0 of `out`, box = 32 rows = one tile.  e0 is the
+// offset (mod 16) of the interior tiles of the full-length chunks; the map is encoded through
+// the runtime's driver entry point (no link against libcuda).  Returns false when the geometry
+// or the address does not allow it (the element kernel runs instead).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+// SS_APPLY_TMA: 0 = element kernel only, 2 = fail instead of falling back (tests); read per call
+static int apply_tma_mode()
+{
+    const char *e = getenv("SS_APPLY_TMA");
+    return e && e[0] == '0' ? 0 : (e && e[0] == '2' ? 2 : 1);
+}
+
+static bool make_out_tensor_map(const FiltGeom &g, double *d_out, CUtensorMap *tm, int *tma_e0)
+{
+    static EncodeTiledFn encode = [] {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess ||
+            qr != cudaDriverEntryPointSuccess)
+            fn = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(fn);
+    }();
+    if (!encode || !d_out) return false;
+    const bool full = g.n_full > 0;
+    const int64_t L = full ? g.chunksize : g.len_last, nt = full ? g.nt_full : g.nt_last;
+    const int64_t pe = nt * FS_T - (L + 2 * (int64_t)g.edge) + g.edge;     // left padding + edge
+    const int e0 = (int)(((-pe) % 16 + 16) % 16);
+    const int64_t total = (g.n_contacts - 1) * g.ld_out + g.n_samples;
+    const int64_t rows = (total - e0) / 16;
+    if (rows < 32 || rows >= (int64_t)1 << 31) return false;
+    if ((reinterpret_cast<uintptr_t>(d_out + e0) & 15) != 0) return false;
+    const cuuint64_t dims[2] = {16, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {16, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_out + e0, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    *tma_e0 = e0;
+    return true;
+}
+
 // one filter pass over the chunk range [j_begin, j_begin + j_count) of every contact;
 // mk != nullptr fuses crossing marking into the apply kernel
 template <int NB, bool FO>
@@ -2305,14 +2590,33 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
         SS_LAUNCH_CHECK("filt_tilescan_kernel");
     }
     if (!(phases & PH_APPLY)) return SS_OK;
+    // orders 1-2 on int16 are bandwidth-bound: both transpositions through the copy engine
+    CUtensorMap tmap;
+    bool tma = false;
+    int tma_e0 = 0;
+    if constexpr (NS <= 2) {
+        const int mode = apply_tma_mode();
+        tma = g.dtype == SS_I16 && mode && make_out_tensor_map(g, d_out, &tmap, &tma_e0);
+        SS_REQUIRE(tma || mode != 2 || g.dtype != SS_I16, SS_ERR_UNSUPPORTED,
+                   "filtfilt: SS_APPLY_TMA=2 and no tensor map for this output (address / geometry)");
+    }
     if (mk) {
         MarkParams mkp = *mk;
         mkp.peer_left = g_peer_halo.left;
         mkp.peer_right = g_peer_halo.right;
         mkp.halo_H = g_peer_halo.H;
         mkp.shard_n = g.n_samples;
-        filt_apply_kernel<NB, FO, true><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, mkp);
-        SS_LAUNCH_CHECK("filt_apply_kernel<mark>");
+        if constexpr (NS <= 2) {
+            if (tma) {
+                filt_apply_tma_kernel<NB, FO, true><<<tile_blocks, 32 * FS_WPB, 0, st>>>(
+                    reinterpret_cast<const int16_t *>(d_x), g, P, Zf, Zb, d_out, mkp, tmap, tma_e0);
+                SS_LAUNCH_CHECK("filt_apply_tma_kernel<mark>");
+            }
+        }
+        if (!tma) {
+            filt_apply_kernel<NB, FO, true><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, mkp);
+            SS_LAUNCH_CHECK("filt_apply_kernel<mark>");
+        }
         const dim3 bgrid((unsigned)ss_cdiv(nt_max, 256), (unsigned)j_count, (unsigned)g.n_contacts);
         // (F / Bz are dead once the tile scan has run: the apply kernel left the tiles' first /
         //  last samples there)
@@ -2321,8 +2625,17 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
     } else {
         MarkParams none = {nullptr, nullptr, 0, 0, 0, g_peer_halo.left, g_peer_halo.right,
                            g_peer_halo.H, g.n_samples};
-        filt_apply_kernel<NB, FO, false><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, none);
-        SS_LAUNCH_CHECK("filt_apply_kernel");
+        if constexpr (NS <= 2) {
+            if (tma) {
+                filt_apply_tma_kernel<NB, FO, false><<<tile_blocks, 32 * FS_WPB, 0, st>>>(
+                    reinterpret_cast<const int16_t *>(d_x), g, P, Zf, Zb, d_out, none, tmap, tma_e0);
+                SS_LAUNCH_CHECK("filt_apply_tma_kernel");
+            }
+        }
+        if (!tma) {
+            filt_apply_kernel<NB, FO, false><<<tile_blocks, 32 * FS_WPB, 0, st>>>(d_x, g, P, Zf, Zb, d_out, none);
+            SS_LAUNCH_CHECK("filt_apply_kernel");
+        }
     }
     return SS_OK;
 }
