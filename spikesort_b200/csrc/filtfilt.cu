@@ -205,10 +205,13 @@ __device__ __forceinline__ void warp_scan(double (&e)[NS], const double (&Pm)[5]
 // inclusive warp scan with A_s^(S 2^k) turns the lane end states into true states, and
 // y[i] += (C_s A_s^i) . (state at the lane's start) corrects the local outputs.
 // SO: second-order section (two states); otherwise first-order (z1 unused).
+// zo: an index offset that is always 0.  The persistent TMA kernel passes an OPAQUE zero (asm
+// volatile) for the h / Pm tables: inside its tile loop the compiler otherwise hoists all of the
+// ~30 loop-invariant coefficient loads into registers and spills the samples instead
 template <bool SO, bool REV>
 __device__ __forceinline__ void section_pass(const double (&c)[5], const double (&h)[FS_S][2],
                                              const double (&Pm)[5][2][2], double (&v)[FS_S],
-                                             double z0, double z1, int lane)
+                                             double z0, double z1, int lane, int zo = 0)
 {
 #pragma unroll
     for (int ii = 0; ii < FS_S; ++ii) {
@@ -231,11 +234,11 @@ __device__ __forceinline__ void section_pass(const double (&c)[5], const double 
         if (SO) {
             const double o1 = REV ? ss_shfl_down(z1, d) : ss_shfl_up(z1, d);
             if (act) {
-                z0 = z0 + Pm[k][0][0] * o0 + Pm[k][0][1] * o1;
-                z1 = z1 + Pm[k][1][0] * o0 + Pm[k][1][1] * o1;
+                z0 = z0 + Pm[k + zo][0][0] * o0 + Pm[k + zo][0][1] * o1;
+                z1 = z1 + Pm[k + zo][1][0] * o0 + Pm[k + zo][1][1] * o1;
             }
         } else if (act) {
-            z0 = z0 + Pm[k][0][0] * o0;
+            z0 = z0 + Pm[k + zo][0][0] * o0;
         }
     }
     // state at the start of the lane's segment (zero for the seeded lane: its local pass
@@ -251,8 +254,8 @@ __device__ __forceinline__ void section_pass(const double (&c)[5], const double 
 #pragma unroll
     for (int ii = 0; ii < FS_S; ++ii) {
         const int i = REV ? FS_S - 1 - ii : ii;
-        double acc = v[i] + h[ii][0] * p0;
-        if (SO) acc += h[ii][1] * p1;
+        double acc = v[i] + h[ii + zo][0] * p0;
+        if (SO) acc += h[ii + zo][1] * p1;
         v[i] = acc;
     }
 }
@@ -260,12 +263,12 @@ __device__ __forceinline__ void section_pass(const double (&c)[5], const double 
 // the whole cascade over the tile, one direction; zt = tile state of the seeded lane
 template <int NB, bool FO, bool REV>
 __device__ __forceinline__ void cascade_pass(const FiltParams<NB, FO> &P, double (&v)[FS_S],
-                                             const double (&zt)[FiltParams<NB, FO>::NS], int lane)
+                                             const double (&zt)[FiltParams<NB, FO>::NS], int lane, int zo = 0)
 {
 #pragma unroll
     for (int s = 0; s < NB; ++s)
-        section_pass<true, REV>(P.sec[s], P.hrow[s], P.P[s], v, zt[2 * s], zt[2 * s + 1], lane);
-    if (FO) section_pass<false, REV>(P.sec[NB], P.hrow[NB], P.P[NB], v, zt[2 * NB], 0.0, lane);
+        section_pass<true, REV>(P.sec[s], P.hrow[s], P.P[s], v, zt[2 * s], zt[2 * s + 1], lane, zo);
+    if (FO) section_pass<false, REV>(P.sec[NB], P.hrow[NB], P.P[NB], v, zt[2 * NB], 0.0, lane, zo);
 }
 
 // interior tile: all FS_S loads of a lane are issued before the first use (the
@@ -779,90 +782,6 @@ filt_summary_wide_kernel(const int16_t *__restrict__ x, const FiltGeom g, const 
     }
 }
 
-// crossing marks of a finished tile from the registers: pairs (i, i+1) with both samples in this
-// tile and this chunk; the pair that ends a tile or a chunk is marked by
-// filt_boundary_mark_kernel afterwards, from the tile's first / last output sample left in the
-// (dead) F / Bz arrays in front of Zf
-template <int NS>
-__device__ __forceinline__ void mark_tile(const FiltGeom &g, const TileInfo &ti, int64_t tile, int64_t r0,
-                                          const double (&v)[FS_S], const double *Zf,
-                                          const MarkParams &mk, int lane)
-{
-    {
-        double *first_s = const_cast<double *>(Zf) - 2 * g.total_tiles * NS;
-        if (lane == 0) first_s[tile] = v[0];
-        if (lane == 31) first_s[g.total_tiles * NS + tile] = v[FS_S - 1];
-    }
-    const double th = __ldg(mk.thr + ti.c);
-    const double nx = ss_shfl_down(v[0], 1);
-    uint32_t bits = 0;
-#pragma unroll
-    for (int i = 0; i < FS_S - 1; ++i)
-        bits |= (uint32_t)ssi::crossing(v[i], v[i + 1], th, mk.falling) << i;
-    if (lane < 31) bits |= (uint32_t)ssi::crossing(v[FS_S - 1], nx, th, mk.falling) << (FS_S - 1);
-    const int64_t rl = r0 + FS_S * lane;                  // chunk-relative index of bit 0
-    if (!(r0 >= 0 && r0 + FS_T <= ti.L)) {
-        // keep bits i with 0 <= rl + i and rl + i + 1 < L
-        const int64_t lo = rl < 0 ? -rl : 0, hi = ti.L - 1 - rl;
-        uint32_t keep = 0;
-        if (lo < FS_S && hi > 0) {
-            const int h = hi < FS_S ? (int)hi : FS_S;
-            keep = ((h >= 32 ? 0xffffffffu : ((1u << h) - 1u))) & ~((1u << (int)lo) - 1u);
-        }
-        bits &= keep;
-    }
-    if (bits) {
-        const int64_t s = ti.cs0 + rl;                    // sample index of bit 0 in the row
-        uint32_t *mrow = mk.mask + ti.c * mk.words_per_row;
-        // a lane that straddles the start of the row has s < 0: its kept bits all land in
-        // word (s >> 5) + 1 = 0, and word -1 must not be touched at all (an atomicOr of
-        // zero there faulted when the mask was the first allocation of its segment)
-        const uint64_t w = (uint64_t)bits << (int)(s & 31);
-        if ((uint32_t)w) atomicOr(mrow + (s >> 5), (uint32_t)w);
-        if (w >> 32) atomicOr(mrow + (s >> 5) + 1, (uint32_t)(w >> 32));
-    }
-}
-
-// the lanes' segments -> padded shared memory -> coalesced float64 stores of the chunk part;
-// tiles holding one of the shard's first / last halo_H samples also store them into the
-// neighbour ranks' arenas
-__device__ __forceinline__ void store_tile(const FiltGeom &g, const TileInfo &ti, int64_t r0,
-                                           const double (&v)[FS_S], double *sm, double *out,
-                                           const MarkParams &mk, int lane)
-{
-#pragma unroll
-    for (int i = 0; i < FS_S; ++i) sm[lane * (FS_S + 1) + i] = v[i];
-    __syncwarp();
-    double *orow = out + ti.c * g.ld_out + ti.cs0;
-    const int base = lane + (lane >> 4);
-    if (r0 >= 0 && r0 + FS_T <= ti.L) {
-        double *o = orow + r0 + lane;
-#pragma unroll
-        for (int k = 0; k < FS_S; ++k) __stcs(o + 32 * k, sm[34 * k + base]);
-    } else {
-#pragma unroll 1
-        for (int k = 0; k < FS_S; ++k) {
-            const int64_t r = r0 + 32 * k + lane;
-            if (r >= 0 && r < ti.L) __stcs(orow + r, sm[34 * k + base]);
-        }
-    }
-    if (mk.peer_left || mk.peer_right) {
-        // (warp-uniform test)
-        const int64_t s_lo = ti.cs0 + r0, H = mk.halo_H, n = mk.shard_n;
-        if (s_lo < H || s_lo + FS_T > n - H) {
-#pragma unroll 1
-            for (int k = 0; k < FS_S; ++k) {
-                const int64_t r = r0 + 32 * k + lane;
-                if (r < 0 || r >= ti.L) continue;
-                const int64_t sidx = ti.cs0 + r;
-                const double val = sm[34 * k + base];
-                if (mk.peer_left && sidx < H) mk.peer_left[ti.c * H + sidx] = val;
-                if (mk.peer_right && sidx >= n - H) mk.peer_right[ti.c * H + (sidx - (n - H))] = val;
-            }
-        }
-    }
-}
-
 // (Tried in round 2 and dropped, both SLOWER on B200 than the coalesced element loads / stores
 //  through padded shared memory below: reading a lane's 32 contiguous int16 bytes with two or
 //  three 128-bit loads, +0.06 ms per configs[1] stage; storing through an XOR-swizzled tile with
@@ -982,11 +901,20 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
 //        SWIZZLE_128B pattern (16-byte chunk j of row l at chunk j ^ (l & 7): eight conflict-free
 //        128-bit shared stores), and ONE tensor store (cp.async.bulk.tensor.2d shared -> global)
 //        through a tensor map that describes the output as rows of 16 float64 writes the 4 KB.
+// A warp walks TM_TPW tiles of one unit (the CTA's four warps side by side): the bulk copy and
+// the start states of tile k + 1 are requested before tile k is computed, the tensor store of
+// tile k is only waited for when the shared tile is needed again.  (The first version - one tile
+// per warp, as filt_apply_kernel - was latency-bound: 2.04 against 1.79 ms per configs[1] step,
+// ncu long_scoreboard 6.8 per issue at 30 warps / SM.)
 // Tiles that touch the padding / odd extension / chunk end, whose first output sample is not a
 // whole number of 128-byte rows from the tensor map's base (odd chunk geometries, the shorter
-// last chunk) or that feed a neighbour shard's halo take the element path of filt_apply_kernel.
-constexpr int TM_SLAB = 5120;              // per warp: 4 KB tile (1024-aligned) + mbarrier, and
-                                           // room for the padded tile of the element path
+// last chunk) or that feed a neighbour shard's halo take an element path (same arithmetic).
+#ifndef TM_TPW
+#define TM_TPW 8                           // tiles per warp
+#endif
+#ifndef TM_MIN_CTAS
+#define TM_MIN_CTAS 8
+#endif
 constexpr int TM_IN_BYTES = FS_T * 2 + 16;
 
 __device__ __forceinline__ uint32_t fa_smem_u32(const void *p)
@@ -997,7 +925,8 @@ __device__ __forceinline__ uint32_t fa_smem_u32(const void *p)
 // bounded wait: a protocol error traps instead of hanging the device
 __device__ __forceinline__ void fa_mbar_wait(uint32_t bar, uint32_t parity)
 {
-    for (long long spin = 0; spin < (1LL << 26); ++spin) {
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 26); ++spin) {
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\t"
                      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -1010,113 +939,325 @@ __device__ __forceinline__ void fa_mbar_wait(uint32_t bar, uint32_t parity)
     __trap();
 }
 
-// values sh .. sh + 15 of the 24 int16 in W (sh = 2 K0 + odd), exact float64
+// values sh .. sh + 15 of the 24 int16 in W (sh = 2 K0 + odd, bsh = 16 * odd), exact float64
+// (I2F.F64.S16 on either half of the realigned word: one instruction per sample)
 template <int K0>
 __device__ __forceinline__ void realign_convert(const uint32_t (&W)[12], int bsh, double (&v)[FS_S])
 {
 #pragma unroll
     for (int m = 0; m < FS_S / 2; ++m) {
         const uint32_t pr = __funnelshift_r(W[m + K0], W[m + K0 + 1], bsh);
-        // two int16 -> float64: offset binary in the low mantissa word of 2^52 (one XOR for both)
-        const uint32_t ob = pr ^ 0x80008000u;
-        v[2 * m] = __hiloint2double(0x43300000, (int)(ob & 0xffffu)) - 4503599627403264.0;
-        v[2 * m + 1] = __hiloint2double(0x43300000, (int)(ob >> 16)) - 4503599627403264.0;
+        v[2 * m] = (double)(short)(pr & 0xffffu);
+        v[2 * m + 1] = (double)(short)(pr >> 16);
     }
 }
 
-#ifndef TM_MIN_CTAS
-#define TM_MIN_CTAS 8
-#endif
+// what the rare paths of a warp (crossing marks to emit, element tiles) need to know about its
+// unit; kept in shared memory so that the streaming path carries no 64-bit geometry in registers
+struct TmUnit {
+    const int16_t *xc;           // the chunk's first input sample
+    double *oc;                  // the chunk's first output sample
+    uint32_t *mrow;              // the contact's mask row
+    double *peer_l, *peer_r;     // the contact's rows of the neighbour shards' halo arrays (or null)
+    int64_t L, cs0;              // chunk length, chunk start in the row
+    int pe, pad;                 // left padding + edge, left padding
+    // the warp's walk (tile t0 + FS_WPB k, k = 0 .. TM_TPW - 1): everything the streaming loop
+    // needs is affine in k and re-read from here every iteration instead of living in registers
+    // across the cascade (the loop-carried 64-bit values were spilled to local memory, and local
+    // stores go through the same L1 -> crossbar port that bounds the kernel)
+    uintptr_t xa0;               // 16-byte aligned window of tile t0
+    const double *zf0, *zb0;     // start states of tile t0
+    double *fl0, *fl1;           // first / last output sample slots of tile t0
+    int t0, t_end, tf_lo, tf_hi; // first tile, end of the range, fast tiles [tf_lo, tf_hi)
+    int32_t trow0;               // tensor-map row of tile t0
+};
+
+// Element path inside the TMA kernel (edge tiles, odd geometries, halo tiles; not inlined, so
+// that it costs the streaming path no registers).  A tile that cannot use the copy engine
+// differs only in how its buffers are filled and emptied:
+// tm_fill_i16 writes the tile's 512 extended-chunk samples (left padding = ext[0], odd extension
+// in int16 arithmetic as NumPy computes it) where the bulk copy would have put them;
+__device__ __noinline__ void tm_fill_i16(const TmUnit *u, int edge, int t, int16_t *dst, int lane)
+{
+    const int16_t *xc = u->xc;
+    const int64_t L = u->L, e_first = (int64_t)t * FS_T - u->pad;
+#pragma unroll 1
+    for (int k = 0; k < FS_S; ++k) {
+        const int j = 32 * k + lane;
+        int64_t e = e_first + j;
+        if (e < 0) e = 0;
+        const int64_t r = e - edge;
+        int16_t val;
+        if (r < 0) {
+            const int16_t two = (int16_t)(2 * (int)__ldg(xc));
+            val = (int16_t)((int)two - (int)__ldg(xc - r));
+        } else if (r < L) {
+            val = __ldg(xc + r);
+        } else {
+            const int16_t two = (int16_t)(2 * (int)__ldg(xc + L - 1));
+            val = (int16_t)((int)two - (int)__ldg(xc + (L - 1) - (r - (L - 1))));
+        }
+        dst[j] = val;
+    }
+    __syncwarp();
+}
+
+// tm_store_elements reads the finished tile back from the swizzled shared layout (row l = lane l's
+// 16 samples, 16-byte chunk j at j ^ (l & 7)) and stores the part inside the chunk, and into the
+// neighbour shards' halo arrays where due.
+__device__ __noinline__ void tm_store_elements(const TmUnit *u, const unsigned char *tile_s, int t,
+                                               int64_t H, int64_t n, int lane)
+{
+    const int64_t r0 = (int64_t)t * FS_T - u->pe, L = u->L, s0 = u->cs0;
+    double *oc = u->oc, *peer_l = u->peer_l, *peer_r = u->peer_r;
+#pragma unroll 1
+    for (int k = 0; k < FS_S; ++k) {
+        const int j = 32 * k + lane;
+        const int64_t r = r0 + j;
+        if (r < 0 || r >= L) continue;
+        const int l = j >> 4, i = j & 15;
+        const double val = *reinterpret_cast<const double *>(tile_s + 128 * l + 16 * ((i >> 1) ^ (l & 7)) + 8 * (i & 1));
+        __stcs(oc + r, val);
+        const int64_t sidx = s0 + r;
+        if (peer_l && sidx < H) peer_l[sidx] = val;
+        if (peer_r && sidx >= n - H) peer_r[sidx - (n - H)] = val;
+    }
+    __syncwarp();
+}
+
+// the crossing bits of a lane's 16 pairs into the detection mask (pairs (i, i+1) with both
+// samples in this tile and this chunk; the pair that ends a tile or a chunk is marked by
+// filt_boundary_mark_kernel afterwards)
+__device__ __noinline__ void tm_emit_marks(const TmUnit *u, uint32_t bits, int t, int lane)
+{
+    const int64_t r0 = (int64_t)t * FS_T - u->pe, L = u->L;
+    const int64_t rl = r0 + FS_S * lane;                  // chunk-relative index of bit 0
+    if (!(r0 >= 0 && r0 + FS_T <= L)) {
+        // keep bits i with 0 <= rl + i and rl + i + 1 < L
+        const int64_t lo = rl < 0 ? -rl : 0, hi = L - 1 - rl;
+        uint32_t keep = 0;
+        if (lo < FS_S && hi > 0) {
+            const int h = hi < FS_S ? (int)hi : FS_S;
+            keep = ((h >= 32 ? 0xffffffffu : ((1u << h) - 1u))) & ~((1u << (int)lo) - 1u);
+        }
+        bits &= keep;
+    }
+    if (bits) {
+        const int64_t s = u->cs0 + rl;                    // sample index of bit 0 in the row
+        uint32_t *mrow = u->mrow;
+        // a lane that straddles the start of the row has s < 0: its kept bits all land in
+        // word (s >> 5) + 1 = 0, and word -1 must not be touched at all
+        const uint64_t w = (uint64_t)bits << (int)(s & 31);
+        if ((uint32_t)w) atomicOr(mrow + (s >> 5), (uint32_t)w);
+        if (w >> 32) atomicOr(mrow + (s >> 5) + 1, (uint32_t)(w >> 32));
+    }
+}
+
 // tma_e0: the tensor map describes the output as rows of 16 float64 starting at element tma_e0
-// of `out`
-template <int NB, bool FO, bool MARK>
+// of `out`; sh_launch: the misalignment (in samples, 0..7) of a tile's first sample inside its
+// 16-byte window that this instantiation (K0 = sh_launch / 2) realigns - units with another one
+// take the element path.  grid (groups of FS_WPB * TM_TPW tiles, chunk, contact)
+template <int NB, bool FO, bool MARK, int K0>
 __global__ void __launch_bounds__(32 * FS_WPB, TM_MIN_CTAS)
 filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
                       const __grid_constant__ FiltParams<NB, FO> P,
                       const double *__restrict__ Zf, const double *__restrict__ Zb,
                       double *__restrict__ out, const MarkParams mk,
-                      const __grid_constant__ CUtensorMap tmap, const int tma_e0)
+                      const __grid_constant__ CUtensorMap tmap, const int tma_e0, const int sh_launch)
 {
     constexpr int NS = FiltParams<NB, FO>::NS;
-    __shared__ __align__(1024) unsigned char slab_all[FS_WPB][TM_SLAB];
+    __shared__ __align__(1024) unsigned char tile_all[FS_WPB][FS_T * 8];
+    __shared__ __align__(16) unsigned char in_all[FS_WPB][2][TM_IN_BYTES];
+    __shared__ __align__(8) uint64_t bar_all[FS_WPB][2];
+    __shared__ __align__(16) TmUnit unit_all[FS_WPB];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    TileInfo ti;
-    int64_t tile;
-    if (!decode_tile(g, warp, ti, tile)) return;
-    unsigned char *slab = slab_all[warp];
-    const int64_t r0 = ti.t * FS_T - ti.pad - g.edge;
-    const int64_t E = ti.c * g.ld_out + ti.cs0 + r0;       // first output element of the tile
-    bool fast = r0 >= 0 && r0 + FS_T <= ti.L && E >= tma_e0 && ((E - tma_e0) & 15) == 0;
-    if (mk.peer_left || mk.peer_right) {
-        const int64_t s_lo = ti.cs0 + r0;
-        if (s_lo < mk.halo_H || s_lo + FS_T > mk.shard_n - mk.halo_H) fast = false;
-    }
-    double v[FS_S];
-    if (!fast) {
-        load_tile(x, g, ti, reinterpret_cast<double *>(slab), lane, v);
-    } else {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(x + ti.c * g.ld_in + ti.cs0 + r0);
-        const uintptr_t a0 = a & ~(uintptr_t)15;
-        const int sh = (int)(a - a0) >> 1;                  // 0..7 samples, warp-uniform
-        const uint32_t bar = fa_smem_u32(slab + FS_T * 8), dst = fa_smem_u32(slab);
-        if (lane == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                         ::"r"(bar), "r"((uint32_t)TM_IN_BYTES) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
-                         "[%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(a0), "r"((uint32_t)TM_IN_BYTES), "r"(bar)
-                         : "memory");
+    const uint32_t bar0 = fa_smem_u32(&bar_all[warp][0]), in0 = fa_smem_u32(in_all[warp][0]);
+    // bulk copy of the window at `a` into input buffer b (one lane)
+    auto request = [&](uintptr_t a, int b) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     ::"r"(bar0 + 8 * b), "r"((uint32_t)TM_IN_BYTES) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes "
+                     "[%0], [%1], %2, [%3];"
+                     ::"r"(in0 + TM_IN_BYTES * b), "l"(a), "r"((uint32_t)TM_IN_BYTES), "r"(bar0 + 8 * b)
+                     : "memory");
+    };
+    bool fast;
+    {
+        const int t = (int)g.t_lo + (int)blockIdx.x * (FS_WPB * TM_TPW) + warp;
+        const TileInfo ti = decode_unit<false>(g, blockIdx.z, g.j_begin + blockIdx.y);
+        const int t_end = (int)(ti.nt < g.t_hi ? ti.nt : g.t_hi);
+        if (t >= t_end) return;
+        const int64_t pe = ti.pad + g.edge;                // chunk sample r = tile sample t * 512 + i - pe
+        const int16_t *xc = x + ti.c * g.ld_in + ti.cs0;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(xc + ((int64_t)t * FS_T - pe));
+        // element of the tensor map where tile t starts: e_unit + 512 t (tiles are 32 rows apart)
+        const int64_t e_unit = ti.c * g.ld_out + ti.cs0 - pe - tma_e0;
+        // fast tiles: interior, the unit's windows realigned by this instantiation, tile starts a
+        // whole number of tensor-map rows from the map's base, no halo duty
+        int64_t lo = (pe + FS_T - 1) / FS_T, hi = (ti.L + pe) / FS_T;
+        if ((int)((a & 15) >> 1) != sh_launch || (e_unit & 15) != 0) hi = 0;
+        if (mk.peer_left || mk.peer_right) {
+            const int64_t l2 = (mk.halo_H - ti.cs0 + pe + FS_T - 1) / FS_T;
+            const int64_t h2 = (mk.shard_n - mk.halo_H - ti.cs0 + pe) / FS_T;
+            lo = lo > l2 ? lo : l2;
+            hi = hi < h2 ? hi : h2;
         }
-        __syncwarp();
-        fa_mbar_wait(bar, 0);
-        uint32_t W[12];
+        const int tf_lo = (int)(lo < 0 ? 0 : (lo > t_end ? t_end : lo));
+        const int tf_hi = (int)(hi < 0 ? 0 : (hi > t_end ? t_end : hi));
+        fast = t >= tf_lo && t < tf_hi;
+        if (lane == 0) {
+            TmUnit u;
+            u.xc = xc;
+            u.oc = out + ti.c * g.ld_out + ti.cs0;
+            u.mrow = MARK ? mk.mask + ti.c * mk.words_per_row : nullptr;
+            u.peer_l = mk.peer_left ? mk.peer_left + ti.c * mk.halo_H : nullptr;
+            u.peer_r = mk.peer_right ? mk.peer_right + ti.c * mk.halo_H : nullptr;
+            u.L = ti.L;
+            u.cs0 = ti.cs0;
+            u.pe = (int)pe;
+            u.pad = (int)ti.pad;
+            u.xa0 = a & ~(uintptr_t)15;
+            u.zf0 = Zf + (ti.g0 + t) * NS;
+            u.zb0 = Zb + (ti.g0 + t) * NS;
+            u.fl0 = const_cast<double *>(Zf) - 2 * g.total_tiles * NS + ti.g0 + t;
+            u.fl1 = u.fl0 + g.total_tiles * NS;
+            u.t0 = t;
+            u.t_end = t_end;
+            u.tf_lo = tf_lo;
+            u.tf_hi = tf_hi;
+            u.trow0 = (int32_t)((e_unit + (int64_t)t * FS_T) >> 4);
+            unit_all[warp] = u;
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if (fast) request(u.xa0, 0);
+        }
+    }
+    __syncwarp();
+    const volatile TmUnit *u = &unit_all[warp];
+    unsigned char *tile_s = tile_all[warp];
+    const int bsh = (sh_launch & 1) * 16;
+    // marks: a crossing needs a sample beyond the threshold; with the usual signs (falling: th < 0,
+    // rising: th > 0) that is an integer comparison of the HIGH words - only tiles holding such a
+    // sample pay for the exact float64 comparisons (mode 0: other signs, always exact)
+    int hth = 0, mode = 0;
+    if (MARK) {
+        const double th = __ldg(mk.thr + blockIdx.z);
+        hth = __double2hiint(th);
+        mode = (mk.falling && th < 0.0) ? 1 : ((!mk.falling && th > 0.0) ? 2 : 0);
+    }
+    const bool zlane = lane == 0 || lane == 31;
+    double zn[NS];
+    {
+        const double *zsrc = lane == 31 ? u->zb0 : u->zf0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) zn[i] = zlane ? __ldg(zsrc + i) : 0.0;
+    }
+    uint32_t phase = 0;                                    // bit b: parity of input barrier b
+    bool store_pending = false;                            // (lane 0) a tensor store may still read tile_s
+
+#pragma unroll 1
+    for (int k = 0; k < TM_TPW; ++k) {
+        const int b = k & 1;
+        const int t = u->t0 + k * FS_WPB;
+        const bool more = k + 1 < TM_TPW && t + FS_WPB < u->t_end;
+        const bool fast_next = more && t + FS_WPB >= u->tf_lo && t + FS_WPB < u->tf_hi;
+        if (fast_next && lane == 0) request(u->xa0 + (uintptr_t)(k + 1) * (FS_WPB * FS_T * 2), b ^ 1);
+        double zc[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) zc[i] = zn[i];
+        if (more && zlane) {
+            const double *zsrc = (lane == 31 ? u->zb0 : u->zf0) + (k + 1) * (FS_WPB * NS);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) zn[i] = __ldg(zsrc + i);
+        }
+        if (fast) {
+            fa_mbar_wait(bar0 + 8 * b, (phase >> b) & 1);
+            phase ^= 1u << b;
+        } else {
+            tm_fill_i16(&unit_all[warp], g.edge, t, reinterpret_cast<int16_t *>(in_all[warp][b]) + sh_launch,
+                        lane);
+        }
+        double v[FS_S];
         {
-            const uint4 *q = reinterpret_cast<const uint4 *>(slab + 32 * lane);
+            uint32_t W[12];
+            const uint4 *q = reinterpret_cast<const uint4 *>(in_all[warp][b] + 32 * lane);
             const uint4 c0 = q[0], c1 = q[1], c2 = q[2];
             W[0] = c0.x; W[1] = c0.y; W[2] = c0.z; W[3] = c0.w;
             W[4] = c1.x; W[5] = c1.y; W[6] = c1.z; W[7] = c1.w;
             W[8] = c2.x; W[9] = c2.y; W[10] = c2.z; W[11] = c2.w;
+            realign_convert<K0>(W, bsh, v);
         }
-        const int bsh = (sh & 1) * 16;
-        switch (sh >> 1) {
-        case 0: realign_convert<0>(W, bsh, v); break;
-        case 1: realign_convert<1>(W, bsh, v); break;
-        case 2: realign_convert<2>(W, bsh, v); break;
-        default: realign_convert<3>(W, bsh, v); break;
+        __syncwarp();                                      // buffer b may be refilled from now on
+
+        // forward from the true tile state, then backward over the forward output
+        double zt[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) zt[i] = (lane == 0) ? zc[i] : 0.0;
+        int zo;
+        asm volatile("mov.u32 %0, 0;" : "=r"(zo));         // (opaque: see section_pass)
+        cascade_pass<NB, FO, false>(P, v, zt, lane, zo);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) zt[i] = (lane == 31) ? zc[i] : 0.0;
+        cascade_pass<NB, FO, true>(P, v, zt, lane, zo);
+
+        if (MARK) {
+            // first / last output sample of the tile into the (dead) F / Bz arrays in front of Zf:
+            // the tile-end pairs are tested from two dense arrays (filt_boundary_mark_kernel)
+            if (zlane) *((lane == 31 ? u->fl1 : u->fl0) + k * FS_WPB) = lane == 0 ? v[0] : v[FS_S - 1];
+            bool maybe = true;
+            if (mode == 1) {
+                unsigned m = 0;
+#pragma unroll
+                for (int i = 0; i < FS_S; ++i) m = max(m, (unsigned)__double2hiint(v[i]));
+                maybe = m >= (unsigned)hth;
+            } else if (mode == 2) {
+                int m = (int)0x80000000;
+#pragma unroll
+                for (int i = 0; i < FS_S; ++i) m = max(m, __double2hiint(v[i]));
+                maybe = m >= hth;
+            }
+            if (__any_sync(SS_FULL, maybe)) {
+                const double th = __ldg(mk.thr + blockIdx.z);
+                const double nx = ss_shfl_down(v[0], 1);
+                uint32_t bits = 0;
+#pragma unroll
+                for (int i = 0; i < FS_S - 1; ++i)
+                    bits |= (uint32_t)ssi::crossing(v[i], v[i + 1], th, mk.falling) << i;
+                if (lane < 31) bits |= (uint32_t)ssi::crossing(v[FS_S - 1], nx, th, mk.falling) << (FS_S - 1);
+                if (bits) tm_emit_marks(&unit_all[warp], bits, t, lane);
+            }
         }
-        __syncwarp();                                       // the tile buffer is reused for the output
-    }
 
-    // forward from the true tile state, then backward over the forward output
-    double zt[NS];
+        // the lane's segment = row `lane` of the swizzled shared tile
+        if (lane == 0 && store_pending) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            store_pending = false;
+        }
+        __syncwarp();
+        double2 *row = reinterpret_cast<double2 *>(tile_s + 128 * lane);
 #pragma unroll
-    for (int i = 0; i < NS; ++i) zt[i] = (lane == 0) ? Zf[tile * NS + i] : 0.0;
-    cascade_pass<NB, FO, false>(P, v, zt, lane);
-#pragma unroll
-    for (int i = 0; i < NS; ++i) zt[i] = (lane == 31) ? Zb[tile * NS + i] : 0.0;
-    cascade_pass<NB, FO, true>(P, v, zt, lane);
-
-    if (MARK) mark_tile<NS>(g, ti, tile, r0, v, Zf, mk, lane);
-    if (!fast) {
-        store_tile(g, ti, r0, v, reinterpret_cast<double *>(slab), out, mk, lane);
-        return;
+        for (int j = 0; j < FS_S / 2; ++j) row[j ^ (lane & 7)] = make_double2(v[2 * j], v[2 * j + 1]);
+        if (fast) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"(u->trow0 + k * (32 * FS_WPB)),
+                               "r"(fa_smem_u32(tile_s))
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                store_pending = true;
+            }
+        } else {
+            __syncwarp();
+            tm_store_elements(&unit_all[warp], tile_s, t, mk.halo_H, mk.shard_n, lane);
+        }
+        if (!more) break;
+        fast = fast_next;
     }
-    double2 *row = reinterpret_cast<double2 *>(slab + 128 * lane);
-#pragma unroll
-    for (int j = 0; j < FS_S / 2; ++j) row[j ^ (lane & 7)] = make_double2(v[2 * j], v[2 * j + 1]);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) {
-        const int32_t r = (int32_t)((E - tma_e0) >> 4);
-        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                     ::"l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"(r), "r"(fa_smem_u32(slab))
-                     : "memory");
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        // the shared tile must outlive the copy engine's read of it
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
+    // the shared tile must outlive the copy engine's read of it
+    if (lane == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
 }
 
@@ -2594,6 +2735,19 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
     CUtensorMap tmap;
     bool tma = false;
     int tma_e0 = 0;
+    const dim3 tma_blocks((unsigned)ss_cdiv(nt_hi > t_lo ? nt_hi - t_lo : 1, FS_WPB * TM_TPW), (unsigned)j_count,
+                          (unsigned)g.n_contacts);
+    // the misalignment of the first unit of the launch decides the instantiation (units with
+    // another one - rows or chunks of odd length, the shorter last chunk - take the element path)
+    int sh_launch = 0;
+    {
+        const bool lastj = j_begin >= g.n_full;
+        const int64_t L0 = lastj ? g.len_last : g.chunksize, nt0 = lastj ? g.nt_last : g.nt_full;
+        const int64_t pe0 = nt0 * FS_T - (L0 + 2 * (int64_t)g.edge) + g.edge;
+        const uintptr_t a0 = reinterpret_cast<uintptr_t>(d_x) + 2 * (uintptr_t)(j_begin * g.chunksize) -
+                             2 * (uintptr_t)pe0;
+        sh_launch = (int)((a0 & 15) >> 1);
+    }
     if constexpr (NS <= 2) {
         const int mode = apply_tma_mode();
         tma = g.dtype == SS_I16 && mode && make_out_tensor_map(g, d_out, &tmap, &tma_e0);
@@ -2608,8 +2762,13 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
         mkp.shard_n = g.n_samples;
         if constexpr (NS <= 2) {
             if (tma) {
-                filt_apply_tma_kernel<NB, FO, true><<<tile_blocks, 32 * FS_WPB, 0, st>>>(
-                    reinterpret_cast<const int16_t *>(d_x), g, P, Zf, Zb, d_out, mkp, tmap, tma_e0);
+#define SS_TMA_CASE(K0_)                                                                               \
+    case K0_:                                                                                          \
+        filt_apply_tma_kernel<NB, FO, true, K0_><<<tma_blocks, 32 * FS_WPB, 0, st>>>(                  \
+            reinterpret_cast<const int16_t *>(d_x), g, P, Zf, Zb, d_out, mkp, tmap, tma_e0, sh_launch); \
+        break;
+                switch (sh_launch >> 1) { SS_TMA_CASE(0) SS_TMA_CASE(1) SS_TMA_CASE(2) SS_TMA_CASE(3) }
+#undef SS_TMA_CASE
                 SS_LAUNCH_CHECK("filt_apply_tma_kernel<mark>");
             }
         }
@@ -2627,8 +2786,13 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
                            g_peer_halo.H, g.n_samples};
         if constexpr (NS <= 2) {
             if (tma) {
-                filt_apply_tma_kernel<NB, FO, false><<<tile_blocks, 32 * FS_WPB, 0, st>>>(
-                    reinterpret_cast<const int16_t *>(d_x), g, P, Zf, Zb, d_out, none, tmap, tma_e0);
+#define SS_TMA_CASE(K0_)                                                                                \
+    case K0_:                                                                                           \
+        filt_apply_tma_kernel<NB, FO, false, K0_><<<tma_blocks, 32 * FS_WPB, 0, st>>>(                  \
+            reinterpret_cast<const int16_t *>(d_x), g, P, Zf, Zb, d_out, none, tmap, tma_e0, sh_launch); \
+        break;
+                switch (sh_launch >> 1) { SS_TMA_CASE(0) SS_TMA_CASE(1) SS_TMA_CASE(2) SS_TMA_CASE(3) }
+#undef SS_TMA_CASE
                 SS_LAUNCH_CHECK("filt_apply_tma_kernel");
             }
         }
