@@ -970,6 +970,7 @@ struct TmUnit {
     double *fl0, *fl1;           // first / last output sample slots of tile t0
     int t0, t_end, tf_lo, tf_hi; // first tile, end of the range, fast tiles [tf_lo, tf_hi)
     int32_t trow0;               // tensor-map row of tile t0
+    int hth, mode;               // crossing pre-test: high word of the threshold, which comparison
 };
 
 // Element path inside the TMA kernel (edge tiles, odd geometries, halo tiles; not inlined, so
@@ -1081,7 +1082,6 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
                      ::"r"(in0 + TM_IN_BYTES * b), "l"(a), "r"((uint32_t)TM_IN_BYTES), "r"(bar0 + 8 * b)
                      : "memory");
     };
-    bool fast;
     {
         const int t = (int)g.t_lo + (int)blockIdx.x * (FS_WPB * TM_TPW) + warp;
         const TileInfo ti = decode_unit<false>(g, blockIdx.z, g.j_begin + blockIdx.y);
@@ -1104,7 +1104,6 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
         }
         const int tf_lo = (int)(lo < 0 ? 0 : (lo > t_end ? t_end : lo));
         const int tf_hi = (int)(hi < 0 ? 0 : (hi > t_end ? t_end : hi));
-        fast = t >= tf_lo && t < tf_hi;
         if (lane == 0) {
             TmUnit u;
             u.xc = xc;
@@ -1126,26 +1125,27 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
             u.tf_lo = tf_lo;
             u.tf_hi = tf_hi;
             u.trow0 = (int32_t)((e_unit + (int64_t)t * FS_T) >> 4);
+            // marks: a crossing needs a sample beyond the threshold; with the usual signs (falling:
+            // th < 0, rising: th > 0) that is an integer comparison of the HIGH words - only tiles
+            // holding such a sample pay for the exact float64 comparisons (mode 0: always exact)
+            u.hth = 0;
+            u.mode = 0;
+            if (MARK) {
+                const double th = __ldg(mk.thr + blockIdx.z);
+                u.hth = __double2hiint(th);
+                u.mode = (mk.falling && th < 0.0) ? 1 : ((!mk.falling && th > 0.0) ? 2 : 0);
+            }
             unit_all[warp] = u;
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8));
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            if (fast) request(u.xa0, 0);
+            if (t >= tf_lo && t < tf_hi) request(u.xa0, 0);
         }
     }
     __syncwarp();
     const volatile TmUnit *u = &unit_all[warp];
     unsigned char *tile_s = tile_all[warp];
     const int bsh = (sh_launch & 1) * 16;
-    // marks: a crossing needs a sample beyond the threshold; with the usual signs (falling: th < 0,
-    // rising: th > 0) that is an integer comparison of the HIGH words - only tiles holding such a
-    // sample pay for the exact float64 comparisons (mode 0: other signs, always exact)
-    int hth = 0, mode = 0;
-    if (MARK) {
-        const double th = __ldg(mk.thr + blockIdx.z);
-        hth = __double2hiint(th);
-        mode = (mk.falling && th < 0.0) ? 1 : ((!mk.falling && th > 0.0) ? 2 : 0);
-    }
     const bool zlane = lane == 0 || lane == 31;
     double zn[NS];
     {
@@ -1153,16 +1153,19 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
 #pragma unroll
         for (int i = 0; i < NS; ++i) zn[i] = zlane ? __ldg(zsrc + i) : 0.0;
     }
-    uint32_t phase = 0;                                    // bit b: parity of input barrier b
-    bool store_pending = false;                            // (lane 0) a tensor store may still read tile_s
 
+    // Input barrier b = k & 1 completes one phase per tile that uses it, fast (the bulk copy's
+    // complete_tx) or not (a plain arrive after the element fill): its parity is (k >> 1) & 1.
 #pragma unroll 1
     for (int k = 0; k < TM_TPW; ++k) {
         const int b = k & 1;
         const int t = u->t0 + k * FS_WPB;
+        const bool fast = t >= u->tf_lo && t < u->tf_hi;
         const bool more = k + 1 < TM_TPW && t + FS_WPB < u->t_end;
-        const bool fast_next = more && t + FS_WPB >= u->tf_lo && t + FS_WPB < u->tf_hi;
-        if (fast_next && lane == 0) request(u->xa0 + (uintptr_t)(k + 1) * (FS_WPB * FS_T * 2), b ^ 1);
+        if (more && lane == 0) {
+            if (t + FS_WPB >= u->tf_lo && t + FS_WPB < u->tf_hi)
+                request(u->xa0 + (uintptr_t)(k + 1) * (FS_WPB * FS_T * 2), b ^ 1);
+        }
         double zc[NS];
 #pragma unroll
         for (int i = 0; i < NS; ++i) zc[i] = zn[i];
@@ -1171,13 +1174,12 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
 #pragma unroll
             for (int i = 0; i < NS; ++i) zn[i] = __ldg(zsrc + i);
         }
-        if (fast) {
-            fa_mbar_wait(bar0 + 8 * b, (phase >> b) & 1);
-            phase ^= 1u << b;
-        } else {
+        if (!fast) {
             tm_fill_i16(&unit_all[warp], g.edge, t, reinterpret_cast<int16_t *>(in_all[warp][b]) + sh_launch,
                         lane);
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * b) : "memory");
         }
+        fa_mbar_wait(bar0 + 8 * b, (k >> 1) & 1);
         double v[FS_S];
         {
             uint32_t W[12];
@@ -1205,6 +1207,7 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
             // first / last output sample of the tile into the (dead) F / Bz arrays in front of Zf:
             // the tile-end pairs are tested from two dense arrays (filt_boundary_mark_kernel)
             if (zlane) *((lane == 31 ? u->fl1 : u->fl0) + k * FS_WPB) = lane == 0 ? v[0] : v[FS_S - 1];
+            const int mode = u->mode, hth = u->hth;
             bool maybe = true;
             if (mode == 1) {
                 unsigned m = 0;
@@ -1229,11 +1232,9 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
             }
         }
 
-        // the lane's segment = row `lane` of the swizzled shared tile
-        if (lane == 0 && store_pending) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            store_pending = false;
-        }
+        // the lane's segment = row `lane` of the swizzled shared tile, once the previous tensor
+        // store has read it (no group pending: returns at once)
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
         double2 *row = reinterpret_cast<double2 *>(tile_s + 128 * lane);
 #pragma unroll
@@ -1242,22 +1243,29 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) {
+#ifdef TM_STORE_HINT
+                uint64_t pol;
+                asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+                             ::"l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"(u->trow0 + k * (32 * FS_WPB)),
+                               "r"(fa_smem_u32(tile_s)), "l"(pol)
+                             : "memory");
+#else
                 asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                              ::"l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"(u->trow0 + k * (32 * FS_WPB)),
                                "r"(fa_smem_u32(tile_s))
                              : "memory");
+#endif
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                store_pending = true;
             }
         } else {
             __syncwarp();
             tm_store_elements(&unit_all[warp], tile_s, t, mk.halo_H, mk.shard_n, lane);
         }
         if (!more) break;
-        fast = fast_next;
     }
     // the shared tile must outlive the copy engine's read of it
-    if (lane == 0 && store_pending) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
 }
 
