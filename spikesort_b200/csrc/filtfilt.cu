@@ -208,7 +208,9 @@ __device__ __forceinline__ void warp_scan(double (&e)[NS], const double (&Pm)[5]
 // zo: an index offset that is always 0.  The persistent TMA kernel passes an OPAQUE zero (asm
 // volatile) for the h / Pm tables: inside its tile loop the compiler otherwise hoists all of the
 // ~30 loop-invariant coefficient loads into registers and spills the samples instead
-template <bool SO, bool REV>
+// BF: branch-free lane scan (inactive lanes add P * 0 - the same value - instead of skipping
+// the update)
+template <bool SO, bool REV, bool BF = false>
 __device__ __forceinline__ void section_pass(const double (&c)[5], const double (&h)[FS_S][2],
                                              const double (&Pm)[5][2][2], double (&v)[FS_S],
                                              double z0, double z1, int lane, int zo = 0)
@@ -230,15 +232,20 @@ __device__ __forceinline__ void section_pass(const double (&c)[5], const double 
     for (int k = 0; k < 5; ++k) {
         const int d = 1 << k;
         const bool act = REV ? (lane + d < 32) : (lane >= d);
-        const double o0 = REV ? ss_shfl_down(z0, d) : ss_shfl_up(z0, d);
+        double o0 = REV ? ss_shfl_down(z0, d) : ss_shfl_up(z0, d);
         if (SO) {
-            const double o1 = REV ? ss_shfl_down(z1, d) : ss_shfl_up(z1, d);
-            if (act) {
+            double o1 = REV ? ss_shfl_down(z1, d) : ss_shfl_up(z1, d);
+            if (BF) {
+                o0 = act ? o0 : 0.0;
+                o1 = act ? o1 : 0.0;
+            }
+            if (BF || act) {
                 z0 = z0 + Pm[k + zo][0][0] * o0 + Pm[k + zo][0][1] * o1;
                 z1 = z1 + Pm[k + zo][1][0] * o0 + Pm[k + zo][1][1] * o1;
             }
-        } else if (act) {
-            z0 = z0 + Pm[k + zo][0][0] * o0;
+        } else {
+            if (BF) o0 = act ? o0 : 0.0;
+            if (BF || act) z0 = z0 + Pm[k + zo][0][0] * o0;
         }
     }
     // state at the start of the lane's segment (zero for the seeded lane: its local pass
@@ -261,14 +268,14 @@ __device__ __forceinline__ void section_pass(const double (&c)[5], const double 
 }
 
 // the whole cascade over the tile, one direction; zt = tile state of the seeded lane
-template <int NB, bool FO, bool REV>
+template <int NB, bool FO, bool REV, bool BF = false>
 __device__ __forceinline__ void cascade_pass(const FiltParams<NB, FO> &P, double (&v)[FS_S],
                                              const double (&zt)[FiltParams<NB, FO>::NS], int lane, int zo = 0)
 {
 #pragma unroll
     for (int s = 0; s < NB; ++s)
-        section_pass<true, REV>(P.sec[s], P.hrow[s], P.P[s], v, zt[2 * s], zt[2 * s + 1], lane, zo);
-    if (FO) section_pass<false, REV>(P.sec[NB], P.hrow[NB], P.P[NB], v, zt[2 * NB], 0.0, lane, zo);
+        section_pass<true, REV, BF>(P.sec[s], P.hrow[s], P.P[s], v, zt[2 * s], zt[2 * s + 1], lane, zo);
+    if (FO) section_pass<false, REV, BF>(P.sec[NB], P.hrow[NB], P.P[NB], v, zt[2 * NB], 0.0, lane, zo);
 }
 
 // interior tile: all FS_S loads of a lane are issued before the first use (the
@@ -915,6 +922,9 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
 #ifndef TM_MIN_CTAS
 #define TM_MIN_CTAS 8
 #endif
+#ifndef TM_BF
+#define TM_BF false                        // branch-free lane scan in the TMA kernel (A/B)
+#endif
 constexpr int TM_IN_BYTES = FS_T * 2 + 16;
 
 __device__ __forceinline__ uint32_t fa_smem_u32(const void *p)
@@ -1198,10 +1208,10 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
         for (int i = 0; i < NS; ++i) zt[i] = (lane == 0) ? zc[i] : 0.0;
         int zo;
         asm volatile("mov.u32 %0, 0;" : "=r"(zo));         // (opaque: see section_pass)
-        cascade_pass<NB, FO, false>(P, v, zt, lane, zo);
+        cascade_pass<NB, FO, false, TM_BF>(P, v, zt, lane, zo);
 #pragma unroll
         for (int i = 0; i < NS; ++i) zt[i] = (lane == 31) ? zc[i] : 0.0;
-        cascade_pass<NB, FO, true>(P, v, zt, lane, zo);
+        cascade_pass<NB, FO, true, TM_BF>(P, v, zt, lane, zo);
 
         if (MARK) {
             // first / last output sample of the tile into the (dead) F / Bz arrays in front of Zf:
