@@ -846,6 +846,70 @@ extern "C" int ss_pca_eig_top(const double *d_gram, const double *d_sum, const i
     return SS_OK;
 }
 
+// K8 for big float32 blocks in contact mode (fetPCA on (n_win, n_spk, n_c) blocks): the scalar
+// kernel above keeps 16 x 128 B per warp in flight and was latency-bound on 10^7 spikes (ncu:
+// long_scoreboard 12.8 per issue, 42-54 % of the HBM peak).  Here a thread owns FOUR consecutive
+// (spike, contact) elements: one 128-bit load per time row (512 B per warp and request, PV rows
+// in flight = 4 KB per warp), and its 4 x ncomps scores leave as 128-bit stores.  Same products
+// in the same order as the scalar kernel (bit-identical scores).  Needs n_spk * n_c % 4 == 0 (row
+// starts 16-byte aligned) and 16-byte aligned pointers; the launcher checks.
+#ifndef PJ_PV
+#define PJ_PV 4                            // time rows in flight per thread (A/B on B200, 10^7 spikes: 4 rows x 4 CTAs 0.79 ms, 6 x 3 0.80, 8 x 2 0.94, 12 x 2 0.98)
+#define PJ_CTAS 4                          // resident CTAs the kernel is compiled for
+#endif
+template <int NC>
+__global__ void __launch_bounds__(256, PJ_CTAS)
+pca_project_vec4_kernel(const float *__restrict__ waves, int n_win, int64_t total, int n_c,
+                        const double *__restrict__ evals, const double *__restrict__ evecs,
+                        double *__restrict__ scores)
+{
+    extern __shared__ double pj_v[];                      // [n_c][n_win][NC]
+    for (int e = threadIdx.x; e < n_c * n_win * NC; e += blockDim.x) {
+        const int g = e / (n_win * NC), rem = e - g * (n_win * NC), w = rem / NC, j = rem - w * NC;
+        pj_v[e] = __ldg(evecs + ((int64_t)g * n_win + w) * n_win + j) / sqrt(__ldg(evals + (int64_t)g * n_win + j));
+    }
+    __syncthreads();
+    const int64_t e0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (e0 >= total) return;
+    const double *V[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) V[e] = pj_v + (int)((e0 + e) % n_c) * n_win * NC;
+    double acc[4][NC];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int j = 0; j < NC; ++j) acc[e][j] = 0.0;
+    constexpr int PV = PJ_PV;
+    const float4 *src = reinterpret_cast<const float4 *>(waves + e0);
+    const int64_t step4 = total / 4;
+    for (int w0 = 0; w0 < n_win; w0 += PV) {
+        float4 raw[PV];
+#pragma unroll
+        for (int u = 0; u < PV; ++u)
+            raw[u] = w0 + u < n_win ? __ldg(src + (int64_t)(w0 + u) * step4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < PV; ++u) {
+            if (w0 + u < n_win) {
+                const double xv[4] = {(double)raw[u].x, (double)raw[u].y, (double)raw[u].z, (double)raw[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+#pragma unroll
+                    for (int j = 0; j < NC; ++j) acc[e][j] = fma(V[e][(w0 + u) * NC + j], xv[e], acc[e][j]);
+            }
+        }
+    }
+    double *o = scores + e0 * NC;
+    if (NC == 2) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) reinterpret_cast<double2 *>(o)[e] = make_double2(acc[e][0], acc[e][1]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int j = 0; j < NC; ++j) o[e * NC + j] = acc[e][j];
+    }
+}
+
 extern "C" int ss_pca_project(const void *d_waves, int dtype, int n_win, int64_t n_spk, int n_c,
                               const int64_t *d_offsets, int64_t n_groups, const double *d_evals,
                               const double *d_evecs, int ncomps, double *d_scores, void *stream)
@@ -858,6 +922,21 @@ extern "C" int ss_pca_project(const void *d_waves, int dtype, int n_win, int64_t
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int64_t total = n_spk * n_c;
     SS_REQUIRE(dtype >= SS_I16 && dtype <= SS_F64, SS_ERR_ARG, "pca_project: bad dtype %d", dtype);
+    // big float32 blocks in contact mode: four elements per thread, 128-bit loads and stores
+    if (dtype == SS_F32 && !d_offsets && ncomps <= 3 && n_c <= 8 && total >= (1 << 20) && total % 4 == 0 &&
+        (reinterpret_cast<uintptr_t>(d_waves) & 15) == 0 && (reinterpret_cast<uintptr_t>(d_scores) & 15) == 0) {
+        const unsigned vblocks = (unsigned)ss_cdiv(total / 4, 256);
+        const size_t vsmem = (size_t)n_c * n_win * ncomps * sizeof(double);
+        const float *wv = reinterpret_cast<const float *>(d_waves);
+        if (ncomps == 1)
+            pca_project_vec4_kernel<1><<<vblocks, 256, vsmem, st>>>(wv, n_win, total, n_c, d_evals, d_evecs, d_scores);
+        else if (ncomps == 2)
+            pca_project_vec4_kernel<2><<<vblocks, 256, vsmem, st>>>(wv, n_win, total, n_c, d_evals, d_evecs, d_scores);
+        else
+            pca_project_vec4_kernel<3><<<vblocks, 256, vsmem, st>>>(wv, n_win, total, n_c, d_evals, d_evecs, d_scores);
+        SS_LAUNCH_CHECK("pca_project_vec4_kernel");
+        return SS_OK;
+    }
     const unsigned blocks = (unsigned)ss_cdiv(total, 256);
     const size_t smem = (size_t)8 * n_win * ncomps * sizeof(double);
 #define SS_PROJECT(T_, NC_)                                                                        \

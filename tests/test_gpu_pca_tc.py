@@ -89,3 +89,27 @@ def test_tc_path_matches_oracle_fetpca(cuda, oracle, force_tc):
     err = rel_err(sign_normalise(got['data'], ref['data']), ref['data'])
     print("tc fetPCA vs oracle rel err %.3g" % err)
     assert err < 1e-5
+
+
+@pytest.mark.parametrize("n_win,n_spk,n_c,ncomps", [(25, 300000, 4, 2), (30, 1100000, 1, 3), (31, 524288, 2, 1),
+                                                    (25, 350001, 3, 2), (25, 262144, 4, 4)])
+def test_vectorised_projection_equals_scalar_kernel(cuda, n_win, n_spk, n_c, ncomps):
+    """Big float32 blocks in contact mode take pca_project_vec4_kernel (four elements per thread,
+    128-bit loads / stores); the same block widened to float64 takes the scalar kernel.  Same
+    products in the same order: the scores are bit-identical.  (350001 x 3 is odd: not a
+    multiple of four elements, scalar kernel both times; ncomps = 4: scalar kernel too.)"""
+    import torch
+    from spikesort_b200 import _ops, synth
+    w = synth.make_waveforms(n_win, n_spk, n_c, seed=5, device=cuda) + 1.5
+    g, s, ref, counts = _ops.pca_gram(w, mode="f64")
+    evals, evecs = _ops.pca_eig(g, s, counts, top=ncomps)
+    a = _ops.pca_project(w, evals, evecs, ncomps)
+    b = _ops.pca_project(w.double(), evals, evecs, ncomps)
+    assert a.shape == (n_spk, ncomps * n_c)
+    assert torch.equal(a, b)
+    # a view whose rows start 4 bytes off a 16-byte boundary: scalar kernel, same scores
+    if n_c == 4:
+        big = torch.empty(w.numel() + 1, dtype=torch.float32, device=cuda)
+        big[1:] = w.reshape(-1)
+        c = _ops.pca_project(big[1:].view(n_win, n_spk, n_c), evals, evecs, ncomps)
+        assert torch.equal(a, c)
