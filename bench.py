@@ -53,7 +53,7 @@ SEED = 2
 RATE_HZ = 10.0
 SM_COUNT = 148                      # B200
 WORKLOAD = "c2"
-TRAFFIC_SCAN_C2 = 7.135e9            # two-sweep scan (default): x read twice + float64 written once
+TRAFFIC_SCAN_C2 = 7.250e9            # two-sweep scan (default): x read twice + float64 written once
 TRAFFIC_SPAN_C2 = 6.18e9            # SS_FILT_SPAN=1: x read once
 FILTER_ARGS = (800., 100.)          # fltLinearIIR(800, 100): order-1 Butterworth high-pass
 CONFIG = {
@@ -516,7 +516,7 @@ def run_gpu(args):
     # PCA kernels run under the filter: the interval is longer than the kernels need and adds up
     # to more than the step), and - `roofline` proper - on one stream right after it, same
     # buffers, same launches, nothing else on the GPU: the number that can be compared with the
-    # serialised ncu launch list (profiles/r02_launches_c2.txt).
+    # serialised ncu launch list (profiles/r02_launches_c2_tma.txt).
     region_ms = filt_ms
     if ms_filter_alone:
         filt_ms = statistics.mean(ms_filter_alone)
@@ -531,7 +531,7 @@ def run_gpu(args):
                 "frac": achieved / peak,
                 "traffic": traffic,
                 "traffic_unit": "bytes per launch (ncu launch list, profiles/r02_launches_c2%s.csv)"
-                                % ("_span" if span else ""),
+                                % ("_span" if span else "_tma"),
                 "frac_moved": (traffic / (filt_ms / 1000.0) / 1e9 / peak) if traffic else None,
                 "kernel": ("ss_filtfilt_detect_sos + ss_detect_emit = filter (%s, crossing marks fused) + "
                            "auto threshold + count/scan/emit: the filter, threshold and detect stages "

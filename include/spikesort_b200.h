@@ -79,6 +79,14 @@ int         ss_max_pca_window(void);        /* largest n_win for the PCA kernels
  * has b2 = a2 = 0 and must come last).  The Python host derives the sections
  * from the reference's (b, a) coefficients (spikesort_b200/_design.py).
  * padlen is the reference's 3*max(len(a), len(b)).
+ *
+ * Which kernels run is a property of the call (filter, dtype, geometry), never of the data.
+ * Two environment switches exist for tests and A/B runs, read at every call:
+ *   SS_APPLY_TMA = 0   second sweep of orders 1-2 on int16 through the element kernel only
+ *                  1   (default) through the copy engine where the output has a tensor map
+ *                  2   as 1, but SS_ERR_UNSUPPORTED instead of falling back
+ *   SS_FILT_SPAN = 1   single-pass span kernel for filters that decay within one tile
+ * All of them produce the same values (the copy-engine and element sweeps bit for bit).
  */
 size_t ss_filtfilt_workspace_bytes(int64_t n_contacts, int64_t n_samples,
                                    int64_t chunksize, int padlen, int n_sections);

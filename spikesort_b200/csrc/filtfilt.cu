@@ -2769,6 +2769,40 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
     if constexpr (NS <= 2) {
         const int mode = apply_tma_mode();
         tma = g.dtype == SS_I16 && mode && make_out_tensor_map(g, d_out, &tmap, &tma_e0);
+        if (tma) {
+            // The copy-engine kernel pays off only where its tiles ARE fast: every unit of the
+            // launch must start its tiles a whole number of tensor-map rows from the map's base
+            // and share the launch's input misalignment (rows / chunks whose length is not a
+            // multiple of 16 samples break that: their tiles would all take the kernel's slow
+            // element path - configs[0], rows of 23 512 500 samples, ran 0.43 -> 0.71 ms).  A
+            // shorter last chunk with another alignment gets its own launch.
+            auto aligned = [&](int64_t jb, int64_t jc) {
+                for (int64_t j = jb; j < jb + jc; ++j) {
+                    const bool lj = j >= g.n_full;
+                    const int64_t Lj = lj ? g.len_last : g.chunksize, ntj = lj ? g.nt_last : g.nt_full;
+                    const int64_t pej = ntj * FS_T - (Lj + 2 * (int64_t)g.edge) + g.edge;
+                    for (int64_t c = 0; c < (g.n_contacts > 1 ? 2 : 1); ++c) {
+                        const int64_t e = c * g.ld_out + j * g.chunksize - pej - tma_e0;
+                        const uintptr_t a = reinterpret_cast<uintptr_t>(d_x) +
+                                            2 * (uintptr_t)(c * g.ld_in + j * g.chunksize - pej);
+                        if ((e & 15) != 0 || (int)((a & 15) >> 1) != sh_launch) return false;
+                    }
+                }
+                return true;
+            };
+            if (!aligned(j_begin, j_count)) {
+                if (has_full && has_last && aligned(j_begin, j_count - 1)) {
+                    // (the later chunk first: the boundary kernel behind the earlier ones tests the
+                    //  pair that straddles the two, whose second sample the last chunk writes)
+                    int rc2 = launch_filter<NB, FO>(d_x, g, j_begin + j_count - 1, 1, T, sos, d_out, d_ws, mk,
+                                                    PH_APPLY, st, t_lo, t_hi, span_warmup);
+                    if (rc2) return rc2;
+                    return launch_filter<NB, FO>(d_x, g, j_begin, j_count - 1, T, sos, d_out, d_ws, mk,
+                                                 PH_APPLY, st, t_lo, t_hi, span_warmup);
+                }
+                tma = false;
+            }
+        }
         SS_REQUIRE(tma || mode != 2 || g.dtype != SS_I16, SS_ERR_UNSUPPORTED,
                    "filtfilt: SS_APPLY_TMA=2 and no tensor map for this output (address / geometry)");
     }

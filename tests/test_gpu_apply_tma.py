@@ -53,6 +53,8 @@ GEOMETRIES = [
     (2, 9999, 5, 9999, 2, 1),          # odd chunk size: every other chunk off the 128-byte rows
     (1, 1000000, 2, 1000000, 0, 0),    # the bench geometry, several CTAs per unit
     (2, 600, 3, 600, 0, 0),            # chunks of two tiles: no interior tile at all
+    (3, 16000, 4, 6004, 0, 0),         # last chunk with another alignment: its own (element) launch
+    (4, 16000, 2, 7500, 0, 4),         # rows of 23 500 + 4 samples (configs[0]-like): element kernel
 ]
 
 
@@ -98,7 +100,8 @@ def test_tma_path_is_taken_and_required_mode_reports(env):
         ops.filtfilt_sos(x.to(torch.float32), sos, padlen, 16000)
 
 
-@pytest.mark.parametrize("cs,n", [(16000, 80000), (60000, 200000), (9999, 54995)])
+@pytest.mark.parametrize("cs,n", [(16000, 80000), (60000, 200000), (9999, 54995), (16000, 70004),
+                                  (16000, 72000)])
 def test_tma_fused_filter_detect(env, cs, n):
     """crossing marks fused into the TMA kernel: outputs, thresholds and spike lists as with
     the element kernel, auto and given thresholds, rising and falling."""
