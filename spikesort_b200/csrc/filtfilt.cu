@@ -330,7 +330,11 @@ __device__ __forceinline__ void load_tile(const void *x, const FiltGeom &g, cons
 constexpr int SM_WPB = 8;            // warps per block
 // tiles processed together (each weight read from shared memory feeds R FMAs); bounded
 // by the accumulator registers R*(2*NS+1)
-__host__ __device__ constexpr int sm_r(int ns) { return ns <= 2 ? 4 : (ns <= 6 ? 2 : 1); }
+#ifndef SM_R_LOW
+#define SM_R_LOW 4                   // tiles per group for orders 1-2 (A/B)
+#define SM_CTAS_LOW 2                // resident CTAs the order 1-2 kernel is compiled for
+#endif
+__host__ __device__ constexpr int sm_r(int ns) { return ns <= 2 ? SM_R_LOW : (ns <= 6 ? 2 : 1); }
 constexpr int SM_TPW = 32;           // tiles per warp (multiple of every sm_r): the weight table is
                                      // loaded once per CTA, i.e. per 256 tiles
 
@@ -470,7 +474,7 @@ __device__ __forceinline__ bool i16_pair_aligned(const void *x, int64_t index)
 }
 
 template <int NS>
-__global__ void __launch_bounds__(32 * SM_WPB, NS <= 2 ? 2 : 1)
+__global__ void __launch_bounds__(32 * SM_WPB, NS <= 2 ? SM_CTAS_LOW : 1)
 filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *__restrict__ tab,
                     double *__restrict__ F, double *__restrict__ Bz, double *__restrict__ ylast)
 {
