@@ -2731,8 +2731,11 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
         SS_CUDA_CHECK(cudaFuncSetAttribute(filt_summary_kernel<NS>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)tab_bytes));
-        if (NS >= 3 && g.dtype == SS_I16) {
-            constexpr int NSW = NS >= 3 ? NS : 3;               // (not instantiated below 3)
+#ifndef SM_WIDE_MIN_NS
+#define SM_WIDE_MIN_NS 3                 // lowest order that takes the tile-per-lane sweep 1 (A/B)
+#endif
+        if (NS >= SM_WIDE_MIN_NS && g.dtype == SS_I16) {
+            constexpr int NSW = NS >= SM_WIDE_MIN_NS ? NS : SM_WIDE_MIN_NS;   // (not instantiated below)
             // persistent grid; the item counter lives in the workspace's spare table region
             unsigned long long *d_next = reinterpret_cast<unsigned long long *>(yl + g.total_tiles);
             SS_CUDA_CHECK(cudaMemsetAsync(d_next, 0, sizeof(unsigned long long), st));
