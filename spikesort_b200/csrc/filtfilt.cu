@@ -1068,17 +1068,19 @@ __device__ __noinline__ void tm_emit_marks(const TmUnit *u, uint32_t bits, int t
     }
 }
 
-// tma_e0: the tensor map describes the output as rows of 16 float64 starting at element tma_e0
-// of `out`; sh_launch: the misalignment (in samples, 0..7) of a tile's first sample inside its
-// 16-byte window that this instantiation (K0 = sh_launch / 2) realigns - units with another one
-// take the element path.  grid (groups of FS_WPB * TM_TPW tiles, chunk, contact)
-template <int NB, bool FO, bool MARK, int K0>
+// tma_e0: the tensor map describes every contact's output row as rows of 16 float64 starting at
+// element tma_e0 of the row (dimension 2 of the map = contact).  The misalignment of a unit's tiles
+// inside their 16-byte input windows (0..7 samples; it depends on the contact and the chunk when
+// their lengths are not multiples of 8) selects one of four copies of the tile loop (K0 = word
+// part, compile-time register indices) and a uniform funnel-shift amount (halfword part).
+// grid (groups of FS_WPB * TM_TPW tiles, chunk, contact)
+template <int NB, bool FO, bool MARK>
 __global__ void __launch_bounds__(32 * FS_WPB, TM_MIN_CTAS)
 filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
                       const __grid_constant__ FiltParams<NB, FO> P,
                       const double *__restrict__ Zf, const double *__restrict__ Zb,
                       double *__restrict__ out, const MarkParams mk,
-                      const __grid_constant__ CUtensorMap tmap, const int tma_e0, const int sh_launch)
+                      const __grid_constant__ CUtensorMap tmap, const int tma_e0)
 {
     constexpr int NS = FiltParams<NB, FO>::NS;
     __shared__ __align__(1024) unsigned char tile_all[FS_WPB][FS_T * 8];
@@ -1096,6 +1098,7 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
                      ::"r"(in0 + TM_IN_BYTES * b), "l"(a), "r"((uint32_t)TM_IN_BYTES), "r"(bar0 + 8 * b)
                      : "memory");
     };
+    int sh;                                                // misalignment of the unit's tiles, samples
     {
         const int t = (int)g.t_lo + (int)blockIdx.x * (FS_WPB * TM_TPW) + warp;
         const TileInfo ti = decode_unit<false>(g, blockIdx.z, g.j_begin + blockIdx.y);
@@ -1104,12 +1107,14 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
         const int64_t pe = ti.pad + g.edge;                // chunk sample r = tile sample t * 512 + i - pe
         const int16_t *xc = x + ti.c * g.ld_in + ti.cs0;
         const uintptr_t a = reinterpret_cast<uintptr_t>(xc + ((int64_t)t * FS_T - pe));
-        // element of the tensor map where tile t starts: e_unit + 512 t (tiles are 32 rows apart)
-        const int64_t e_unit = ti.c * g.ld_out + ti.cs0 - pe - tma_e0;
+        sh = (int)((a & 15) >> 1);
+        // element of the contact's tensor-map rows where tile t starts: e_unit + 512 t (tiles are
+        // 32 rows apart)
+        const int64_t e_unit = ti.cs0 - pe - tma_e0;
         // fast tiles: interior, the unit's windows realigned by this instantiation, tile starts a
         // whole number of tensor-map rows from the map's base, no halo duty
         int64_t lo = (pe + FS_T - 1) / FS_T, hi = (ti.L + pe) / FS_T;
-        if ((int)((a & 15) >> 1) != sh_launch || (e_unit & 15) != 0) hi = 0;
+        if ((e_unit & 15) != 0) hi = 0;
         if (mk.peer_left || mk.peer_right) {
             const int64_t l2 = (mk.halo_H - ti.cs0 + pe + FS_T - 1) / FS_T;
             const int64_t h2 = (mk.shard_n - mk.halo_H - ti.cs0 + pe) / FS_T;
@@ -1157,9 +1162,11 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
         }
     }
     __syncwarp();
+    auto walk = [&](auto k0_c) {
+    constexpr int K0 = decltype(k0_c)::value;
     const volatile TmUnit *u = &unit_all[warp];
     unsigned char *tile_s = tile_all[warp];
-    const int bsh = (sh_launch & 1) * 16;
+    const int bsh = (sh & 1) * 16;
     const bool zlane = lane == 0 || lane == 31;
     double zn[NS];
     {
@@ -1189,8 +1196,7 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
             for (int i = 0; i < NS; ++i) zn[i] = __ldg(zsrc + i);
         }
         if (!fast) {
-            tm_fill_i16(&unit_all[warp], g.edge, t, reinterpret_cast<int16_t *>(in_all[warp][b]) + sh_launch,
-                        lane);
+            tm_fill_i16(&unit_all[warp], g.edge, t, reinterpret_cast<int16_t *>(in_all[warp][b]) + sh, lane);
             if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * b) : "memory");
         }
         fa_mbar_wait(bar0 + 8 * b, (k >> 1) & 1);
@@ -1260,14 +1266,14 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
 #ifdef TM_STORE_HINT
                 uint64_t pol;
                 asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2, %3}], [%4], %5;"
                              ::"l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"(u->trow0 + k * (32 * FS_WPB)),
-                               "r"(fa_smem_u32(tile_s)), "l"(pol)
+                               "r"((int)blockIdx.z), "r"(fa_smem_u32(tile_s)), "l"(pol)
                              : "memory");
 #else
-                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
                              ::"l"(reinterpret_cast<uint64_t>(&tmap)), "r"(0), "r"(u->trow0 + k * (32 * FS_WPB)),
-                               "r"(fa_smem_u32(tile_s))
+                               "r"((int)blockIdx.z), "r"(fa_smem_u32(tile_s))
                              : "memory");
 #endif
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -1281,6 +1287,13 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
     // the shared tile must outlive the copy engine's read of it
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
+    };
+    switch (sh >> 1) {
+    case 0: walk(std::integral_constant<int, 0>{}); break;
+    case 1: walk(std::integral_constant<int, 1>{}); break;
+    case 2: walk(std::integral_constant<int, 2>{}); break;
+    default: walk(std::integral_constant<int, 3>{}); break;
+    }
 }
 
 // ---------------------------------------------------------------- single-pass span kernel
@@ -2586,16 +2599,18 @@ static bool make_out_tensor_map(const FiltGeom &g, double *d_out, CUtensorMap *t
     const int64_t L = full ? g.chunksize : g.len_last, nt = full ? g.nt_full : g.nt_last;
     const int64_t pe = nt * FS_T - (L + 2 * (int64_t)g.edge) + g.edge;     // left padding + edge
     const int e0 = (int)(((-pe) % 16 + 16) % 16);
-    const int64_t total = (g.n_contacts - 1) * g.ld_out + g.n_samples;
-    const int64_t rows = (total - e0) / 16;
+    // rows of 16 float64 per CONTACT (dimension 2 = contact, stride ld_out): the row length of
+    // the recording need not be a multiple of 16 samples, only even (16-byte strides)
+    const int64_t rows = (g.n_samples - e0) / 16;
     if (rows < 32 || rows >= (int64_t)1 << 31) return false;
     if ((reinterpret_cast<uintptr_t>(d_out + e0) & 15) != 0) return false;
-    const cuuint64_t dims[2] = {16, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {16, 32};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, d_out + e0, dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+    if (g.n_contacts > 1 && (g.ld_out & 1)) return false;
+    const cuuint64_t dims[3] = {16, (cuuint64_t)rows, (cuuint64_t)g.n_contacts};
+    const cuuint64_t strides[2] = {128, g.n_contacts > 1 ? (cuuint64_t)g.ld_out * 8 : (cuuint64_t)rows * 128};
+    const cuuint32_t box[3] = {16, 32, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, d_out + e0, dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     *tma_e0 = e0;
@@ -2762,38 +2777,26 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
     int tma_e0 = 0;
     const dim3 tma_blocks((unsigned)ss_cdiv(nt_hi > t_lo ? nt_hi - t_lo : 1, FS_WPB * TM_TPW), (unsigned)j_count,
                           (unsigned)g.n_contacts);
-    // the misalignment of the first unit of the launch decides the instantiation (units with
-    // another one - rows or chunks of odd length, the shorter last chunk - take the element path)
-    int sh_launch = 0;
-    {
-        const bool lastj = j_begin >= g.n_full;
-        const int64_t L0 = lastj ? g.len_last : g.chunksize, nt0 = lastj ? g.nt_last : g.nt_full;
-        const int64_t pe0 = nt0 * FS_T - (L0 + 2 * (int64_t)g.edge) + g.edge;
-        const uintptr_t a0 = reinterpret_cast<uintptr_t>(d_x) + 2 * (uintptr_t)(j_begin * g.chunksize) -
-                             2 * (uintptr_t)pe0;
-        sh_launch = (int)((a0 & 15) >> 1);
-    }
     if constexpr (NS <= 2) {
         const int mode = apply_tma_mode();
         tma = g.dtype == SS_I16 && mode && make_out_tensor_map(g, d_out, &tmap, &tma_e0);
+        // (mode 2 reports an output that cannot have a map at all; a chunk range whose tiles do
+        //  not start on the map's rows still falls back to the element kernel)
+        SS_REQUIRE(tma || mode != 2 || g.dtype != SS_I16, SS_ERR_UNSUPPORTED,
+                   "filtfilt: SS_APPLY_TMA=2 and no tensor map for this output (address / geometry)");
         if (tma) {
-            // The copy-engine kernel pays off only where its tiles ARE fast: every unit of the
-            // launch must start its tiles a whole number of tensor-map rows from the map's base
-            // and share the launch's input misalignment (rows / chunks whose length is not a
-            // multiple of 16 samples break that: their tiles would all take the kernel's slow
-            // element path - configs[0], rows of 23 512 500 samples, ran 0.43 -> 0.71 ms).  A
+            // The copy-engine kernel pays off only where its tiles ARE fast: every chunk of the
+            // launch must start its tiles a whole number of tensor-map rows from the start of the
+            // contact's row (chunk sizes that are not a multiple of 16 samples break that: their
+            // tiles would all take the kernel's slow element path).  Rows of any even length and
+            // any input alignment are fine (per-contact map rows, per-unit realignment).  A
             // shorter last chunk with another alignment gets its own launch.
             auto aligned = [&](int64_t jb, int64_t jc) {
                 for (int64_t j = jb; j < jb + jc; ++j) {
                     const bool lj = j >= g.n_full;
                     const int64_t Lj = lj ? g.len_last : g.chunksize, ntj = lj ? g.nt_last : g.nt_full;
                     const int64_t pej = ntj * FS_T - (Lj + 2 * (int64_t)g.edge) + g.edge;
-                    for (int64_t c = 0; c < (g.n_contacts > 1 ? 2 : 1); ++c) {
-                        const int64_t e = c * g.ld_out + j * g.chunksize - pej - tma_e0;
-                        const uintptr_t a = reinterpret_cast<uintptr_t>(d_x) +
-                                            2 * (uintptr_t)(c * g.ld_in + j * g.chunksize - pej);
-                        if ((e & 15) != 0 || (int)((a & 15) >> 1) != sh_launch) return false;
-                    }
+                    if (((j * g.chunksize - pej - tma_e0) & 15) != 0) return false;
                 }
                 return true;
             };
@@ -2810,8 +2813,6 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
                 tma = false;
             }
         }
-        SS_REQUIRE(tma || mode != 2 || g.dtype != SS_I16, SS_ERR_UNSUPPORTED,
-                   "filtfilt: SS_APPLY_TMA=2 and no tensor map for this output (address / geometry)");
     }
     if (mk) {
         MarkParams mkp = *mk;
@@ -2821,13 +2822,8 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
         mkp.shard_n = g.n_samples;
         if constexpr (NS <= 2) {
             if (tma) {
-#define SS_TMA_CASE(K0_)                                                                               \
-    case K0_:                                                                                          \
-        filt_apply_tma_kernel<NB, FO, true, K0_><<<tma_blocks, 32 * FS_WPB, 0, st>>>(                  \
-            reinterpret_cast<const int16_t *>(d_x), g, P, Zf, Zb, d_out, mkp, tmap, tma_e0, sh_launch); \
-        break;
-                switch (sh_launch >> 1) { SS_TMA_CASE(0) SS_TMA_CASE(1) SS_TMA_CASE(2) SS_TMA_CASE(3) }
-#undef SS_TMA_CASE
+                filt_apply_tma_kernel<NB, FO, true><<<tma_blocks, 32 * FS_WPB, 0, st>>>(
+                    reinterpret_cast<const int16_t *>(d_x), g, P, Zf, Zb, d_out, mkp, tmap, tma_e0);
                 SS_LAUNCH_CHECK("filt_apply_tma_kernel<mark>");
             }
         }
@@ -2845,13 +2841,8 @@ static int launch_filter(const void *d_x, FiltGeom g, int64_t j_begin, int64_t j
                            g_peer_halo.H, g.n_samples};
         if constexpr (NS <= 2) {
             if (tma) {
-#define SS_TMA_CASE(K0_)                                                                                \
-    case K0_:                                                                                           \
-        filt_apply_tma_kernel<NB, FO, false, K0_><<<tma_blocks, 32 * FS_WPB, 0, st>>>(                  \
-            reinterpret_cast<const int16_t *>(d_x), g, P, Zf, Zb, d_out, none, tmap, tma_e0, sh_launch); \
-        break;
-                switch (sh_launch >> 1) { SS_TMA_CASE(0) SS_TMA_CASE(1) SS_TMA_CASE(2) SS_TMA_CASE(3) }
-#undef SS_TMA_CASE
+                filt_apply_tma_kernel<NB, FO, false><<<tma_blocks, 32 * FS_WPB, 0, st>>>(
+                    reinterpret_cast<const int16_t *>(d_x), g, P, Zf, Zb, d_out, none, tmap, tma_e0);
                 SS_LAUNCH_CHECK("filt_apply_tma_kernel");
             }
         }

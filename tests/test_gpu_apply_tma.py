@@ -54,7 +54,9 @@ GEOMETRIES = [
     (1, 1000000, 2, 1000000, 0, 0),    # the bench geometry, several CTAs per unit
     (2, 600, 3, 600, 0, 0),            # chunks of two tiles: no interior tile at all
     (3, 16000, 4, 6004, 0, 0),         # last chunk with another alignment: its own (element) launch
-    (4, 16000, 2, 7500, 0, 4),         # rows of 23 500 + 4 samples (configs[0]-like): element kernel
+    (4, 16000, 2, 7500, 0, 4),         # rows of 23 500 + 4 samples (configs[0]-like): per-contact map rows
+    (5, 16000, 3, 16000, 3, 5),        # rows of odd length in the PARENT (input misalignment differs per contact)
+    (3, 16000, 3, 8002, 1, 0),         # output rows of even, non-multiple-of-16 length
 ]
 
 
@@ -98,6 +100,11 @@ def test_tma_path_is_taken_and_required_mode_reports(env):
             ops.filtfilt_sos(x[:, :3 * 15999], sos, padlen, 15999)
         # float input never takes it and is not an error
         ops.filtfilt_sos(x.to(torch.float32), sos, padlen, 16000)
+        # rows of any even length and any input alignment have a map (per-contact rows of the
+        # tensor map, per-unit realignment): 4 contacts x 40 004 samples, views 1..3 samples in
+        parent = torch.zeros((4, 40004 + 8), dtype=torch.int16, device=env['dev'])
+        for off in (0, 1, 2, 3):
+            ops.filtfilt_sos(parent[:, off:off + 40004], sos, padlen, 16000)
 
 
 @pytest.mark.parametrize("cs,n", [(16000, 80000), (60000, 200000), (9999, 54995), (16000, 70004),
