@@ -26,6 +26,12 @@ def _rows_on_device(spike_data, rows):
     return _lib.to_device_2d(sub), {r: i for i, r in enumerate(rows)}
 
 
+def _to_host(ten):
+    """Big blocks through a pooled pinned buffer (pipeline.to_host), small ones plainly."""
+    from .pipeline import to_host
+    return to_host(ten)
+
+
 def _n_pts(spike_data):
     sp_data = spike_data['data']
     try:
@@ -94,9 +100,9 @@ def extract_spikes(spike_data, spt_dict, sp_win, resample=1, contacts='all'):
              "resample_spikes", DeprecationWarning)
         # extract.py:183 returns resample_spikes' fresh dict: no 'is_valid'
         plan = _spline.spline_plan(time, FS * resample)
-        return {"data": _ops.resample(waves, plan).cpu().numpy(), "time": plan.new_time.copy(),
+        return {"data": _to_host(_ops.resample(waves, plan)), "time": plan.new_time.copy(),
                 "FS": FS}
-    wavedict = {"data": waves.cpu().numpy(), "time": time, "FS": FS}
+    wavedict = {"data": _to_host(waves), "time": time, "FS": FS}
     if int(n_invalid.item()) != 0:
         wavedict['is_valid'] = valid.cpu().numpy().astype(bool)
     return wavedict
@@ -112,7 +118,7 @@ def resample_spikes(spikes_dict, FS_new):
     time = np.asarray(spikes_dict['time'], dtype=np.float64)
     plan = _spline.spline_plan(time, FS_new)
     waves = t.as_tensor(np.ascontiguousarray(sp_waves)).to(_lib.device())
-    return {"data": _ops.resample(waves, plan).cpu().numpy(), "time": plan.new_time.copy(),
+    return {"data": _to_host(_ops.resample(waves, plan)), "time": plan.new_time.copy(),
             "FS": spikes_dict['FS']}
 
 

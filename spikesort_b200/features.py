@@ -107,7 +107,8 @@ def fetPCA(spikes_data, ncomps=2, contacts='all'):
     contact; columns ``Ch{i}:PC{j}``, contact-major.  A 2-D block counts as one contact."""
     dev = _device_block(_select_contacts(spikes_data["data"], contacts))
     _, _, score = _principal_axes(dev, ncomps, leading_only=True)
-    return {'data': score.cpu().numpy(),
+    from .pipeline import to_host
+    return {'data': to_host(score),
             'names': _named("Ch%d:PC%d", dev.shape[2], range(ncomps))}
 
 
