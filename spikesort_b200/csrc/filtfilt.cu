@@ -924,8 +924,9 @@ filt_apply_kernel(const void *__restrict__ x, const FiltGeom g,
 #define TM_TPW 8                           // tiles per warp
 #endif
 #ifndef TM_MIN_CTAS
-#define TM_MIN_CTAS 8
-#endif
+#define TM_MIN_CTAS 6                      // resident CTAs the kernel is compiled for (A/B on B200 with the
+#endif                                     // four-copy loop: 6 (80 registers) 1.664-1.674 ms/step, 7 1.653-1.686,
+                                           // 8 1.690-1.707, 9 1.80-1.83, 10 1.96-2.02)
 #ifndef TM_BF
 #define TM_BF false                        // branch-free lane scan in the TMA kernel (A/B)
 #endif
