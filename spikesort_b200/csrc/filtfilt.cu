@@ -344,7 +344,9 @@ template <typename T, int NS>
 __device__ __forceinline__ void summary_group_fast(const T *__restrict__ p, int lane,
                                                    const double *tab_s, double (&acc)[sm_r(NS)][2 * NS + 1])
 {
-    constexpr int NQ = 2 * NS + 1;
+    // (interior tiles only: the last-output functional, row 2 NS of the table, is read by the
+    //  tile scan for a unit's LAST tile alone, which is never interior - see filt_summary_kernel)
+    constexpr int NQ = 2 * NS;
     constexpr int SM_R = sm_r(NS);
     T raw[SM_R][FS_S];
 #pragma unroll
@@ -385,7 +387,7 @@ __device__ __forceinline__ void summary_compute_i16x2(const unsigned (&raw)[sm_r
                                                       const double *tab_s,
                                                       double (&acc)[sm_r(NS)][2 * NS + 1])
 {
-    constexpr int NQ = 2 * NS + 1;
+    constexpr int NQ = 2 * NS;                              // F and Bz only (interior tiles)
     constexpr int SM_R = sm_r(NS);
 #pragma unroll
     for (int k = 0; k < FS_S / 2; ++k) {
@@ -463,7 +465,9 @@ __device__ __forceinline__ bool summary_group_interior(const FiltGeom &g, const 
 {
     constexpr int SM_R = sm_r(NS);
     r0 = t0 * FS_T - ti.pad - g.edge;
-    return t0 + SM_R <= ti.nt && r0 >= 0 && r0 + SM_R * FS_T <= ti.L;
+    // (never the unit's last tile: its last-output functional is the one the tile scan reads,
+    //  and only the element path computes it - with padlen 0 that tile would otherwise qualify)
+    return t0 + SM_R < ti.nt && r0 >= 0 && r0 + SM_R * FS_T <= ti.L;
 }
 
 // 32-bit loads of int16 pairs need a 4-byte aligned ADDRESS (the recording may be a view
@@ -490,6 +494,13 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *
     bool red_owner;
     const int red_id = multi_reduce_id<SM_R * NQ>(lane, red_owner);
     const int red_r = red_id / NQ, red_q = red_id - red_r * NQ;
+    // Interior groups leave the last-output functional (table row 2 NS, `ylast`) out: the tile
+    // scan reads it for the LAST tile of a unit only, and that tile - it holds the right odd
+    // extension - always takes the element path below.  A third of the dot products of order 1.
+    constexpr int NQF = 2 * NS;
+    bool red_owner_f;
+    const int red_id_f = multi_reduce_id<SM_R * NQF>(lane, red_owner_f);
+    const int red_r_f = red_id_f / NQF, red_q_f = red_id_f - red_r_f * NQF;
     // int16 groups are software-pipelined: the 32-bit loads of group it+1 are issued before
     // the dot products of group it, so every warp always has one group (128 B per lane) in
     // flight (ncu r01_c: the unpipelined loop sat at 32 % of DRAM peak on long_scoreboard)
@@ -514,6 +525,7 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *
             for (int q = 0; q < NQ; ++q) acc[r][q] = 0.0;
         int64_t r0;
         const bool interior = summary_group_interior<NS>(g, ti, t0, r0);
+        const bool group_fast = nxt_ok || interior;            // F / Bz only (see above)
         if (nxt_ok) {
             unsigned raw[SM_R][FS_S / 2];
 #pragma unroll
@@ -561,17 +573,31 @@ filt_summary_kernel(const void *__restrict__ x, const FiltGeom g, const double *
                 }
             }
         }
-        double flat[SM_R * NQ];
+        if (group_fast) {
+            double flat[SM_R * NQF];
 #pragma unroll
-        for (int r = 0; r < SM_R; ++r)
+            for (int r = 0; r < SM_R; ++r)
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) flat[r * NQ + q] = acc[r][q];
-        multi_reduce<SM_R * NQ>(flat, lane);
-        if (red_owner && red_r < nr) {
-            const int64_t tile = ti.g0 + t0 + red_r;
-            if (red_q < NS) F[tile * NS + red_q] = flat[0];
-            else if (red_q < 2 * NS) Bz[tile * NS + red_q - NS] = flat[0];
-            else ylast[tile] = flat[0];
+                for (int q = 0; q < NQF; ++q) flat[r * NQF + q] = acc[r][q];
+            multi_reduce<SM_R * NQF>(flat, lane);
+            if (red_owner_f && red_r_f < nr) {
+                const int64_t tile = ti.g0 + t0 + red_r_f;
+                if (red_q_f < NS) F[tile * NS + red_q_f] = flat[0];
+                else Bz[tile * NS + red_q_f - NS] = flat[0];
+            }
+        } else {
+            double flat[SM_R * NQ];
+#pragma unroll
+            for (int r = 0; r < SM_R; ++r)
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) flat[r * NQ + q] = acc[r][q];
+            multi_reduce<SM_R * NQ>(flat, lane);
+            if (red_owner && red_r < nr) {
+                const int64_t tile = ti.g0 + t0 + red_r;
+                if (red_q < NS) F[tile * NS + red_q] = flat[0];
+                else if (red_q < 2 * NS) Bz[tile * NS + red_q - NS] = flat[0];
+                else ylast[tile] = flat[0];
+            }
         }
     }
 }

@@ -130,3 +130,22 @@ def test_tma_fused_filter_detect(env, cs, n):
             for t0, t1 in zip(a_, b_):
                 assert torch.equal(t0, t1)
         assert res[1][2].numel() > n // 10
+
+
+@pytest.mark.parametrize("dtype", ["int16", "float32"])
+def test_no_padding_last_tile_is_a_whole_tile(env, dtype):
+    """padlen = 0 and chunks of a whole number of tiles: the unit's LAST tile holds no extension at
+    all, yet its last-output functional is the one the backward pass starts from - sweep 1 leaves
+    that functional out for interior tiles, so this tile must not count as one."""
+    from spikesort_b200._design import tf2sos_exact
+    torch, ops = env['torch'], env['ops']
+    b, a = DESIGNS['hp1']()
+    sos, _ = tf2sos_exact(b, a)
+    rng = np.random.default_rng(3)
+    for n, cs in [(4096, 2048), (8192, 8192), (3 * 4096 + 1024, 4096)]:
+        x = np.round(rng.standard_normal((2, n)) * 300 + 50)
+        x = x.astype(np.int16) if dtype == "int16" else x.astype(np.float32)
+        got = ops.filtfilt_sos(torch.from_numpy(x).to(env['dev']), sos, 0, cs).cpu().numpy()
+        ref = np.stack([np.concatenate([signal.filtfilt(b, a, x[c, lo:lo + cs].astype(np.float64), padlen=0)
+                                        for lo in range(0, n, cs)]) for c in range(2)])
+        assert rel_err(got, ref) < 1e-12, (n, cs)

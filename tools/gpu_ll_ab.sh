@@ -7,5 +7,5 @@ for lib in default spikesort_b200/build/lib_v*.so; do
   name=$(basename $lib .so)
   W=c2 SKIP=${SKIP:-78} COUNT=${COUNT:-52} bash tools/gpu_launchlist.sh > /dev/null
   cp gpurun_out/launches_c2.csv gpurun_out/launches_$name.csv
-  echo "== $name"; python tools/ncu_summary.py launches gpurun_out/launches_$name.csv | grep -i "filt_\|kernel time" | head -12
+  echo "== $name"; python tools/launch_table.py gpurun_out/launches_$name.csv | grep -i "filt_\|kernel time" | cut -c1-112
 done
