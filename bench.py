@@ -53,7 +53,7 @@ SEED = 2
 RATE_HZ = 10.0
 SM_COUNT = 148                      # B200
 WORKLOAD = "c2"
-TRAFFIC_SCAN_C2 = 7.250e9            # two-sweep scan (default): x read twice + float64 written once
+TRAFFIC_SCAN_C2 = 7.154e9            # two-sweep scan (default): x read twice + float64 written once
 TRAFFIC_SPAN_C2 = 6.18e9            # SS_FILT_SPAN=1: x read once
 FILTER_ARGS = (800., 100.)          # fltLinearIIR(800, 100): order-1 Butterworth high-pass
 CONFIG = {
