@@ -26,6 +26,10 @@ def launches(path):
     lines = [l for l in open(path) if not l.startswith('==')]
     agg = collections.OrderedDict()
     for row in csv.DictReader(lines):
+        # launch lists taken with several metrics (duration + DRAM bytes) have one row per metric
+        # and launch: only the durations belong in this table (tools/launch_table.py prints all)
+        if row.get('Metric Name', 'gpu__time_duration.sum') != 'gpu__time_duration.sum':
+            continue
         name = row['Kernel Name'].split('(')[0].replace('void ', '').replace('<unnamed>::', '')
         agg.setdefault(name, []).append(float(row['Metric Value'].replace(',', '')))
     tot = sum(sum(v) for v in agg.values())
