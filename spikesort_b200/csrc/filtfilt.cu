@@ -1758,6 +1758,7 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
     // clipping: straight-line code without the joins that cost ~100 register moves per tile),
     // and the general one.  The choice is CTA-uniform, both run the same two barriers.
     const int64_t r_first = (int64_t)own_lo * FS_T - ti.pad - g.edge;
+    (void)r_first;                                                 // (general owners only)
     const bool fast = span_fast(span);
     auto owners = [&](auto fast_c) {
     constexpr bool FAST = decltype(fast_c)::value;
@@ -1803,6 +1804,7 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
     double en[NS];
     {
         double p0 = 0.0, p1 = 0.0;
+        (void)p0; (void)p1;                                        // (single-section filters only)
         if constexpr (SINGLE) {
             double e1 = 0.0;
             span_section<SO1, false>(P.sec[0], SP.al[0], P.P[0], v, zt[0], SO1 ? zt[NS - 1] : 0.0, lane,
@@ -1830,6 +1832,7 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
         __syncthreads();
         // start state = zero-start end state of the tile before (helper F for the first warp)
         const bool have = FAST || owned;
+        (void)have;
         const int src = warp > 0 ? warp - 1 : SP_HELP_F;
         double z[NS];
 #pragma unroll
@@ -1885,6 +1888,7 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
             for (int i = 0; i < NS; ++i) zt[i] = lane == 31 ? SP.zi[i] * yl : 0.0;
         }
         double p0 = 0.0, p1 = 0.0;
+        (void)p0; (void)p1;
         if constexpr (SINGLE) {
             double e1 = 0.0;
             span_section<SO1, true>(P.sec[0], SP.al[0], P.P[0], v, zt[0], SO1 ? zt[NS - 1] : 0.0, lane,
@@ -1914,6 +1918,7 @@ filt_span_kernel(const void *__restrict__ x, const FiltGeom g,
         // start state = zero-start end state of the tile behind (helper B for the last warp; it
         // wrote zeros when the span ends with the unit, whose last tile was seeded above)
         const bool have = true;
+        (void)have;
         const int src = warp + 1 < n_own ? warp + 1 : SP_HELP_B;
         double z[NS];
 #pragma unroll
