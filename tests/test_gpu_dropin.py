@@ -379,3 +379,23 @@ def test_chain_with_resampled_alignment(ss, golden):
         wv = ss.extract.extract_spikes(f10, spa, [-0.2, 0.8], contacts=c)
         assert np.array_equal(outs[0]['sp_waves'][c]['data'], wv['data'])
         assert np.array_equal(outs[1]['sp_waves'][c]['data'], wv['data'])
+
+
+def test_sort_frontend_pageable_numpy_recording(cuda, monkeypatch):
+    """A big pageable NumPy recording goes through the slab feeder's pinned double buffer
+    (threaded copies one slab ahead of the DMA); the result is the one of the plain path."""
+    import spikesort_b200 as ss
+    from spikesort_b200 import filters, synth
+    FS, C, N = 30000, 8, 4200000                              # 67 MB of int16: above the 64 MB bar
+    arr = synth.make_recording(C, N, FS, seed=21, device=cuda, rate_hz=15.0, noise=10.0).cpu().numpy().copy()
+    kw = dict(filt=filters.Filter(800., 100.), sp_win=[-0.2, 0.8], edge='falling', align_type='min',
+              thresh='auto', ncomps=2, chunksize=1000000)
+    monkeypatch.setenv("SS_PAGEABLE_STAGING", "0")
+    plain = ss.sort_frontend({'data': arr, 'FS': FS, 'n_contacts': C}, **kw)
+    monkeypatch.setenv("SS_PAGEABLE_STAGING", "1")
+    monkeypatch.setenv("SS_STAGING_THREADS", "3")
+    staged = ss.sort_frontend({'data': arr, 'FS': FS, 'n_contacts': C}, **kw)
+    assert sum(len(plain['spt_aligned'][c]['data']) for c in range(C)) > 100
+    for c in range(C):
+        for key in ('spt', 'spt_aligned', 'sp_waves', 'features'):
+            assert np.array_equal(plain[key][c]['data'], staged[key][c]['data']), (c, key)
