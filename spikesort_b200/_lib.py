@@ -183,6 +183,55 @@ def np_dtype_full(torch_dtype):
                      t.int64: np.int64, t.int32: np.int32, t.uint8: np.uint8}[torch_dtype])
 
 
+_STAGE = {}                      # device index -> two pinned uint8 staging buffers
+
+
+def upload(host):
+    """CPU torch tensor -> CUDA tensor of the same shape.  Pinned and small tensors are one
+    (asynchronous) copy.  A big PAGEABLE tensor - the usual NumPy array - would be staged by the
+    CUDA runtime itself at a fraction of the PCIe rate; it goes through two pinned 32 MB buffers
+    instead: a few threads copy chunk k + 1 into one of them (NumPy's copy releases the GIL) while
+    the DMA of chunk k runs out of the other.  SS_PAGEABLE_STAGING=0 switches that off."""
+    t = torch()
+    nbytes = host.numel() * host.element_size()
+    if host.is_cuda or nbytes < (64 << 20) or not host.is_contiguous() or host.is_pinned() or \
+            os.environ.get("SS_PAGEABLE_STAGING", "1")[:1] == "0":
+        return host.to(device(), non_blocking=True)
+    import concurrent.futures
+    dev = t.empty(host.shape, dtype=host.dtype, device=device())
+    src = host.reshape(-1).view(t.uint8).numpy()
+    dst = dev.reshape(-1).view(t.uint8)
+    chunk = 32 << 20
+    key = t.cuda.current_device()
+    if key not in _STAGE:
+        _STAGE[key] = [t.empty(chunk, dtype=t.uint8).pin_memory() for _ in range(2)]
+    bufs = _STAGE[key]
+    views = [b.numpy() for b in bufs]
+    n_thr = int(os.environ.get("SS_STAGING_THREADS", "0")) or max(1, min(8, (os.cpu_count() or 2) // 2))
+    done = [None, None]
+    with concurrent.futures.ThreadPoolExecutor(max_workers=n_thr) as pool:
+        for i, off in enumerate(range(0, nbytes, chunk)):
+            slot = i & 1
+            n = min(chunk, nbytes - off)
+            if done[slot] is not None:
+                done[slot].synchronize()                  # the DMA out of this buffer has finished
+            part = (n + n_thr - 1) // n_thr
+
+            def copy(p0, slot=slot, off=off, n=n, part=part):
+                p1 = min(p0 + part, n)
+                np.copyto(views[slot][p0:p1], src[off + p0:off + p1])
+
+            list(pool.map(copy, range(0, n, part)))
+            dst[off:off + n].copy_(bufs[slot][:n], non_blocking=True)
+            ev = t.cuda.Event()
+            ev.record()
+            done[slot] = ev
+    for ev in done:                                       # the staging buffers are reused by the next call
+        if ev is not None:
+            ev.synchronize()
+    return dev
+
+
 def to_device_2d(data):
     """Recording (n_contacts, n_samples) -> CUDA tensor of a supported dtype with
     unit stride along time.  Accepts DeviceSignal, torch tensors and anything
@@ -202,7 +251,7 @@ def to_device_2d(data):
         x = x.to(t.float64)
     if x.dim() == 1:
         x = x.unsqueeze(0)
-    x = x.to(device(), non_blocking=True)
+    x = upload(x)
     if x.stride(-1) != 1:
         x = x.contiguous()
     return x

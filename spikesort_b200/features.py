@@ -50,7 +50,7 @@ def _device_block(block):
         dev = t.from_numpy(np.ascontiguousarray(host))
     if dev.dim() == 2:
         dev = dev.unsqueeze(2)
-    return dev.to(_lib.device()).contiguous()
+    return _lib.upload(dev).contiguous()
 
 
 def _float_block(block):

@@ -399,3 +399,22 @@ def test_sort_frontend_pageable_numpy_recording(cuda, monkeypatch):
     for c in range(C):
         for key in ('spt', 'spt_aligned', 'sp_waves', 'features'):
             assert np.array_equal(plain[key][c]['data'], staged[key][c]['data']), (c, key)
+
+
+@pytest.mark.parametrize("shape,dtype", [((9, 4000001), np.int16), ((25, 700001, 1), np.float32),
+                                         ((3, 3000000), np.float64)])
+def test_staged_upload_of_pageable_arrays(cuda, monkeypatch, shape, dtype):
+    """_lib.upload: big pageable arrays go through two pinned staging buffers (threaded chunk
+    copies under the DMA of the chunk before); byte-identical to torch's own copy, odd sizes and
+    a chunk-sized tail included."""
+    import torch
+    from spikesort_b200 import _lib
+    rng = np.random.default_rng(1)
+    host = (rng.standard_normal(shape) * 1000).astype(dtype)
+    assert host.nbytes >= 64 << 20
+    monkeypatch.setenv("SS_STAGING_THREADS", "3")
+    got = _lib.upload(torch.from_numpy(host))
+    assert got.is_cuda and got.shape == torch.Size(shape)
+    assert torch.equal(got.cpu(), torch.from_numpy(host))
+    monkeypatch.setenv("SS_PAGEABLE_STAGING", "0")
+    assert torch.equal(_lib.upload(torch.from_numpy(host)), got)
