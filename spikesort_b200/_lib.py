@@ -184,6 +184,7 @@ def np_dtype_full(torch_dtype):
 
 
 _STAGE = {}                      # device index -> two pinned uint8 staging buffers
+_STAGE_LOCK = __import__("threading").Lock()   # the staging buffers serve one upload at a time
 
 
 def upload(host):
@@ -197,6 +198,11 @@ def upload(host):
     if host.is_cuda or nbytes < (64 << 20) or not host.is_contiguous() or host.is_pinned() or \
             os.environ.get("SS_PAGEABLE_STAGING", "1")[:1] == "0":
         return host.to(device(), non_blocking=True)
+    with _STAGE_LOCK:
+        return _staged_upload(t, host, nbytes)
+
+
+def _staged_upload(t, host, nbytes):
     import concurrent.futures
     dev = t.empty(host.shape, dtype=host.dtype, device=device())
     src = host.reshape(-1).view(t.uint8).numpy()
