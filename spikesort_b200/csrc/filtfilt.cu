@@ -1148,7 +1148,10 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
         const int64_t e_unit = ti.cs0 - pe - tma_e0;
         // fast tiles: interior, the unit's windows realigned by this instantiation, tile starts a
         // whole number of tensor-map rows from the map's base, no halo duty
-        int64_t lo = (pe + FS_T - 1) / FS_T, hi = (ti.L + pe) / FS_T;
+        // (a fast tile ends at least 8 samples inside its chunk: the 1040-byte window of its bulk
+        //  copy may reach 14 bytes behind the tile - only with padlen 0 can a unit's last tile end
+        //  exactly with the chunk, and the recording)
+        int64_t lo = (pe + FS_T - 1) / FS_T, hi = (ti.L + pe - 8) / FS_T;
         if ((e_unit & 15) != 0) hi = 0;
         if (mk.peer_left || mk.peer_right) {
             const int64_t l2 = (mk.halo_H - ti.cs0 + pe + FS_T - 1) / FS_T;
