@@ -1150,8 +1150,9 @@ filt_apply_tma_kernel(const int16_t *__restrict__ x, const FiltGeom g,
         // whole number of tensor-map rows from the map's base, no halo duty
         // (a fast tile ends at least 8 samples inside its chunk: the 1040-byte window of its bulk
         //  copy may reach 14 bytes behind the tile - only with padlen 0 can a unit's last tile end
-        //  exactly with the chunk, and the recording)
-        int64_t lo = (pe + FS_T - 1) / FS_T, hi = (ti.L + pe - 8) / FS_T;
+        //  exactly with the chunk, and the recording;
+        //  ... and starts at least 8 samples inside it: the window may begin 14 bytes in front)
+        int64_t lo = (pe + 8 + FS_T - 1) / FS_T, hi = (ti.L + pe - 8) / FS_T;
         if ((e_unit & 15) != 0) hi = 0;
         if (mk.peer_left || mk.peer_right) {
             const int64_t l2 = (mk.halo_H - ti.cs0 + pe + FS_T - 1) / FS_T;
