@@ -104,3 +104,26 @@ def test_read_sp_streams_to_device(cuda, tmp_path):
     for c in range(4):
         assert filecmp.cmp(str(tmp_path / ("Gollum_5gollum01_el3_c%d.sp" % (c + 1))),
                            str(tmp_path / ("Gollum_5gollum01_el4_c%d.sp" % (c + 1))), shallow=False)
+
+
+def test_pageable_source_copies_slabs_with_threads():
+    """pipeline._PageableSource (an in-memory NumPy recording as a slab source of the feeder):
+    any slab, any thread count, ragged last slab - the bytes of arr[:, a:b], nothing else touched."""
+    from spikesort_b200 import pipeline
+    rng = np.random.default_rng(0)
+    arr = rng.integers(-30000, 30000, size=(7, 5003)).astype(np.int16)
+    src = pipeline._PageableSource(arr)
+    assert src.shape == (7, 5003) and src.dtype == np.int16
+    default_threads = pipeline._PageableSource.THREADS
+    for threads in (1, 3, 16):
+        pipeline._PageableSource.THREADS = threads
+        for a, b in [(0, 1000), (1000, 5003), (4999, 5003), (17, 18)]:
+            out = np.full((7, 4100), 7, dtype=np.int16)
+            src.read_slab(a, b, out[:, :b - a] if b - a < 4100 else out)
+            assert np.array_equal(out[:, :b - a], arr[:, a:b])
+            assert (out[:, b - a:] == 7).all()
+    pipeline._PageableSource.THREADS = default_threads
+    single = pipeline._PageableSource(arr[:1])
+    out = np.zeros((1, 10), np.int16)
+    single.read_slab(5, 15, out)
+    assert np.array_equal(out, arr[:1, 5:15])
